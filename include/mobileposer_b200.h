@@ -1,0 +1,164 @@
+/*
+ * mobileposer_b200 -- C ABI of the B200 (sm_100a) hot path.
+ *
+ * The reference (SPICExLAB/MobilePoser) has no FFI: its boundary for this path is the
+ * Python class surface of `MobilePoserNet`.  Each entry point
+ * below replaces one torch call chain of that surface; the host-side mirror in
+ * mobileposer_b200/{modules,net}.py binds them with ctypes (INTEGRATION.md shows the
+ * stub a reference maintainer would add).  Citations are relative to /root/reference.
+ *
+ * Conventions
+ *   - all tensors are fp32, row-major contiguous, DEVICE pointers owned by the caller
+ *     (torch), unless the name ends in `_host`;
+ *   - `stream` is a cudaStream_t passed as void*; work is enqueued, never synchronised
+ *     (except the `_host` entry points, which return after the results are on the host);
+ *   - no allocation on the forward path: scratch comes from the caller (`*_workspace_bytes`);
+ *   - return value: MP_OK (0) or a negative mp_status; mp_last_error() gives the message
+ *     (thread local).  The Python mirror raises RuntimeError on non-zero;
+ *   - a handle may be used from one thread / one stream at a time.
+ */
+#ifndef MOBILEPOSER_B200_H_
+#define MOBILEPOSER_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MP_ABI_VERSION 1
+
+typedef enum mp_status {
+    MP_OK = 0,
+    MP_ERR_INVALID = -1,     /* bad argument (shape, null pointer, alignment)               */
+    MP_ERR_CUDA = -2,        /* a CUDA runtime call or launch failed                        */
+    MP_ERR_WORKSPACE = -3,   /* workspace smaller than *_workspace_bytes()                   */
+    MP_ERR_STATE = -4,       /* carried LSTM state does not match the batch (velocity.py:45) */
+    MP_ERR_UNSUPPORTED = -5  /* not an sm_100 device / shape outside the built kernels       */
+} mp_status;
+
+typedef struct mp_rnn mp_rnn_t; /* packed weights of one RNN head  */
+typedef struct mp_net mp_net_t; /* four heads + streams + graphs   */
+typedef void* mp_stream_t;      /* cudaStream_t                    */
+
+int mp_abi_version(void);
+const char* mp_last_error(void);
+/* MP_OK iff the current CUDA device is compute capability 10.x. */
+int mp_device_check(void);
+
+/* ------------------------------------------------------------------------------------------
+ * One RNN head = mobileposer/models/rnn.py:13-33 (linear1 -> ReLU -> 2-layer LSTM -> linear2).
+ * Pointers are the tensors of the head's state_dict in torch's own layouts
+ * (weight_ih_l{k}[_reverse] [4H, In], weight_hh [4H, H], biases [4H]; gate rows i,f,g,o).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct mp_rnn_weights {
+    int32_t n_input, n_output, n_hidden, n_layers, bidirectional;
+    const float* linear1_w; /* [H, n_input]        */
+    const float* linear1_b; /* [H]                 */
+    const float* linear2_w; /* [n_output, dirs*H]  */
+    const float* linear2_b; /* [n_output]          */
+    const float* w_ih[2][2]; /* [layer][dir]       */
+    const float* w_hh[2][2];
+    const float* b_ih[2][2];
+    const float* b_hh[2][2];
+} mp_rnn_weights_t;
+
+/* Repack the weights into the library's resident layout (device allocations; cold path). */
+int mp_rnn_create(mp_rnn_t** out, const mp_rnn_weights_t* w, mp_stream_t stream);
+void mp_rnn_destroy(mp_rnn_t* rnn);
+size_t mp_rnn_workspace_bytes(const mp_rnn_t* rnn, int32_t B, int32_t T);
+
+/* RNN.forward(x, seq_lengths, h) -> (y, (h_n, c_n))            [rnn.py:20-33]
+ *   input  = concat(xa [B,T,ka], xb [B,T,kb]) on the last dim (xb may be NULL, kb = 0): the
+ *            torch.cat of net.py:106,113 is folded into the first GEMM;
+ *   lengths [B] int32 device (NULL = all T): packed-sequence semantics -- the reverse
+ *            direction of sequence b starts at frame lengths[b]-1, frames >= lengths[b] of the
+ *            LSTM output are zero so y there equals linear2.bias (pad_packed_sequence);
+ *   h0/c0, hn/cn [layers*dirs, B, H] (NULL = zeros / not wanted);
+ *   y [B, T, n_output].                                                                      */
+int mp_rnn_forward(const mp_rnn_t* rnn, const float* xa, int32_t ka, const float* xb, int32_t kb,
+                   int32_t B, int32_t T, const int32_t* lengths,
+                   const float* h0, const float* c0, float* hn, float* cn, float* y,
+                   void* workspace, size_t workspace_bytes, mp_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Kinematic tail.
+ * ---------------------------------------------------------------------------------------- */
+/* MobilePoserNet._reduced_global_to_full                         [net.py:93-99]
+ *   r6d [n_frames, 96] -> local rotations [n_frames, 24, 3, 3]
+ *   (angular.py:167-182 Gram-Schmidt with NaN->0, model_utils.py:18-25 scatter,
+ *    spatial.py:115-123 inverse tree, ignored joints -> I, root = global root).              */
+int mp_pose_reduced_global_to_full(const float* r6d, int64_t n_frames, float* pose, mp_stream_t stream);
+
+/* Translation fusion of forward_offline                          [net.py:125-154]
+ *   joints [B,T,72], vel [B,T,72], contact [B,T,2] logits -> tran [B,T,3]; per sequence b only
+ *   frames < lengths[b] are written (rest zero).  Floor clamp replayed sequentially with the
+ *   reference's float64 scalars; prefix sums accumulated in float64.                          */
+int mp_tran_offline(const float* joints, const float* vel, const float* contact, const int32_t* lengths,
+                    int32_t B, int32_t T, float* tran, mp_stream_t stream);
+
+/* Per-stream state of forward_online                             [net.py:59-64,84-88,173-219]
+ * One block of MP_ONLINE_STATE_FLOATS floats + 1 double per stream, device resident:
+ *   [0:3] last_lfoot_pos  [3:6] last_rfoot_pos  [6:9] last_root_pos ; double current_root_y   */
+#define MP_ONLINE_STATE_FLOATS 12
+typedef struct mp_online_state {
+    float last_lfoot[3];
+    float last_rfoot[3];
+    float last_root[3];
+    float pad_[3];
+    double current_root_y;
+    double pad2_;
+} mp_online_state_t;
+
+/* Online tick tail for S streams: takes frame `frame_idx` (= past_frames) of the forward outputs
+ * pose [S*W,24,3,3], joints/vel [S,W,72], contact [S,W,2]; updates state[S]; writes
+ * pose_out [S,24,9], root_out [S,3], contact_out [S,2].                  [net.py:181-208,219] */
+int mp_online_update(mp_online_state_t* state, const float* pose, const float* joints, const float* vel,
+                     const float* contact, int32_t S, int32_t W, int32_t frame_idx,
+                     float* pose_out, float* root_out, float* contact_out, mp_stream_t stream);
+/* Sliding IMU window of forward_online (net.py:175): win_out[s] = cat(win_in[s][1:], frame[s]);
+ * cold != 0 replicates frame[s] over the whole window (first tick).  win_in != win_out.       */
+int mp_online_push_frame(const float* win_in, float* win_out, const float* frame, int32_t S, int32_t W,
+                         int32_t cold, mp_stream_t stream);
+/* reset(): current_root_y = 0, last_root_pos = 0 (feet NOT reset, net.py:84-88);
+ * full != 0 additionally restores the zero-pose feet (constructor values, net.py:59).         */
+int mp_online_reset(mp_online_state_t* state, int32_t S, int32_t full, mp_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Whole net = MobilePoserNet.forward / forward_offline           [net.py:101-171]
+ * ---------------------------------------------------------------------------------------- */
+/* The net borrows the four heads (they must outlive it). */
+int mp_net_create(mp_net_t** out, const mp_rnn_t* joints, const mp_rnn_t* pose,
+                  const mp_rnn_t* foot_contact, const mp_rnn_t* velocity);
+void mp_net_destroy(mp_net_t* net);
+size_t mp_net_workspace_bytes(const mp_net_t* net, int32_t B, int32_t T);
+/* 1 = replay the forward as a cached CUDA graph keyed on (pointers, B, T) (default 1). */
+int mp_net_set_graph(mp_net_t* net, int32_t enabled);
+
+/* forward: joints -> {pose -> K5, foot_contact, velocity(stateful)} on forked streams.
+ *   imu [B,T,60]; vel_h0/c0 -> vel_hn/cn [2,B,256] carried velocity state (NULL h0 = zeros);
+ *   outputs: pose [B*T,24,3,3], joints [B,T,72], vel [B,T,72], contact [B,T,2];
+ *   tran [B,T,3] may be NULL (forward) or non-NULL (forward_offline's translation, K6).       */
+int mp_net_forward(mp_net_t* net, const float* imu, int32_t B, int32_t T, const int32_t* lengths,
+                   const float* vel_h0, const float* vel_c0, float* vel_hn, float* vel_cn,
+                   float* pose, float* joints, float* vel, float* contact, float* tran,
+                   void* workspace, size_t workspace_bytes, mp_stream_t stream);
+
+/* Same through HOST buffers (pinned recommended): H2D of imu/lengths, forward_offline, D2H of
+ * pose/joints/tran/contact, then a stream synchronise.  `dev_io` is device staging of at least
+ * mp_net_host_staging_bytes(B,T).  Used for the end-to-end number of bench.py.               */
+size_t mp_net_host_staging_bytes(int32_t B, int32_t T);
+int mp_net_forward_offline_host(mp_net_t* net, const float* imu_host, int32_t B, int32_t T,
+                                const int32_t* lengths_host, float* pose_host, float* joints_host,
+                                float* tran_host, float* contact_host, void* dev_io,
+                                void* workspace, size_t workspace_bytes, mp_stream_t stream);
+
+/* How many kernels of this library the last mp_net_forward / mp_rnn_forward enqueued
+ * (bench.py's gpu_launches).                                                                 */
+int64_t mp_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MOBILEPOSER_B200_H_ */

@@ -1,0 +1,86 @@
+"""ctypes binding of include/mobileposer_b200.h (the only way the package reaches the GPU kernels).
+
+There is deliberately no fallback: if the shared library is missing, or the device is not an
+sm_100 part, every entry point raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from .build import LIB_PATH
+
+_lib = None
+
+c_float_p = C.c_void_p     # device / host pointers travel as integers (tensor.data_ptr())
+c_int_p = C.c_void_p
+c_stream = C.c_void_p
+
+
+class RnnWeights(C.Structure):
+    """struct mp_rnn_weights (include/mobileposer_b200.h)."""
+    _fields_ = [
+        ('n_input', C.c_int32), ('n_output', C.c_int32), ('n_hidden', C.c_int32),
+        ('n_layers', C.c_int32), ('bidirectional', C.c_int32),
+        ('linear1_w', C.c_void_p), ('linear1_b', C.c_void_p),
+        ('linear2_w', C.c_void_p), ('linear2_b', C.c_void_p),
+        ('w_ih', (C.c_void_p * 2) * 2), ('w_hh', (C.c_void_p * 2) * 2),
+        ('b_ih', (C.c_void_p * 2) * 2), ('b_hh', (C.c_void_p * 2) * 2),
+    ]
+
+
+ONLINE_STATE_BYTES = 64   # sizeof(mp_online_state_t)
+
+# name -> (restype, argtypes); must list every symbol the header declares (tests/test_cabi.py)
+SIGNATURES = {
+    'mp_abi_version': (C.c_int, []),
+    'mp_last_error': (C.c_char_p, []),
+    'mp_device_check': (C.c_int, []),
+    'mp_launch_count': (C.c_int64, []),
+    'mp_rnn_create': (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(RnnWeights), c_stream]),
+    'mp_rnn_destroy': (None, [C.c_void_p]),
+    'mp_rnn_workspace_bytes': (C.c_size_t, [C.c_void_p, C.c_int32, C.c_int32]),
+    'mp_rnn_forward': (C.c_int, [C.c_void_p, c_float_p, C.c_int32, c_float_p, C.c_int32, C.c_int32, C.c_int32,
+                                 c_int_p, c_float_p, c_float_p, c_float_p, c_float_p, c_float_p,
+                                 C.c_void_p, C.c_size_t, c_stream]),
+    'mp_pose_reduced_global_to_full': (C.c_int, [c_float_p, C.c_int64, c_float_p, c_stream]),
+    'mp_tran_offline': (C.c_int, [c_float_p, c_float_p, c_float_p, c_int_p, C.c_int32, C.c_int32, c_float_p, c_stream]),
+    'mp_online_update': (C.c_int, [C.c_void_p, c_float_p, c_float_p, c_float_p, c_float_p, C.c_int32, C.c_int32,
+                                   C.c_int32, c_float_p, c_float_p, c_float_p, c_stream]),
+    'mp_online_push_frame': (C.c_int, [c_float_p, c_float_p, c_float_p, C.c_int32, C.c_int32, C.c_int32, c_stream]),
+    'mp_online_reset': (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, c_stream]),
+    'mp_net_create': (C.c_int, [C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    'mp_net_destroy': (None, [C.c_void_p]),
+    'mp_net_workspace_bytes': (C.c_size_t, [C.c_void_p, C.c_int32, C.c_int32]),
+    'mp_net_set_graph': (C.c_int, [C.c_void_p, C.c_int32]),
+    'mp_net_forward': (C.c_int, [C.c_void_p, c_float_p, C.c_int32, C.c_int32, c_int_p, c_float_p, c_float_p,
+                                 c_float_p, c_float_p, c_float_p, c_float_p, c_float_p, c_float_p, c_float_p,
+                                 C.c_void_p, C.c_size_t, c_stream]),
+    'mp_net_host_staging_bytes': (C.c_size_t, [C.c_int32, C.c_int32]),
+    'mp_net_forward_offline_host': (C.c_int, [C.c_void_p, c_float_p, C.c_int32, C.c_int32, c_int_p, c_float_p,
+                                              c_float_p, c_float_p, c_float_p, C.c_void_p, C.c_void_p, C.c_size_t,
+                                              c_stream]),
+}
+
+
+def lib():
+    """Load (once) and return the shared library; raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f'{LIB_PATH} is missing: build it with `python -m mobileposer_b200.build` '
+                '(mobileposer_b200 has no CPU or eager fallback).')
+        handle = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def check(status: int, what: str = '') -> None:
+    if status != 0:
+        msg = lib().mp_last_error().decode('utf-8', 'replace')
+        raise RuntimeError(f'mobileposer_b200 {what} failed (status {status}): {msg}')

@@ -1,0 +1,56 @@
+"""Build libmobileposer_b200.so in-tree with nvcc for sm_100a (no JIT cache: the .so travels with the repo).
+
+    python -m mobileposer_b200.build [--force]
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(PKG, 'csrc')
+LIB_DIR = os.path.join(PKG, 'lib')
+LIB_PATH = os.path.join(LIB_DIR, 'libmobileposer_b200.so')
+SOURCES = ['gemm.cu', 'lstm_rec.cu', 'kinematics.cu', 'api.cu']
+HEADERS = [os.path.join(CSRC, 'mp_common.cuh'),
+           os.path.join(os.path.dirname(PKG), 'include', 'mobileposer_b200.h')]
+NVCC_FLAGS = ['-std=c++17', '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3',
+              '-Xcompiler', '-fPIC', '-shared']
+
+
+def _nvcc() -> str:
+    exe = shutil.which('nvcc') or '/usr/local/cuda/bin/nvcc'
+    if not os.path.exists(exe):
+        raise RuntimeError('nvcc not found: cannot build libmobileposer_b200.so')
+    return exe
+
+
+def is_stale() -> bool:
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    deps = [os.path.join(CSRC, s) for s in SOURCES] + HEADERS
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile every CUDA source for sm_100a into one shared library; returns its path."""
+    if not force and not is_stale():
+        return LIB_PATH
+    os.makedirs(LIB_DIR, exist_ok=True)
+    cmd = [_nvcc(), *NVCC_FLAGS, '-o', LIB_PATH, *[os.path.join(CSRC, s) for s in SOURCES]]
+    if verbose:
+        cmd.insert(1, '-Xptxas=-v')
+        print(' '.join(cmd))
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError('nvcc failed:\n' + res.stdout + res.stderr)
+    if verbose:
+        print(res.stderr)
+    return LIB_PATH
+
+
+if __name__ == '__main__':
+    print(build(force='--force' in sys.argv, verbose='-v' in sys.argv))

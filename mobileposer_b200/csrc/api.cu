@@ -1,0 +1,462 @@
+// C ABI of mobileposer_b200 (include/mobileposer_b200.h): weight packing, one-head forward,
+// whole-net forward on forked streams replayed as a CUDA graph, host-buffer entry point.
+#include "mp_common.cuh"
+
+#include <stdarg.h>
+
+#include <vector>
+
+namespace mp {
+
+static thread_local char g_err[512] = "";
+static thread_local int64_t g_launches = 0;
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+void count_launch(int n) { g_launches += n; }
+
+namespace {
+
+inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+__global__ void bias_sum_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ o, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) o[i] = a[i] + b[i];
+}
+
+}  // namespace
+}  // namespace mp
+
+using namespace mp;
+
+struct mp_rnn {
+    int n_in = 0, n_out = 0, H = 0, dirs = 1;
+    void* blob = nullptr;
+    float *w1 = nullptr, *b1 = nullptr, *w2 = nullptr, *b2 = nullptr;
+    float* wih[2] = {nullptr, nullptr};    // [dirs*4H, In_l]   both directions stacked on N
+    float* bsum[2] = {nullptr, nullptr};   // [dirs*4H]         b_ih + b_hh
+    float4* whh_pack[2] = {nullptr, nullptr};
+    float* whh_t[2] = {nullptr, nullptr};
+};
+
+struct mp_net {
+    const mp_rnn *joints = nullptr, *pose = nullptr, *foot = nullptr, *vel = nullptr;
+    cudaStream_t s_foot = nullptr, s_vel = nullptr, s_cap = nullptr;
+    cudaEvent_t ev_joints = nullptr, ev_foot = nullptr, ev_vel = nullptr;
+    int graph_enabled = 1;
+    struct Entry {
+        std::vector<uintptr_t> key;
+        cudaGraphExec_t exec = nullptr;
+        int64_t kernels = 0;
+        uint64_t stamp = 0;
+    };
+    std::vector<Entry> cache;
+    uint64_t clock = 0;
+};
+
+extern "C" {
+
+int mp_abi_version(void) { return MP_ABI_VERSION; }
+const char* mp_last_error(void) { return g_err; }
+int64_t mp_launch_count(void) { return g_launches; }
+
+int mp_device_check(void) {
+    int dev = 0, major = 0;
+    MP_CUDA_TRY(cudaGetDevice(&dev));
+    MP_CUDA_TRY(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+    if (major != 10) {
+        set_error("mobileposer_b200 is built for sm_100a only; device %d is compute capability %d.x", dev, major);
+        return MP_ERR_UNSUPPORTED;
+    }
+    return MP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+int mp_rnn_create(mp_rnn_t** out, const mp_rnn_weights_t* w, mp_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    MP_REQUIRE(out && w, "rnn_create: null argument");
+    MP_REQUIRE(w->n_layers == 2, "rnn_create: only the reference's 2-layer LSTM is built (got %d)", w->n_layers);
+    MP_REQUIRE(w->n_hidden == 256 || w->n_hidden == 64, "rnn_create: hidden size %d not built (64, 256)", w->n_hidden);
+    MP_REQUIRE(w->n_input > 0 && (w->n_input & 3) == 0, "rnn_create: n_input %d must be a multiple of 4", w->n_input);
+    MP_REQUIRE(w->n_output > 0, "rnn_create: n_output");
+    MP_TRY(mp_device_check());
+    const int H = w->n_hidden, dirs = w->bidirectional ? 2 : 1;
+    MP_REQUIRE(w->linear1_w && w->linear1_b && w->linear2_w && w->linear2_b, "rnn_create: null linear weights");
+    for (int l = 0; l < 2; ++l)
+        for (int d = 0; d < dirs; ++d)
+            MP_REQUIRE(w->w_ih[l][d] && w->w_hh[l][d] && w->b_ih[l][d] && w->b_hh[l][d], "rnn_create: null LSTM weights (layer %d dir %d)", l, d);
+
+    mp_rnn* r = new mp_rnn();
+    r->n_in = w->n_input; r->n_out = w->n_output; r->H = H; r->dirs = dirs;
+    const int in_l[2] = {H, dirs * H};
+    size_t off = 0;
+    auto take = [&](size_t floats) { size_t o = off; off = align_up(off + floats * sizeof(float)); return o; };
+    const size_t o_w1 = take((size_t)H * r->n_in), o_b1 = take(H);
+    const size_t o_w2 = take((size_t)r->n_out * dirs * H), o_b2 = take(r->n_out);
+    size_t o_wih[2], o_bs[2], o_pk[2], o_wt[2];
+    for (int l = 0; l < 2; ++l) {
+        o_wih[l] = take((size_t)dirs * 4 * H * in_l[l]);
+        o_bs[l] = take((size_t)dirs * 4 * H);
+        o_pk[l] = take(whh_pack_float4s(H, dirs) * 4);
+        o_wt[l] = take((size_t)dirs * 4 * H * H);
+    }
+    cudaError_t e = cudaMalloc(&r->blob, off);
+    if (e != cudaSuccess) {
+        delete r;
+        set_error("rnn_create: cudaMalloc(%zu) failed: %s", off, cudaGetErrorString(e));
+        return MP_ERR_CUDA;
+    }
+    char* base = (char*)r->blob;
+    r->w1 = (float*)(base + o_w1); r->b1 = (float*)(base + o_b1);
+    r->w2 = (float*)(base + o_w2); r->b2 = (float*)(base + o_b2);
+    int st = MP_OK;
+    auto copy = [&](float* dst, const float* src, size_t floats) {
+        if (st == MP_OK && cudaMemcpyAsync(dst, src, floats * sizeof(float), cudaMemcpyDeviceToDevice, stream) != cudaSuccess) {
+            set_error("rnn_create: weight copy failed: %s", cudaGetErrorString(cudaGetLastError()));
+            st = MP_ERR_CUDA;
+        }
+    };
+    copy(r->w1, w->linear1_w, (size_t)H * r->n_in);
+    copy(r->b1, w->linear1_b, H);
+    copy(r->w2, w->linear2_w, (size_t)r->n_out * dirs * H);
+    copy(r->b2, w->linear2_b, r->n_out);
+    for (int l = 0; l < 2 && st == MP_OK; ++l) {
+        r->wih[l] = (float*)(base + o_wih[l]);
+        r->bsum[l] = (float*)(base + o_bs[l]);
+        r->whh_pack[l] = (float4*)(base + o_pk[l]);
+        r->whh_t[l] = (float*)(base + o_wt[l]);
+        const float* whh[2] = {w->w_hh[l][0], w->w_hh[l][dirs - 1]};
+        for (int d = 0; d < dirs; ++d) {
+            copy(r->wih[l] + (size_t)d * 4 * H * in_l[l], w->w_ih[l][d], (size_t)4 * H * in_l[l]);
+            bias_sum_kernel<<<(4 * H + 255) / 256, 256, 0, stream>>>(w->b_ih[l][d], w->b_hh[l][d], r->bsum[l] + (size_t)d * 4 * H, 4 * H);
+        }
+        if (st == MP_OK) st = launch_pack_whh(whh, H, dirs, r->whh_pack[l], r->whh_t[l], stream);
+    }
+    if (st == MP_OK && cudaStreamSynchronize(stream) != cudaSuccess) {
+        set_error("rnn_create: packing failed: %s", cudaGetErrorString(cudaGetLastError()));
+        st = MP_ERR_CUDA;
+    }
+    if (st != MP_OK) {
+        cudaFree(r->blob);
+        delete r;
+        return st;
+    }
+    *out = r;
+    return MP_OK;
+}
+
+void mp_rnn_destroy(mp_rnn_t* r) {
+    if (!r) return;
+    cudaFree(r->blob);
+    delete r;
+}
+
+static void rnn_ws_layout(const mp_rnn* r, size_t M, size_t* o_x1, size_t* o_gin, size_t* o_y0, size_t* o_y1, size_t* total) {
+    size_t off = 0;
+    auto take = [&](size_t floats) { size_t o = off; off = align_up(off + floats * sizeof(float)); return o; };
+    *o_x1 = take(M * r->H);
+    *o_gin = take(M * r->dirs * 4 * r->H);
+    *o_y0 = take(M * r->dirs * r->H);
+    *o_y1 = take(M * r->dirs * r->H);
+    *total = off;
+}
+
+size_t mp_rnn_workspace_bytes(const mp_rnn_t* r, int32_t B, int32_t T) {
+    if (!r || B <= 0 || T <= 0) return 0;
+    size_t a, b, c, d, total;
+    rnn_ws_layout(r, (size_t)B * T, &a, &b, &c, &d, &total);
+    return total;
+}
+
+static int rnn_forward_impl(const mp_rnn_t* r, const float* xa, int32_t ka, const float* xb, int32_t kb, int32_t B, int32_t T,
+                            const int32_t* lengths, const float* h0, const float* c0, float* hn, float* cn, float* y,
+                            void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+    MP_REQUIRE(r && xa && y && workspace, "rnn_forward: null argument");
+    MP_REQUIRE(B > 0 && T > 0, "rnn_forward: empty batch (B=%d T=%d)", B, T);
+    MP_REQUIRE(ka + kb == r->n_in, "rnn_forward: input width %d+%d != n_input %d", ka, kb, r->n_in);
+    MP_REQUIRE((h0 == nullptr) == (c0 == nullptr), "rnn_forward: h0 and c0 must both be given or both be null");
+    MP_REQUIRE(((uintptr_t)workspace & 255) == 0, "rnn_forward: workspace must be 256-byte aligned");
+    const size_t M = (size_t)B * T;
+    MP_REQUIRE(M * (size_t)r->dirs * 4 * r->H < (size_t)1 << 40, "rnn_forward: batch too large");
+    size_t o_x1, o_gin, o_y0, o_y1, total;
+    rnn_ws_layout(r, M, &o_x1, &o_gin, &o_y0, &o_y1, &total);
+    if (workspace_bytes < total) {
+        set_error("rnn_forward: workspace %zu < required %zu", workspace_bytes, total);
+        return MP_ERR_WORKSPACE;
+    }
+    char* ws = (char*)workspace;
+    float* x1 = (float*)(ws + o_x1);
+    float* gin = (float*)(ws + o_gin);
+    float* ybuf[2] = {(float*)(ws + o_y0), (float*)(ws + o_y1)};
+    const int H = r->H, dirs = r->dirs;
+    // linear1 + ReLU (dropout is the identity in eval)                         rnn.py:22
+    MP_TRY(launch_gemm_bias_act(xa, ka, xb, kb, r->w1, r->b1, x1, (int)M, H, 1, stream));
+    const float* layer_in = x1;
+    int in_w = H;
+    for (int l = 0; l < 2; ++l) {
+        // hoisted input projection of both directions                        rnn.py:27 (W_ih x + b_ih + b_hh)
+        MP_TRY(launch_gemm_bias_act(layer_in, in_w, nullptr, 0, r->wih[l], r->bsum[l], gin, (int)M, dirs * 4 * H, 0, stream));
+        RecLayerArgs a;
+        a.gin = gin; a.wpack = r->whh_pack[l]; a.wT = r->whh_t[l]; a.y = ybuf[l];
+        const size_t so = (size_t)l * dirs * B * H;
+        a.h0 = h0 ? h0 + so : nullptr; a.c0 = c0 ? c0 + so : nullptr;
+        a.hn = hn ? hn + so : nullptr; a.cn = cn ? cn + so : nullptr;
+        a.lengths = lengths; a.B = B; a.T = T; a.H = H; a.dirs = dirs;
+        MP_TRY(launch_lstm_recurrence(a, stream));
+        layer_in = ybuf[l];
+        in_w = dirs * H;
+    }
+    // linear2                                                                 rnn.py:32
+    MP_TRY(launch_gemm_bias_act(layer_in, in_w, nullptr, 0, r->w2, r->b2, y, (int)M, r->n_out, 0, stream));
+    return MP_OK;
+}
+
+int mp_rnn_forward(const mp_rnn_t* r, const float* xa, int32_t ka, const float* xb, int32_t kb, int32_t B, int32_t T,
+                   const int32_t* lengths, const float* h0, const float* c0, float* hn, float* cn, float* y,
+                   void* workspace, size_t workspace_bytes, mp_stream_t stream) {
+    g_launches = 0;
+    return rnn_forward_impl(r, xa, ka, xb, kb, B, T, lengths, h0, c0, hn, cn, y, workspace, workspace_bytes,
+                            (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------------------------------------
+int mp_pose_reduced_global_to_full(const float* r6d, int64_t n_frames, float* pose, mp_stream_t stream) {
+    return launch_reduced_global_to_full(r6d, n_frames, pose, (cudaStream_t)stream);
+}
+int mp_tran_offline(const float* joints, const float* vel, const float* contact, const int32_t* lengths, int32_t B,
+                    int32_t T, float* tran, mp_stream_t stream) {
+    return launch_tran_offline(joints, vel, contact, lengths, B, T, tran, (cudaStream_t)stream);
+}
+int mp_online_update(mp_online_state_t* state, const float* pose, const float* joints, const float* vel,
+                     const float* contact, int32_t S, int32_t W, int32_t frame_idx, float* pose_out, float* root_out,
+                     float* contact_out, mp_stream_t stream) {
+    return launch_online_update(state, pose, joints, vel, contact, S, W, frame_idx, pose_out, root_out, contact_out,
+                                (cudaStream_t)stream);
+}
+int mp_online_push_frame(const float* win_in, float* win_out, const float* frame, int32_t S, int32_t W, int32_t cold,
+                         mp_stream_t stream) {
+    MP_REQUIRE(win_in != win_out, "online push: in-place shift is not supported");
+    return launch_online_push(win_in, win_out, frame, S, W, cold, (cudaStream_t)stream);
+}
+int mp_online_reset(mp_online_state_t* state, int32_t S, int32_t full, mp_stream_t stream) {
+    return launch_online_reset(state, S, full, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------------------------------------
+int mp_net_create(mp_net_t** out, const mp_rnn_t* joints, const mp_rnn_t* pose, const mp_rnn_t* foot,
+                  const mp_rnn_t* velocity) {
+    MP_REQUIRE(out && joints && pose && foot && velocity, "net_create: null argument");
+    MP_REQUIRE(joints->n_in == 60 && joints->n_out == 72, "net_create: joints head must be 60 -> 72");
+    MP_REQUIRE(pose->n_in == 132 && pose->n_out == 96, "net_create: pose head must be 132 -> 96");
+    MP_REQUIRE(foot->n_in == 132 && foot->n_out == 2, "net_create: foot_contact head must be 132 -> 2");
+    MP_REQUIRE(velocity->n_in == 132 && velocity->n_out == 72 && velocity->dirs == 1, "net_create: velocity head must be a unidirectional 132 -> 72");
+    MP_TRY(mp_device_check());
+    mp_net* n = new mp_net();
+    n->joints = joints; n->pose = pose; n->foot = foot; n->vel = velocity;
+    cudaError_t e = cudaSuccess;
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&n->s_foot, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&n->s_vel, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&n->s_cap, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&n->ev_joints, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&n->ev_foot, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&n->ev_vel, cudaEventDisableTiming);
+    if (e != cudaSuccess) {
+        set_error("net_create: %s", cudaGetErrorString(e));
+        mp_net_destroy(n);
+        return MP_ERR_CUDA;
+    }
+    *out = n;
+    return MP_OK;
+}
+
+void mp_net_destroy(mp_net_t* n) {
+    if (!n) return;
+    for (auto& en : n->cache)
+        if (en.exec) cudaGraphExecDestroy(en.exec);
+    if (n->ev_joints) cudaEventDestroy(n->ev_joints);
+    if (n->ev_foot) cudaEventDestroy(n->ev_foot);
+    if (n->ev_vel) cudaEventDestroy(n->ev_vel);
+    if (n->s_foot) cudaStreamDestroy(n->s_foot);
+    if (n->s_vel) cudaStreamDestroy(n->s_vel);
+    if (n->s_cap) cudaStreamDestroy(n->s_cap);
+    delete n;
+}
+
+int mp_net_set_graph(mp_net_t* n, int32_t enabled) {
+    MP_REQUIRE(n, "net_set_graph: null");
+    n->graph_enabled = enabled ? 1 : 0;
+    return MP_OK;
+}
+
+static void net_ws_layout(const mp_net* n, int B, int T, size_t off[5], size_t* total) {
+    size_t o = 0;
+    const mp_rnn* heads[4] = {n->joints, n->pose, n->foot, n->vel};
+    for (int i = 0; i < 4; ++i) {
+        off[i] = o;
+        o = align_up(o + mp_rnn_workspace_bytes(heads[i], B, T));
+    }
+    off[4] = o;   // r6d [B*T, 96]
+    o = align_up(o + (size_t)B * T * 96 * sizeof(float));
+    *total = o;
+}
+
+size_t mp_net_workspace_bytes(const mp_net_t* n, int32_t B, int32_t T) {
+    if (!n || B <= 0 || T <= 0) return 0;
+    size_t off[5], total;
+    net_ws_layout(n, B, T, off, &total);
+    return total;
+}
+
+struct NetArgs {
+    const float* imu; int B, T; const int32_t* lengths;
+    const float *vel_h0, *vel_c0; float *vel_hn, *vel_cn;
+    float *pose, *joints, *vel, *contact, *tran;
+    void* ws; size_t ws_bytes;
+};
+
+// Enqueue the whole forward: joints on `s`, then pose(+K5) on `s`, foot_contact and velocity on the
+// net's side streams (forked after joints, joined before K6).          net.py:101-119,125-154
+static int net_enqueue(mp_net* n, const NetArgs& a, cudaStream_t s) {
+    size_t off[5], total;
+    net_ws_layout(n, a.B, a.T, off, &total);
+    char* ws = (char*)a.ws;
+    auto wsz = [&](int i) { return (i < 3 ? off[i + 1] : off[4]) - off[i]; };
+    float* r6d = (float*)(ws + off[4]);
+    MP_TRY(rnn_forward_impl(n->joints, a.imu, 60, nullptr, 0, a.B, a.T, a.lengths, nullptr, nullptr, nullptr, nullptr,
+                          a.joints, ws + off[0], wsz(0), s));
+    MP_CUDA_TRY(cudaEventRecord(n->ev_joints, s));
+    MP_CUDA_TRY(cudaStreamWaitEvent(n->s_foot, n->ev_joints, 0));
+    MP_CUDA_TRY(cudaStreamWaitEvent(n->s_vel, n->ev_joints, 0));
+    // velocity first on its own stream: it is the longest side branch (unidirectional, 2 x T steps)
+    MP_TRY(rnn_forward_impl(n->vel, a.joints, 72, a.imu, 60, a.B, a.T, a.lengths, a.vel_h0, a.vel_c0, a.vel_hn, a.vel_cn,
+                          a.vel, ws + off[3], wsz(3), n->s_vel));
+    MP_CUDA_TRY(cudaEventRecord(n->ev_vel, n->s_vel));
+    MP_TRY(rnn_forward_impl(n->foot, a.joints, 72, a.imu, 60, a.B, a.T, a.lengths, nullptr, nullptr, nullptr, nullptr,
+                          a.contact, ws + off[2], wsz(2), n->s_foot));
+    MP_CUDA_TRY(cudaEventRecord(n->ev_foot, n->s_foot));
+    MP_TRY(rnn_forward_impl(n->pose, a.joints, 72, a.imu, 60, a.B, a.T, a.lengths, nullptr, nullptr, nullptr, nullptr, r6d,
+                          ws + off[1], wsz(1), s));
+    MP_TRY(launch_reduced_global_to_full(r6d, (int64_t)a.B * a.T, a.pose, s));
+    MP_CUDA_TRY(cudaStreamWaitEvent(s, n->ev_foot, 0));
+    MP_CUDA_TRY(cudaStreamWaitEvent(s, n->ev_vel, 0));
+    if (a.tran) MP_TRY(launch_tran_offline(a.joints, a.vel, a.contact, a.lengths, a.B, a.T, a.tran, s));
+    return MP_OK;
+}
+
+int mp_net_forward(mp_net_t* n, const float* imu, int32_t B, int32_t T, const int32_t* lengths, const float* vel_h0,
+                   const float* vel_c0, float* vel_hn, float* vel_cn, float* pose, float* joints, float* vel,
+                   float* contact, float* tran, void* workspace, size_t workspace_bytes, mp_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    MP_REQUIRE(n && imu && pose && joints && vel && contact && workspace, "net_forward: null argument");
+    MP_REQUIRE(B > 0 && T > 0, "net_forward: empty batch (B=%d T=%d)", B, T);
+    MP_REQUIRE((vel_h0 == nullptr) == (vel_c0 == nullptr), "net_forward: velocity h0/c0 must come together");
+    const size_t need = mp_net_workspace_bytes(n, B, T);
+    if (workspace_bytes < need) {
+        set_error("net_forward: workspace %zu < required %zu", workspace_bytes, need);
+        return MP_ERR_WORKSPACE;
+    }
+    NetArgs a{imu, B, T, lengths, vel_h0, vel_c0, vel_hn, vel_cn, pose, joints, vel, contact, tran, workspace, workspace_bytes};
+    g_launches = 0;
+    if (!n->graph_enabled) return net_enqueue(n, a, stream);
+
+    std::vector<uintptr_t> key = {(uintptr_t)imu, (uintptr_t)B, (uintptr_t)T, (uintptr_t)lengths, (uintptr_t)vel_h0,
+                                  (uintptr_t)vel_c0, (uintptr_t)vel_hn, (uintptr_t)vel_cn, (uintptr_t)pose,
+                                  (uintptr_t)joints, (uintptr_t)vel, (uintptr_t)contact, (uintptr_t)tran,
+                                  (uintptr_t)workspace};
+    mp_net::Entry* hit = nullptr;
+    for (auto& en : n->cache)
+        if (en.key == key) hit = &en;
+    if (!hit) {
+        // first sight of this signature: run eagerly (also loads the kernels, which must not happen
+        // inside a capture) and remember it; the next call with the same signature is captured.
+        if (n->cache.size() >= 32) {
+            size_t victim = 0;
+            for (size_t i = 1; i < n->cache.size(); ++i)
+                if (n->cache[i].stamp < n->cache[victim].stamp) victim = i;
+            if (n->cache[victim].exec) cudaGraphExecDestroy(n->cache[victim].exec);
+            n->cache.erase(n->cache.begin() + victim);
+        }
+        mp_net::Entry en;
+        en.key = key;
+        en.stamp = ++n->clock;
+        n->cache.push_back(en);
+        return net_enqueue(n, a, stream);
+    }
+    hit->stamp = ++n->clock;
+    if (!hit->exec) {
+        cudaGraph_t graph = nullptr;
+        MP_CUDA_TRY(cudaStreamBeginCapture(n->s_cap, cudaStreamCaptureModeThreadLocal));
+        int st = net_enqueue(n, a, n->s_cap);
+        cudaError_t e = cudaStreamEndCapture(n->s_cap, &graph);
+        if (st != MP_OK) {
+            if (graph) cudaGraphDestroy(graph);
+            return st;
+        }
+        if (e != cudaSuccess) {
+            set_error("net_forward: graph capture failed: %s", cudaGetErrorString(e));
+            return MP_ERR_CUDA;
+        }
+        e = cudaGraphInstantiate(&hit->exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (e != cudaSuccess) {
+            hit->exec = nullptr;
+            set_error("net_forward: graph instantiate failed: %s", cudaGetErrorString(e));
+            return MP_ERR_CUDA;
+        }
+        hit->kernels = g_launches;
+    }
+    MP_CUDA_TRY(cudaGraphLaunch(hit->exec, stream));
+    g_launches = hit->kernels;
+    return MP_OK;
+}
+
+// staging layout: imu | lengths | pose | joints | tran | contact | vel
+static void host_staging_layout(size_t B, size_t T, size_t off[7], size_t* total) {
+    size_t o = 0;
+    const size_t sz[7] = {B * T * 60 * 4, B * 4, B * T * 216 * 4, B * T * 72 * 4, B * T * 3 * 4, B * T * 2 * 4, B * T * 72 * 4};
+    for (int i = 0; i < 7; ++i) {
+        off[i] = o;
+        o = align_up(o + sz[i]);
+    }
+    *total = o;
+}
+
+size_t mp_net_host_staging_bytes(int32_t B, int32_t T) {
+    if (B <= 0 || T <= 0) return 0;
+    size_t off[7], total;
+    host_staging_layout(B, T, off, &total);
+    return total;
+}
+
+int mp_net_forward_offline_host(mp_net_t* n, const float* imu_host, int32_t B, int32_t T, const int32_t* lengths_host,
+                                float* pose_host, float* joints_host, float* tran_host, float* contact_host, void* dev_io,
+                                void* workspace, size_t workspace_bytes, mp_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    MP_REQUIRE(n && imu_host && dev_io && pose_host && joints_host && tran_host && contact_host, "forward_offline_host: null argument");
+    MP_REQUIRE(B > 0 && T > 0, "forward_offline_host: empty batch");
+    MP_REQUIRE(((uintptr_t)dev_io & 255) == 0, "forward_offline_host: staging must be 256-byte aligned");
+    size_t off[7], total;
+    host_staging_layout(B, T, off, &total);
+    char* d = (char*)dev_io;
+    float* d_imu = (float*)(d + off[0]);
+    int32_t* d_len = (int32_t*)(d + off[1]);
+    float *d_pose = (float*)(d + off[2]), *d_joints = (float*)(d + off[3]), *d_tran = (float*)(d + off[4]),
+          *d_contact = (float*)(d + off[5]), *d_vel = (float*)(d + off[6]);
+    const size_t F = (size_t)B * T;
+    MP_CUDA_TRY(cudaMemcpyAsync(d_imu, imu_host, F * 60 * 4, cudaMemcpyHostToDevice, stream));
+    if (lengths_host) MP_CUDA_TRY(cudaMemcpyAsync(d_len, lengths_host, (size_t)B * 4, cudaMemcpyHostToDevice, stream));
+    MP_TRY(mp_net_forward(n, d_imu, B, T, lengths_host ? d_len : nullptr, nullptr, nullptr, nullptr, nullptr, d_pose,
+                          d_joints, d_vel, d_contact, d_tran, workspace, workspace_bytes, stream));
+    MP_CUDA_TRY(cudaMemcpyAsync(pose_host, d_pose, F * 216 * 4, cudaMemcpyDeviceToHost, stream));
+    MP_CUDA_TRY(cudaMemcpyAsync(joints_host, d_joints, F * 72 * 4, cudaMemcpyDeviceToHost, stream));
+    MP_CUDA_TRY(cudaMemcpyAsync(tran_host, d_tran, F * 3 * 4, cudaMemcpyDeviceToHost, stream));
+    MP_CUDA_TRY(cudaMemcpyAsync(contact_host, d_contact, F * 2 * 4, cudaMemcpyDeviceToHost, stream));
+    MP_CUDA_TRY(cudaStreamSynchronize(stream));
+    return MP_OK;
+}
+
+}  // extern "C"

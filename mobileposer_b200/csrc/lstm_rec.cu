@@ -1,0 +1,510 @@
+// Persistent LSTM recurrence: one launch walks every timestep of one layer (all directions,
+// all sequences), W_hh resident in REGISTERS across timesteps, h exchanged between the CTAs of a
+// thread-block cluster through distributed shared memory.
+//
+// Replaces the time loop inside torch's `_VF.lstm` as configured at mobileposer/models/rnn.py:15,27
+// (2 layers, gate rows i,f,g,o, b_ih + b_hh, zero or carried initial state, packed-sequence
+// semantics for ragged lengths: rnn.py:24-31).  The input projection W_ih x_t + b_ih + b_hh is
+// hoisted into gemm.cu (`gin`); this kernel adds W_hh h_{t-1}, applies the gate nonlinearities
+// and the cell update, and emits h_t.
+//
+// Decomposition (H = hidden, C = cluster size, UC = H / C hidden units per CTA):
+//   * CTA `rank` of a cluster owns hidden units [rank*UC, rank*UC+UC) => the 4*UC gate rows of
+//     W_hh that produce them, so the cell update never leaves the CTA.
+//   * thread = (unit, gate, kq): 4 lanes (kq) split the K = H reduction of one gate row, the 4 gates
+//     of a unit sit in the same warp (lane = unit_in_warp*16 + gate*4 + kq), so both the K-reduction
+//     and the i/f/g/o gather are warp shuffles -- no shared-memory round trip, no block barrier.
+//     Each thread keeps its H/4 weights in registers for the whole sequence (H=256: 64 registers).
+//   * h_{t} lives in shared memory of EVERY CTA of the cluster, double buffered by step parity.
+//     After the cell update the owning CTA pushes its UC new values to all C CTAs, either with
+//     per-value `st.async ... mbarrier::complete_tx` (latency path, batch tile of 1..4 sequences) or
+//     staged + `cp.async.bulk shared::cluster` rows (throughput path).  Each CTA waits on its own
+//     mbarrier (transaction bytes) -- there is no cluster-wide barrier inside the time loop.
+//   * a cluster serves a tile of NB sequences (weights reused NB times per step); the grid is
+//     (C * n_tiles, dirs).  Reverse direction of sequence b walks t = len_b-1 .. 0.
+#include "mp_common.cuh"
+
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+
+namespace mp {
+
+namespace {
+
+struct RecParams {
+    const float* gin;
+    const float4* wpack;
+    float* y;
+    const float* h0;
+    const float* c0;
+    float* hn;
+    float* cn;
+    const int32_t* lengths;
+    int B, T, dirs, NB, bulk;
+};
+
+template <int H, int C>
+struct RecCfg {
+    static constexpr int UC = H / C;          // hidden units owned by one CTA
+    static constexpr int THREADS = UC * 16;   // 4 gates x 4 k-quarters per unit
+    static constexpr int NCHUNK = H / 16;     // float4 weight chunks per thread
+    static_assert(UC % 4 == 0 && UC >= 4, "unit slice must be float4 aligned");
+    static_assert(THREADS <= 1024 && THREADS >= 32, "block size");
+};
+
+// Dynamic shared memory carve-up (floats unless noted):
+//   hbuf   [2][NB][H]    h_t of every sequence of the tile, double buffered
+//   hstage [2][NB][UC]   this CTA's new slice, source of the bulk copies
+//   cbuf   [NB][UC]      cell state of the owned units
+//   lens   [NB] int
+//   bars   [2] uint64    mbarriers, one per hbuf parity
+template <int H, int C>
+__host__ __device__ inline size_t rec_smem_bytes(int NB) {
+    return sizeof(float) * ((size_t)2 * NB * H + (size_t)2 * NB * RecCfg<H, C>::UC + (size_t)NB * RecCfg<H, C>::UC) +
+           sizeof(int) * NB + 2 * sizeof(unsigned long long) + 16;
+}
+
+template <int H, int C, int BG>
+__global__ void __launch_bounds__(RecCfg<H, C>::THREADS, 1) lstm_rec_kernel(const RecParams p) {
+    using Cfg = RecCfg<H, C>;
+    constexpr int UC = Cfg::UC, THREADS = Cfg::THREADS, NCHUNK = Cfg::NCHUNK;
+    static_assert(BG == 1 || BG == 4, "batch group");
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int NB = p.NB;
+    float* hbuf = reinterpret_cast<float*>(smem_raw);
+    float* hstage = hbuf + (size_t)2 * NB * H;
+    float* cbuf = hstage + (size_t)2 * NB * UC;
+    int* lens = reinterpret_cast<int*>(cbuf + (size_t)NB * UC);
+    unsigned long long* bars =
+        reinterpret_cast<unsigned long long*>((reinterpret_cast<uintptr_t>(lens + NB) + 15) & ~uintptr_t(15));
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int rank = (C > 1) ? (int)cluster_ctarank() : 0;
+    const int tile = blockIdx.x / C, dir = blockIdx.y;
+    const int b_begin = tile * NB;
+    const int nb = min(NB, p.B - b_begin);
+    const int u_local = warp * 2 + (lane >> 4);
+    const int gate = (lane >> 2) & 3, kq = lane & 3;
+    const int unit = rank * UC + u_local;           // hidden unit in [0, H)
+    const int row_g = gate * H + unit;              // gate row in [0, 4H)
+    const int G4 = p.dirs * 4 * H, Y2 = p.dirs * H;
+
+    // ---- resident weights: H/4 floats of one gate row per thread ---------------------------
+    float4 w[NCHUNK];
+    {
+        const float4* wp = p.wpack + ((size_t)(dir * C + rank) * NCHUNK) * THREADS + tid;
+#pragma unroll
+        for (int i = 0; i < NCHUNK; ++i) w[i] = __ldg(wp + (size_t)i * THREADS);
+    }
+
+    // ---- tile state ------------------------------------------------------------------------
+    for (int i = tid; i < NB; i += THREADS)
+        lens[i] = (i < nb) ? (p.lengths ? min(max(p.lengths[b_begin + i], 0), p.T) : p.T) : 0;
+    for (int i = tid; i < NB * H; i += THREADS) {
+        const int b = i / H, k = i - b * H;
+        hbuf[i] = (p.h0 && b < nb) ? p.h0[((size_t)dir * p.B + b_begin + b) * H + k] : 0.f;
+    }
+    for (int i = tid; i < NB * UC; i += THREADS) {
+        const int b = i / UC, u = i - b * UC;
+        cbuf[i] = (p.c0 && b < nb) ? p.c0[((size_t)dir * p.B + b_begin + b) * H + rank * UC + u] : 0.f;
+    }
+    const uint32_t bar_addr[2] = {smem_u32(&bars[0]), smem_u32(&bars[1])};
+    if (C > 1 && tid == 0) {
+        mbar_init(bar_addr[0], 1);
+        mbar_init(bar_addr[1], 1);
+        mbar_fence_init_cluster();
+    }
+    __syncthreads();
+    if (C > 1) cluster_sync_all();
+
+    int maxlen = 0;
+    for (int i = 0; i < nb; ++i) maxlen = max(maxlen, lens[i]);
+
+    // latency path: gin of the next step is fetched one step ahead
+    float gi_next[4] = {0.f, 0.f, 0.f, 0.f};
+    // latency path: remote views of hbuf / mbarriers in the CTA this lane feeds (rank = lane & 15)
+    uint32_t rem_hbuf = 0, rem_bar[2] = {0, 0};
+    if constexpr (C > 1) {
+        const uint32_t r = (lane & 15) < C ? (lane & 15) : 0;
+        rem_hbuf = mapa_u32(smem_u32(hbuf), r);
+        rem_bar[0] = mapa_u32(bar_addr[0], r);
+        rem_bar[1] = mapa_u32(bar_addr[1], r);
+    }
+    if constexpr (BG == 1) {
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            gi_next[b] = 0.f;
+            if (b < nb && lens[b] > 0) {
+                const int t = dir ? lens[b] - 1 : 0;
+                gi_next[b] = __ldg(p.gin + ((size_t)(b_begin + b) * p.T + t) * G4 + dir * 4 * H + row_g);
+            }
+        }
+    }
+
+    for (int s = 0; s < maxlen; ++s) {
+        const int par = s & 1;
+        const bool send = (s + 1 < maxlen);
+        if constexpr (C > 1) {
+            if (s > 0) mbar_wait_cluster(bar_addr[par], ((s - 1) >> 1) & 1);
+            if (tid == 0 && send) {
+                int nsend = nb;
+                if (!p.bulk) {
+                    nsend = 0;
+                    for (int i = 0; i < nb; ++i) nsend += (lens[i] > s);
+                }
+                mbar_arrive_expect_tx(bar_addr[par ^ 1], (uint32_t)nsend * H * sizeof(float));
+            }
+        }
+        const float* hcur = hbuf + (size_t)par * NB * H;
+        float* hnext = hbuf + (size_t)(par ^ 1) * NB * H;
+        float* hst = hstage + (size_t)par * NB * UC;
+
+        if constexpr (BG == 1) {
+            // ---------------- latency path: 1..4 sequences, one at a time ----------------------
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                if (b >= nb) break;
+                const int len = lens[b];
+                if (s >= len) continue;
+                const int t = dir ? len - 1 - s : s;
+                const float gi = gi_next[b];
+                if (s + 1 < len) {
+                    const int tn = dir ? len - 2 - s : s + 1;
+                    gi_next[b] = __ldg(p.gin + ((size_t)(b_begin + b) * p.T + tn) * G4 + dir * 4 * H + row_g);
+                }
+                const float* hb = hcur + b * H + kq * 4;
+                float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+                for (int i = 0; i < NCHUNK; ++i) {
+                    const float4 hv = *reinterpret_cast<const float4*>(hb + i * 16);
+                    a0 = fmaf(w[i].x, hv.x, a0);
+                    a1 = fmaf(w[i].y, hv.y, a1);
+                    a2 = fmaf(w[i].z, hv.z, a2);
+                    a3 = fmaf(w[i].w, hv.w, a3);
+                }
+                float tot = (a0 + a1) + (a2 + a3);
+                tot += __shfl_xor_sync(0xffffffffu, tot, 1);
+                tot += __shfl_xor_sync(0xffffffffu, tot, 2);
+                const float pre = tot + gi;
+                const float act = (gate == 2) ? tanhf(pre) : sigmoidf_acc(pre);
+                const int base = lane & ~0xC;
+                const float iv = __shfl_sync(0xffffffffu, act, base);
+                const float fv = __shfl_sync(0xffffffffu, act, base | 4);
+                const float gv = __shfl_sync(0xffffffffu, act, base | 8);
+                const float ov = __shfl_sync(0xffffffffu, act, base | 12);
+                const float c_new = fmaf(fv, cbuf[b * UC + u_local], iv * gv);
+                const float h_new = ov * tanhf(c_new);
+                __syncwarp();
+                if ((lane & 15) == 0) {
+                    cbuf[b * UC + u_local] = c_new;
+                    p.y[((size_t)(b_begin + b) * p.T + t) * Y2 + dir * H + unit] = h_new;
+                    if (s == len - 1) {
+                        if (p.hn) p.hn[((size_t)dir * p.B + b_begin + b) * H + unit] = h_new;
+                        if (p.cn) p.cn[((size_t)dir * p.B + b_begin + b) * H + unit] = c_new;
+                    }
+                }
+                if (send) {
+                    if constexpr (C == 1) {
+                        if ((lane & 15) == 0) hnext[b * H + unit] = h_new;
+                    } else {
+                        if (!p.bulk) {
+                            // 16 lanes of a unit hold h_new; lane r of them feeds CTA r
+                            if ((lane & 15) < C)
+                                st_async_f32(rem_hbuf + (uint32_t)(((par ^ 1) * NB + b) * H + unit) * 4u, h_new,
+                                             rem_bar[par ^ 1]);
+                        } else if ((lane & 15) == 0) {
+                            hst[b * UC + u_local] = h_new;
+                        }
+                    }
+                }
+            }
+        } else {
+            // ---------------- throughput path: groups of 4 sequences, lane kq owns sequence g0+kq
+            for (int g0 = 0; g0 < nb; g0 += 4) {
+                int glen = 0;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) glen = max(glen, lens[g0 + q]);   // lens[>=nb] == 0, NB % 4 == 0
+                if (s >= glen) continue;
+                const int b = g0 + kq;
+                const int len = lens[b];
+                const bool active = s < len;
+                const int t = dir ? len - 1 - s : s;
+                float gi = 0.f;
+                if (active) gi = __ldg(p.gin + ((size_t)(b_begin + b) * p.T + t) * G4 + dir * 4 * H + row_g);
+                const float* hb = hcur + g0 * H + kq * 4;
+                float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int i = 0; i < NCHUNK; ++i) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const float4 hv = *reinterpret_cast<const float4*>(hb + q * H + i * 16);
+                        acc[q] = fmaf(w[i].x, hv.x, acc[q]);
+                        acc[q] = fmaf(w[i].y, hv.y, acc[q]);
+                        acc[q] = fmaf(w[i].z, hv.z, acc[q]);
+                        acc[q] = fmaf(w[i].w, hv.w, acc[q]);
+                    }
+                }
+                // reduce-scatter over the 4 kq lanes: lane kq ends with the sum for sequence g0+kq
+                const bool hi = kq & 2, lo = kq & 1;
+                float k0 = hi ? acc[2] : acc[0], k1 = hi ? acc[3] : acc[1];
+                const float s0 = hi ? acc[0] : acc[2], s1 = hi ? acc[1] : acc[3];
+                k0 += __shfl_xor_sync(0xffffffffu, s0, 2);
+                k1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+                float tot = lo ? k1 : k0;
+                const float s2 = lo ? k0 : k1;
+                tot += __shfl_xor_sync(0xffffffffu, s2, 1);
+                const float pre = tot + gi;
+                const float act = (gate == 2) ? tanhf(pre) : sigmoidf_acc(pre);
+                const int base = lane & ~0xC;
+                const float iv = __shfl_sync(0xffffffffu, act, base);
+                const float fv = __shfl_sync(0xffffffffu, act, base | 4);
+                const float gv = __shfl_sync(0xffffffffu, act, base | 8);
+                const float ov = __shfl_sync(0xffffffffu, act, base | 12);
+                const float c_new = fmaf(fv, cbuf[b * UC + u_local], iv * gv);
+                const float h_new = ov * tanhf(c_new);
+                __syncwarp();
+                if (active) {
+                    if (gate == 0) {
+                        cbuf[b * UC + u_local] = c_new;
+                        p.y[((size_t)(b_begin + b) * p.T + t) * Y2 + dir * H + unit] = h_new;
+                        if (s == len - 1) {
+                            if (p.hn) p.hn[((size_t)dir * p.B + b_begin + b) * H + unit] = h_new;
+                            if (p.cn) p.cn[((size_t)dir * p.B + b_begin + b) * H + unit] = c_new;
+                        }
+                    }
+                    if (send) {
+                        if constexpr (C == 1) {
+                            if (gate == 0) hnext[b * H + unit] = h_new;
+                        } else {
+                            if (!p.bulk) {
+                                // the 4 gate lanes of (unit, sequence) hold h_new; gate lane g feeds CTAs g, g+4, ..
+                                for (int r = gate; r < C; r += 4)
+                                    st_async_f32(mapa_u32(smem_u32(hnext + b * H + unit), r), h_new,
+                                                 mapa_u32(bar_addr[par ^ 1], r));
+                            } else if (gate == 0) {
+                                hst[b * UC + u_local] = h_new;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+
+        if constexpr (C == 1) {
+            __syncthreads();
+        } else if (p.bulk && send) {
+            // staged slice -> every CTA of the cluster, one 4*UC-byte row per (sequence, destination)
+            fence_proxy_async_smem();
+            __syncthreads();
+            for (int j = tid; j < nb * C; j += THREADS) {
+                const int b = j / C, r = j - b * C;
+                bulk_copy_s2c(mapa_u32(smem_u32(hnext + b * H + rank * UC), r), smem_u32(hst + b * UC),
+                              UC * sizeof(float), mapa_u32(bar_addr[par ^ 1], r));
+            }
+        }
+    }
+
+    // frames >= len of the layer output are zero (pad_packed_sequence, rnn.py:31)
+    for (int b = 0; b < nb; ++b) {
+        const int len = lens[b];
+        const int n = (p.T - len) * UC;
+        for (int i = tid; i < n; i += THREADS) {
+            const int t = len + i / UC, u = i % UC;
+            p.y[((size_t)(b_begin + b) * p.T + t) * Y2 + dir * H + rank * UC + u] = 0.f;
+        }
+    }
+    if (C > 1) cluster_sync_all();   // nobody exits while a peer may still address its shared memory
+}
+
+// ---------------------------------------------------------------------------------------------
+// Debug kernel (MP_REC_IMPL=simple): one CTA per (sequence, direction), W_hh^T streamed from L2
+// every step.  Same arithmetic, no clusters / mbarriers -- used to bisect failures of the kernel
+// above on hardware.  Never selected by default.
+// ---------------------------------------------------------------------------------------------
+template <int H>
+__global__ void __launch_bounds__(4 * H > 1024 ? 1024 : 4 * H) lstm_rec_simple_kernel(
+    const float* __restrict__ gin, const float* __restrict__ wT, float* __restrict__ y,
+    const float* __restrict__ h0, const float* __restrict__ c0, float* __restrict__ hn,
+    float* __restrict__ cn, const int32_t* __restrict__ lengths, int B, int T, int dirs) {
+    __shared__ float h[H];
+    __shared__ float g[4 * H];
+    const int b = blockIdx.x, dir = blockIdx.y, tid = threadIdx.x, nthr = blockDim.x;
+    const int len = lengths ? min(max(lengths[b], 0), T) : T;
+    const float* wt = wT + (size_t)dir * H * 4 * H;
+    float c = 0.f;
+    if (tid < H) {
+        h[tid] = h0 ? h0[((size_t)dir * B + b) * H + tid] : 0.f;
+        c = c0 ? c0[((size_t)dir * B + b) * H + tid] : 0.f;
+    }
+    __syncthreads();
+    for (int s = 0; s < len; ++s) {
+        const int t = dir ? len - 1 - s : s;
+        for (int r = tid; r < 4 * H; r += nthr) {
+            float acc = 0.f;
+            for (int k = 0; k < H; ++k) acc = fmaf(wt[(size_t)k * 4 * H + r], h[k], acc);
+            g[r] = acc + gin[((size_t)b * T + t) * (dirs * 4 * H) + dir * 4 * H + r];
+        }
+        __syncthreads();
+        if (tid < H) {
+            const float iv = sigmoidf_acc(g[tid]), fv = sigmoidf_acc(g[H + tid]);
+            const float gv = tanhf(g[2 * H + tid]), ov = sigmoidf_acc(g[3 * H + tid]);
+            c = fmaf(fv, c, iv * gv);
+            const float hv = ov * tanhf(c);
+            h[tid] = hv;
+            y[((size_t)b * T + t) * (dirs * H) + dir * H + tid] = hv;
+            if (s == len - 1) {
+                if (hn) hn[((size_t)dir * B + b) * H + tid] = hv;
+                if (cn) cn[((size_t)dir * B + b) * H + tid] = c;
+            }
+        }
+        __syncthreads();
+    }
+    if (tid < H)
+        for (int t = len; t < T; ++t) y[((size_t)b * T + t) * (dirs * H) + dir * H + tid] = 0.f;
+}
+
+// W_hh [4H, H] (torch) -> wpack[dir][rank][chunk][tid] float4 + wT[dir][k][row]
+template <int H, int C>
+__global__ void pack_whh_kernel(const float* __restrict__ w0, const float* __restrict__ w1,
+                                float4* __restrict__ wpack, float* __restrict__ wT, int dirs) {
+    using Cfg = RecCfg<H, C>;
+    const size_t total = (size_t)dirs * C * Cfg::NCHUNK * Cfg::THREADS;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (size_t)gridDim.x * blockDim.x) {
+        const int tid = idx % Cfg::THREADS;
+        const int i = (idx / Cfg::THREADS) % Cfg::NCHUNK;
+        const int rank = (idx / ((size_t)Cfg::THREADS * Cfg::NCHUNK)) % C;
+        const int dir = idx / ((size_t)Cfg::THREADS * Cfg::NCHUNK * C);
+        const int lane = tid & 31, warp = tid >> 5;
+        const int unit = rank * Cfg::UC + warp * 2 + (lane >> 4);
+        const int gate = (lane >> 2) & 3, kq = lane & 3;
+        const float* W = dir ? w1 : w0;
+        const float* src = W + (size_t)(gate * H + unit) * H + i * 16 + kq * 4;
+        wpack[idx] = make_float4(src[0], src[1], src[2], src[3]);
+    }
+    const size_t tt = (size_t)dirs * 4 * H * H;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < tt;
+         idx += (size_t)gridDim.x * blockDim.x) {
+        const int r = idx % (4 * H);
+        const int k = (idx / (4 * H)) % H;
+        const int dir = idx / ((size_t)4 * H * H);
+        const float* W = dir ? w1 : w0;
+        wT[idx] = W[(size_t)r * H + k];
+    }
+}
+
+int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return (v && *v) ? atoi(v) : dflt;
+}
+bool env_is(const char* name, const char* val) {
+    const char* v = getenv(name);
+    return v && strcmp(v, val) == 0;
+}
+
+// concurrent clusters of 8 CTAs a B200 can hold (8 GPCs x 2; DESIGN.md "cluster placement")
+constexpr int kClusterSlots = 16;
+constexpr size_t kMaxSmem = 227 * 1024;
+
+template <int H, int C, int BG>
+int launch_cluster(const RecLayerArgs& a, int NB, int bulk, cudaStream_t stream) {
+    using Cfg = RecCfg<H, C>;
+    RecParams p{a.gin, a.wpack, a.y, a.h0, a.c0, a.hn, a.cn, a.lengths, a.B, a.T, a.dirs, NB, bulk};
+    const size_t smem = rec_smem_bytes<H, C>(NB);
+    auto kern = lstm_rec_kernel<H, C, BG>;
+    MP_REQUIRE(smem <= kMaxSmem, "lstm: tile of %d sequences needs %zu B of shared memory", NB, smem);
+    static bool configured = false;   // one device per process (one rank per GPU)
+    if (!configured) {
+        MP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
+        if (C > 8) MP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        configured = true;
+    }
+    const int n_tiles = (a.B + NB - 1) / NB;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(C * n_tiles, a.dirs, 1);
+    cfg.blockDim = dim3(Cfg::THREADS, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = C;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = (C > 1) ? 1 : 0;
+    MP_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, p));
+    count_launch();
+    return MP_OK;
+}
+
+template <int H, int C>
+int launch_for(const RecLayerArgs& a, cudaStream_t stream) {
+    // tile policy: small batches -> one sequence per cluster (latency path); otherwise size the
+    // tile so that one wave of clusters covers the batch, capped by shared memory.
+    const int slots = (C == 1) ? 148 : std::max(1, kClusterSlots * 8 / C);
+    const int forced = env_int("MP_REC_NB", 0);
+    const int bulk = env_is("MP_REC_SEND", "stasync") ? 0 : (env_is("MP_REC_SEND", "bulk") ? 1 : -1);
+    int NB;
+    if (forced > 0) {
+        NB = forced;
+    } else if (a.B * a.dirs <= slots) {
+        NB = 1;
+    } else {
+        const int per = std::max(1, slots / a.dirs);
+        NB = (a.B + per - 1) / per;
+        NB = std::min(32, ((NB + 3) / 4) * 4);
+    }
+    if (NB < 4) return launch_cluster<H, C, 1>(a, NB, bulk == 1 ? 1 : 0, stream);
+    NB = ((NB + 3) / 4) * 4;
+    return launch_cluster<H, C, 4>(a, NB, bulk == 0 ? 0 : 1, stream);
+}
+
+}  // namespace
+
+int rec_cluster_size(int H) {
+    if (H == 64) return 1;
+    return env_int("MP_REC_CLUSTER", 8) == 16 ? 16 : 8;
+}
+
+size_t whh_pack_float4s(int H, int dirs) { return (size_t)dirs * 4 * H * H / 4; }
+
+int launch_pack_whh(const float* const* w_hh_dirs, int H, int dirs, float4* wpack, float* wT, cudaStream_t stream) {
+    const float* w0 = w_hh_dirs[0];
+    const float* w1 = dirs > 1 ? w_hh_dirs[1] : w_hh_dirs[0];
+    const int C = rec_cluster_size(H);
+    if (H == 256 && C == 8) pack_whh_kernel<256, 8><<<296, 256, 0, stream>>>(w0, w1, wpack, wT, dirs);
+    else if (H == 256 && C == 16) pack_whh_kernel<256, 16><<<296, 256, 0, stream>>>(w0, w1, wpack, wT, dirs);
+    else if (H == 64) pack_whh_kernel<64, 1><<<296, 256, 0, stream>>>(w0, w1, wpack, wT, dirs);
+    else {
+        set_error("lstm: hidden size %d not built (64, 256)", H);
+        return MP_ERR_UNSUPPORTED;
+    }
+    MP_CUDA_TRY(cudaGetLastError());
+    return MP_OK;
+}
+
+int launch_lstm_recurrence(const RecLayerArgs& a, cudaStream_t stream) {
+    MP_REQUIRE(a.gin && a.wpack && a.y && a.B > 0 && a.T > 0 && (a.dirs == 1 || a.dirs == 2), "lstm: bad arguments");
+    if (env_is("MP_REC_IMPL", "simple")) {
+        dim3 grid(a.B, a.dirs);
+        if (a.H == 256)
+            lstm_rec_simple_kernel<256><<<grid, 1024, 0, stream>>>(a.gin, a.wT, a.y, a.h0, a.c0, a.hn, a.cn, a.lengths, a.B, a.T, a.dirs);
+        else if (a.H == 64)
+            lstm_rec_simple_kernel<64><<<grid, 256, 0, stream>>>(a.gin, a.wT, a.y, a.h0, a.c0, a.hn, a.cn, a.lengths, a.B, a.T, a.dirs);
+        else {
+            set_error("lstm: hidden size %d not built", a.H);
+            return MP_ERR_UNSUPPORTED;
+        }
+        MP_CUDA_TRY(cudaGetLastError());
+        count_launch();
+        return MP_OK;
+    }
+    if (a.H == 256) return rec_cluster_size(256) == 16 ? launch_for<256, 16>(a, stream) : launch_for<256, 8>(a, stream);
+    if (a.H == 64) return launch_for<64, 1>(a, stream);
+    set_error("lstm: hidden size %d not built (64, 256)", a.H);
+    return MP_ERR_UNSUPPORTED;
+}
+
+}  // namespace mp

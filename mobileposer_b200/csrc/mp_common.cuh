@@ -1,0 +1,136 @@
+// Shared helpers of the mobileposer_b200 kernels (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+#include "../../include/mobileposer_b200.h"
+
+namespace mp {
+
+void set_error(const char* fmt, ...);
+void count_launch(int n = 1);
+
+#define MP_CUDA_TRY(expr)                                                                         \
+    do {                                                                                          \
+        cudaError_t err__ = (expr);                                                               \
+        if (err__ != cudaSuccess) {                                                               \
+            mp::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(err__), __FILE__,    \
+                          __LINE__);                                                              \
+            return MP_ERR_CUDA;                                                                   \
+        }                                                                                         \
+    } while (0)
+
+#define MP_TRY(expr)                       \
+    do {                                   \
+        int st__ = (expr);                 \
+        if (st__ != MP_OK) return st__;    \
+    } while (0)
+
+#define MP_REQUIRE(cond, ...)              \
+    do {                                   \
+        if (!(cond)) {                     \
+            mp::set_error(__VA_ARGS__);    \
+            return MP_ERR_INVALID;         \
+        }                                  \
+    } while (0)
+
+// ---- launchers implemented in the .cu files ------------------------------------------------
+
+// C[M,N] = act(cat(A1[M,K1], A2[M,K2]) * W[N,K1+K2]^T + bias[N]);   relu != 0 applies max(.,0)
+int launch_gemm_bias_act(const float* A1, int K1, const float* A2, int K2, const float* W,
+                         const float* bias, float* C, int M, int N, int relu, cudaStream_t stream);
+
+struct RecLayerArgs {
+    const float* gin;     // [B, T, dirs*4H]  input projection + both biases
+    const float4* wpack;  // packed W_hh for this layer (all dirs), see pack_whh
+    const float* wT;      // [dirs][H][4H] transposed W_hh (debug kernel)
+    float* y;             // [B, T, dirs*H]
+    const float* h0;      // [dirs, B, H] or null
+    const float* c0;
+    float* hn;            // [dirs, B, H] or null
+    float* cn;
+    const int32_t* lengths;  // [B] or null
+    int B, T, H, dirs;
+};
+int launch_lstm_recurrence(const RecLayerArgs& a, cudaStream_t stream);
+// number of float4 in the packed recurrent weights of one layer
+size_t whh_pack_float4s(int H, int dirs);
+// pack W_hh[dirs][4H,H] (device, torch layout) into the register-resident layout + transpose
+int launch_pack_whh(const float* const* w_hh_dirs, int H, int dirs, float4* wpack, float* wT,
+                    cudaStream_t stream);
+int rec_cluster_size(int H);
+
+int launch_reduced_global_to_full(const float* r6d, int64_t n, float* pose, cudaStream_t stream);
+int launch_tran_offline(const float* joints, const float* vel, const float* contact,
+                        const int32_t* lengths, int B, int T, float* tran, cudaStream_t stream);
+int launch_online_update(mp_online_state_t* st, const float* pose, const float* joints,
+                         const float* vel, const float* contact, int S, int W, int frame,
+                         float* pose_out, float* root_out, float* contact_out, cudaStream_t stream);
+int launch_online_reset(mp_online_state_t* st, int S, int full, cudaStream_t stream);
+int launch_online_push(const float* win_in, float* win_out, const float* frame, int S, int W, int cold,
+                       cudaStream_t stream);
+
+// ---- PTX helpers (clusters, mbarrier, distributed shared memory) ---------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cta address -> shared::cluster address of the same offset in CTA `rank`
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init_cluster() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "MP_WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra MP_DONE_%=;\n\t"
+        "bra MP_WAIT_%=;\n\t"
+        "MP_DONE_%=:\n\t"
+        "}" ::"r"(bar), "r"(parity)
+        : "memory");
+}
+// 4-byte remote store that completes `4` tx bytes on the destination CTA's mbarrier
+__device__ __forceinline__ void st_async_f32(uint32_t remote_addr, float v, uint32_t remote_bar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(remote_addr),
+                 "r"(__float_as_uint(v)), "r"(remote_bar)
+                 : "memory");
+}
+// bulk copy local smem -> (possibly remote) cluster smem, completing tx bytes on the remote mbarrier
+__device__ __forceinline__ void bulk_copy_s2c(uint32_t remote_dst, uint32_t local_src, uint32_t bytes,
+                                              uint32_t remote_bar) {
+    asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     remote_dst),
+                 "r"(local_src), "r"(bytes), "r"(remote_bar)
+                 : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ float sigmoidf_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
+#endif
+
+}  // namespace mp

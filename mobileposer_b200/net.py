@@ -1,0 +1,334 @@
+"""`MobilePoserNet` drop-in: same ctor, attributes, state_dict and methods as the reference class
+(mobileposer/models/net.py:22-219), with every forward executed by the sm_100a kernels behind the
+C ABI (include/mobileposer_b200.h).
+
+Differences that are deliberate and documented (DESIGN.md section "boundary"):
+  * `forward_offline` also accepts B > 1: per-sequence semantics equal B independent reference calls
+    with a fresh velocity state per sequence; B == 1 keeps the reference's shapes and
+    its velocity-state carry across calls.
+  * the online state (feet, root, current_root_y) lives on the device; `forward_online_batch` runs S
+    independent streams (one state block each) in one launch sequence.
+  * inference only; dropout is the identity.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+import torch.nn as nn
+
+from . import _cabi
+from .config import (FLOOR_Y, SMPL_J_ZERO, SMPL_PARENT, joint_set, model_config)
+from .modules import FootContact, Joints, Poser, Velocity, _require_cuda, _f32c, current_stream_ptr
+
+
+def getenv(key: str, default=0):
+    """mobileposer/helpers.py:4-5."""
+    return type(default)(os.getenv(key, default))
+
+
+class _Slot:
+    """Static device buffers for one (B, T, device): stable pointers make the C-side CUDA graph reusable."""
+
+    def __init__(self, lib, net_handle, B, T, dev):
+        f32 = dict(device=dev, dtype=torch.float32)
+        self.B, self.T = B, T
+        self.imu = torch.empty(B, T, 60, **f32)
+        self.lengths = torch.empty(B, device=dev, dtype=torch.int32)
+        self.pose = torch.empty(B * T, 24, 3, 3, **f32)
+        self.joints = torch.empty(B, T, 72, **f32)
+        self.vel = torch.empty(B, T, 72, **f32)
+        self.contact = torch.empty(B, T, 2, **f32)
+        self.tran = torch.empty(B, T, 3, **f32)
+        self.h0 = torch.empty(2, B, 256, **f32)
+        self.c0 = torch.empty(2, B, 256, **f32)
+        self.hn = torch.empty(2, B, 256, **f32)
+        self.cn = torch.empty(2, B, 256, **f32)
+        self.ws_bytes = lib.mp_net_workspace_bytes(net_handle, B, T)
+        self.ws = torch.empty(self.ws_bytes, device=dev, dtype=torch.uint8)
+
+
+class MobilePoserNet(nn.Module):
+    """
+    Inputs: N IMUs.  Outputs: SMPL pose (local rotation matrices) and root translation.
+    """
+
+    def __init__(self, poser: Poser = None, joints: Joints = None, foot_contact: FootContact = None,
+                 velocity: Velocity = None, finetune: bool = False):
+        super().__init__()
+        self.C = model_config
+        self.finetune = finetune
+
+        # same construction order as net.py:40-43 (seeded default init is then identical)
+        self.pose = poser if poser else Poser()
+        self.joints = joints if joints else Joints()
+        self.foot_contact = foot_contact if foot_contact else FootContact()
+        self.velocity = velocity if velocity else Velocity()
+
+        # constants (net.py:46-56)
+        self.parent = list(SMPL_PARENT)
+        self.j = torch.tensor(SMPL_J_ZERO, dtype=torch.float32)
+        self.feet_pos = self.j[10:12].clone()
+        self.floor_y = FLOOR_Y
+        self.gravity_velocity = torch.tensor([0, joint_set.gravity_velocity, 0])
+        self.prob_threshold = (0.5, 0.9)
+        self.num_past_frames = model_config.past_frames
+        self.num_future_frames = model_config.future_frames
+        self.num_total_frames = self.num_past_frames + self.num_future_frames
+
+        # variables (net.py:58-64); the online ones are mirrored by device state blocks
+        self.rnn_state = None
+        self.imu = None
+        self.reuse_outputs = False        # True: return views of the static buffers (no clone)
+
+        if getenv("PHYSICS"):
+            # net.py:66-69: the reference imports a module that is not in its tree
+            from dynamics import PhysicsOptimizer
+            self.dynamics_optimizer = PhysicsOptimizer(debug=False)
+            self.dynamics_optimizer.reset_states()
+
+        self._net = None
+        self._net_key = None
+        self._slots = {}
+        self._online = None
+        self.last_launches = 0
+
+    # ---- handles -------------------------------------------------------------------------------
+    def _device(self):
+        return next(self.parameters()).device
+
+    def _net_handle(self):
+        heads = (self.joints.joints, self.pose.pose, self.foot_contact.footcontact, self.velocity.vel)
+        handles = tuple(h.packed_handle() for h in heads)
+        if self._net is None or handles != self._net_key:
+            self._close_net()
+            out = C.c_void_p()
+            with torch.cuda.device(self._device()):
+                _cabi.check(_cabi.lib().mp_net_create(C.byref(out), *handles), 'mp_net_create')
+            self._net, self._net_key = out.value, handles
+            self._slots = {}
+        return self._net
+
+    def _close_net(self):
+        if self._net is not None:
+            _cabi.lib().mp_net_destroy(self._net)
+            self._net = None
+            self._net_key = None
+
+    def __del__(self):
+        try:
+            self._close_net()
+        except Exception:
+            pass
+
+    def set_graph(self, enabled: bool):
+        _cabi.check(_cabi.lib().mp_net_set_graph(self._net_handle(), int(enabled)), 'mp_net_set_graph')
+
+    def _slot(self, B, T, dev):
+        key = (B, T, dev.index)
+        if key not in self._slots:
+            if len(self._slots) >= 8:
+                self._slots.pop(next(iter(self._slots)))
+            self._slots[key] = _Slot(_cabi.lib(), self._net_handle(), B, T, dev)
+        return self._slots[key]
+
+    # ---- reference surface -----------------------------------------------------------------------
+    @classmethod
+    def from_pretrained(cls, model_path):
+        model = cls()
+        model.load_state_dict(torch.load(model_path, map_location='cpu'))
+        model.finetune = True
+        return model
+
+    def reset(self):
+        """net.py:84-88: clears imu / root position / current_root_y; NOT the feet, NOT velocity.rnn_state."""
+        self.rnn_state = None
+        self.imu = None
+        if self._online is not None:
+            self._online.reset(full=False)
+
+    def _prob_to_weight(self, p):
+        lo, hi = self.prob_threshold
+        return (p.clamp(lo, hi) - lo) / (hi - lo)
+
+    @torch.no_grad()
+    def _reduced_global_to_full(self, reduced_pose):
+        """net.py:93-99 through mp_pose_reduced_global_to_full."""
+        _require_cuda(reduced_pose, 'reduced pose')
+        r6d = _f32c(reduced_pose).view(-1, 96)
+        out = torch.empty(r6d.shape[0], 24, 3, 3, device=r6d.device, dtype=torch.float32)
+        with torch.cuda.device(r6d.device):
+            _cabi.check(_cabi.lib().mp_pose_reduced_global_to_full(r6d.data_ptr(), r6d.shape[0], out.data_ptr(),
+                                                                   current_stream_ptr(r6d.device)), 'K5')
+        return out
+
+    def _lengths(self, input_lengths, B, T):
+        lens = [int(v) for v in (input_lengths.tolist() if torch.is_tensor(input_lengths) else input_lengths)]
+        if len(lens) != B:
+            raise ValueError(f'input_lengths has {len(lens)} entries for a batch of {B}')
+        if min(lens) <= 0 or max(lens) > T:
+            raise RuntimeError('Length of all samples has to be greater than 0 and at most the padded length')
+        return lens
+
+    @torch.no_grad()
+    def _run(self, batch, input_lengths, want_tran, carry_velocity):
+        """One fused mp_net_forward; returns the slot holding the results."""
+        _require_cuda(batch, 'input batch')
+        lib = _cabi.lib()
+        x = _f32c(batch)
+        if x.dim() != 3 or x.shape[2] != 60:
+            raise ValueError(f'expected [B, T, 60] IMU input, got {tuple(x.shape)}')
+        B, T = x.shape[0], x.shape[1]
+        dev = x.device
+        lens = self._lengths(input_lengths, B, T)
+        net = self._net_handle()
+        s = self._slot(B, T, dev)
+        s.imu.copy_(x)
+        ragged = min(lens) < T
+        if ragged:
+            s.lengths.copy_(torch.tensor(lens, dtype=torch.int32), non_blocking=True)
+        h0 = c0 = None
+        if carry_velocity and self.velocity.rnn_state is not None:
+            sh, sc = self.velocity.rnn_state
+            if tuple(sh.shape) != (2, B, 256):
+                raise RuntimeError(f'Expected hidden[0] size (2, {B}, 256), got {list(sh.shape)}')
+            s.h0.copy_(sh)
+            s.c0.copy_(sc)
+            h0, c0 = s.h0, s.c0
+        with torch.cuda.device(dev):
+            _cabi.check(lib.mp_net_forward(
+                net, s.imu.data_ptr(), B, T, s.lengths.data_ptr() if ragged else None,
+                h0.data_ptr() if h0 is not None else None, c0.data_ptr() if c0 is not None else None,
+                s.hn.data_ptr(), s.cn.data_ptr(), s.pose.data_ptr(), s.joints.data_ptr(), s.vel.data_ptr(),
+                s.contact.data_ptr(), s.tran.data_ptr() if want_tran else None, s.ws.data_ptr(), s.ws_bytes,
+                current_stream_ptr(dev)), 'mp_net_forward')
+        self.last_launches = int(lib.mp_launch_count())
+        if carry_velocity:
+            self.velocity.rnn_state = (s.hn.clone(), s.cn.clone())
+        return s, max(lens)
+
+    def _out(self, t):
+        return t if self.reuse_outputs else t.clone()
+
+    @torch.no_grad()
+    def forward(self, batch, input_lengths=None):
+        """net.py:101-119 -> (pose [B*T,24,3,3], joints [B,T,72], vel ([T,72] if B == 1 else [B,T,72]), contact [B,T,2])."""
+        if input_lengths is None:
+            return self._forward_unfused(batch)
+        s, tmax = self._run(batch, input_lengths, want_tran=False, carry_velocity=True)
+        if tmax < s.T:
+            raise RuntimeError('padded length must equal max(input_lengths) (torch.cat in net.py:106 requires it)')
+        return self._out(s.pose), self._out(s.joints), self._out(s.vel).squeeze(0), self._out(s.contact)
+
+    def _forward_unfused(self, batch):
+        """input_lengths=None: the reference then runs every LSTM sequence-first (rnn.py:15); head by head."""
+        pred_joints = self.joints(batch, None)
+        pred_pose = self._reduced_global_to_full(self.pose.pose(pred_joints, None, None, x2=batch)[0])
+        contact = self.foot_contact.footcontact(pred_joints, None, None, x2=batch)[0]
+        vel, _, self.velocity.rnn_state = self.velocity.vel(pred_joints, None, self.velocity.rnn_state, x2=batch)
+        return pred_pose, pred_joints, vel.squeeze(0), contact
+
+    @torch.no_grad()
+    def forward_offline(self, imu, input_lengths=None):
+        """net.py:121-171.  B == 1: (pose [T,24,3,3], joints [1,T,72], tran [T,3], contact [T,2]);
+        B > 1: (pose [B*T,24,3,3], joints [B,T,72], tran [B,T,3], contact [B,T,2]), fresh velocity state per sequence."""
+        if input_lengths is None:
+            raise ValueError('forward_offline needs input_lengths (every reference caller passes them)')
+        B = imu.shape[0]
+        s, tmax = self._run(imu, input_lengths, want_tran=True, carry_velocity=(B == 1))
+        if tmax < s.T:
+            raise RuntimeError('padded length must equal max(input_lengths)')
+        pose, joints, tran, contact = self._out(s.pose), self._out(s.joints), self._out(s.tran), self._out(s.contact)
+        if getenv("PHYSICS"):
+            raise NotImplementedError('PHYSICS=1: the reference optimizer module `dynamics` is not part of its tree')
+        if B == 1:
+            return pose, joints, tran[0], contact[0]
+        return pose, joints, tran, contact
+
+    # ---- online ------------------------------------------------------------------------------------
+    def _online_state(self, S, dev):
+        if self._online is None or self._online.S != S or self._online.dev != dev:
+            self._online = OnlineStreams(self, S, dev)
+        return self._online
+
+    @torch.no_grad()
+    def forward_online(self, data, input_lengths=None):
+        """net.py:173-219 for one frame [60] -> (pose [24,9], joints [W,72], root [3], contact [2])."""
+        _require_cuda(data, 'input frame')
+        st = self._online_state(1, data.device)
+        pose, joints, root, contact = st.step(data.reshape(1, 60))
+        self.imu = st.window[0]
+        return pose[0].view(24, 9), joints[0], root[0].clone(), contact[0]
+
+    @torch.no_grad()
+    def forward_online_batch(self, frames):
+        """S independent live streams: frames [S,60] -> (pose [S,24,9], joints [S,W,72], root [S,3], contact [S,2])."""
+        _require_cuda(frames, 'input frames')
+        st = self._online_state(frames.shape[0], frames.device)
+        pose, joints, root, contact = st.step(frames)
+        return pose.view(-1, 24, 9), joints, root.clone(), contact
+
+    @property
+    def last_root_pos(self):
+        if self._online is None:
+            return torch.zeros(3)
+        return self._online.state_floats()[0, 6:9].clone()
+
+    @property
+    def current_root_y(self):
+        if self._online is None:
+            return 0
+        return float(self._online.state.view(torch.float64)[0, 6].item())
+
+
+class OnlineStreams:
+    """Device-resident state of S `forward_online` streams (net.py:58-64,84-88,173-219)."""
+
+    def __init__(self, net: MobilePoserNet, S: int, dev, window: int = None):
+        self.net, self.S, self.dev = net, S, dev
+        self.W = window or net.num_total_frames
+        self.P = net.num_past_frames if window is None else window - net.num_future_frames
+        lib = _cabi.lib()
+        self.state = torch.zeros(S, _cabi.ONLINE_STATE_BYTES, device=dev, dtype=torch.uint8)
+        self.win = [torch.zeros(S, self.W, 60, device=dev), torch.zeros(S, self.W, 60, device=dev)]
+        self.cur = 0
+        self.cold = True
+        self.pose = torch.empty(S, 24, 3, 3, device=dev)
+        self.root = torch.empty(S, 3, device=dev)
+        self.contact = torch.empty(S, 2, device=dev)
+        self.lengths = [self.W] * S
+        with torch.cuda.device(dev):
+            _cabi.check(lib.mp_online_reset(self.state.data_ptr(), S, 1, current_stream_ptr(dev)), 'mp_online_reset')
+
+    @property
+    def window(self):
+        return self.win[self.cur]
+
+    def state_floats(self):
+        return self.state.view(torch.float32)
+
+    def reset(self, full=False):
+        with torch.cuda.device(self.dev):
+            _cabi.check(_cabi.lib().mp_online_reset(self.state.data_ptr(), self.S, int(full), current_stream_ptr(self.dev)),
+                        'mp_online_reset')
+        self.cold = True
+
+    def step(self, frames):
+        lib = _cabi.lib()
+        net = self.net
+        frames = _f32c(frames).view(self.S, 60)
+        nxt = self.cur ^ 1
+        with torch.cuda.device(self.dev):
+            stream = current_stream_ptr(self.dev)
+            _cabi.check(lib.mp_online_push_frame(self.win[self.cur].data_ptr(), self.win[nxt].data_ptr(), frames.data_ptr(),
+                                                 self.S, self.W, int(self.cold), stream), 'mp_online_push_frame')
+            self.cur, self.cold = nxt, False
+            # the four heads over the whole window (velocity carries its state)
+            s, _ = net._run(self.win[self.cur], self.lengths, want_tran=False, carry_velocity=True)
+            # state machine on frame P of the window outputs (K7)
+            _cabi.check(lib.mp_online_update(self.state.data_ptr(), s.pose.data_ptr(), s.joints.data_ptr(),
+                                             s.vel.data_ptr(), s.contact.data_ptr(), self.S, self.W, self.P,
+                                             self.pose.data_ptr(), self.root.data_ptr(), self.contact.data_ptr(), stream),
+                        'mp_online_update')
+        return self.pose, s.joints if net.reuse_outputs else s.joints.clone(), self.root, self.contact.clone()
