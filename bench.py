@@ -1,0 +1,396 @@
+#!/usr/bin/env python
+"""bench.py -- frames/s of MobilePoser's per-frame hot path on synthetic 5-IMU windows.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg3|cfg2]
+
+Workloads (BASELINE.json configs):
+  cfg3 (default): MobilePoserNet 4 heads + kinematic tail (K5) + translation (K6) = forward_offline on a batch
+                  of 256 sequences x 300 frames per GPU (weak scaling: every rank gets its own 256 sequences);
+  cfg2:           the same path at batch 1 (one 300-frame window), also reported inside the cfg3 line as "batch1".
+A "step" is one forward_offline pass over the batch.  `value` = frames/s with inputs resident in HBM,
+`e2e` = the same through the host-buffer C-ABI entry (pinned host imu in, pose/joints/tran/contact out),
+`roofline` = the dominant kernel (cluster LSTM recurrence, H=256) against the measured HBM peak,
+`cpu_baseline` = the oracle port (the reference's torch-CPU path) timed on this box's host cores.
+
+--impl reference times the reference's CPU implementation of the path (oracle/torch_port.py, which calls the
+same torch CPU nn.LSTM/Linear kernels the reference calls) on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch
+
+T_FRAMES = 300
+METRIC = 'frames/sec (batch=1 and 256) synthetic 5-IMU@60Hz at 1/2/4/8 B200 vs CPU ref'
+IO_BYTES_PER_FRAME = 240 + 864 + 288 + 12 + 8          # imu in; pose, joints, tran, contact out
+WEIGHT_BYTES = 26_699_976
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--workload', default='cfg3', choices=['cfg3', 'cfg2'])
+    ap.add_argument('--batch', type=int, default=0, help='override sequences per GPU')
+    ap.add_argument('--cpu-sample', type=int, default=32, help='sequences in the CPU-baseline sample')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    return ap.parse_args()
+
+
+def measured_peak_gbs():
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+            return float(json.load(f)['hbm_gbs']), 'measured (MEASURED_PEAKS.json)'
+    except Exception:
+        return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index):
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.path = None
+
+    def __enter__(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix='.csv')
+            os.close(fd)
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
+                                          '-lms', '200', '-i', str(self.gpu_index)],
+                                         stdout=open(self.path, 'w'), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+        return self
+
+    def __exit__(self, *exc):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        out = {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
+        if not self.path or not os.path.exists(self.path):
+            return out
+        sm, mx, reasons = [], [], set()
+        for line in open(self.path):
+            p = [v.strip() for v in line.split(',')]
+            if len(p) < 9:
+                continue
+            try:
+                sm.append(float(p[1])); mx.append(float(p[2]))
+            except ValueError:
+                continue
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), p[5:9]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        os.unlink(self.path)
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def dist_env():
+    rank = int(os.environ.get('RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    local = int(os.environ.get('LOCAL_RANK', 0))
+    return rank, world, local
+
+
+# ------------------------------------------------------------------------------------------------------
+def cpu_reference_pass(oracle, x, lens):
+    """The reference's CPU path for a batch: batched net.forward (net.py:101-119) + the per-sequence
+    translation tail of forward_offline (net.py:125-154)."""
+    from oracle.torch_port import offline_translation
+    oracle.vel_state = None
+    pose, joints, vel, contact = oracle.forward(x, lens)
+    vel = vel.view(x.shape[0], x.shape[1], 72)
+    trans = [offline_translation(joints[b, :L], vel[b, :L], contact[b, :L]) for b, L in enumerate(lens)]
+    return pose, joints, trans, contact
+
+
+def time_cpu_sample(sd, x_sample, budget_s=20.0, min_passes=2):
+    """frames/s of the oracle port on this box's host cores for a bounded sample; returns the cpu_baseline dict."""
+    from oracle.torch_port import OraclePoser
+    oracle = OraclePoser(sd)
+    B, T = x_sample.shape[0], x_sample.shape[1]
+    lens = [T] * B
+    with torch.no_grad():
+        cpu_reference_pass(oracle, x_sample[:2], lens[:2])      # warm-up (MKL thread pools)
+        t0 = time.perf_counter()
+        passes = 0
+        while passes < min_passes or (time.perf_counter() - t0 < budget_s * 0.6 and passes < 50):
+            cpu_reference_pass(oracle, x_sample, lens)
+            passes += 1
+        dt_batched = (time.perf_counter() - t0) / passes
+        # the reference's own evaluate.py call pattern: one sequence at a time (forward_offline, B = 1)
+        t1 = time.perf_counter()
+        n1 = 0
+        while n1 < 2 or (time.perf_counter() - t1 < budget_s * 0.3 and n1 < B):
+            oracle.vel_state = None
+            oracle.forward_offline(x_sample[n1 % B:n1 % B + 1], [T])
+            n1 += 1
+        dt_single = (time.perf_counter() - t1) / n1
+    fps_batched, fps_single = B * T / dt_batched, T / dt_single
+    return {
+        'value': max(fps_batched, fps_single), 'unit': 'frames/s', 'cores': torch.get_num_threads(),
+        'host_cpus': os.cpu_count(), 'kind': 'port',
+        'sample': (f'{B} of the workload\'s sequences x {T} frames: batched forward + per-sequence translation tail '
+                   f'= {fps_batched:.0f} frames/s ({passes} passes); evaluate.py-style one sequence at a time '
+                   f'(forward_offline, B=1) = {fps_single:.0f} frames/s ({n1} sequences); torch {torch.__version__} CPU'),
+        'batched_fps': fps_batched, 'single_sequence_fps': fps_single,
+    }
+
+
+def seeded_state_dict():
+    import mobileposer_b200 as mp
+    torch.manual_seed(0)
+    net = mp.MobilePoserNet().eval()
+    return net, {k: v.clone() for k, v in net.state_dict().items()}
+
+
+# ------------------------------------------------------------------------------------------------------
+def run_reference(args):
+    rank, world, local = dist_env()
+    if rank != 0:
+        return
+    from mobileposer_b200.synthetic import synthetic_imu_batch
+    from oracle.torch_port import OraclePoser
+    B = (args.batch or (256 if args.workload == 'cfg3' else 1))
+    Bs = min(B, args.cpu_sample)
+    _, sd = seeded_state_dict()
+    x = synthetic_imu_batch(list(range(Bs)), T_FRAMES)
+    oracle = OraclePoser(sd)
+    lens = [T_FRAMES] * Bs
+    with torch.no_grad():
+        for _ in range(args.warmup):
+            cpu_reference_pass(oracle, x, lens)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            cpu_reference_pass(oracle, x, lens)
+        dt = time.perf_counter() - t0
+    fps = Bs * T_FRAMES * args.steps / dt
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': fps, 'unit': 'frames/s', 'n_gpus': args.gpus,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': dt / args.steps * 1e3, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': workload_name(args.workload, B), 'sample': f'{Bs} sequences x {T_FRAMES} frames per step',
+                   'combo': 'lw_rp', 'weights': 'torch.manual_seed(0) default init'},
+        'cpu_baseline': {'value': fps, 'unit': 'frames/s', 'cores': torch.get_num_threads(), 'host_cpus': os.cpu_count(),
+                         'kind': 'port', 'sample': f'{Bs} sequences x {T_FRAMES} frames per step, batched forward + '
+                                                   f'per-sequence translation tail, torch {torch.__version__} CPU'},
+        'e2e': {'value': fps, 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_name(w, B):
+    if w == 'cfg3':
+        return (f'cfg3: MobilePoserNet 4 heads + kinematic tail + translation (forward_offline), batch={B} sequences x '
+                f'{T_FRAMES} frames per GPU, combo lw_rp')
+    return f'cfg2: full MobilePoserNet forward_offline, batch={B}, {T_FRAMES}-frame window, combo lw_rp'
+
+
+def timed_device_steps(fn, steps, warmup, dist):
+    """W warm-ups, then K steps between CUDA events, barrier + synchronize on both sides; max over ranks."""
+    for i in range(warmup):
+        fn(i)
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        fn(warmup + i)
+    e1.record()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    ms = e0.elapsed_time(e1)
+    if dist is not None:
+        t = torch.tensor([ms], device='cuda')
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.item()
+    return ms
+
+
+def run_ours(args):
+    rank, world, local = dist_env()
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py --impl ours needs a CUDA device (there is no CPU fallback)')
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist_mod.init_process_group('nccl', device_id=dev)
+        dist = dist_mod
+
+    import mobileposer_b200 as mp
+    from mobileposer_b200 import _cabi
+    from mobileposer_b200.synthetic import synthetic_imu_batch
+
+    B = args.batch or (256 if args.workload == 'cfg3' else 1)
+    T = T_FRAMES
+    net, sd = seeded_state_dict()
+    net = net.to(dev)
+    net.reuse_outputs = True
+    lens = [T] * B
+
+    # several distinct input sets so a step never finds its inputs in L2 from the previous step
+    n_sets = 8 if B > 1 else 64
+    base = rank * B * n_sets
+    xs_host = [synthetic_imu_batch(list(range(base + i * B, base + (i + 1) * B)), T).pin_memory() for i in range(n_sets)]
+    xs = [x.to(dev) for x in xs_host]
+
+    def step(i):
+        net.velocity.rnn_state = None
+        return net.forward_offline(xs[i % n_sets], lens)
+
+    with ClockSampler(local) as clocks:
+        ms = timed_device_steps(step, args.steps, args.warmup, dist)
+    launches = net.last_launches
+    frames_per_step = B * T * world
+    value = frames_per_step * args.steps / (ms / 1e3)
+
+    # ---- e2e: host buffers through the C ABI, copies inside the timed region ------------------------
+    host = mp.HostOffline(net, B, T)
+
+    def e2e_step(i):
+        host.run(xs_host[i % n_sets], None)
+
+    for i in range(max(3, args.warmup)):
+        e2e_step(i)
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        e2e_step(i)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if dist is not None:
+        t = torch.tensor([e2e_s], device='cuda')
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = t.item()
+    e2e = {'value': frames_per_step * args.steps / e2e_s, 'unit': 'frames/s', 'h2d_bytes_per_step': B * T * 60 * 4,
+           'd2h_bytes_per_step': B * T * (216 + 72 + 3 + 2) * 4, 'ms_per_step': e2e_s / args.steps * 1e3}
+
+    # ---- per-kernel durations (CUDA events on the launching streams), same steps, graphs bypassed ----
+    lib = _cabi.lib()
+    _cabi.check(lib.mp_profile_enable(1))
+    for i in range(args.steps):
+        step(i)
+    prof = _cabi.profile_collect()
+    _cabi.check(lib.mp_profile_enable(0))
+    peak, peak_src = measured_peak_gbs()
+    dom = prof.get('lstm_rec_h256', None)
+    roofline = None
+    if dom:
+        gbs = dom['algorithmic_bytes'] / (dom['total_ms'] / 1e3) / 1e9
+        roofline = {'bound': 'hbm', 'kernel': 'lstm_rec_kernel<256,8,*>', 'achieved': gbs, 'peak': peak, 'unit': 'GB/s',
+                    'frac': gbs / peak, 'traffic': load_traffic('lstm_rec_h256'), 'peak_source': peak_src,
+                    'avg_launch_ms': dom['total_ms'] / dom['launches'],
+                    'algorithmic_bytes_per_launch': dom['algorithmic_bytes'] / dom['launches'],
+                    'note': 'recurrence is serial in T: latency/FFMA-bound by construction, see DESIGN.md'}
+    whole = (WEIGHT_BYTES + B * T * IO_BYTES_PER_FRAME) / (ms / args.steps / 1e3) / 1e9
+    kernels = {k: {'launches_per_step': v['launches'] / args.steps, 'ms_per_step': v['total_ms'] / args.steps,
+                   'algorithmic_GBps': v['algorithmic_bytes'] / (v['total_ms'] / 1e3) / 1e9} for k, v in prof.items()}
+
+    # ---- end-of-run exchange: the only collective of the path (per-sequence metric rows) --------------
+    gathered = None
+    if dist is not None:
+        pose, joints, tran, contact = step(0)
+        rows = sequence_summary(pose, tran, contact, B, T)
+        out = torch.empty(world * B, rows.shape[1], device=dev)
+        dist.all_gather_into_tensor(out, rows)
+        gathered = list(out.shape)
+
+    # ---- batch-1 latency configuration (cfg2) on rank 0's GPU, every rank a replica --------------------
+    batch1 = None
+    if args.workload == 'cfg3':
+        x1 = [synthetic_imu_batch([90000 + rank * 64 + i], T).to(dev) for i in range(16)]
+
+        def step1(i):
+            net.velocity.rnn_state = None
+            return net.forward_offline(x1[i % 16], [T])
+        k1 = max(args.steps, 50)
+        ms1 = timed_device_steps(step1, k1, max(args.warmup, 5), dist)
+        batch1 = {'workload': workload_name('cfg2', 1), 'value': world * T * k1 / (ms1 / 1e3), 'unit': 'frames/s',
+                  'ms_per_step': ms1 / k1, 'steps': k1, 'gpu_launches': net.last_launches,
+                  'hbm_roofline_frac_whole_path': (WEIGHT_BYTES + T * IO_BYTES_PER_FRAME) / (ms1 / k1 / 1e3) / 1e9 / peak}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = time_cpu_sample(sd, xs_host[0][:min(B, args.cpu_sample)].clone())
+
+    if rank == 0:
+        line = {
+            'metric': METRIC, 'value': value, 'unit': 'frames/s', 'n_gpus': world, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': workload_name(args.workload, B), 'frames_per_step': frames_per_step,
+                       'weights': 'torch.manual_seed(0) default init (bit-identical to the reference init)',
+                       'l2': f'{n_sets} distinct resident input sets rotate between steps; per-step intermediates '
+                             f'({net_workspace_mb(net, B, T):.0f} MB) exceed the 126 MB L2',
+                       'parallelism': f'{world} x (one process per GPU, sequences sharded, no data-path collective)'},
+            'e2e': e2e, 'gpu_launches': launches * args.steps, 'gpu_launches_per_step': launches,
+            'roofline': roofline, 'whole_path_algorithmic_GBps': whole, 'whole_path_hbm_frac': whole / peak,
+            'kernels': kernels, 'cpu_baseline': cpu, 'batch1': batch1, 'clocks': clocks.summary(),
+            'all_gather_shape': gathered,
+        }
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def net_workspace_mb(net, B, T):
+    from mobileposer_b200 import _cabi
+    return _cabi.lib().mp_net_workspace_bytes(net._net_handle(), B, T) / 1e6
+
+
+def sequence_summary(pose, tran, contact, B, T):
+    """Per-sequence metric rows that get all-gathered at the end of a sharded run."""
+    p = pose.view(B, T, 24, 9)
+    eye = torch.eye(3, device=pose.device).view(1, 1, 1, 9)
+    return torch.stack([(p - eye).abs().mean(dim=(1, 2, 3)), tran[:, -1].norm(dim=1), tran.abs().amax(dim=(1, 2)),
+                        (contact[..., 0] > contact[..., 1]).float().mean(dim=1)], dim=1).contiguous()
+
+
+def load_traffic(kernel):
+    """dram bytes per launch from the committed ncu capture summary (profiles/ncu_summary.json), else null."""
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'ncu_summary.json')) as f:
+            return json.load(f)[kernel]['dram_bytes_per_launch']
+    except Exception:
+        return None
+
+
+if __name__ == '__main__':
+    a = parse_args()
+    if a.impl == 'reference':
+        run_reference(a)
+    else:
+        run_ours(a)

@@ -154,6 +154,18 @@ int mp_net_forward_offline_host(mp_net_t* net, const float* imu_host, int32_t B,
                                 float* tran_host, float* contact_host, void* dev_io,
                                 void* workspace, size_t workspace_bytes, mp_stream_t stream);
 
+/* Per-kernel timing with CUDA events on the launching stream.  While enabled every kernel launch of the
+ * library is bracketed by an event pair (graphs are bypassed); mp_profile_collect synchronises the
+ * device and returns one aggregated entry per kernel name.  bench.py's `roofline` comes from here.  */
+typedef struct mp_profile_entry {
+    char name[32];
+    int64_t launches;
+    double total_ms;          /* sum of the launches' device durations            */
+    double algorithmic_bytes; /* sum of the launches' algorithmic bytes */
+} mp_profile_entry_t;
+int mp_profile_enable(int32_t on);
+int mp_profile_collect(mp_profile_entry_t* out, int32_t capacity, int32_t* n_out);
+
 /* How many kernels of this library the last mp_net_forward / mp_rnn_forward enqueued
  * (bench.py's gpu_launches).                                                                 */
 int64_t mp_launch_count(void);

@@ -7,11 +7,11 @@ CPU or eager fallback (the package raises if the library or an sm_100 device is 
 """
 from .config import amass, datasets, joint_set, model_config  # noqa: F401
 from .modules import RNN, FootContact, Joints, Poser, Velocity  # noqa: F401
-from .net import MobilePoserNet, OnlineStreams, getenv  # noqa: F401
+from .net import HostOffline, MobilePoserNet, OnlineStreams, getenv  # noqa: F401
 from .model_utils import load_model, reduced_pose_to_full  # noqa: F401
 
 # mobileposer/constants.py:6-11
 MODULES = {'poser': Poser, 'joints': Joints, 'foot_contact': FootContact, 'velocity': Velocity}
 
-__all__ = ['MobilePoserNet', 'Joints', 'Poser', 'FootContact', 'Velocity', 'RNN', 'OnlineStreams', 'load_model',
+__all__ = ['MobilePoserNet', 'Joints', 'Poser', 'FootContact', 'Velocity', 'RNN', 'OnlineStreams', 'HostOffline', 'load_model',
            'reduced_pose_to_full', 'MODULES', 'getenv', 'model_config', 'amass', 'datasets', 'joint_set']

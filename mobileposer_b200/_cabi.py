@@ -29,6 +29,12 @@ class RnnWeights(C.Structure):
     ]
 
 
+class ProfileEntry(C.Structure):
+    """struct mp_profile_entry."""
+    _fields_ = [('name', C.c_char * 32), ('launches', C.c_int64), ('total_ms', C.c_double),
+                ('algorithmic_bytes', C.c_double)]
+
+
 ONLINE_STATE_BYTES = 64   # sizeof(mp_online_state_t)
 
 # name -> (restype, argtypes); must list every symbol the header declares (tests/test_cabi.py)
@@ -37,6 +43,8 @@ SIGNATURES = {
     'mp_last_error': (C.c_char_p, []),
     'mp_device_check': (C.c_int, []),
     'mp_launch_count': (C.c_int64, []),
+    'mp_profile_enable': (C.c_int, [C.c_int32]),
+    'mp_profile_collect': (C.c_int, [C.POINTER(ProfileEntry), C.c_int32, C.POINTER(C.c_int32)]),
     'mp_rnn_create': (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(RnnWeights), c_stream]),
     'mp_rnn_destroy': (None, [C.c_void_p]),
     'mp_rnn_workspace_bytes': (C.c_size_t, [C.c_void_p, C.c_int32, C.c_int32]),
@@ -84,3 +92,12 @@ def check(status: int, what: str = '') -> None:
     if status != 0:
         msg = lib().mp_last_error().decode('utf-8', 'replace')
         raise RuntimeError(f'mobileposer_b200 {what} failed (status {status}): {msg}')
+
+
+def profile_collect():
+    """-> {kernel name: dict(launches, total_ms, algorithmic_bytes)} since mp_profile_enable(1)."""
+    arr = (ProfileEntry * 32)()
+    n = C.c_int32(0)
+    check(lib().mp_profile_collect(arr, 32, C.byref(n)), 'mp_profile_collect')
+    return {arr[i].name.decode(): dict(launches=int(arr[i].launches), total_ms=float(arr[i].total_ms),
+                                       algorithmic_bytes=float(arr[i].algorithmic_bytes)) for i in range(n.value)}

@@ -3,6 +3,7 @@
 #include "mp_common.cuh"
 
 #include <stdarg.h>
+#include <string.h>
 
 #include <vector>
 
@@ -18,6 +19,28 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 void count_launch(int n) { g_launches += n; }
+
+struct ProfileRec {
+    char name[32];
+    double bytes;
+    cudaEvent_t e0, e1;
+};
+static bool g_profile = false;
+static std::vector<ProfileRec> g_profile_recs;
+bool profile_enabled() { return g_profile; }
+ProfileScope::ProfileScope(const char* name, double bytes, cudaStream_t stream) : stream_(stream), index_(-1) {
+    if (!g_profile) return;
+    ProfileRec r;
+    snprintf(r.name, sizeof(r.name), "%s", name);
+    r.bytes = bytes;
+    if (cudaEventCreate(&r.e0) != cudaSuccess || cudaEventCreate(&r.e1) != cudaSuccess) return;
+    cudaEventRecord(r.e0, stream);
+    index_ = (int)g_profile_recs.size();
+    g_profile_recs.push_back(r);
+}
+ProfileScope::~ProfileScope() {
+    if (index_ >= 0) cudaEventRecord(g_profile_recs[index_].e1, stream_);
+}
 
 namespace {
 
@@ -63,6 +86,39 @@ extern "C" {
 int mp_abi_version(void) { return MP_ABI_VERSION; }
 const char* mp_last_error(void) { return g_err; }
 int64_t mp_launch_count(void) { return g_launches; }
+
+int mp_profile_enable(int32_t on) {
+    for (auto& r : g_profile_recs) {
+        cudaEventDestroy(r.e0);
+        cudaEventDestroy(r.e1);
+    }
+    g_profile_recs.clear();
+    g_profile = on != 0;
+    return MP_OK;
+}
+
+int mp_profile_collect(mp_profile_entry_t* out, int32_t capacity, int32_t* n_out) {
+    MP_REQUIRE(out && n_out && capacity > 0, "profile_collect: bad arguments");
+    MP_CUDA_TRY(cudaDeviceSynchronize());
+    int n = 0;
+    for (auto& r : g_profile_recs) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, r.e0, r.e1) != cudaSuccess) continue;
+        int k = 0;
+        while (k < n && strncmp(out[k].name, r.name, sizeof(out[k].name)) != 0) ++k;
+        if (k == n) {
+            if (n == capacity) continue;
+            memset(&out[n], 0, sizeof(out[n]));
+            snprintf(out[n].name, sizeof(out[n].name), "%s", r.name);
+            ++n;
+        }
+        out[k].launches += 1;
+        out[k].total_ms += ms;
+        out[k].algorithmic_bytes += r.bytes;
+    }
+    *n_out = n;
+    return MP_OK;
+}
 
 int mp_device_check(void) {
     int dev = 0, major = 0;
@@ -361,7 +417,7 @@ int mp_net_forward(mp_net_t* n, const float* imu, int32_t B, int32_t T, const in
     }
     NetArgs a{imu, B, T, lengths, vel_h0, vel_c0, vel_hn, vel_cn, pose, joints, vel, contact, tran, workspace, workspace_bytes};
     g_launches = 0;
-    if (!n->graph_enabled) return net_enqueue(n, a, stream);
+    if (!n->graph_enabled || profile_enabled()) return net_enqueue(n, a, stream);
 
     std::vector<uintptr_t> key = {(uintptr_t)imu, (uintptr_t)B, (uintptr_t)T, (uintptr_t)lengths, (uintptr_t)vel_h0,
                                   (uintptr_t)vel_c0, (uintptr_t)vel_hn, (uintptr_t)vel_cn, (uintptr_t)pose,

@@ -164,6 +164,8 @@ int launch_gemm_bias_act(const float* A1, int K1, const float* A2, int K2, const
     MP_REQUIRE(K2 == 0 || A2, "gemm: second operand missing");
     MP_REQUIRE(((uintptr_t)A1 & 15) == 0 && ((uintptr_t)A2 & 15) == 0 && ((uintptr_t)W & 15) == 0 &&
                    ((uintptr_t)C & 15) == 0, "gemm: pointers must be 16-byte aligned");
+    ProfileScope prof(N >= 512 ? "gemm_input_proj" : "gemm_linear",
+                      4.0 * ((double)N * (K1 + K2) + N + (double)M * (K1 + K2) + (double)M * N), stream);
     const long big_ctas = (long)((M + 127) / 128) * ((N + 127) / 128);
     if (big_ctas >= 148) {
         dim3 grid((N + 127) / 128, (M + 127) / 128);

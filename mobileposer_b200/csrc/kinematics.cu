@@ -261,6 +261,7 @@ int launch_reduced_global_to_full(const float* r6d, int64_t n, float* pose, cuda
     if (n <= 0) return MP_OK;
     MP_REQUIRE(r6d && pose, "pose: null pointer");
     MP_REQUIRE(((uintptr_t)r6d & 7) == 0, "pose: r6d must be 8-byte aligned");
+    ProfileScope prof("k5_pose", 4.0 * (96 + 216) * (double)n, stream);
     const long long blocks = (n + 7) / 8;
     const int grid = (int)(blocks < 148LL * 16 ? blocks : 148LL * 16);
     reduced_global_to_full_kernel<<<grid, 256, 0, stream>>>(r6d, n, pose);
@@ -273,6 +274,7 @@ int launch_tran_offline(const float* joints, const float* vel, const float* cont
                         int B, int T, float* tran, cudaStream_t stream) {
     if (B <= 0 || T <= 0) return MP_OK;
     MP_REQUIRE(joints && vel && contact && tran, "tran: null pointer");
+    ProfileScope prof("k6_tran", 4.0 * (6 + 3 + 2 + 3) * (double)B * T, stream);
     tran_offline_kernel<<<(B + 3) / 4, 128, 0, stream>>>(joints, vel, contact, lengths, B, T, tran);
     MP_CUDA_TRY(cudaGetLastError());
     count_launch();

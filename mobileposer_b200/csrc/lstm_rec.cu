@@ -487,6 +487,11 @@ int launch_pack_whh(const float* const* w_hh_dirs, int H, int dirs, float4* wpac
 
 int launch_lstm_recurrence(const RecLayerArgs& a, cudaStream_t stream) {
     MP_REQUIRE(a.gin && a.wpack && a.y && a.B > 0 && a.T > 0 && (a.dirs == 1 || a.dirs == 2), "lstm: bad arguments");
+    // algorithmic bytes of the recurrence: W_hh once + the layer's h output; the gate
+    // pre-activations it reads are an intermediate of this design, charged as what a fully fused
+    // layer would read instead (the layer input, counted with the input-projection GEMM).
+    ProfileScope prof(a.H == 256 ? "lstm_rec_h256" : "lstm_rec_h64",
+                      4.0 * ((double)a.dirs * 4 * a.H * a.H + (double)a.B * a.T * a.dirs * a.H), stream);
     if (env_is("MP_REC_IMPL", "simple")) {
         dim3 grid(a.B, a.dirs);
         if (a.H == 256)

@@ -13,6 +13,15 @@ namespace mp {
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
 
+// Per-kernel CUDA-event timing on the launching stream (mp_profile_enable / mp_profile_collect).
+bool profile_enabled();
+struct ProfileScope {
+    ProfileScope(const char* name, double algorithmic_bytes, cudaStream_t stream);
+    ~ProfileScope();
+    cudaStream_t stream_;
+    int index_;
+};
+
 #define MP_CUDA_TRY(expr)                                                                         \
     do {                                                                                          \
         cudaError_t err__ = (expr);                                                               \

@@ -332,3 +332,41 @@ class OnlineStreams:
                                              self.pose.data_ptr(), self.root.data_ptr(), self.contact.data_ptr(), stream),
                         'mp_online_update')
         return self.pose, s.joints if net.reuse_outputs else s.joints.clone(), self.root, self.contact.clone()
+
+
+class HostOffline:
+    """forward_offline through HOST buffers: one C-ABI call does H2D of the IMU batch, the whole forward, D2H of
+    (pose, joints, tran, contact) and a stream synchronise (mp_net_forward_offline_host).  Fresh velocity state per
+    call.  Buffers (device staging, workspace, pinned outputs) are allocated once for a fixed (B, T)."""
+
+    def __init__(self, net: MobilePoserNet, B: int, T: int, device=None):
+        lib = _cabi.lib()
+        self.net, self.B, self.T = net, B, T
+        self.dev = device or net._device()
+        handle = net._net_handle()
+        with torch.cuda.device(self.dev):
+            self.staging = torch.empty(lib.mp_net_host_staging_bytes(B, T), device=self.dev, dtype=torch.uint8)
+            self.ws_bytes = lib.mp_net_workspace_bytes(handle, B, T)
+            self.ws = torch.empty(self.ws_bytes, device=self.dev, dtype=torch.uint8)
+        self.pose = torch.empty(B * T, 24, 3, 3).pin_memory()
+        self.joints = torch.empty(B, T, 72).pin_memory()
+        self.tran = torch.empty(B, T, 3).pin_memory()
+        self.contact = torch.empty(B, T, 2).pin_memory()
+        self.lengths = torch.empty(B, dtype=torch.int32).pin_memory()
+
+    def run(self, imu_host: torch.Tensor, input_lengths=None):
+        if imu_host.is_cuda or imu_host.dtype != torch.float32 or not imu_host.is_contiguous():
+            raise ValueError('HostOffline.run expects a contiguous float32 host tensor')
+        if tuple(imu_host.shape) != (self.B, self.T, 60):
+            raise ValueError(f'expected {(self.B, self.T, 60)}, got {tuple(imu_host.shape)}')
+        lens_ptr = None
+        if input_lengths is not None:
+            lens = self.net._lengths(input_lengths, self.B, self.T)
+            self.lengths.copy_(torch.tensor(lens, dtype=torch.int32))
+            lens_ptr = self.lengths.data_ptr()
+        with torch.cuda.device(self.dev):
+            _cabi.check(_cabi.lib().mp_net_forward_offline_host(
+                self.net._net_handle(), imu_host.data_ptr(), self.B, self.T, lens_ptr, self.pose.data_ptr(),
+                self.joints.data_ptr(), self.tran.data_ptr(), self.contact.data_ptr(), self.staging.data_ptr(),
+                self.ws.data_ptr(), self.ws_bytes, current_stream_ptr(self.dev)), 'mp_net_forward_offline_host')
+        return self.pose, self.joints, self.tran, self.contact

@@ -1,0 +1,340 @@
+"""GPU suite: the CUDA path (through the C ABI, via the MobilePoserNet mirror) against
+  (1) the committed fixtures produced by the live reference (tests/golden/),
+  (2) the CPU oracle (oracle/torch_port.py) on fresh seeded inputs,
+  (3) size-independent properties at BASELINE.json's full sizes.
+Tolerances are the north star's: joint angles <= 1e-4 rad, root translation <= 1e-4 m, contact argmax
+identical (tests/parity.py)."""
+import os
+
+import pytest
+import torch
+
+from conftest import load_golden
+from parity import ANGLE_TOL, TRAN_TOL, VALUE_TOL, argmax_equal, max_abs, max_angle, min_margin
+
+pytestmark = pytest.mark.gpu
+
+DEV = 'cuda:0'
+
+
+@pytest.fixture(scope='module')
+def net(seeded_state_dict):
+    import mobileposer_b200 as mp
+    n = mp.MobilePoserNet()
+    n.load_state_dict(seeded_state_dict)
+    return n.to(DEV).eval()
+
+
+@pytest.fixture()
+def env():
+    """Set MP_* switches for one test and restore them afterwards."""
+    saved = {}
+
+    def setter(**kw):
+        for k, v in kw.items():
+            saved.setdefault(k, os.environ.get(k))
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = str(v)
+    yield setter
+    for k, v in saved.items():
+        if v is None:
+            os.environ.pop(k, None)
+        else:
+            os.environ[k] = v
+
+
+def check_pose_tran(pose, tran, contact, g_pose, g_tran, g_contact, what=''):
+    a = max_angle(pose, g_pose)
+    assert a <= ANGLE_TOL, f'{what}: max joint angle error {a:.3e} rad'
+    if tran is not None:
+        t = max_abs(tran, g_tran)
+        assert t <= TRAN_TOL, f'{what}: max translation error {t:.3e} m'
+    assert argmax_equal(contact, g_contact), f'{what}: contact argmax differs (min margin {min_margin(g_contact):.3e})'
+
+
+# ---- fixtures from the live reference ---------------------------------------------------------------
+def test_cfg1_joints_head(net):
+    g = load_golden('cfg1_joints_T300')
+    y = net.joints(g['imu'][None].to(DEV), [300])
+    assert max_abs(y[0], g['joints']) <= VALUE_TOL
+
+
+def test_cfg2_forward_and_offline(net):
+    g = load_golden('cfg2_forward_T300')
+    x = g['imu'][None].to(DEV)
+    net.velocity.rnn_state = None
+    pose, joints, vel, contact = net.forward(x, [300])
+    assert pose.shape == (300, 24, 3, 3) and joints.shape == (1, 300, 72) and vel.shape == (300, 72)
+    assert contact.shape == (1, 300, 2)
+    check_pose_tran(pose, None, contact[0], g['pose'], None, g['contact'], 'forward')
+    assert max_abs(joints[0], g['joints']) <= VALUE_TOL and max_abs(vel, g['vel']) <= VALUE_TOL
+    assert max_abs(contact[0], g['contact']) <= VALUE_TOL
+    hn, cn = net.velocity.rnn_state
+    assert max_abs(hn, g['vel_hn']) <= VALUE_TOL and max_abs(cn, g['vel_cn']) <= VALUE_TOL
+    net.velocity.rnn_state = None
+    net.reset()
+    pose, joints, tran, contact = net.forward_offline(x, [300])
+    assert pose.shape == (300, 24, 3, 3) and joints.shape == (1, 300, 72) and tran.shape == (300, 3)
+    assert contact.shape == (300, 2)
+    check_pose_tran(pose, tran, contact, g['pose'], g['tran'], g['contact'], 'forward_offline')
+
+
+def test_ragged_batch(net):
+    g = load_golden('ragged_forward_B3')
+    lens = g['lengths'].tolist()
+    net.velocity.rnn_state = None
+    pose, joints, vel, contact = net.forward(g['imu'].to(DEV), lens)
+    # padded frames included: the reference leaves linear2.bias there (pad_packed_sequence zero-fills first)
+    assert max_abs(joints, g['joints']) <= VALUE_TOL and max_abs(vel, g['vel']) <= VALUE_TOL
+    assert max_abs(contact, g['contact']) <= VALUE_TOL
+    assert max_angle(pose, g['pose']) <= ANGLE_TOL
+    for b, L in enumerate(lens):
+        assert argmax_equal(contact[b, :L], g['contact'][b, :L])
+    hn, cn = net.velocity.rnn_state
+    assert max_abs(hn, g['vel_hn']) <= VALUE_TOL and max_abs(cn, g['vel_cn']) <= VALUE_TOL
+
+
+def test_velocity_state_leak_is_reproduced(net):
+    g = load_golden('state_leak_T100')
+    net.velocity.rnn_state = None
+    net.reset()
+    assert max_abs(net.forward_offline(g['imu_a'][None].to(DEV), [100])[2], g['tran_a']) <= TRAN_TOL
+    net.reset()        # like the reference, does not clear the velocity state
+    assert max_abs(net.forward_offline(g['imu_b'][None].to(DEV), [100])[2], g['tran_b_leak']) <= TRAN_TOL
+    net.velocity.rnn_state = None
+    assert max_abs(net.forward_offline(g['imu_b'][None].to(DEV), [100])[2], g['tran_b_clean']) <= TRAN_TOL
+
+
+def test_carried_state_rejects_a_batch_size_change(net):
+    net.velocity.rnn_state = None
+    net.forward(torch.zeros(2, 8, 60, device=DEV), [8, 8])
+    with pytest.raises(RuntimeError, match='Expected hidden'):
+        net.forward(torch.zeros(3, 8, 60, device=DEV), [8, 8, 8])
+    net.velocity.rnn_state = None
+
+
+def test_online_ticks(seeded_state_dict):
+    import mobileposer_b200 as mp
+    g = load_golden('online_60ticks')
+    n = mp.MobilePoserNet()
+    n.load_state_dict(seeded_state_dict)
+    n = n.to(DEV).eval()
+    for i, f in enumerate(g['imu'].to(DEV)):
+        pose, joints, root, contact = n.forward_online(f)
+        assert pose.shape == (24, 9) and joints.shape == (45, 72) and root.shape == (3,) and contact.shape == (2,)
+        assert max_angle(pose.view(24, 3, 3), g['pose'][i].view(24, 3, 3)) <= ANGLE_TOL, i
+        assert max_abs(root, g['root'][i]) <= TRAN_TOL, i
+        assert argmax_equal(contact, g['contact'][i]), i
+    assert max_abs(joints, g['last_joints']) <= VALUE_TOL
+    assert max_abs(n.velocity.rnn_state[0], g['vel_hn']) <= VALUE_TOL
+    # reset(): root and current_root_y cleared, window cold-starts again (net.py:84-88)
+    n.reset()
+    assert n.last_root_pos.abs().max().item() == 0 and n.current_root_y == 0
+
+
+@pytest.mark.parametrize('T', [1, 3])
+def test_tiny_lengths(net, T):
+    g = load_golden(f'edge_T{T}')
+    net.velocity.rnn_state = None
+    pose, joints, tran, contact = net.forward_offline(g['imu'][None].to(DEV), [T])
+    check_pose_tran(pose, tran, contact, g['pose'], g['tran'], g['contact'], f'T={T}')
+    assert max_abs(joints[0], g['joints']) <= VALUE_TOL
+
+
+def test_k5_unit_including_degenerate_rows(net):
+    g = load_golden('k5_unit')
+    out = net._reduced_global_to_full(g['r6d'].to(DEV)).cpu()
+    assert not torch.isnan(out).any()
+    mask = torch.ones(40, 24, dtype=torch.bool)
+    mask[5, [1, 4]] = False      # colinear r6d columns: ill-conditioned in the reference itself
+    assert max_abs(out[mask], g['pose'][mask]) <= 1e-5
+    assert torch.equal(out[7], g['pose'][7])     # all-degenerate frame: zeros / identities exactly
+
+
+def test_k6_unit_floor_clamp_and_ties():
+    from mobileposer_b200 import _cabi
+    g = load_golden('k6_unit')
+    T = g['joints'].shape[0]
+    j, v, c = (g[k].to(DEV).contiguous() for k in ('joints', 'vel', 'contact'))
+    tran = torch.empty(1, T, 3, device=DEV)
+    _cabi.check(_cabi.lib().mp_tran_offline(j.data_ptr(), v.data_ptr(), c.data_ptr(), None, 1, T, tran.data_ptr(),
+                                            torch.cuda.current_stream().cuda_stream))
+    assert max_abs(tran[0], g['tran']) <= 2e-6
+
+
+def test_k7_unit_online_state_machine():
+    from mobileposer_b200 import _cabi
+    lib = _cabi.lib()
+    g = load_golden('k7_unit')
+    n, W, P = g['joints'].shape[0], 45, 40
+    state = torch.zeros(1, _cabi.ONLINE_STATE_BYTES, device=DEV, dtype=torch.uint8)
+    stream = torch.cuda.current_stream().cuda_stream
+    _cabi.check(lib.mp_online_reset(state.data_ptr(), 1, 1, stream))
+    pose_out, root, cont = torch.empty(1, 216, device=DEV), torch.empty(1, 3, device=DEV), torch.empty(1, 2, device=DEV)
+    for k in range(n):
+        r6d = g['r6d'][k].repeat(W, 1).to(DEV)
+        pose = torch.empty(W, 216, device=DEV)
+        _cabi.check(lib.mp_pose_reduced_global_to_full(r6d.data_ptr(), W, pose.data_ptr(), stream))
+        j = g['joints'][k].repeat(1, W, 1).to(DEV).contiguous()
+        v = g['vel'][k].repeat(1, W, 1).to(DEV).contiguous()
+        c = g['contact'][k].repeat(1, W, 1).to(DEV).contiguous()
+        _cabi.check(lib.mp_online_update(state.data_ptr(), pose.data_ptr(), j.data_ptr(), v.data_ptr(), c.data_ptr(),
+                                         1, W, P, pose_out.data_ptr(), root.data_ptr(), cont.data_ptr(), stream))
+        assert max_abs(root[0], g['root'][k]) <= 2e-6, k
+        assert max_abs(pose_out[0].view(24, 9), g['pose'][k]) <= 1e-5, k
+
+
+def test_batch_equals_independent_reference_calls(net):
+    g = load_golden('batch8_T64')
+    pose, joints, tran, contact = net.forward_offline(g['imu'].to(DEV), [64] * 8)
+    assert pose.shape == (8 * 64, 24, 3, 3) and tran.shape == (8, 64, 3)
+    check_pose_tran(pose.view(8, 64, 24, 3, 3), tran, contact, g['pose'], g['tran'], g['contact'], 'batch8')
+    assert max_abs(joints, g['joints']) <= VALUE_TOL
+
+
+# ---- against the CPU oracle on fresh inputs, every kernel variant --------------------------------------
+@pytest.mark.parametrize('variant', [
+    dict(),                                              # default policy
+    dict(MP_REC_IMPL='simple'),                          # debug kernel
+    dict(MP_REC_NB=1, MP_REC_SEND='bulk'),               # latency path with bulk sends
+    dict(MP_REC_NB=4),                                   # throughput path, bulk sends
+    dict(MP_REC_NB=4, MP_REC_SEND='stasync'),            # throughput path, st.async sends
+    dict(MP_REC_NB=8),
+    dict(MP_REC_NB=3),                                   # latency path, several sequences per cluster
+])
+def test_recurrence_variants_against_oracle(net, oracle, env, variant):
+    from mobileposer_b200.synthetic import synthetic_imu_batch
+    env(**variant)
+    lens = [40, 9, 33, 40, 1, 17, 25, 40, 38, 2, 31]
+    x = synthetic_imu_batch(list(range(100, 111)), 40)
+    for b, L in enumerate(lens):
+        x[b, L:] = 0
+    oracle.vel_state = None
+    o_pose, o_joints, o_vel, o_contact = oracle.forward(x, lens)
+    o_state = oracle.vel_state
+    net.velocity.rnn_state = None
+    net.set_graph(False)
+    try:
+        pose, joints, vel, contact = net.forward(x.to(DEV), lens)
+        state = net.velocity.rnn_state
+        # second call: carried velocity state (h0/c0 path of the kernel)
+        pose2, _, vel2, _ = net.forward(x.to(DEV), lens)
+    finally:
+        net.set_graph(True)
+        net.velocity.rnn_state = None
+    _, _, o_vel2, _ = oracle.forward(x, lens)
+    oracle.vel_state = None
+    assert max_abs(joints, o_joints) <= VALUE_TOL and max_abs(vel, o_vel) <= VALUE_TOL
+    assert max_abs(contact, o_contact) <= VALUE_TOL
+    assert max_angle(pose, o_pose) <= ANGLE_TOL
+    assert max_abs(state[0], o_state[0]) <= VALUE_TOL and max_abs(state[1], o_state[1]) <= VALUE_TOL
+    assert max_abs(vel2, o_vel2) <= VALUE_TOL
+    for b, L in enumerate(lens):
+        assert argmax_equal(contact[b, :L], o_contact[b, :L])
+
+
+def test_rnn_module_surface(net, oracle):
+    """RNN.forward(x, seq_lengths, h) return convention incl. the sequence-first case (rnn.py:15)."""
+    from oracle.torch_port import _Head  # noqa: F401
+    x = torch.randn(5, 7, 60, generator=torch.Generator().manual_seed(5))
+    rnn = net.joints.joints
+    y, out_lens, (hn, cn) = rnn(x.to(DEV), [7, 3, 5, 7, 2])
+    assert y.shape == (5, 7, 72) and out_lens.tolist() == [7, 3, 5, 7, 2] and hn.shape == (4, 5, 256)
+    ref = oracle.heads['joints'](x, [7, 3, 5, 7, 2])[0]
+    assert max_abs(y, ref) <= VALUE_TOL
+    # max(len) < padded length: output is cut like pad_packed_sequence does
+    y, _, _ = rnn(x.to(DEV), [6, 3, 5, 6, 2])
+    assert y.shape == (5, 6, 72)
+    # no lengths: dim 0 is time (nn.LSTM batch_first=False)
+    y, out_lens, _ = rnn(x.to(DEV))
+    assert out_lens is None and y.shape == (5, 7, 72)
+    ref = oracle.heads['joints'](x.transpose(0, 1).contiguous(), [5] * 7)[0].transpose(0, 1)
+    assert max_abs(y, ref) <= VALUE_TOL
+
+
+def test_graph_replay_is_bitwise_identical(net):
+    from mobileposer_b200.synthetic import synthetic_imu_batch
+    x = synthetic_imu_batch([7, 8], 50).to(DEV)
+    outs = []
+    for i in range(4):          # call 1 eager, call 2 captures, calls 3-4 replay
+        net.velocity.rnn_state = None
+        outs.append([t.clone() for t in net.forward_offline(x, [50, 50])])
+    for o in outs[1:]:
+        for a, b in zip(outs[0], o):
+            assert torch.equal(a, b)
+    assert net.last_launches >= 20
+
+
+# ---- BASELINE.json sizes: properties --------------------------------------------------------------------
+def test_cfg3_batch256_is_batch_invariant_and_matches_oracle(net, oracle):
+    from mobileposer_b200.synthetic import synthetic_imu_batch
+    ids = list(range(1000, 1256))
+    x = synthetic_imu_batch(ids, 300)
+    xd = x.to(DEV)
+    pose, joints, tran, contact = net.forward_offline(xd, [300] * 256)
+    pose = pose.view(256, 300, 24, 3, 3)
+    assert torch.isfinite(pose).all() and torch.isfinite(tran).all()
+    # rotations are orthonormal (non-ignored joints)
+    R = pose[::16, ::10].reshape(-1, 3, 3).double()
+    # (fp32 Gram-Schmidt: the reference's own rotations are orthonormal to ~1e-5 as well)
+    assert (R @ R.transpose(1, 2) - torch.eye(3, device=R.device, dtype=R.dtype)).abs().max() < 5e-5
+    # the same sequences run alone (latency kernels, B = 1) give the same answer as inside the batch
+    for b in (0, 101, 255):
+        net.velocity.rnn_state = None
+        p1, j1, t1, c1 = net.forward_offline(xd[b:b + 1], [300])
+        assert max_angle(p1, pose[b]) <= ANGLE_TOL and max_abs(t1, tran[b]) <= TRAN_TOL
+        assert max_abs(j1[0], joints[b]) <= VALUE_TOL and argmax_equal(c1, contact[b])
+    # ... and the oracle agrees on a sample of them
+    for b in (3, 200):
+        oracle.vel_state = None
+        op, oj, ot, oc = oracle.forward_offline(x[b:b + 1], [300])
+        check_pose_tran(pose[b], tran[b], contact[b], op, ot, oc, f'cfg3 seq {b}')
+    net.velocity.rnn_state = None
+
+
+def test_cfg4_long_sequence_T3000(net, oracle):
+    from mobileposer_b200.synthetic import synthetic_imu
+    x = synthetic_imu(4242, 3000)
+    net.velocity.rnn_state = None
+    pose, joints, tran, contact = net.forward_offline(x[None].to(DEV), [3000])
+    oracle.vel_state = None
+    op, oj, ot, oc = oracle.forward_offline(x[None], [3000])
+    check_pose_tran(pose, tran, contact, op, ot, oc, 'T=3000')
+    net.velocity.rnn_state = None
+
+
+def test_online_batch_streams_equal_single_streams(seeded_state_dict):
+    """cfg5 shape: S concurrent live streams == S independent forward_online instances."""
+    import mobileposer_b200 as mp
+    from mobileposer_b200.synthetic import synthetic_imu_batch
+    combos = ['lw_rp', 'rw_rp', 'lw_lp', 'rw_lp', 'lw_rp_h']
+    x = torch.stack([synthetic_imu_batch([900], 12, combo=c)[0] for c in combos]).to(DEV)   # [5, 12, 60]
+    nb = mp.MobilePoserNet(); nb.load_state_dict(seeded_state_dict); nb = nb.to(DEV).eval()
+    singles = []
+    for s in range(5):
+        n1 = mp.MobilePoserNet(); n1.load_state_dict(seeded_state_dict); singles.append(n1.to(DEV).eval())
+    for t in range(12):
+        pose, joints, root, contact = nb.forward_online_batch(x[:, t])
+        for s in range(5):
+            p1, j1, r1, c1 = singles[s].forward_online(x[s, t])
+            assert max_angle(pose[s].view(24, 3, 3), p1.view(24, 3, 3)) <= ANGLE_TOL
+            assert max_abs(root[s], r1) <= TRAN_TOL and argmax_equal(contact[s], c1)
+
+
+def test_host_buffer_entry_matches_device_entry(net):
+    """mp_net_forward_offline_host (bench.py's e2e path) == forward_offline on device tensors."""
+    import mobileposer_b200 as mp
+    from mobileposer_b200.synthetic import synthetic_imu_batch
+    x = synthetic_imu_batch([61, 62, 63], 40)
+    lens = [40, 22, 35]
+    for b, L in enumerate(lens):
+        x[b, L:] = 0
+    host = mp.HostOffline(net, 3, 40)
+    pose_h, joints_h, tran_h, contact_h = host.run(x.pin_memory(), lens)
+    pose, joints, tran, contact = net.forward_offline(x.to(DEV), lens)
+    assert torch.equal(pose_h, pose.cpu()) and torch.equal(joints_h, joints.cpu())
+    assert torch.equal(contact_h, contact.cpu())
+    for b, L in enumerate(lens):
+        assert torch.equal(tran_h[b, :L], tran[b, :L].cpu())
