@@ -46,9 +46,18 @@ namespace {
 
 inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 
-__global__ void bias_sum_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ o, int n) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) o[i] = a[i] + b[i];
+// The recurrence kernel wants the 4 gate pre-activations of a hidden unit next to each other, so the
+// rows of W_ih (and the summed biases) are re-ordered from torch's (gate, unit) to (unit, gate).
+__global__ void bias_sum_permute_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ o, int H) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;   // torch row = gate*H + unit
+    if (i < 4 * H) o[(i % H) * 4 + i / H] = a[i] + b[i];
+}
+__global__ void permute_wih_kernel(const float* __restrict__ w, float* __restrict__ o, int H, int in) {
+    const size_t n = (size_t)4 * H * in;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int row = i / in, k = i - (size_t)row * in;
+        o[((size_t)(row % H) * 4 + row / H) * in + k] = w[i];
+    }
 }
 
 }  // namespace
@@ -187,8 +196,8 @@ int mp_rnn_create(mp_rnn_t** out, const mp_rnn_weights_t* w, mp_stream_t stream_
         r->whh_t[l] = (float*)(base + o_wt[l]);
         const float* whh[2] = {w->w_hh[l][0], w->w_hh[l][dirs - 1]};
         for (int d = 0; d < dirs; ++d) {
-            copy(r->wih[l] + (size_t)d * 4 * H * in_l[l], w->w_ih[l][d], (size_t)4 * H * in_l[l]);
-            bias_sum_kernel<<<(4 * H + 255) / 256, 256, 0, stream>>>(w->b_ih[l][d], w->b_hh[l][d], r->bsum[l] + (size_t)d * 4 * H, 4 * H);
+            permute_wih_kernel<<<296, 256, 0, stream>>>(w->w_ih[l][d], r->wih[l] + (size_t)d * 4 * H * in_l[l], H, in_l[l]);
+            bias_sum_permute_kernel<<<(4 * H + 255) / 256, 256, 0, stream>>>(w->b_ih[l][d], w->b_hh[l][d], r->bsum[l] + (size_t)d * 4 * H, H);
         }
         if (st == MP_OK) st = launch_pack_whh(whh, H, dirs, r->whh_pack[l], r->whh_t[l], stream);
     }

@@ -54,15 +54,29 @@ struct RecCfg {
 };
 
 // Dynamic shared memory carve-up (floats unless noted):
-//   hbuf   [2][NB][H]    h_t of every sequence of the tile, double buffered
-//   hstage [2][NB][UC]   this CTA's new slice, source of the bulk copies
-//   cbuf   [NB][UC]      cell state of the owned units
+//   hbuf   [2][C][NB][UC]  h_t of every sequence of the tile, double buffered by step parity; the slice
+//                          written by source CTA `src` is contiguous so it travels as ONE bulk copy
+//   hstage [2][NB][UC]     this CTA's new slice, source of the bulk copies
+//   cbuf   [NB][UC]        cell state of the owned units
 //   lens   [NB] int
-//   bars   [2] uint64    mbarriers, one per hbuf parity
+//   bars   [2] uint64      mbarriers, one per hbuf parity
 template <int H, int C>
 __host__ __device__ inline size_t rec_smem_bytes(int NB) {
     return sizeof(float) * ((size_t)2 * NB * H + (size_t)2 * NB * RecCfg<H, C>::UC + (size_t)NB * RecCfg<H, C>::UC) +
            sizeof(int) * NB + 2 * sizeof(unsigned long long) + 16;
+}
+
+// gate nonlinearity + i/f/g/o gather + cell update for one (unit, sequence); every lane of the 4x4
+// (gate, kq) group of a unit returns the same h_new / c_new.
+__device__ __forceinline__ void lstm_cell(float pre, int gate, int lane, float c_old, float& c_new, float& h_new) {
+    const float act = (gate == 2) ? tanhf(pre) : sigmoidf_acc(pre);
+    const int base = lane & ~0xC;
+    const float iv = __shfl_sync(0xffffffffu, act, base);
+    const float fv = __shfl_sync(0xffffffffu, act, base | 4);
+    const float gv = __shfl_sync(0xffffffffu, act, base | 8);
+    const float ov = __shfl_sync(0xffffffffu, act, base | 12);
+    c_new = fmaf(fv, c_old, iv * gv);
+    h_new = ov * tanhf(c_new);
 }
 
 template <int H, int C, int BG>
@@ -70,9 +84,11 @@ __global__ void __launch_bounds__(RecCfg<H, C>::THREADS, 1) lstm_rec_kernel(cons
     using Cfg = RecCfg<H, C>;
     constexpr int UC = Cfg::UC, THREADS = Cfg::THREADS, NCHUNK = Cfg::NCHUNK;
     static_assert(BG == 1 || BG == 4, "batch group");
+    static_assert(UC % 16 == 0, "a 16-float k chunk must not straddle two source slices");
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int NB = p.NB;
+    const int NB = (BG == 1) ? 1 : p.NB;      // latency path: one sequence per cluster
+    const int SRC = NB * UC;                  // floats in one source CTA's slice of hbuf
     float* hbuf = reinterpret_cast<float*>(smem_raw);
     float* hstage = hbuf + (size_t)2 * NB * H;
     float* cbuf = hstage + (size_t)2 * NB * UC;
@@ -88,8 +104,8 @@ __global__ void __launch_bounds__(RecCfg<H, C>::THREADS, 1) lstm_rec_kernel(cons
     const int u_local = warp * 2 + (lane >> 4);
     const int gate = (lane >> 2) & 3, kq = lane & 3;
     const int unit = rank * UC + u_local;           // hidden unit in [0, H)
-    const int row_g = gate * H + unit;              // gate row in [0, 4H)
     const int G4 = p.dirs * 4 * H, Y2 = p.dirs * H;
+    const int gcol = dir * 4 * H + unit * 4 + gate;  // gin columns are (unit, gate)-ordered (api.cu permutes W_ih)
 
     // ---- resident weights: H/4 floats of one gate row per thread ---------------------------
     float4 w[NCHUNK];
@@ -102,18 +118,19 @@ __global__ void __launch_bounds__(RecCfg<H, C>::THREADS, 1) lstm_rec_kernel(cons
     // ---- tile state ------------------------------------------------------------------------
     for (int i = tid; i < NB; i += THREADS)
         lens[i] = (i < nb) ? (p.lengths ? min(max(p.lengths[b_begin + i], 0), p.T) : p.T) : 0;
-    for (int i = tid; i < NB * H; i += THREADS) {
-        const int b = i / H, k = i - b * H;
-        hbuf[i] = (p.h0 && b < nb) ? p.h0[((size_t)dir * p.B + b_begin + b) * H + k] : 0.f;
+    for (int i = tid; i < NB * H; i += THREADS) {      // parity-0 buffer <- h0 (or zeros)
+        const int src = i / SRC, rem = i - src * SRC;
+        const int b = rem / UC, u = rem - b * UC;
+        hbuf[i] = (p.h0 && b < nb) ? p.h0[((size_t)dir * p.B + b_begin + b) * H + src * UC + u] : 0.f;
     }
     for (int i = tid; i < NB * UC; i += THREADS) {
         const int b = i / UC, u = i - b * UC;
         cbuf[i] = (p.c0 && b < nb) ? p.c0[((size_t)dir * p.B + b_begin + b) * H + rank * UC + u] : 0.f;
     }
-    const uint32_t bar_addr[2] = {smem_u32(&bars[0]), smem_u32(&bars[1])};
+    const uint32_t bar0 = smem_u32(&bars[0]), bar1 = bar0 + 8;
     if (C > 1 && tid == 0) {
-        mbar_init(bar_addr[0], 1);
-        mbar_init(bar_addr[1], 1);
+        mbar_init(bar0, 1);
+        mbar_init(bar1, 1);
         mbar_fence_init_cluster();
     }
     __syncthreads();
@@ -122,39 +139,34 @@ __global__ void __launch_bounds__(RecCfg<H, C>::THREADS, 1) lstm_rec_kernel(cons
     int maxlen = 0;
     for (int i = 0; i < nb; ++i) maxlen = max(maxlen, lens[i]);
 
-    // latency path: gin of the next step is fetched one step ahead
-    float gi_next[4] = {0.f, 0.f, 0.f, 0.f};
-    // latency path: remote views of hbuf / mbarriers in the CTA this lane feeds (rank = lane & 15)
-    uint32_t rem_hbuf = 0, rem_bar[2] = {0, 0};
-    if constexpr (C > 1) {
+    // latency path: this lane feeds CTA (lane & 15) of the cluster; remote views of hbuf / mbarriers
+    uint32_t rem_hbuf = 0, rem_bar0 = 0;
+    if constexpr (C > 1 && BG == 1) {
         const uint32_t r = (lane & 15) < C ? (lane & 15) : 0;
         rem_hbuf = mapa_u32(smem_u32(hbuf), r);
-        rem_bar[0] = mapa_u32(bar_addr[0], r);
-        rem_bar[1] = mapa_u32(bar_addr[1], r);
+        rem_bar0 = mapa_u32(bar0, r);
     }
+    // latency path: gin of step s+1 is fetched during step s (kept in a register, never on the stack)
+    float gi_next = 0.f;
+    const int len0 = lens[0];
     if constexpr (BG == 1) {
-#pragma unroll
-        for (int b = 0; b < 4; ++b) {
-            gi_next[b] = 0.f;
-            if (b < nb && lens[b] > 0) {
-                const int t = dir ? lens[b] - 1 : 0;
-                gi_next[b] = __ldg(p.gin + ((size_t)(b_begin + b) * p.T + t) * G4 + dir * 4 * H + row_g);
-            }
-        }
+        if (len0 > 0) gi_next = __ldg(p.gin + ((size_t)b_begin * p.T + (dir ? len0 - 1 : 0)) * G4 + gcol);
     }
 
     for (int s = 0; s < maxlen; ++s) {
         const int par = s & 1;
         const bool send = (s + 1 < maxlen);
         if constexpr (C > 1) {
-            if (s > 0) mbar_wait_cluster(bar_addr[par], ((s - 1) >> 1) & 1);
+            if (s > 0) mbar_wait_cluster(par ? bar1 : bar0, ((s - 1) >> 1) & 1);
             if (tid == 0 && send) {
                 int nsend = nb;
-                if (!p.bulk) {
+                if (BG == 4 && !p.bulk) {
                     nsend = 0;
                     for (int i = 0; i < nb; ++i) nsend += (lens[i] > s);
+                } else if (BG == 4) {
+                    nsend = NB;
                 }
-                mbar_arrive_expect_tx(bar_addr[par ^ 1], (uint32_t)nsend * H * sizeof(float));
+                mbar_arrive_expect_tx(par ? bar0 : bar1, (uint32_t)nsend * H * sizeof(float));
             }
         }
         const float* hcur = hbuf + (size_t)par * NB * H;
@@ -162,62 +174,41 @@ __global__ void __launch_bounds__(RecCfg<H, C>::THREADS, 1) lstm_rec_kernel(cons
         float* hst = hstage + (size_t)par * NB * UC;
 
         if constexpr (BG == 1) {
-            // ---------------- latency path: 1..4 sequences, one at a time ----------------------
+            // ---------------- latency path: the cluster's single sequence ------------------------
+            const int t = dir ? len0 - 1 - s : s;
+            const float gi = gi_next;
+            if (send) gi_next = __ldg(p.gin + ((size_t)b_begin * p.T + (dir ? t - 1 : t + 1)) * G4 + gcol);
+            const float* hb = hcur + kq * 4;
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll
-            for (int b = 0; b < 4; ++b) {
-                if (b >= nb) break;
-                const int len = lens[b];
-                if (s >= len) continue;
-                const int t = dir ? len - 1 - s : s;
-                const float gi = gi_next[b];
-                if (s + 1 < len) {
-                    const int tn = dir ? len - 2 - s : s + 1;
-                    gi_next[b] = __ldg(p.gin + ((size_t)(b_begin + b) * p.T + tn) * G4 + dir * 4 * H + row_g);
+            for (int i = 0; i < NCHUNK; ++i) {
+                const float4 hv = *reinterpret_cast<const float4*>(hb + i * 16);   // NB == 1: slices are contiguous in k
+                a0 = fmaf(w[i].x, hv.x, a0);
+                a1 = fmaf(w[i].y, hv.y, a1);
+                a2 = fmaf(w[i].z, hv.z, a2);
+                a3 = fmaf(w[i].w, hv.w, a3);
+            }
+            float tot = (a0 + a1) + (a2 + a3);
+            tot += __shfl_xor_sync(0xffffffffu, tot, 1);
+            tot += __shfl_xor_sync(0xffffffffu, tot, 2);
+            float c_new, h_new;
+            lstm_cell(tot + gi, gate, lane, cbuf[u_local], c_new, h_new);
+            __syncwarp();
+            if (send) {
+                if constexpr (C == 1) {
+                    if ((lane & 15) == 0) hnext[unit] = h_new;
+                } else {
+                    // the 16 lanes of a unit all hold h_new; lane r of them feeds CTA r
+                    if ((lane & 15) < C)
+                        st_async_f32(rem_hbuf + (uint32_t)((par ^ 1) * H + unit) * 4u, h_new, rem_bar0 + (par ? 0u : 8u));
                 }
-                const float* hb = hcur + b * H + kq * 4;
-                float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll
-                for (int i = 0; i < NCHUNK; ++i) {
-                    const float4 hv = *reinterpret_cast<const float4*>(hb + i * 16);
-                    a0 = fmaf(w[i].x, hv.x, a0);
-                    a1 = fmaf(w[i].y, hv.y, a1);
-                    a2 = fmaf(w[i].z, hv.z, a2);
-                    a3 = fmaf(w[i].w, hv.w, a3);
-                }
-                float tot = (a0 + a1) + (a2 + a3);
-                tot += __shfl_xor_sync(0xffffffffu, tot, 1);
-                tot += __shfl_xor_sync(0xffffffffu, tot, 2);
-                const float pre = tot + gi;
-                const float act = (gate == 2) ? tanhf(pre) : sigmoidf_acc(pre);
-                const int base = lane & ~0xC;
-                const float iv = __shfl_sync(0xffffffffu, act, base);
-                const float fv = __shfl_sync(0xffffffffu, act, base | 4);
-                const float gv = __shfl_sync(0xffffffffu, act, base | 8);
-                const float ov = __shfl_sync(0xffffffffu, act, base | 12);
-                const float c_new = fmaf(fv, cbuf[b * UC + u_local], iv * gv);
-                const float h_new = ov * tanhf(c_new);
-                __syncwarp();
-                if ((lane & 15) == 0) {
-                    cbuf[b * UC + u_local] = c_new;
-                    p.y[((size_t)(b_begin + b) * p.T + t) * Y2 + dir * H + unit] = h_new;
-                    if (s == len - 1) {
-                        if (p.hn) p.hn[((size_t)dir * p.B + b_begin + b) * H + unit] = h_new;
-                        if (p.cn) p.cn[((size_t)dir * p.B + b_begin + b) * H + unit] = c_new;
-                    }
-                }
-                if (send) {
-                    if constexpr (C == 1) {
-                        if ((lane & 15) == 0) hnext[b * H + unit] = h_new;
-                    } else {
-                        if (!p.bulk) {
-                            // 16 lanes of a unit hold h_new; lane r of them feeds CTA r
-                            if ((lane & 15) < C)
-                                st_async_f32(rem_hbuf + (uint32_t)(((par ^ 1) * NB + b) * H + unit) * 4u, h_new,
-                                             rem_bar[par ^ 1]);
-                        } else if ((lane & 15) == 0) {
-                            hst[b * UC + u_local] = h_new;
-                        }
-                    }
+            }
+            if ((lane & 15) == 0) {
+                cbuf[u_local] = c_new;
+                p.y[((size_t)b_begin * p.T + t) * Y2 + dir * H + unit] = h_new;
+                if (s == len0 - 1) {
+                    if (p.hn) p.hn[((size_t)dir * p.B + b_begin) * H + unit] = h_new;
+                    if (p.cn) p.cn[((size_t)dir * p.B + b_begin) * H + unit] = c_new;
                 }
             }
         } else {
@@ -232,14 +223,16 @@ __global__ void __launch_bounds__(RecCfg<H, C>::THREADS, 1) lstm_rec_kernel(cons
                 const bool active = s < len;
                 const int t = dir ? len - 1 - s : s;
                 float gi = 0.f;
-                if (active) gi = __ldg(p.gin + ((size_t)(b_begin + b) * p.T + t) * G4 + dir * 4 * H + row_g);
-                const float* hb = hcur + g0 * H + kq * 4;
+                if (active) gi = __ldg(p.gin + ((size_t)(b_begin + b) * p.T + t) * G4 + gcol);
+                const float* hb = hcur + g0 * UC + kq * 4;
                 float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
                 for (int i = 0; i < NCHUNK; ++i) {
+                    // k = i*16 + kq*4 lives in source slice (i*16)/UC at unit offset (i*16)%UC + kq*4
+                    const float* hs = hb + ((i * 16) / UC) * SRC + (i * 16) % UC;
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
-                        const float4 hv = *reinterpret_cast<const float4*>(hb + q * H + i * 16);
+                        const float4 hv = *reinterpret_cast<const float4*>(hs + q * UC);
                         acc[q] = fmaf(w[i].x, hv.x, acc[q]);
                         acc[q] = fmaf(w[i].y, hv.y, acc[q]);
                         acc[q] = fmaf(w[i].z, hv.z, acc[q]);
@@ -255,15 +248,8 @@ __global__ void __launch_bounds__(RecCfg<H, C>::THREADS, 1) lstm_rec_kernel(cons
                 float tot = lo ? k1 : k0;
                 const float s2 = lo ? k0 : k1;
                 tot += __shfl_xor_sync(0xffffffffu, s2, 1);
-                const float pre = tot + gi;
-                const float act = (gate == 2) ? tanhf(pre) : sigmoidf_acc(pre);
-                const int base = lane & ~0xC;
-                const float iv = __shfl_sync(0xffffffffu, act, base);
-                const float fv = __shfl_sync(0xffffffffu, act, base | 4);
-                const float gv = __shfl_sync(0xffffffffu, act, base | 8);
-                const float ov = __shfl_sync(0xffffffffu, act, base | 12);
-                const float c_new = fmaf(fv, cbuf[b * UC + u_local], iv * gv);
-                const float h_new = ov * tanhf(c_new);
+                float c_new, h_new;
+                lstm_cell(tot + gi, gate, lane, cbuf[b * UC + u_local], c_new, h_new);
                 __syncwarp();
                 if (active) {
                     if (gate == 0) {
@@ -276,13 +262,13 @@ __global__ void __launch_bounds__(RecCfg<H, C>::THREADS, 1) lstm_rec_kernel(cons
                     }
                     if (send) {
                         if constexpr (C == 1) {
-                            if (gate == 0) hnext[b * H + unit] = h_new;
+                            if (gate == 0) hnext[b * UC + u_local] = h_new;
                         } else {
                             if (!p.bulk) {
                                 // the 4 gate lanes of (unit, sequence) hold h_new; gate lane g feeds CTAs g, g+4, ..
                                 for (int r = gate; r < C; r += 4)
-                                    st_async_f32(mapa_u32(smem_u32(hnext + b * H + unit), r), h_new,
-                                                 mapa_u32(bar_addr[par ^ 1], r));
+                                    st_async_f32(mapa_u32(smem_u32(hnext + rank * SRC + b * UC + u_local), r), h_new,
+                                                 mapa_u32(par ? bar0 : bar1, r));
                             } else if (gate == 0) {
                                 hst[b * UC + u_local] = h_new;
                             }
@@ -294,15 +280,13 @@ __global__ void __launch_bounds__(RecCfg<H, C>::THREADS, 1) lstm_rec_kernel(cons
 
         if constexpr (C == 1) {
             __syncthreads();
-        } else if (p.bulk && send) {
-            // staged slice -> every CTA of the cluster, one 4*UC-byte row per (sequence, destination)
+        } else if (BG == 4 && p.bulk && send) {
+            // staged slice -> every CTA of the cluster: ONE contiguous NB*UC*4-byte bulk copy per destination
             fence_proxy_async_smem();
             __syncthreads();
-            for (int j = tid; j < nb * C; j += THREADS) {
-                const int b = j / C, r = j - b * C;
-                bulk_copy_s2c(mapa_u32(smem_u32(hnext + b * H + rank * UC), r), smem_u32(hst + b * UC),
-                              UC * sizeof(float), mapa_u32(bar_addr[par ^ 1], r));
-            }
+            if (tid < C)
+                bulk_copy_s2c(mapa_u32(smem_u32(hnext + rank * SRC), tid), smem_u32(hst), SRC * sizeof(float),
+                              mapa_u32(par ? bar0 : bar1, tid));
         }
     }
 
@@ -344,7 +328,7 @@ __global__ void __launch_bounds__(4 * H > 1024 ? 1024 : 4 * H) lstm_rec_simple_k
         for (int r = tid; r < 4 * H; r += nthr) {
             float acc = 0.f;
             for (int k = 0; k < H; ++k) acc = fmaf(wt[(size_t)k * 4 * H + r], h[k], acc);
-            g[r] = acc + gin[((size_t)b * T + t) * (dirs * 4 * H) + dir * 4 * H + r];
+            g[r] = acc + gin[((size_t)b * T + t) * (dirs * 4 * H) + dir * 4 * H + (r % H) * 4 + r / H];   // (unit, gate) columns
         }
         __syncthreads();
         if (tid < H) {
@@ -456,7 +440,7 @@ int launch_for(const RecLayerArgs& a, cudaStream_t stream) {
         NB = (a.B + per - 1) / per;
         NB = std::min(32, ((NB + 3) / 4) * 4);
     }
-    if (NB < 4) return launch_cluster<H, C, 1>(a, NB, bulk == 1 ? 1 : 0, stream);
+    if (NB == 1) return launch_cluster<H, C, 1>(a, 1, 0, stream);
     NB = ((NB + 3) / 4) * 4;
     return launch_cluster<H, C, 4>(a, NB, bulk == 0 ? 0 : 1, stream);
 }
