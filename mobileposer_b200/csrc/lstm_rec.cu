@@ -11,15 +11,20 @@
 // Decomposition (H = hidden, C = cluster size, UC = H / C hidden units per CTA):
 //   * CTA `rank` of a cluster owns hidden units [rank*UC, rank*UC+UC) => the 4*UC gate rows of
 //     W_hh that produce them, so the cell update never leaves the CTA.
-//   * thread = (unit, gate, kq): 4 lanes (kq) split the K = H reduction of one gate row, the 4 gates
-//     of a unit sit in the same warp (lane = unit_in_warp*16 + gate*4 + kq), so both the K-reduction
-//     and the i/f/g/o gather are warp shuffles -- no shared-memory round trip, no block barrier.
-//     Each thread keeps its H/4 weights in registers for the whole sequence (H=256: 64 registers).
+//   * a warp owns 8 gate rows (2 units x 4 gates) and splits the K = H reduction across its lanes:
+//     lane kl holds, for R rows, the float4 chunks {kl, kl + KQ, ..} of each row (KQ = 32 lanes for
+//     H = 256, 16 for H = 64), 64 (16) weight registers per thread for the whole sequence.  One
+//     LDS.128 per lane then fetches 512 DISTINCT bytes of h per warp and feeds R*4 FFMAs -- ncu on the
+//     first version (4 lanes per row) showed a broadcast LDS.128 still costs 4 shared-memory
+//     wavefronts, which made the recurrence 4x LSU-bound (profiles/r01_notes.md).
+//   * the per-lane partial sums (rows x sequences) are combined with a shuffle reduce-scatter whose
+//     result layout is lane = unit_in_warp*16 + gate*4 + sequence_in_group, so the i/f/g/o gather and
+//     the cell update stay inside the warp -- no shared-memory round trip, no block barrier.
 //   * h_{t} lives in shared memory of EVERY CTA of the cluster, double buffered by step parity.
 //     After the cell update the owning CTA pushes its UC new values to all C CTAs, either with
-//     per-value `st.async ... mbarrier::complete_tx` (latency path, batch tile of 1..4 sequences) or
-//     staged + `cp.async.bulk shared::cluster` rows (throughput path).  Each CTA waits on its own
-//     mbarrier (transaction bytes) -- there is no cluster-wide barrier inside the time loop.
+//     per-value `st.async ... mbarrier::complete_tx` (latency path, one sequence per cluster) or
+//     staged + ONE `cp.async.bulk shared::cluster` per destination (throughput path).  Each CTA waits
+//     on its own mbarrier (transaction bytes) -- there is no cluster-wide barrier inside the time loop.
 //   * a cluster serves a tile of NB sequences (weights reused NB times per step); the grid is
 //     (C * n_tiles, dirs).  Reverse direction of sequence b walks t = len_b-1 .. 0.
 #include "mp_common.cuh"
@@ -46,12 +51,36 @@ struct RecParams {
 
 template <int H, int C>
 struct RecCfg {
-    static constexpr int UC = H / C;          // hidden units owned by one CTA
-    static constexpr int THREADS = UC * 16;   // 4 gates x 4 k-quarters per unit
-    static constexpr int NCHUNK = H / 16;     // float4 weight chunks per thread
-    static_assert(UC % 4 == 0 && UC >= 4, "unit slice must be float4 aligned");
+    static constexpr int UC = H / C;                 // hidden units owned by one CTA
+    static constexpr int THREADS = UC * 16;          // one warp per 2 units (8 gate rows)
+    static constexpr int KQ = (H >= 128) ? 32 : 16;  // lanes that split K
+    static constexpr int RG = 32 / KQ;               // row groups per warp (1 or 2)
+    static constexpr int R = 8 / RG;                 // gate rows held by one lane
+    static constexpr int CPL = H / 4 / KQ;           // float4 k-chunks per lane and row
+    static constexpr int NW4 = R * CPL;              // float4 weight registers per thread
+    static_assert(UC % 16 == 0, "unit slice must hold whole 16-float groups");
     static_assert(THREADS <= 1024 && THREADS >= 32, "block size");
+    static_assert(CPL >= 1 && NW4 * 4 * THREADS == 4 * UC * H, "weights must tile the CTA's rows exactly");
 };
+
+// Shuffle reduce-scatter: v[a] (a in [0, NV)) are per-lane partial sums; the lanes that differ in the lane
+// bits topbit, topbit/2, .. are summed, and the lane whose those bits spell `a` ends with the total of v[a].
+template <int NV>
+__device__ __forceinline__ float reduce_scatter(float (&v)[NV], int lane, int topbit) {
+    int bit = topbit;
+#pragma unroll
+    for (int half = NV / 2; half >= 1; half >>= 1) {
+        const bool up = (lane & bit) != 0;
+#pragma unroll
+        for (int i = 0; i < half; ++i) {
+            const float keep = up ? v[i + half] : v[i];
+            const float give = up ? v[i] : v[i + half];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, give, bit);
+        }
+        bit >>= 1;
+    }
+    return v[0];
+}
 
 // Dynamic shared memory carve-up (floats unless noted):
 //   hbuf   [2][C][NB][UC]  h_t of every sequence of the tile, double buffered by step parity; the slice
@@ -82,16 +111,15 @@ __device__ __forceinline__ void lstm_cell(float pre, int gate, int lane, float c
 template <int H, int C, int BG>
 __global__ void __launch_bounds__(RecCfg<H, C>::THREADS, 1) lstm_rec_kernel(const RecParams p) {
     using Cfg = RecCfg<H, C>;
-    constexpr int UC = Cfg::UC, THREADS = Cfg::THREADS, NCHUNK = Cfg::NCHUNK;
+    constexpr int UC = Cfg::UC, THREADS = Cfg::THREADS, KQ = Cfg::KQ, R = Cfg::R, CPL = Cfg::CPL, NW4 = Cfg::NW4;
     static_assert(BG == 1 || BG == 4, "batch group");
-    static_assert(UC % 16 == 0, "a 16-float k chunk must not straddle two source slices");
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int NB = (BG == 1) ? 1 : p.NB;      // latency path: one sequence per cluster
     const int SRC = NB * UC;                  // floats in one source CTA's slice of hbuf
     float* hbuf = reinterpret_cast<float*>(smem_raw);
     float* hstage = hbuf + (size_t)2 * NB * H;
-    float* cbuf = hstage + (size_t)2 * NB * UC;
+    float* cbuf = hstage + (size_t)2 * NB * UC;          // [UC][NB]
     int* lens = reinterpret_cast<int*>(cbuf + (size_t)NB * UC);
     unsigned long long* bars =
         reinterpret_cast<unsigned long long*>((reinterpret_cast<uintptr_t>(lens + NB) + 15) & ~uintptr_t(15));
@@ -101,18 +129,27 @@ __global__ void __launch_bounds__(RecCfg<H, C>::THREADS, 1) lstm_rec_kernel(cons
     const int tile = blockIdx.x / C, dir = blockIdx.y;
     const int b_begin = tile * NB;
     const int nb = min(NB, p.B - b_begin);
+    // after the reduce-scatter lane = unit_in_warp*16 + gate*4 + q owns (unit, gate, sequence g0+q)
     const int u_local = warp * 2 + (lane >> 4);
-    const int gate = (lane >> 2) & 3, kq = lane & 3;
+    const int gate = (lane >> 2) & 3, qn = lane & 3;
     const int unit = rank * UC + u_local;           // hidden unit in [0, H)
     const int G4 = p.dirs * 4 * H, Y2 = p.dirs * H;
     const int gcol = dir * 4 * H + unit * 4 + gate;  // gin columns are (unit, gate)-ordered (api.cu permutes W_ih)
+    const int kl = lane % KQ;                        // this lane's slot in the K split
 
-    // ---- resident weights: H/4 floats of one gate row per thread ---------------------------
-    float4 w[NCHUNK];
+    // ---- resident weights: NW4 float4 per thread (row r = j / CPL of this lane's rows, k-chunk kl + (j % CPL)*KQ)
+    float4 w[NW4];
     {
-        const float4* wp = p.wpack + ((size_t)(dir * C + rank) * NCHUNK) * THREADS + tid;
+        const float4* wp = p.wpack + ((size_t)(dir * C + rank) * NW4) * THREADS + tid;
 #pragma unroll
-        for (int i = 0; i < NCHUNK; ++i) w[i] = __ldg(wp + (size_t)i * THREADS);
+        for (int j = 0; j < NW4; ++j) w[j] = __ldg(wp + (size_t)j * THREADS);
+    }
+    // float offsets of this lane's k-chunks inside one parity buffer of hbuf ([src][b][u], b = 0)
+    int hoff[CPL];
+#pragma unroll
+    for (int c = 0; c < CPL; ++c) {
+        const int k = (c * KQ + kl) * 4;
+        hoff[c] = (k / UC) * SRC + (k % UC);
     }
 
     // ---- tile state ------------------------------------------------------------------------
@@ -124,7 +161,7 @@ __global__ void __launch_bounds__(RecCfg<H, C>::THREADS, 1) lstm_rec_kernel(cons
         hbuf[i] = (p.h0 && b < nb) ? p.h0[((size_t)dir * p.B + b_begin + b) * H + src * UC + u] : 0.f;
     }
     for (int i = tid; i < NB * UC; i += THREADS) {
-        const int b = i / UC, u = i - b * UC;
+        const int u = i / NB, b = i - u * NB;
         cbuf[i] = (p.c0 && b < nb) ? p.c0[((size_t)dir * p.B + b_begin + b) * H + rank * UC + u] : 0.f;
     }
     const uint32_t bar0 = smem_u32(&bars[0]), bar1 = bar0 + 8;
@@ -146,18 +183,22 @@ __global__ void __launch_bounds__(RecCfg<H, C>::THREADS, 1) lstm_rec_kernel(cons
         rem_hbuf = mapa_u32(smem_u32(hbuf), r);
         rem_bar0 = mapa_u32(bar0, r);
     }
-    // latency path: gin of step s+1 is fetched during step s (kept in a register, never on the stack)
+    // gate pre-activations are fetched ahead of use and kept in a register (never on the stack):
+    // one step ahead on the latency path, one sequence group ahead on the throughput path
     float gi_next = 0.f;
     const int len0 = lens[0];
     if constexpr (BG == 1) {
         if (len0 > 0) gi_next = __ldg(p.gin + ((size_t)b_begin * p.T + (dir ? len0 - 1 : 0)) * G4 + gcol);
+    } else {
+        const int l = lens[qn];
+        if (l > 0) gi_next = __ldg(p.gin + ((size_t)(b_begin + qn) * p.T + (dir ? l - 1 : 0)) * G4 + gcol);
     }
 
     for (int s = 0; s < maxlen; ++s) {
         const int par = s & 1;
         const bool send = (s + 1 < maxlen);
         if constexpr (C > 1) {
-            if (s > 0) mbar_wait_cluster(par ? bar1 : bar0, ((s - 1) >> 1) & 1);
+            if (s > 0) mbar_wait(par ? bar1 : bar0, ((s - 1) >> 1) & 1);
             if (tid == 0 && send) {
                 int nsend = nb;
                 if (BG == 4 && !p.bulk) {
@@ -178,19 +219,25 @@ __global__ void __launch_bounds__(RecCfg<H, C>::THREADS, 1) lstm_rec_kernel(cons
             const int t = dir ? len0 - 1 - s : s;
             const float gi = gi_next;
             if (send) gi_next = __ldg(p.gin + ((size_t)b_begin * p.T + (dir ? t - 1 : t + 1)) * G4 + gcol);
-            const float* hb = hcur + kq * 4;
-            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+            float acc[R];
 #pragma unroll
-            for (int i = 0; i < NCHUNK; ++i) {
-                const float4 hv = *reinterpret_cast<const float4*>(hb + i * 16);   // NB == 1: slices are contiguous in k
-                a0 = fmaf(w[i].x, hv.x, a0);
-                a1 = fmaf(w[i].y, hv.y, a1);
-                a2 = fmaf(w[i].z, hv.z, a2);
-                a3 = fmaf(w[i].w, hv.w, a3);
+            for (int r = 0; r < R; ++r) acc[r] = 0.f;
+#pragma unroll
+            for (int c = 0; c < CPL; ++c) {
+                const float4 hv = *reinterpret_cast<const float4*>(hcur + hoff[c]);
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const float4 wv = w[r * CPL + c];
+                    acc[r] = fmaf(wv.x, hv.x, acc[r]);
+                    acc[r] = fmaf(wv.y, hv.y, acc[r]);
+                    acc[r] = fmaf(wv.z, hv.z, acc[r]);
+                    acc[r] = fmaf(wv.w, hv.w, acc[r]);
+                }
             }
-            float tot = (a0 + a1) + (a2 + a3);
-            tot += __shfl_xor_sync(0xffffffffu, tot, 1);
+            // rows -> lane bits 4..2 (unit, gate); then the 4 lanes of a (unit, gate) all get the total
+            float tot = reduce_scatter<R>(acc, lane, KQ / 2);
             tot += __shfl_xor_sync(0xffffffffu, tot, 2);
+            tot += __shfl_xor_sync(0xffffffffu, tot, 1);
             float c_new, h_new;
             lstm_cell(tot + gi, gate, lane, cbuf[u_local], c_new, h_new);
             __syncwarp();
@@ -212,48 +259,53 @@ __global__ void __launch_bounds__(RecCfg<H, C>::THREADS, 1) lstm_rec_kernel(cons
                 }
             }
         } else {
-            // ---------------- throughput path: groups of 4 sequences, lane kq owns sequence g0+kq
+            // ---------------- throughput path: groups of 4 sequences; after the reduce lane q owns sequence g0+q
             for (int g0 = 0; g0 < nb; g0 += 4) {
+                const int b = g0 + qn;
+                const int len = lens[b];
+                const bool active = s < len;
+                const int t = dir ? len - 1 - s : s;
+                const float gi = gi_next;
+                {   // prefetch the gate pre-activation of the NEXT group (or of group 0 of the next step)
+                    const bool wrap = (g0 + 4 >= nb);
+                    const int bn = wrap ? qn : b + 4;
+                    const int sn = wrap ? s + 1 : s;
+                    const int ln = lens[bn];
+                    if (sn < ln) gi_next = __ldg(p.gin + ((size_t)(b_begin + bn) * p.T + (dir ? ln - 1 - sn : sn)) * G4 + gcol);
+                }
                 int glen = 0;
 #pragma unroll
                 for (int q = 0; q < 4; ++q) glen = max(glen, lens[g0 + q]);   // lens[>=nb] == 0, NB % 4 == 0
                 if (s >= glen) continue;
-                const int b = g0 + kq;
-                const int len = lens[b];
-                const bool active = s < len;
-                const int t = dir ? len - 1 - s : s;
-                float gi = 0.f;
-                if (active) gi = __ldg(p.gin + ((size_t)(b_begin + b) * p.T + t) * G4 + gcol);
-                const float* hb = hcur + g0 * UC + kq * 4;
-                float acc[4] = {0.f, 0.f, 0.f, 0.f};
+                float acc[R * 4];
 #pragma unroll
-                for (int i = 0; i < NCHUNK; ++i) {
-                    // k = i*16 + kq*4 lives in source slice (i*16)/UC at unit offset (i*16)%UC + kq*4
-                    const float* hs = hb + ((i * 16) / UC) * SRC + (i * 16) % UC;
+                for (int a = 0; a < R * 4; ++a) acc[a] = 0.f;
+                const float* hg = hcur + g0 * UC;
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const float4 hv = *reinterpret_cast<const float4*>(hs + q * UC);
-                        acc[q] = fmaf(w[i].x, hv.x, acc[q]);
-                        acc[q] = fmaf(w[i].y, hv.y, acc[q]);
-                        acc[q] = fmaf(w[i].z, hv.z, acc[q]);
-                        acc[q] = fmaf(w[i].w, hv.w, acc[q]);
+                for (int q = 0; q < 4; ++q) {
+#pragma unroll
+                    for (int c = 0; c < CPL; ++c) {
+                        const float4 hv = *reinterpret_cast<const float4*>(hg + q * UC + hoff[c]);
+#pragma unroll
+                        for (int r = 0; r < R; ++r) {
+                            const float4 wv = w[r * CPL + c];
+                            float a = acc[r * 4 + q];
+                            a = fmaf(wv.x, hv.x, a);
+                            a = fmaf(wv.y, hv.y, a);
+                            a = fmaf(wv.z, hv.z, a);
+                            a = fmaf(wv.w, hv.w, a);
+                            acc[r * 4 + q] = a;
+                        }
                     }
                 }
-                // reduce-scatter over the 4 kq lanes: lane kq ends with the sum for sequence g0+kq
-                const bool hi = kq & 2, lo = kq & 1;
-                float k0 = hi ? acc[2] : acc[0], k1 = hi ? acc[3] : acc[1];
-                const float s0 = hi ? acc[0] : acc[2], s1 = hi ? acc[1] : acc[3];
-                k0 += __shfl_xor_sync(0xffffffffu, s0, 2);
-                k1 += __shfl_xor_sync(0xffffffffu, s1, 2);
-                float tot = lo ? k1 : k0;
-                const float s2 = lo ? k0 : k1;
-                tot += __shfl_xor_sync(0xffffffffu, s2, 1);
+                // (row, sequence) -> lane bits: lane = unit_in_warp*16 + gate*4 + q
+                const float tot = reduce_scatter<R * 4>(acc, lane, KQ / 2);
                 float c_new, h_new;
-                lstm_cell(tot + gi, gate, lane, cbuf[b * UC + u_local], c_new, h_new);
+                lstm_cell(tot + gi, gate, lane, cbuf[u_local * NB + b], c_new, h_new);
                 __syncwarp();
                 if (active) {
                     if (gate == 0) {
-                        cbuf[b * UC + u_local] = c_new;
+                        cbuf[u_local * NB + b] = c_new;
                         p.y[((size_t)(b_begin + b) * p.T + t) * Y2 + dir * H + unit] = h_new;
                         if (s == len - 1) {
                             if (p.hn) p.hn[((size_t)dir * p.B + b_begin + b) * H + unit] = h_new;
@@ -349,23 +401,28 @@ __global__ void __launch_bounds__(4 * H > 1024 ? 1024 : 4 * H) lstm_rec_simple_k
         for (int t = len; t < T; ++t) y[((size_t)b * T + t) * (dirs * H) + dir * H + tid] = 0.f;
 }
 
-// W_hh [4H, H] (torch) -> wpack[dir][rank][chunk][tid] float4 + wT[dir][k][row]
+// W_hh [4H, H] (torch) -> wpack[dir][rank][j][tid] float4 (j = row_of_lane * CPL + chunk) + wT[dir][k][row]
 template <int H, int C>
 __global__ void pack_whh_kernel(const float* __restrict__ w0, const float* __restrict__ w1,
                                 float4* __restrict__ wpack, float* __restrict__ wT, int dirs) {
     using Cfg = RecCfg<H, C>;
-    const size_t total = (size_t)dirs * C * Cfg::NCHUNK * Cfg::THREADS;
+    const size_t total = (size_t)dirs * C * Cfg::NW4 * Cfg::THREADS;
     for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
          idx += (size_t)gridDim.x * blockDim.x) {
         const int tid = idx % Cfg::THREADS;
-        const int i = (idx / Cfg::THREADS) % Cfg::NCHUNK;
-        const int rank = (idx / ((size_t)Cfg::THREADS * Cfg::NCHUNK)) % C;
-        const int dir = idx / ((size_t)Cfg::THREADS * Cfg::NCHUNK * C);
+        const int j = (idx / Cfg::THREADS) % Cfg::NW4;
+        const int rank = (idx / ((size_t)Cfg::THREADS * Cfg::NW4)) % C;
+        const int dir = idx / ((size_t)Cfg::THREADS * Cfg::NW4 * C);
         const int lane = tid & 31, warp = tid >> 5;
-        const int unit = rank * Cfg::UC + warp * 2 + (lane >> 4);
-        const int gate = (lane >> 2) & 3, kq = lane & 3;
+        const int r = j / Cfg::CPL, c = j % Cfg::CPL;
+        // lane row r -> (unit_in_warp, gate): with one row group (KQ = 32) r = u*4 + g; with two (KQ = 16) the
+        // row group is the unit and r is the gate
+        const int u_in_warp = (Cfg::RG == 1) ? (r >> 2) : (lane / Cfg::KQ);
+        const int gate = r & 3;
+        const int unit = rank * Cfg::UC + warp * 2 + u_in_warp;
+        const int k = (c * Cfg::KQ + lane % Cfg::KQ) * 4;
         const float* W = dir ? w1 : w0;
-        const float* src = W + (size_t)(gate * H + unit) * H + i * 16 + kq * 4;
+        const float* src = W + (size_t)(gate * H + unit) * H + k;
         wpack[idx] = make_float4(src[0], src[1], src[2], src[3]);
     }
     const size_t tt = (size_t)dirs * 4 * H * H;
@@ -388,9 +445,20 @@ bool env_is(const char* name, const char* val) {
     return v && strcmp(v, val) == 0;
 }
 
-// concurrent clusters of 8 CTAs a B200 can hold (8 GPCs x 2; DESIGN.md "cluster placement")
-constexpr int kClusterSlots = 16;
 constexpr size_t kMaxSmem = 227 * 1024;
+constexpr int kMaxTile = 64;   // sequences per cluster (H=256: 2*64*1 KiB of h + staging fits 227 KB)
+
+template <int H, int C, int BG>
+int configure_kernel() {
+    static bool configured = false;   // one device per process (one rank per GPU)
+    if (!configured) {
+        auto kern = lstm_rec_kernel<H, C, BG>;
+        MP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
+        if (C > 8) MP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        configured = true;
+    }
+    return MP_OK;
+}
 
 template <int H, int C, int BG>
 int launch_cluster(const RecLayerArgs& a, int NB, int bulk, cudaStream_t stream) {
@@ -399,12 +467,7 @@ int launch_cluster(const RecLayerArgs& a, int NB, int bulk, cudaStream_t stream)
     const size_t smem = rec_smem_bytes<H, C>(NB);
     auto kern = lstm_rec_kernel<H, C, BG>;
     MP_REQUIRE(smem <= kMaxSmem, "lstm: tile of %d sequences needs %zu B of shared memory", NB, smem);
-    static bool configured = false;   // one device per process (one rank per GPU)
-    if (!configured) {
-        MP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
-        if (C > 8) MP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-        configured = true;
-    }
+    MP_TRY((configure_kernel<H, C, BG>()));
     const int n_tiles = (a.B + NB - 1) / NB;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(C * n_tiles, a.dirs, 1);
@@ -423,26 +486,63 @@ int launch_cluster(const RecLayerArgs& a, int NB, int bulk, cudaStream_t stream)
     return MP_OK;
 }
 
+// How many clusters of this kernel the device can hold at once (GPC / TPC packing decides; on B200 a
+// cluster of 8 one-CTA-per-SM blocks does NOT get 148 / 8 slots).  Queried once per kernel.
+template <int H, int C, int BG>
+int cluster_slots() {
+    static int slots = 0;
+    if (slots > 0) return slots;
+    using Cfg = RecCfg<H, C>;
+    configure_kernel<H, C, BG>();
+    int n = 0;
+    if (C == 1) {
+        int per_sm = 0, sms = 0, dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lstm_rec_kernel<H, C, BG>, Cfg::THREADS, rec_smem_bytes<H, C>(4));
+        n = per_sm * sms;
+    } else {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(C * 64, 1, 1);
+        cfg.blockDim = dim3(Cfg::THREADS, 1, 1);
+        cfg.dynamicSmemBytes = rec_smem_bytes<H, C>(BG == 1 ? 1 : 32);
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = C;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        if (cudaOccupancyMaxActiveClusters(&n, lstm_rec_kernel<H, C, BG>, &cfg) != cudaSuccess) {
+            cudaGetLastError();
+            n = 0;
+        }
+    }
+    const int forced = env_int("MP_REC_SLOTS", 0);
+    slots = forced > 0 ? forced : (n > 0 ? n : (C == 1 ? 148 : 8));
+    return slots;
+}
+
 template <int H, int C>
 int launch_for(const RecLayerArgs& a, cudaStream_t stream) {
-    // tile policy: small batches -> one sequence per cluster (latency path); otherwise size the
-    // tile so that one wave of clusters covers the batch, capped by shared memory.
-    const int slots = (C == 1) ? 148 : std::max(1, kClusterSlots * 8 / C);
+    // tile policy: if every (sequence, direction) can have its own cluster, run the latency path; otherwise size
+    // the tile so that ONE wave of resident clusters covers the batch (a second, nearly empty wave would double the
+    // time), capped by shared memory.
     const int forced = env_int("MP_REC_NB", 0);
-    const int bulk = env_is("MP_REC_SEND", "stasync") ? 0 : (env_is("MP_REC_SEND", "bulk") ? 1 : -1);
+    const int bulk = env_is("MP_REC_SEND", "stasync") ? 0 : 1;
     int NB;
     if (forced > 0) {
         NB = forced;
-    } else if (a.B * a.dirs <= slots) {
+    } else if (a.B * a.dirs <= cluster_slots<H, C, 1>()) {
         NB = 1;
     } else {
-        const int per = std::max(1, slots / a.dirs);
+        const int per = std::max(1, cluster_slots<H, C, 4>() / a.dirs);
         NB = (a.B + per - 1) / per;
-        NB = std::min(32, ((NB + 3) / 4) * 4);
+        NB = std::min(kMaxTile, ((NB + 3) / 4) * 4);
     }
     if (NB == 1) return launch_cluster<H, C, 1>(a, 1, 0, stream);
     NB = ((NB + 3) / 4) * 4;
-    return launch_cluster<H, C, 4>(a, NB, bulk == 0 ? 0 : 1, stream);
+    return launch_cluster<H, C, 4>(a, NB, bulk, stream);
 }
 
 }  // namespace

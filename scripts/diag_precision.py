@@ -15,6 +15,26 @@ from oracle import np_port
 from oracle.torch_port import OraclePoser, reduced_global_to_full
 from parity import geodesic
 
+def k5_f64(r6d):
+    """K5 in float64 (same algebra as oracle.torch_port.reduced_global_to_full)."""
+    v = r6d.double().reshape(-1, 6)
+    a, b = v[:, :3], v[:, 3:]
+    c0 = a / a.norm(dim=1, keepdim=True)
+    b = b - (c0 * b).sum(dim=1, keepdim=True) * c0
+    c1 = b / b.norm(dim=1, keepdim=True)
+    c2 = torch.linalg.cross(c0, c1, dim=1)
+    g16 = torch.stack((c0, c1, c2), dim=-1).view(-1, 16, 3, 3)
+    n = g16.shape[0]
+    glb = torch.eye(3, dtype=torch.float64).repeat(n, 24, 1, 1)
+    glb[:, C.joint_set.reduced] = g16
+    loc = glb.clone()
+    for i in range(1, 24):
+        loc[:, i] = glb[:, C.SMPL_PARENT[i]].transpose(1, 2) @ glb[:, i]
+    loc[:, C.joint_set.ignored] = torch.eye(3, dtype=torch.float64)
+    loc[:, 0] = glb[:, 0]
+    return loc
+
+
 T = int(sys.argv[1]) if len(sys.argv) > 1 else 3000
 torch.manual_seed(0)
 net = mp.MobilePoserNet().eval()
@@ -27,7 +47,7 @@ sdn = {k: v.numpy() for k, v in sd.items()}
 j64, _ = np_port.rnn_head(sdn, C.HEAD_PREFIX['joints'], x[None].numpy(), [T], True)
 feat64 = np.concatenate([j64, x[None].numpy().astype(np.float64)], axis=2)
 r64, _ = np_port.rnn_head(sdn, C.HEAD_PREFIX['pose'], feat64, [T], True)
-pose64 = reduced_global_to_full(torch.from_numpy(r64[0]).double().float().double())  # K5 in float64-ish
+pose64 = k5_f64(torch.from_numpy(r64[0]))
 # CPU fp32 reference port
 o = OraclePoser(sd)
 jo = o.heads['joints'](x[None], [T])[0]
