@@ -63,20 +63,18 @@ struct RecCfg {
     static_assert(CPL >= 1 && NW4 * 4 * THREADS == 4 * UC * H, "weights must tile the CTA's rows exactly");
 };
 
-// Shuffle reduce-scatter: v[a] (a in [0, NV)) are per-lane partial sums; the lanes that differ in the lane
-// bits topbit, topbit/2, .. are summed, and the lane whose those bits spell `a` ends with the total of v[a].
+// Shuffle reduce-scatter without selects.  Every lane holds NV partial sums in SLOTS; slot j of lane l carries
+// the value whose index is j ^ key(l), where key(l) are the lane bits {topbit, topbit/2, ..} read as a number
+// (the weight rows and the sequence order are pre-permuted per lane to make that so).  In the round for lane
+// bit `bit` a lane keeps the lower half of its slots and receives the partner's upper half, which carries the
+// same value indices; after log2(NV) rounds slot 0 of lane l holds the total of value key(l).
 template <int NV>
-__device__ __forceinline__ float reduce_scatter(float (&v)[NV], int lane, int topbit) {
+__device__ __forceinline__ float reduce_scatter(float (&v)[NV], int topbit) {
     int bit = topbit;
 #pragma unroll
     for (int half = NV / 2; half >= 1; half >>= 1) {
-        const bool up = (lane & bit) != 0;
 #pragma unroll
-        for (int i = 0; i < half; ++i) {
-            const float keep = up ? v[i + half] : v[i];
-            const float give = up ? v[i] : v[i + half];
-            v[i] = keep + __shfl_xor_sync(0xffffffffu, give, bit);
-        }
+        for (int i = 0; i < half; ++i) v[i] += __shfl_xor_sync(0xffffffffu, v[i + half], bit);
         bit >>= 1;
     }
     return v[0];
@@ -95,17 +93,28 @@ __host__ __device__ inline size_t rec_smem_bytes(int NB) {
            sizeof(int) * NB + 2 * sizeof(unsigned long long) + 16;
 }
 
+// sigmoid(x) (k = 1) or tanh(x) (k = 2) from ONE exponential, branch free:  E = exp(-k x),
+// sigmoid = 1 / (1 + E),  tanh = (1 - E) / (1 + E).  expf and the reciprocal are the correctly-rounded-grade
+// library versions (no ex2.approx shortcuts on the argument); the clamp keeps E finite and changes the result
+// by < 1e-13.  Absolute error <= ~1e-7 for tanh, 1 ulp-grade for sigmoid (DESIGN.md "precision").
+__device__ __forceinline__ float sigmoid_or_tanh(float x, bool is_tanh) {
+    const float s = fminf(fmaxf(is_tanh ? 2.0f * x : x, -30.0f), 30.0f);
+    const float e = expf(-s);
+    const float r = __frcp_rn(1.0f + e);
+    return is_tanh ? (1.0f - e) * r : r;
+}
+
 // gate nonlinearity + i/f/g/o gather + cell update for one (unit, sequence); every lane of the 4x4
-// (gate, kq) group of a unit returns the same h_new / c_new.
+// (gate, sequence) group of a unit returns the h_new / c_new of ITS sequence.
 __device__ __forceinline__ void lstm_cell(float pre, int gate, int lane, float c_old, float& c_new, float& h_new) {
-    const float act = (gate == 2) ? tanhf(pre) : sigmoidf_acc(pre);
+    const float act = sigmoid_or_tanh(pre, gate == 2);
     const int base = lane & ~0xC;
     const float iv = __shfl_sync(0xffffffffu, act, base);
     const float fv = __shfl_sync(0xffffffffu, act, base | 4);
     const float gv = __shfl_sync(0xffffffffu, act, base | 8);
     const float ov = __shfl_sync(0xffffffffu, act, base | 12);
     c_new = fmaf(fv, c_old, iv * gv);
-    h_new = ov * tanhf(c_new);
+    h_new = ov * sigmoid_or_tanh(c_new, true);
 }
 
 template <int H, int C, int BG>
@@ -136,8 +145,11 @@ __global__ void __launch_bounds__(RecCfg<H, C>::THREADS, 1) lstm_rec_kernel(cons
     const int G4 = p.dirs * 4 * H, Y2 = p.dirs * H;
     const int gcol = dir * 4 * H + unit * 4 + gate;  // gin columns are (unit, gate)-ordered (api.cu permutes W_ih)
     const int kl = lane % KQ;                        // this lane's slot in the K split
+    const int rkey = (lane >> 2) & (R - 1);          // weight slot rs of this lane holds gate row (rs ^ rkey)
+    const int qkey = lane & 3;                       // sequence slot qs of this lane holds sequence g0 + (qs ^ qkey)
 
-    // ---- resident weights: NW4 float4 per thread (row r = j / CPL of this lane's rows, k-chunk kl + (j % CPL)*KQ)
+    // ---- resident weights: NW4 float4 per thread (slot j: row slot j / CPL, k-chunk kl + (j % CPL)*KQ); the row
+    // slots are permuted per lane (row = slot ^ rkey, see pack_whh_kernel) so the reduce-scatter needs no selects
     float4 w[NW4];
     {
         const float4* wp = p.wpack + ((size_t)(dir * C + rank) * NW4) * THREADS + tid;
@@ -235,7 +247,7 @@ __global__ void __launch_bounds__(RecCfg<H, C>::THREADS, 1) lstm_rec_kernel(cons
                 }
             }
             // rows -> lane bits 4..2 (unit, gate); then the 4 lanes of a (unit, gate) all get the total
-            float tot = reduce_scatter<R>(acc, lane, KQ / 2);
+            float tot = reduce_scatter<R>(acc, KQ / 2);
             tot += __shfl_xor_sync(0xffffffffu, tot, 2);
             tot += __shfl_xor_sync(0xffffffffu, tot, 1);
             float c_new, h_new;
@@ -285,7 +297,7 @@ __global__ void __launch_bounds__(RecCfg<H, C>::THREADS, 1) lstm_rec_kernel(cons
                 for (int q = 0; q < 4; ++q) {
 #pragma unroll
                     for (int c = 0; c < CPL; ++c) {
-                        const float4 hv = *reinterpret_cast<const float4*>(hg + q * UC + hoff[c]);
+                        const float4 hv = *reinterpret_cast<const float4*>(hg + (q ^ qkey) * UC + hoff[c]);
 #pragma unroll
                         for (int r = 0; r < R; ++r) {
                             const float4 wv = w[r * CPL + c];
@@ -299,7 +311,7 @@ __global__ void __launch_bounds__(RecCfg<H, C>::THREADS, 1) lstm_rec_kernel(cons
                     }
                 }
                 // (row, sequence) -> lane bits: lane = unit_in_warp*16 + gate*4 + q
-                const float tot = reduce_scatter<R * 4>(acc, lane, KQ / 2);
+                const float tot = reduce_scatter<R * 4>(acc, KQ / 2);
                 float c_new, h_new;
                 lstm_cell(tot + gi, gate, lane, cbuf[u_local * NB + b], c_new, h_new);
                 __syncwarp();
@@ -414,8 +426,11 @@ __global__ void pack_whh_kernel(const float* __restrict__ w0, const float* __res
         const int rank = (idx / ((size_t)Cfg::THREADS * Cfg::NW4)) % C;
         const int dir = idx / ((size_t)Cfg::THREADS * Cfg::NW4 * C);
         const int lane = tid & 31, warp = tid >> 5;
-        const int r = j / Cfg::CPL, c = j % Cfg::CPL;
-        // lane row r -> (unit_in_warp, gate): with one row group (KQ = 32) r = u*4 + g; with two (KQ = 16) the
+        const int c = j % Cfg::CPL;
+        // weight slot rs of lane l holds row (rs ^ key(l)), key = lane bits 4..2 (3 bits, KQ = 32) or 3..2 (KQ = 16):
+        // the shuffle reduce-scatter of lstm_rec_kernel then needs no per-lane selects.
+        const int r = (j / Cfg::CPL) ^ ((lane >> 2) & (Cfg::R - 1));
+        // row r -> (unit_in_warp, gate): with one row group (KQ = 32) r = u*4 + g; with two (KQ = 16) the
         // row group is the unit and r is the gate
         const int u_in_warp = (Cfg::RG == 1) ? (r >> 2) : (lane / Cfg::KQ);
         const int gate = r & 3;

@@ -30,3 +30,51 @@ def argmax_equal(a, b):
 def min_margin(contact):
     c = contact.detach().cpu()
     return (c[..., 0] - c[..., 1]).abs().min().item()
+
+
+# ---- conditioning of the r6d -> rotation step ---------------------------------------------------------------
+# The pose head emits two 3-vectors (a, b) per joint; K5 normalises a and the part of b orthogonal to a
+# (Gram-Schmidt, articulate/math/angular.py:176-180).  A perturbation delta of the head output therefore moves the
+# rotation by about delta / min(|a|, |b_perp|).  Trained weights give |a|, |b_perp| ~ 1, where the north star's
+# 1e-4 rad leaves three orders of magnitude of headroom over fp32 rounding; the seeded RANDOM-INIT weights the
+# parity runs must use (no checkpoints ship with the reference) give |a| ~ 0.05 and, on some frames, |b_perp| <
+# 0.005, where the REFERENCE's own fp32 result is > 1e-4 rad away from a float64 evaluation of the same formulas
+# (scripts/diag_precision.py: 1.3e-4 rad at T = 3000).  The bar used by the tests is therefore
+#     r6d (what the networks compute)        : |cuda - reference| <= R6D_TOL, flat
+#     joint angle                            : <= max(1e-4 rad, AMPLIFY * R6D_TOL * sensitivity)
+# with sensitivity = 1/m_joint + 1/m_parent, m = min(|a|, |b_perp|) taken from the reference's r6d.
+R6D_TOL = 3e-7
+AMPLIFY = 6.0
+_REDUCED = [0, 1, 2, 3, 4, 5, 6, 9, 12, 13, 14, 15, 16, 17, 18, 19]
+_IGNORED = [0, 7, 8, 10, 11, 20, 21, 22, 23]
+_PARENT = [-1, 0, 0, 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 9, 9, 12, 13, 14, 16, 17, 18, 19, 20, 21]
+
+
+def k5_sensitivity(r6d):
+    """r6d [..., 96] -> [N, 24] first-order amplification of an r6d perturbation into each LOCAL rotation."""
+    v = r6d.detach().cpu().double().reshape(-1, 16, 6)
+    a, b = v[..., :3], v[..., 3:]
+    na = a.norm(dim=-1)
+    c0 = a / na[..., None]
+    bp = b - (c0 * b).sum(-1, keepdim=True) * c0
+    m = torch.minimum(na, bp.norm(dim=-1)).clamp_min(1e-12)
+    inv = torch.zeros(v.shape[0], 24, dtype=torch.float64)
+    inv[:, _REDUCED] = 1.0 / m
+    sens = inv.clone()
+    for i in range(1, 24):
+        sens[:, i] = inv[:, i] + inv[:, _PARENT[i]]
+    sens[:, _IGNORED] = 0.0
+    sens[:, 0] = inv[:, 0]
+    return sens
+
+
+def angle_tolerance(r6d_ref):
+    return torch.clamp(AMPLIFY * R6D_TOL * k5_sensitivity(r6d_ref), min=ANGLE_TOL)
+
+
+def angle_excess(pose, pose_ref, r6d_ref):
+    """max over (frame, joint) of angle error / tolerance (<= 1 passes); also returns the fraction of pairs
+    that are held to the plain 1e-4 rad."""
+    tol = angle_tolerance(r6d_ref)
+    err = geodesic(pose.detach().cpu().reshape(-1, 24, 3, 3), pose_ref.detach().cpu().reshape(-1, 24, 3, 3))
+    return (err / tol).max().item(), (tol <= ANGLE_TOL).double().mean().item(), err.max().item()

@@ -10,7 +10,8 @@ import pytest
 import torch
 
 from conftest import load_golden
-from parity import ANGLE_TOL, TRAN_TOL, VALUE_TOL, argmax_equal, max_abs, max_angle, min_margin
+from parity import (ANGLE_TOL, R6D_TOL, TRAN_TOL, VALUE_TOL, angle_excess, argmax_equal, max_abs, max_angle,
+                    min_margin)
 
 pytestmark = pytest.mark.gpu
 
@@ -45,9 +46,27 @@ def env():
             os.environ[k] = v
 
 
-def check_pose_tran(pose, tran, contact, g_pose, g_tran, g_contact, what=''):
-    a = max_angle(pose, g_pose)
-    assert a <= ANGLE_TOL, f'{what}: max joint angle error {a:.3e} rad'
+def reference_r6d(oracle, imu, lens):
+    """The reference pose head's r6d output for a batch (through the CPU oracle): conditioning of K5."""
+    joints = oracle.heads['joints'](imu, lens)[0]
+    return oracle.heads['pose'](torch.cat((joints, imu), dim=-1), lens)[0]
+
+
+def cuda_r6d(net, imu, lens):
+    joints = net.joints(imu, lens)
+    return net.pose.pose(joints, lens, None, x2=imu)[0]
+
+
+def check_pose_tran(pose, tran, contact, g_pose, g_tran, g_contact, what='', r6d_ref=None):
+    if r6d_ref is None:
+        a = max_angle(pose, g_pose)
+        assert a <= ANGLE_TOL, f'{what}: max joint angle error {a:.3e} rad'
+    else:
+        # 1e-4 rad wherever the Gram-Schmidt step is well conditioned, scaled by its conditioning elsewhere
+        # (tests/parity.py explains why random-init weights need this)
+        excess, flat_fraction, worst = angle_excess(pose, g_pose, r6d_ref)
+        assert excess <= 1.0, f'{what}: joint angle error {excess:.2f}x its tolerance (max {worst:.3e} rad)'
+        assert flat_fraction >= 0.98, f'{what}: only {flat_fraction:.3f} of (frame, joint) pairs are held to 1e-4 rad'
     if tran is not None:
         t = max_abs(tran, g_tran)
         assert t <= TRAN_TOL, f'{what}: max translation error {t:.3e} m'
@@ -61,14 +80,16 @@ def test_cfg1_joints_head(net):
     assert max_abs(y[0], g['joints']) <= VALUE_TOL
 
 
-def test_cfg2_forward_and_offline(net):
+def test_cfg2_forward_and_offline(net, oracle):
     g = load_golden('cfg2_forward_T300')
     x = g['imu'][None].to(DEV)
+    r6d_ref = reference_r6d(oracle, g['imu'][None], [300])
+    assert max_abs(cuda_r6d(net, x, [300]), r6d_ref) <= R6D_TOL
     net.velocity.rnn_state = None
     pose, joints, vel, contact = net.forward(x, [300])
     assert pose.shape == (300, 24, 3, 3) and joints.shape == (1, 300, 72) and vel.shape == (300, 72)
     assert contact.shape == (1, 300, 2)
-    check_pose_tran(pose, None, contact[0], g['pose'], None, g['contact'], 'forward')
+    check_pose_tran(pose, None, contact[0], g['pose'], None, g['contact'], 'forward', r6d_ref)
     assert max_abs(joints[0], g['joints']) <= VALUE_TOL and max_abs(vel, g['vel']) <= VALUE_TOL
     assert max_abs(contact[0], g['contact']) <= VALUE_TOL
     hn, cn = net.velocity.rnn_state
@@ -78,18 +99,19 @@ def test_cfg2_forward_and_offline(net):
     pose, joints, tran, contact = net.forward_offline(x, [300])
     assert pose.shape == (300, 24, 3, 3) and joints.shape == (1, 300, 72) and tran.shape == (300, 3)
     assert contact.shape == (300, 2)
-    check_pose_tran(pose, tran, contact, g['pose'], g['tran'], g['contact'], 'forward_offline')
+    check_pose_tran(pose, tran, contact, g['pose'], g['tran'], g['contact'], 'forward_offline', r6d_ref)
 
 
-def test_ragged_batch(net):
+def test_ragged_batch(net, oracle):
     g = load_golden('ragged_forward_B3')
     lens = g['lengths'].tolist()
+    r6d_ref = reference_r6d(oracle, g['imu'], lens)
     net.velocity.rnn_state = None
     pose, joints, vel, contact = net.forward(g['imu'].to(DEV), lens)
     # padded frames included: the reference leaves linear2.bias there (pad_packed_sequence zero-fills first)
     assert max_abs(joints, g['joints']) <= VALUE_TOL and max_abs(vel, g['vel']) <= VALUE_TOL
     assert max_abs(contact, g['contact']) <= VALUE_TOL
-    assert max_angle(pose, g['pose']) <= ANGLE_TOL
+    assert angle_excess(pose, g['pose'], r6d_ref)[0] <= 1.0
     for b, L in enumerate(lens):
         assert argmax_equal(contact[b, :L], g['contact'][b, :L])
     hn, cn = net.velocity.rnn_state
@@ -186,11 +208,12 @@ def test_k7_unit_online_state_machine():
         assert max_abs(pose_out[0].view(24, 9), g['pose'][k]) <= 1e-5, k
 
 
-def test_batch_equals_independent_reference_calls(net):
+def test_batch_equals_independent_reference_calls(net, oracle):
     g = load_golden('batch8_T64')
+    r6d_ref = reference_r6d(oracle, g['imu'], [64] * 8)
     pose, joints, tran, contact = net.forward_offline(g['imu'].to(DEV), [64] * 8)
     assert pose.shape == (8 * 64, 24, 3, 3) and tran.shape == (8, 64, 3)
-    check_pose_tran(pose.view(8, 64, 24, 3, 3), tran, contact, g['pose'], g['tran'], g['contact'], 'batch8')
+    check_pose_tran(pose.view(8, 64, 24, 3, 3), tran, contact, g['pose'], g['tran'], g['contact'], 'batch8', r6d_ref)
     assert max_abs(joints, g['joints']) <= VALUE_TOL
 
 
@@ -228,7 +251,7 @@ def test_recurrence_variants_against_oracle(net, oracle, env, variant):
     oracle.vel_state = None
     assert max_abs(joints, o_joints) <= VALUE_TOL and max_abs(vel, o_vel) <= VALUE_TOL
     assert max_abs(contact, o_contact) <= VALUE_TOL
-    assert max_angle(pose, o_pose) <= ANGLE_TOL
+    assert angle_excess(pose, o_pose, reference_r6d(oracle, x, lens))[0] <= 1.0
     assert max_abs(state[0], o_state[0]) <= VALUE_TOL and max_abs(state[1], o_state[1]) <= VALUE_TOL
     assert max_abs(vel2, o_vel2) <= VALUE_TOL
     for b, L in enumerate(lens):
@@ -284,13 +307,14 @@ def test_cfg3_batch256_is_batch_invariant_and_matches_oracle(net, oracle):
     for b in (0, 101, 255):
         net.velocity.rnn_state = None
         p1, j1, t1, c1 = net.forward_offline(xd[b:b + 1], [300])
-        assert max_angle(p1, pose[b]) <= ANGLE_TOL and max_abs(t1, tran[b]) <= TRAN_TOL
+        assert angle_excess(p1, pose[b], reference_r6d(oracle, x[b:b + 1], [300]))[0] <= 1.0
+        assert max_abs(t1, tran[b]) <= TRAN_TOL
         assert max_abs(j1[0], joints[b]) <= VALUE_TOL and argmax_equal(c1, contact[b])
     # ... and the oracle agrees on a sample of them
     for b in (3, 200):
         oracle.vel_state = None
         op, oj, ot, oc = oracle.forward_offline(x[b:b + 1], [300])
-        check_pose_tran(pose[b], tran[b], contact[b], op, ot, oc, f'cfg3 seq {b}')
+        check_pose_tran(pose[b], tran[b], contact[b], op, ot, oc, f'cfg3 seq {b}', reference_r6d(oracle, x[b:b + 1], [300]))
     net.velocity.rnn_state = None
 
 
@@ -301,7 +325,9 @@ def test_cfg4_long_sequence_T3000(net, oracle):
     pose, joints, tran, contact = net.forward_offline(x[None].to(DEV), [3000])
     oracle.vel_state = None
     op, oj, ot, oc = oracle.forward_offline(x[None], [3000])
-    check_pose_tran(pose, tran, contact, op, ot, oc, 'T=3000')
+    r6d_ref = reference_r6d(oracle, x[None], [3000])
+    assert max_abs(cuda_r6d(net, x[None].to(DEV), [3000]), r6d_ref) <= R6D_TOL
+    check_pose_tran(pose, tran, contact, op, ot, oc, 'T=3000', r6d_ref)
     net.velocity.rnn_state = None
 
 
@@ -338,3 +364,24 @@ def test_host_buffer_entry_matches_device_entry(net):
     assert torch.equal(contact_h, contact.cpu())
     for b, L in enumerate(lens):
         assert torch.equal(tran_h[b, :L], tran[b, :L].cpu())
+
+
+def test_float64_arbitration(net, oracle, seeded_state_dict):
+    """Both fp32 implementations against a float64 evaluation of the same equations (oracle/np_port.py): the CUDA
+    path must be as close to the exact answer as the reference's own CPU path is (it cannot be asked to be closer
+    to the reference than the reference is to the truth)."""
+    import numpy as np
+    from mobileposer_b200 import config as C
+    from mobileposer_b200.synthetic import synthetic_imu
+    from oracle import np_port
+    T = 300
+    x = synthetic_imu(777, T)[None]
+    sd = {k: v.numpy() for k, v in seeded_state_dict.items()}
+    j64, _ = np_port.rnn_head(sd, C.HEAD_PREFIX['joints'], x.numpy(), [T], True)
+    r64, _ = np_port.rnn_head(sd, C.HEAD_PREFIX['pose'], np.concatenate([j64, x.numpy().astype(np.float64)], 2), [T], True)
+    r_ref = reference_r6d(oracle, x, [T])
+    r_gpu = cuda_r6d(net, x.to(DEV), [T]).cpu()
+    e_ref = np.abs(r_ref.numpy().astype(np.float64) - r64).max()
+    e_gpu = np.abs(r_gpu.numpy().astype(np.float64) - r64).max()
+    assert e_ref < 2e-7 and e_gpu < 3e-7, (e_ref, e_gpu)
+    assert e_gpu <= 3.0 * e_ref + 5e-8, (e_ref, e_gpu)
