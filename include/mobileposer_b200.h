@@ -82,6 +82,12 @@ int mp_rnn_forward(const mp_rnn_t* rnn, const float* xa, int32_t ka, const float
                    const float* h0, const float* c0, float* hn, float* cn, float* y,
                    void* workspace, size_t workspace_bytes, mp_stream_t stream);
 
+/* The dense contraction under every Linear / LSTM input projection of the path (rnn.py:22,27,32):
+ *   C[M,N] = act(A[M,K] * W[N,K]^T + bias[N]).  mode 0 = library's choice, 1 = fp32 FFMA kernel,
+ *   2 = tcgen05 3xTF32 tensor-core kernel (needs N % 256 == 0, K % 16 == 0, relu == 0).  Exposed for tests.   */
+int mp_gemm_bias(const float* A, const float* W, const float* bias, float* C, int32_t M, int32_t N, int32_t K,
+                 int32_t relu, int32_t mode, mp_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * Kinematic tail.
  * ---------------------------------------------------------------------------------------- */

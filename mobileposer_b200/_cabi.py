@@ -51,6 +51,8 @@ SIGNATURES = {
     'mp_rnn_forward': (C.c_int, [C.c_void_p, c_float_p, C.c_int32, c_float_p, C.c_int32, C.c_int32, C.c_int32,
                                  c_int_p, c_float_p, c_float_p, c_float_p, c_float_p, c_float_p,
                                  C.c_void_p, C.c_size_t, c_stream]),
+    'mp_gemm_bias': (C.c_int, [c_float_p, c_float_p, c_float_p, c_float_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                               C.c_int32, c_stream]),
     'mp_pose_reduced_global_to_full': (C.c_int, [c_float_p, C.c_int64, c_float_p, c_stream]),
     'mp_tran_offline': (C.c_int, [c_float_p, c_float_p, c_float_p, c_int_p, C.c_int32, C.c_int32, c_float_p, c_stream]),
     'mp_online_update': (C.c_int, [C.c_void_p, c_float_p, c_float_p, c_float_p, c_float_p, C.c_int32, C.c_int32,

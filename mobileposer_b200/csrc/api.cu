@@ -288,6 +288,17 @@ int mp_rnn_forward(const mp_rnn_t* r, const float* xa, int32_t ka, const float* 
                             (cudaStream_t)stream);
 }
 
+int mp_gemm_bias(const float* A, const float* W, const float* bias, float* C, int32_t M, int32_t N, int32_t K,
+                 int32_t relu, int32_t mode, mp_stream_t stream) {
+    g_launches = 0;
+    if (mode == 1) return launch_gemm_ffma(A, K, nullptr, 0, W, bias, C, M, N, relu, (cudaStream_t)stream);
+    if (mode == 2) {
+        MP_REQUIRE(!relu, "gemm_bias: the tensor-core path has no activation");
+        return launch_gemm_tf32x3(A, W, bias, C, M, N, K, (cudaStream_t)stream);
+    }
+    return launch_gemm_bias_act(A, K, nullptr, 0, W, bias, C, M, N, relu, (cudaStream_t)stream);
+}
+
 // ------------------------------------------------------------------------------------------------
 int mp_pose_reduced_global_to_full(const float* r6d, int64_t n_frames, float* pose, mp_stream_t stream) {
     return launch_reduced_global_to_full(r6d, n_frames, pose, (cudaStream_t)stream);

@@ -158,6 +158,13 @@ gemm_bias_act_kernel(const float* __restrict__ A1, int K1, const float* __restri
 
 int launch_gemm_bias_act(const float* A1, int K1, const float* A2, int K2, const float* W,
                          const float* bias, float* C, int M, int N, int relu, cudaStream_t stream) {
+    // large single-source projections without activation go to the tensor cores (gemm_tc.cu)
+    if (!relu && K2 == 0 && gemm_tc_eligible(M, N, K1)) return launch_gemm_tf32x3(A1, W, bias, C, M, N, K1, stream);
+    return launch_gemm_ffma(A1, K1, A2, K2, W, bias, C, M, N, relu, stream);
+}
+
+int launch_gemm_ffma(const float* A1, int K1, const float* A2, int K2, const float* W,
+                     const float* bias, float* C, int M, int N, int relu, cudaStream_t stream) {
     if (M <= 0 || N <= 0) return MP_OK;
     MP_REQUIRE(A1 && W && bias && C, "gemm: null pointer");
     MP_REQUIRE(K1 > 0 && (K1 & 3) == 0 && K2 >= 0 && (K2 & 3) == 0, "gemm: K1=%d K2=%d must be multiples of 4", K1, K2);

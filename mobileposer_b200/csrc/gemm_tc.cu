@@ -1,0 +1,277 @@
+// Tensor-core input projection for large batches:  C[M,N] = A[M,K] * W[N,K]^T + bias[N]  with fp32-grade
+// accuracy from TF32 tensor cores ("3xTF32").
+//
+// Replaces the hoisted input projection W_ih x_t + b_ih + b_hh of nn.LSTM (mobileposer/models/rnn.py:27) when
+// M = B*T is large -- 57 % of the path's FLOPs and the only place where hidden_dim makes
+// a real dense contraction.
+//
+// Why 3xTF32: the parity bar (1e-4 rad / 1e-4 m through 4 chained LSTM stacks) needs fp32-accurate gate
+// pre-activations; a single TF32 pass (10-bit mantissa) is ~1e-3 relative.  Each fp32 operand x is split
+// EXACTLY into x = hi + lo with hi = x & 0xFFFFE000 (representable in TF32) and lo = x - hi (13 significant
+// bits, of which TF32 keeps 11), and  A*W ~= A_lo*W_hi + A_hi*W_lo + A_hi*W_hi  is accumulated in fp32 in
+// tensor memory: the dropped terms are <= 2^-21 relative.
+//
+// Structure (one 128 x 256 output tile per CTA, K walked in 16-float slabs, 4-stage ring):
+//   warp 0      TMA producer: cp.async.bulk.tensor (64B swizzle) of the fp32 A and W slabs into shared memory
+//   warps 2-5   splitter: rewrite each landed slab in place as `hi` and write `lo` next to it (element-wise, so the
+//               TMA swizzle is preserved), fence.proxy.async, arrive on the stage's "split" mbarrier; after the
+//               K loop the same warps are the epilogue: tcgen05.ld the accumulator, add the bias, store fp32 rows
+//   warp 1      TMEM allocation + single-thread tcgen05.mma issue: 3 products x 2 K-steps (UMMA 128x256x8, kind::tf32)
+//               per slab, tcgen05.commit releases the stage to the producer; a final commit hands the accumulator
+//               to the epilogue
+#include "mp_common.cuh"
+
+#include <cuda.h>
+
+#include <cstdlib>
+#include <cstring>
+
+namespace mp {
+
+namespace {
+
+constexpr int TC_BM = 128, TC_BN = 256, TC_BK = 16, TC_STAGES = 4;
+constexpr int TC_THREADS = 192;
+constexpr uint32_t A_TILE = TC_BM * TC_BK * 4;   // 8 KiB
+constexpr uint32_t W_TILE = TC_BN * TC_BK * 4;   // 16 KiB
+constexpr uint32_t STAGE_BYTES = 2 * A_TILE + 2 * W_TILE;
+constexpr uint32_t TC_SMEM = TC_STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr uint32_t TMEM_COLS = 256;
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar)
+        : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// K-major operand slab with 64-byte rows, SWIZZLE_64B: 8-row groups are 512 B apart (SBO), LBO unused (1)
+__device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | (1ull << 16) | ((uint64_t)(512 >> 4) << 32) | (1ull << 46) | (4ull << 61);
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
+                   const float* __restrict__ bias, float* __restrict__ C, int M, int N, int K) {
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bars = base + TC_STAGES * STAGE_BYTES;
+    // barrier map (8 B each): [0,S) tma_full, [S,2S) split_done, [2S,3S) mma_done, [3S] accum_full, then tmem slot
+    auto bar_full = [&](int s) { return bars + 8u * s; };
+    auto bar_split = [&](int s) { return bars + 8u * (TC_STAGES + s); };
+    auto bar_free = [&](int s) { return bars + 8u * (2 * TC_STAGES + s); };
+    const uint32_t bar_accum = bars + 8u * (3 * TC_STAGES);
+    const uint32_t tmem_slot = bars + 8u * (3 * TC_STAGES + 1);
+    unsigned char* gen = smem_raw + (base - smem_u32(smem_raw));   // generic pointer to the aligned region
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int n0 = blockIdx.x * TC_BN, m0 = blockIdx.y * TC_BM;
+    const int KB = K / TC_BK;
+
+    if (tid == 0) {
+        for (int s = 0; s < TC_STAGES; ++s) {
+            mbar_init(bar_full(s), 1);
+            mbar_init(bar_split(s), 128);
+            mbar_init(bar_free(s), 1);
+        }
+        mbar_init(bar_accum, 1);
+        mbar_fence_init_cluster();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(gen + (tmem_slot - base));
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int kb = 0; kb < KB; ++kb) {
+                const int s = kb % TC_STAGES;
+                if (kb >= TC_STAGES) mbar_wait(bar_free(s), ((kb / TC_STAGES) - 1) & 1);
+                mbar_arrive_expect_tx(bar_full(s), A_TILE + W_TILE);
+                const uint32_t st = base + s * STAGE_BYTES;
+                tma_load_2d(st, &map_a, kb * TC_BK, m0, bar_full(s));
+                tma_load_2d(st + 2 * A_TILE, &map_w, kb * TC_BK, n0, bar_full(s));
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // instruction descriptor: D = f32, A = B = tf32, both K-major, N = 256, M = 128
+            constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+            for (int kb = 0; kb < KB; ++kb) {
+                const int s = kb % TC_STAGES;
+                mbar_wait(bar_split(s), (kb / TC_STAGES) & 1);
+                tcgen05_fence_after();
+                const uint32_t a_hi = base + s * STAGE_BYTES, a_lo = a_hi + A_TILE;
+                const uint32_t w_hi = a_hi + 2 * A_TILE, w_lo = w_hi + W_TILE;
+#pragma unroll
+                for (int p = 0; p < 3; ++p) {           // small terms first
+                    const uint32_t a = (p == 0) ? a_lo : a_hi;
+                    const uint32_t w = (p == 1) ? w_lo : w_hi;
+#pragma unroll
+                    for (int k2 = 0; k2 < TC_BK / 8; ++k2)
+                        umma_tf32(tmem, umma_desc_sw64(a + k2 * 32), umma_desc_sw64(w + k2 * 32), idesc,
+                                  (kb | p | k2) != 0 ? 1u : 0u);
+                }
+                tcgen05_commit(bar_free(s));             // arrives when the MMAs above have finished reading the stage
+            }
+            tcgen05_commit(bar_accum);
+        }
+    } else {
+        // ---- splitter ----------------------------------------------------------------------------------------
+        const int t = tid - 64;
+        for (int kb = 0; kb < KB; ++kb) {
+            const int s = kb % TC_STAGES;
+            mbar_wait(bar_full(s), (kb / TC_STAGES) & 1);
+            uint4* a_hi = reinterpret_cast<uint4*>(gen + s * STAGE_BYTES);
+            uint4* a_lo = a_hi + A_TILE / 16;
+            uint4* w_hi = a_hi + 2 * A_TILE / 16;
+            uint4* w_lo = w_hi + W_TILE / 16;
+            auto split = [](uint4* hi_p, uint4* lo_p, int i) {
+                const uint4 v = hi_p[i];
+                uint4 h, l;
+                h.x = v.x & 0xFFFFE000u; h.y = v.y & 0xFFFFE000u; h.z = v.z & 0xFFFFE000u; h.w = v.w & 0xFFFFE000u;
+                l.x = __float_as_uint(__uint_as_float(v.x) - __uint_as_float(h.x));
+                l.y = __float_as_uint(__uint_as_float(v.y) - __uint_as_float(h.y));
+                l.z = __float_as_uint(__uint_as_float(v.z) - __uint_as_float(h.z));
+                l.w = __float_as_uint(__uint_as_float(v.w) - __uint_as_float(h.w));
+                hi_p[i] = h;
+                lo_p[i] = l;
+            };
+#pragma unroll
+            for (int i = 0; i < (int)(A_TILE / 16 / 128); ++i) split(a_hi, a_lo, t + i * 128);
+#pragma unroll
+            for (int i = 0; i < (int)(W_TILE / 16 / 128); ++i) split(w_hi, w_lo, t + i * 128);
+            fence_proxy_async_smem();
+            mbar_arrive(bar_split(s));
+        }
+        // ---- epilogue: TMEM -> registers -> +bias -> global ---------------------------------------------------
+        mbar_wait(bar_accum, 0);
+        tcgen05_fence_after();
+        const int wq = warp & 3;                         // TMEM lane quarter this warp may read
+        const int row = m0 + wq * 32 + lane;
+        for (int c0 = 0; c0 < TC_BN; c0 += 32) {
+            uint32_t v[32];
+            const uint32_t taddr = tmem + ((uint32_t)(wq * 32) << 16) + (uint32_t)c0;
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                  "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                  "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                  "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                : "r"(taddr)
+                : "memory");
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (row < M) {
+                float* dst = C + (size_t)row * N + n0 + c0;
+                const float4* b4 = reinterpret_cast<const float4*>(bias + n0 + c0);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float4 b = __ldg(b4 + j);
+                    float4 o;
+                    o.x = __uint_as_float(v[4 * j + 0]) + b.x;
+                    o.y = __uint_as_float(v[4 * j + 1]) + b.y;
+                    o.z = __uint_as_float(v[4 * j + 2]) + b.z;
+                    o.w = __uint_as_float(v[4 * j + 3]) + b.w;
+                    reinterpret_cast<float4*>(dst)[j] = o;
+                }
+            }
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// [rows, K] fp32 row-major -> 2-D tensor map with a (16 x box_rows) box, 64-byte swizzle
+int make_map(CUtensorMap* map, const float* ptr, int rows, int K, int box_rows) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) {
+        set_error("gemm_tc: cuTensorMapEncodeTiled is not available from this driver");
+        return MP_ERR_CUDA;
+    }
+    const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)K * 4};
+    const cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("gemm_tc: cuTensorMapEncodeTiled failed with CUresult %d (rows=%d K=%d)", (int)r, rows, K);
+        return MP_ERR_CUDA;
+    }
+    return MP_OK;
+}
+
+}  // namespace
+
+bool gemm_tc_eligible(int M, int N, int K) {
+    const char* v = getenv("MP_GEMM");
+    if (v && strcmp(v, "ffma") == 0) return false;
+    const int min_m = (v && strcmp(v, "tc") == 0) ? 1 : 2048;
+    return M >= min_m && N % TC_BN == 0 && K % TC_BK == 0 && K >= TC_BK;
+}
+
+int launch_gemm_tf32x3(const float* A, const float* W, const float* bias, float* C, int M, int N, int K, cudaStream_t stream) {
+    MP_REQUIRE(A && W && bias && C && M > 0, "gemm_tc: bad arguments");
+    MP_REQUIRE(N % TC_BN == 0 && K % TC_BK == 0, "gemm_tc: N=%d must be a multiple of %d and K=%d of %d", N, TC_BN, K, TC_BK);
+    MP_REQUIRE(((uintptr_t)A & 15) == 0 && ((uintptr_t)W & 15) == 0 && ((uintptr_t)C & 15) == 0 && ((uintptr_t)bias & 15) == 0,
+               "gemm_tc: pointers must be 16-byte aligned");
+    alignas(64) CUtensorMap map_a, map_w;
+    MP_TRY(make_map(&map_a, A, M, K, TC_BM));
+    MP_TRY(make_map(&map_w, W, N, K, TC_BN));
+    static bool configured = false;
+    if (!configured) {
+        MP_CUDA_TRY(cudaFuncSetAttribute(gemm_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
+        configured = true;
+    }
+    ProfileScope prof("gemm_tf32x3", 4.0 * ((double)N * K + N + (double)M * K + (double)M * N), stream);
+    dim3 grid(N / TC_BN, (M + TC_BM - 1) / TC_BM);
+    gemm_tf32x3_kernel<<<grid, TC_THREADS, TC_SMEM, stream>>>(map_a, map_w, bias, C, M, N, K);
+    MP_CUDA_TRY(cudaGetLastError());
+    count_launch();
+    return MP_OK;
+}
+
+}  // namespace mp

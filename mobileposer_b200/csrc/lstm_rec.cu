@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(RecCfg<H, C>::THREADS, 1) lstm_rec_kernel(cons
     const int G4 = p.dirs * 4 * H, Y2 = p.dirs * H;
     const int gcol = dir * 4 * H + unit * 4 + gate;  // gin columns are (unit, gate)-ordered (api.cu permutes W_ih)
     const int kl = lane % KQ;                        // this lane's slot in the K split
-    const int rkey = (lane >> 2) & (R - 1);          // weight slot rs of this lane holds gate row (rs ^ rkey)
+    // (weight slot rs of this lane holds gate row rs ^ ((lane >> 2) & (R - 1)); the permutation lives in pack_whh_kernel)
     const int qkey = lane & 3;                       // sequence slot qs of this lane holds sequence g0 + (qs ^ qkey)
 
     // ---- resident weights: NW4 float4 per thread (slot j: row slot j / CPL, k-chunk kl + (j % CPL)*KQ); the row

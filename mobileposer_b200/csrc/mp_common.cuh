@@ -52,6 +52,13 @@ struct ProfileScope {
 int launch_gemm_bias_act(const float* A1, int K1, const float* A2, int K2, const float* W,
                          const float* bias, float* C, int M, int N, int relu, cudaStream_t stream);
 
+// same contraction on the tensor cores (3xTF32, fp32-grade accuracy), single-source A, no activation
+bool gemm_tc_eligible(int M, int N, int K);
+int launch_gemm_tf32x3(const float* A, const float* W, const float* bias, float* C, int M, int N, int K,
+                       cudaStream_t stream);
+int launch_gemm_ffma(const float* A1, int K1, const float* A2, int K2, const float* W, const float* bias, float* C,
+                     int M, int N, int relu, cudaStream_t stream);
+
 struct RecLayerArgs {
     const float* gin;     // [B, T, dirs*4H]  input projection + both biases
     const float4* wpack;  // packed W_hh for this layer (all dirs), see pack_whh
