@@ -80,17 +80,33 @@ __device__ __forceinline__ float reduce_scatter(float (&v)[NV], int topbit) {
     return v[0];
 }
 
+// Blackwell packed fp32: one FFMA2 issue slot does two FMAs (SASS `FFMA2 Rd, Ra.F32x2, Rb.F32, Rc.F32x2` -- the
+// scalar operand is broadcast).  The recurrence is issue-slot bound (ncu: 50 % of the instruction stream was
+// non-FMA work), so halving the FMA issue count is a direct win.  A pair = the same k of TWO gate rows.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 ffma2(f32x2 a, float b, f32x2 c) {
+    f32x2 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(pack2(b, b)), "l"(c));
+    return d;
+}
+
 // Dynamic shared memory carve-up (floats unless noted):
 //   hbuf   [2][C][NB][UC]  h_t of every sequence of the tile, double buffered by step parity; the slice
 //                          written by source CTA `src` is contiguous so it travels as ONE bulk copy
 //   hstage [2][NB][UC]     this CTA's new slice, source of the bulk copies
 //   cbuf   [NB][UC]        cell state of the owned units
-//   lens   [NB] int
+//   lens   [NB] int, goff [NB] uint32 (element offset of sequence b in gin), yoff [NB] uint32 (same for y)
 //   bars   [2] uint64      mbarriers, one per hbuf parity
 template <int H, int C>
 __host__ __device__ inline size_t rec_smem_bytes(int NB) {
     return sizeof(float) * ((size_t)2 * NB * H + (size_t)2 * NB * RecCfg<H, C>::UC + (size_t)NB * RecCfg<H, C>::UC) +
-           sizeof(int) * NB + 2 * sizeof(unsigned long long) + 16;
+           sizeof(int) * 3 * NB + 2 * sizeof(unsigned long long) + 16;
 }
 
 // sigmoid(x) (k = 1) or tanh(x) (k = 2) from ONE exponential, branch free:  E = exp(-k x),
@@ -130,8 +146,10 @@ __global__ void __launch_bounds__(RecCfg<H, C>::THREADS, 1) lstm_rec_kernel(cons
     float* hstage = hbuf + (size_t)2 * NB * H;
     float* cbuf = hstage + (size_t)2 * NB * UC;          // [UC][NB]
     int* lens = reinterpret_cast<int*>(cbuf + (size_t)NB * UC);
+    uint32_t* goff = reinterpret_cast<uint32_t*>(lens + NB);
+    uint32_t* yoff = goff + NB;
     unsigned long long* bars =
-        reinterpret_cast<unsigned long long*>((reinterpret_cast<uintptr_t>(lens + NB) + 15) & ~uintptr_t(15));
+        reinterpret_cast<unsigned long long*>((reinterpret_cast<uintptr_t>(yoff + NB) + 15) & ~uintptr_t(15));
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int rank = (C > 1) ? (int)cluster_ctarank() : 0;
@@ -143,18 +161,25 @@ __global__ void __launch_bounds__(RecCfg<H, C>::THREADS, 1) lstm_rec_kernel(cons
     const int gate = (lane >> 2) & 3, qn = lane & 3;
     const int unit = rank * UC + u_local;           // hidden unit in [0, H)
     const int G4 = p.dirs * 4 * H, Y2 = p.dirs * H;
-    const int gcol = dir * 4 * H + unit * 4 + gate;  // gin columns are (unit, gate)-ordered (api.cu permutes W_ih)
+    const int gcol0 = dir * 4 * H;                   // this direction's block of gin columns
+    const int gcol = gcol0 + unit * 4 + gate;        // gin columns are (unit, gate)-ordered (api.cu permutes W_ih)
+    const int gcol_l = unit * 4 + gate;
     const int kl = lane % KQ;                        // this lane's slot in the K split
     // (weight slot rs of this lane holds gate row rs ^ ((lane >> 2) & (R - 1)); the permutation lives in pack_whh_kernel)
     const int qkey = lane & 3;                       // sequence slot qs of this lane holds sequence g0 + (qs ^ qkey)
 
     // ---- resident weights: NW4 float4 per thread (slot j: row slot j / CPL, k-chunk kl + (j % CPL)*KQ); the row
     // slots are permuted per lane (row = slot ^ rkey, see pack_whh_kernel) so the reduce-scatter needs no selects
-    float4 w[NW4];
+    // Register layout: w2[(rp*CPL + c)*4 + e] = pair (row slot 2rp, row slot 2rp+1) at k = chunk c, element e.
+    f32x2 w2[NW4 * 2];
     {
         const float4* wp = p.wpack + ((size_t)(dir * C + rank) * NW4) * THREADS + tid;
 #pragma unroll
-        for (int j = 0; j < NW4; ++j) w[j] = __ldg(wp + (size_t)j * THREADS);
+        for (int j = 0; j < NW4; ++j) {
+            const float4 v = __ldg(wp + (size_t)j * THREADS);
+            w2[2 * j] = pack2(v.x, v.y);
+            w2[2 * j + 1] = pack2(v.z, v.w);
+        }
     }
     // float offsets of this lane's k-chunks inside one parity buffer of hbuf ([src][b][u], b = 0)
     int hoff[CPL];
@@ -165,8 +190,11 @@ __global__ void __launch_bounds__(RecCfg<H, C>::THREADS, 1) lstm_rec_kernel(cons
     }
 
     // ---- tile state ------------------------------------------------------------------------
-    for (int i = tid; i < NB; i += THREADS)
+    for (int i = tid; i < NB; i += THREADS) {
         lens[i] = (i < nb) ? (p.lengths ? min(max(p.lengths[b_begin + i], 0), p.T) : p.T) : 0;
+        goff[i] = (uint32_t)(b_begin + min(i, nb - 1)) * (uint32_t)p.T * (uint32_t)G4 + (uint32_t)gcol0;
+        yoff[i] = (uint32_t)(b_begin + min(i, nb - 1)) * (uint32_t)p.T * (uint32_t)Y2 + (uint32_t)(dir * H);
+    }
     for (int i = tid; i < NB * H; i += THREADS) {      // parity-0 buffer <- h0 (or zeros)
         const int src = i / SRC, rem = i - src * SRC;
         const int b = rem / UC, u = rem - b * UC;
@@ -203,7 +231,7 @@ __global__ void __launch_bounds__(RecCfg<H, C>::THREADS, 1) lstm_rec_kernel(cons
         if (len0 > 0) gi_next = __ldg(p.gin + ((size_t)b_begin * p.T + (dir ? len0 - 1 : 0)) * G4 + gcol);
     } else {
         const int l = lens[qn];
-        if (l > 0) gi_next = __ldg(p.gin + ((size_t)(b_begin + qn) * p.T + (dir ? l - 1 : 0)) * G4 + gcol);
+        if (l > 0) gi_next = __ldg(p.gin + (goff[qn] + (uint32_t)(dir ? l - 1 : 0) * (uint32_t)G4 + (uint32_t)gcol_l));
     }
 
     for (int s = 0; s < maxlen; ++s) {
@@ -231,21 +259,24 @@ __global__ void __launch_bounds__(RecCfg<H, C>::THREADS, 1) lstm_rec_kernel(cons
             const int t = dir ? len0 - 1 - s : s;
             const float gi = gi_next;
             if (send) gi_next = __ldg(p.gin + ((size_t)b_begin * p.T + (dir ? t - 1 : t + 1)) * G4 + gcol);
-            float acc[R];
+            f32x2 acc2[R / 2];
 #pragma unroll
-            for (int r = 0; r < R; ++r) acc[r] = 0.f;
+            for (int rp = 0; rp < R / 2; ++rp) acc2[rp] = 0ull;
 #pragma unroll
             for (int c = 0; c < CPL; ++c) {
                 const float4 hv = *reinterpret_cast<const float4*>(hcur + hoff[c]);
 #pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    const float4 wv = w[r * CPL + c];
-                    acc[r] = fmaf(wv.x, hv.x, acc[r]);
-                    acc[r] = fmaf(wv.y, hv.y, acc[r]);
-                    acc[r] = fmaf(wv.z, hv.z, acc[r]);
-                    acc[r] = fmaf(wv.w, hv.w, acc[r]);
+                for (int rp = 0; rp < R / 2; ++rp) {
+                    const int wi = (rp * CPL + c) * 4;
+                    acc2[rp] = ffma2(w2[wi + 0], hv.x, acc2[rp]);
+                    acc2[rp] = ffma2(w2[wi + 1], hv.y, acc2[rp]);
+                    acc2[rp] = ffma2(w2[wi + 2], hv.z, acc2[rp]);
+                    acc2[rp] = ffma2(w2[wi + 3], hv.w, acc2[rp]);
                 }
             }
+            float acc[R];
+#pragma unroll
+            for (int rp = 0; rp < R / 2; ++rp) unpack2(acc2[rp], acc[2 * rp], acc[2 * rp + 1]);
             // rows -> lane bits 4..2 (unit, gate); then the 4 lanes of a (unit, gate) all get the total
             float tot = reduce_scatter<R>(acc, KQ / 2);
             tot += __shfl_xor_sync(0xffffffffu, tot, 2);
@@ -283,15 +314,15 @@ __global__ void __launch_bounds__(RecCfg<H, C>::THREADS, 1) lstm_rec_kernel(cons
                     const int bn = wrap ? qn : b + 4;
                     const int sn = wrap ? s + 1 : s;
                     const int ln = lens[bn];
-                    if (sn < ln) gi_next = __ldg(p.gin + ((size_t)(b_begin + bn) * p.T + (dir ? ln - 1 - sn : sn)) * G4 + gcol);
+                    if (sn < ln) gi_next = __ldg(p.gin + (goff[bn] + (uint32_t)(dir ? ln - 1 - sn : sn) * (uint32_t)G4 + (uint32_t)gcol_l));
                 }
                 int glen = 0;
 #pragma unroll
                 for (int q = 0; q < 4; ++q) glen = max(glen, lens[g0 + q]);   // lens[>=nb] == 0, NB % 4 == 0
                 if (s >= glen) continue;
-                float acc[R * 4];
+                f32x2 acc2[R / 2 * 4];
 #pragma unroll
-                for (int a = 0; a < R * 4; ++a) acc[a] = 0.f;
+                for (int a = 0; a < R / 2 * 4; ++a) acc2[a] = 0ull;
                 const float* hg = hcur + g0 * UC;
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
@@ -299,17 +330,22 @@ __global__ void __launch_bounds__(RecCfg<H, C>::THREADS, 1) lstm_rec_kernel(cons
                     for (int c = 0; c < CPL; ++c) {
                         const float4 hv = *reinterpret_cast<const float4*>(hg + (q ^ qkey) * UC + hoff[c]);
 #pragma unroll
-                        for (int r = 0; r < R; ++r) {
-                            const float4 wv = w[r * CPL + c];
-                            float a = acc[r * 4 + q];
-                            a = fmaf(wv.x, hv.x, a);
-                            a = fmaf(wv.y, hv.y, a);
-                            a = fmaf(wv.z, hv.z, a);
-                            a = fmaf(wv.w, hv.w, a);
-                            acc[r * 4 + q] = a;
+                        for (int rp = 0; rp < R / 2; ++rp) {
+                            const int wi = (rp * CPL + c) * 4;
+                            f32x2 a = acc2[rp * 4 + q];
+                            a = ffma2(w2[wi + 0], hv.x, a);
+                            a = ffma2(w2[wi + 1], hv.y, a);
+                            a = ffma2(w2[wi + 2], hv.z, a);
+                            a = ffma2(w2[wi + 3], hv.w, a);
+                            acc2[rp * 4 + q] = a;
                         }
                     }
                 }
+                float acc[R * 4];     // value slot = row_slot*4 + q, row_slot = 2*rp + {0,1}
+#pragma unroll
+                for (int rp = 0; rp < R / 2; ++rp)
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) unpack2(acc2[rp * 4 + q], acc[(2 * rp) * 4 + q], acc[(2 * rp + 1) * 4 + q]);
                 // (row, sequence) -> lane bits: lane = unit_in_warp*16 + gate*4 + q
                 const float tot = reduce_scatter<R * 4>(acc, KQ / 2);
                 float c_new, h_new;
@@ -318,7 +354,7 @@ __global__ void __launch_bounds__(RecCfg<H, C>::THREADS, 1) lstm_rec_kernel(cons
                 if (active) {
                     if (gate == 0) {
                         cbuf[u_local * NB + b] = c_new;
-                        p.y[((size_t)(b_begin + b) * p.T + t) * Y2 + dir * H + unit] = h_new;
+                        p.y[yoff[b] + (uint32_t)t * (uint32_t)Y2 + (uint32_t)unit] = h_new;
                         if (s == len - 1) {
                             if (p.hn) p.hn[((size_t)dir * p.B + b_begin + b) * H + unit] = h_new;
                             if (p.cn) p.cn[((size_t)dir * p.B + b_begin + b) * H + unit] = c_new;
@@ -426,19 +462,26 @@ __global__ void pack_whh_kernel(const float* __restrict__ w0, const float* __res
         const int rank = (idx / ((size_t)Cfg::THREADS * Cfg::NW4)) % C;
         const int dir = idx / ((size_t)Cfg::THREADS * Cfg::NW4 * C);
         const int lane = tid & 31, warp = tid >> 5;
-        const int c = j % Cfg::CPL;
-        // weight slot rs of lane l holds row (rs ^ key(l)), key = lane bits 4..2 (3 bits, KQ = 32) or 3..2 (KQ = 16):
-        // the shuffle reduce-scatter of lstm_rec_kernel then needs no per-lane selects.
-        const int r = (j / Cfg::CPL) ^ ((lane >> 2) & (Cfg::R - 1));
-        // row r -> (unit_in_warp, gate): with one row group (KQ = 32) r = u*4 + g; with two (KQ = 16) the
-        // row group is the unit and r is the gate
-        const int u_in_warp = (Cfg::RG == 1) ? (r >> 2) : (lane / Cfg::KQ);
-        const int gate = r & 3;
-        const int unit = rank * Cfg::UC + warp * 2 + u_in_warp;
-        const int k = (c * Cfg::KQ + lane % Cfg::KQ) * 4;
+        // float4 j = ((rp*CPL + c)*2 + hf) holds (W[r0][k], W[r1][k], W[r0][k+1], W[r1][k+1]), k = chunk c + 2*hf, for the
+        // row-slot pair (2rp, 2rp+1).  Row slot rs of lane l is gate row rs ^ key(l), key = lane bits 4..2 (KQ = 32) or
+        // 3..2 (KQ = 16): the shuffle reduce-scatter of lstm_rec_kernel then needs no per-lane selects.
+        const int hf = j & 1, c = (j >> 1) % Cfg::CPL, rp = (j >> 1) / Cfg::CPL;
+        const int key = (lane >> 2) & (Cfg::R - 1);
+        const int k = (c * Cfg::KQ + lane % Cfg::KQ) * 4 + 2 * hf;
         const float* W = dir ? w1 : w0;
-        const float* src = W + (size_t)(gate * H + unit) * H + k;
-        wpack[idx] = make_float4(src[0], src[1], src[2], src[3]);
+        float v[2][2];
+        for (int e = 0; e < 2; ++e) {
+            const int r = (2 * rp + e) ^ key;
+            // row r -> (unit_in_warp, gate): with one row group (KQ = 32) r = u*4 + g; with two (KQ = 16) the row group is
+            // the unit and r is the gate
+            const int u_in_warp = (Cfg::RG == 1) ? (r >> 2) : (lane / Cfg::KQ);
+            const int gate = r & 3;
+            const int unit = rank * Cfg::UC + warp * 2 + u_in_warp;
+            const float* src = W + (size_t)(gate * H + unit) * H + k;
+            v[e][0] = src[0];
+            v[e][1] = src[1];
+        }
+        wpack[idx] = make_float4(v[0][0], v[1][0], v[0][1], v[1][1]);
     }
     const size_t tt = (size_t)dirs * 4 * H * H;
     for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < tt;
@@ -586,6 +629,8 @@ int launch_pack_whh(const float* const* w_hh_dirs, int H, int dirs, float4* wpac
 
 int launch_lstm_recurrence(const RecLayerArgs& a, cudaStream_t stream) {
     MP_REQUIRE(a.gin && a.wpack && a.y && a.B > 0 && a.T > 0 && (a.dirs == 1 || a.dirs == 2), "lstm: bad arguments");
+    MP_REQUIRE((double)a.B * a.T * a.dirs * 4 * a.H < 4.0e9, "lstm: B*T = %lld frames exceeds the 32-bit gate buffer indexing of one launch",
+               (long long)a.B * a.T);
     // algorithmic bytes of the recurrence: W_hh once + the layer's h output; the gate
     // pre-activations it reads are an intermediate of this design, charged as what a fully fused
     // layer would read instead (the layer input, counted with the input-projection GEMM).
