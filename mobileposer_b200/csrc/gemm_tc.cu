@@ -36,7 +36,7 @@ constexpr uint32_t A_TILE = TC_BM * TC_BK * 4;   // 8 KiB
 constexpr uint32_t W_TILE = TC_BN * TC_BK * 4;   // 16 KiB
 constexpr uint32_t STAGE_BYTES = 2 * A_TILE + 2 * W_TILE;
 constexpr uint32_t TC_SMEM = TC_STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
-constexpr uint32_t TMEM_COLS = 256;
+constexpr uint32_t TMEM_COLS = 512;   // two fp32 accumulators: [0,256) main (hi*hi), [256,512) correction (lo*hi + hi*lo)
 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
@@ -129,14 +129,18 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                 tcgen05_fence_after();
                 const uint32_t a_hi = base + s * STAGE_BYTES, a_lo = a_hi + A_TILE;
                 const uint32_t w_hi = a_hi + 2 * A_TILE, w_lo = w_hi + W_TILE;
+                // The tensor core truncates its fp32 accumulator on every add; keeping the 2^-11-sized correction
+                // products in their own accumulator means those truncations are 2^-11 smaller too, and the main
+                // chain sees K/8 adds instead of 3K/8 (measured: 4e-6 -> see test_tensor_core_gemm_matches_fp32).
 #pragma unroll
-                for (int p = 0; p < 3; ++p) {           // small terms first
+                for (int p = 0; p < 3; ++p) {
                     const uint32_t a = (p == 0) ? a_lo : a_hi;
                     const uint32_t w = (p == 1) ? w_lo : w_hi;
+                    const uint32_t d = (p == 2) ? tmem : tmem + TC_BN;
 #pragma unroll
                     for (int k2 = 0; k2 < TC_BK / 8; ++k2)
-                        umma_tf32(tmem, umma_desc_sw64(a + k2 * 32), umma_desc_sw64(w + k2 * 32), idesc,
-                                  (kb | p | k2) != 0 ? 1u : 0u);
+                        umma_tf32(d, umma_desc_sw64(a + k2 * 32), umma_desc_sw64(w + k2 * 32), idesc,
+                                  (kb | (p == 1 ? 1 : 0) | k2) != 0 ? 1u : 0u);
                 }
                 tcgen05_commit(bar_free(s));             // arrives when the MMAs above have finished reading the stage
             }
@@ -190,7 +194,20 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                   "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
                 : "r"(taddr)
                 : "memory");
+            uint32_t u[32];
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]),
+                  "=r"(u[8]), "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15]),
+                  "=r"(u[16]), "=r"(u[17]), "=r"(u[18]), "=r"(u[19]), "=r"(u[20]), "=r"(u[21]), "=r"(u[22]), "=r"(u[23]),
+                  "=r"(u[24]), "=r"(u[25]), "=r"(u[26]), "=r"(u[27]), "=r"(u[28]), "=r"(u[29]), "=r"(u[30]), "=r"(u[31])
+                : "r"(taddr + (uint32_t)TC_BN)
+                : "memory");
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(u[j]));
             if (row < M) {
                 float* dst = C + (size_t)row * N + n0 + c0;
                 const float4* b4 = reinterpret_cast<const float4*>(bias + n0 + c0);

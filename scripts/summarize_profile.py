@@ -1,0 +1,86 @@
+"""Turn the ncu artefacts of a GPU visit (gpurun_out/) into the tracked summaries under profiles/.
+
+    python scripts/summarize_profile.py r01        # reads gpurun_out/launches.csv, gpurun_out/prof_*.ncu-rep
+
+Writes profiles/<round>_launches.csv (kernel, grid, block, duration), profiles/<round>_ncu_<name>.csv (selected raw
+metrics of each full-set capture) and refreshes profiles/ncu_summary.json (per-launch DRAM traffic that bench.py
+reports as roofline.traffic)."""
+import csv
+import glob
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+OUT = os.path.join(ROOT, 'profiles')
+SRC = os.path.join(ROOT, 'gpurun_out')
+KEEP = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum', 'sm__cycles_elapsed.max',
+        'smsp__cycles_active.avg', 'smsp__inst_executed.sum', 'smsp__issue_active.avg.pct_of_peak_sustained_active',
+        'sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active',
+        'sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active',
+        'sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active',
+        'sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active',
+        'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active',
+        'sm__inst_executed_pipe_tensor.avg.pct_of_peak_sustained_active',
+        'sm__warps_active.avg.pct_of_peak_sustained_active', 'launch__registers_per_thread',
+        'launch__cluster_max_active', 'launch__grid_size', 'launch__block_size',
+        'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed', 'dram__cycles_active.avg.pct_of_peak_sustained_elapsed',
+        'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum', 'lts__t_bytes.sum',
+        'smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio',
+        'smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio',
+        'smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio',
+        'smsp__average_warps_issue_stalled_wait_per_issue_active.ratio',
+        'smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio']
+
+
+def launches(tag):
+    path = os.path.join(SRC, 'launches.csv')
+    if not os.path.exists(path):
+        return
+    lines = [l for l in open(path) if not l.startswith('==')]
+    rows = list(csv.DictReader(lines))
+    with open(os.path.join(OUT, f'{tag}_launches.csv'), 'w', newline='') as f:
+        w = csv.writer(f)
+        w.writerow(['id', 'kernel', 'grid', 'block', 'duration_ns'])
+        for r in rows:
+            w.writerow([r['ID'], r['Kernel Name'].replace('mp::<unnamed>::', ''), r['Grid Size'], r['Block Size'], r['Metric Value']])
+    print('wrote', f'{tag}_launches.csv', len(rows), 'launches')
+
+
+def full_sets(tag):
+    summary_path = os.path.join(OUT, 'ncu_summary.json')
+    summary = json.load(open(summary_path)) if os.path.exists(summary_path) else {}
+    for rep in sorted(glob.glob(os.path.join(SRC, 'prof_*.ncu-rep'))):
+        name = os.path.basename(rep)[5:-8]
+        raw = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+        rows = list(csv.reader(raw.splitlines()))
+        if len(rows) < 3:
+            continue
+        hdr, units = rows[0], rows[1]
+        idx = {h: i for i, h in enumerate(hdr)}
+        with open(os.path.join(OUT, f'{tag}_ncu_{name}.csv'), 'w', newline='') as f:
+            w = csv.writer(f)
+            w.writerow(['kernel', 'metric', 'unit', 'value'])
+            for r in rows[2:]:
+                kname = r[idx['Kernel Name']]
+                for m in KEEP:
+                    if m in idx:
+                        w.writerow([kname, m, units[idx[m]], r[idx[m]]])
+        r = rows[2]
+        def val(m):
+            v, u = float(r[idx[m]]), units[idx[m]].lower()
+            return v * {'byte': 1, 'kbyte': 1e3, 'mbyte': 1e6, 'gbyte': 1e9}.get(u, 1)
+        key = {'rec_b256': 'lstm_rec_h256', 'rec_b1': 'lstm_rec_h256_b1', 'gemm_tc': 'gemm_tf32x3'}.get(name, name)
+        summary[key] = {'round': tag, 'kernel': r[idx['Kernel Name']], 'grid': r[idx['Grid Size']],
+                        'dram_bytes_per_launch': val('dram__bytes_read.sum') + val('dram__bytes_write.sum'),
+                        'duration_ms_under_ncu': float(r[idx['gpu__time_duration.sum']]) * {'us': 1e-3, 'ms': 1, 'ns': 1e-6, 's': 1e3}.get(units[idx['gpu__time_duration.sum']].replace('second', 's'), 1)}
+        print('wrote', f'{tag}_ncu_{name}.csv', summary[key])
+    json.dump(summary, open(summary_path, 'w'), indent=1, sort_keys=True)
+
+
+if __name__ == '__main__':
+    tag = sys.argv[1] if len(sys.argv) > 1 else 'r01'
+    os.makedirs(OUT, exist_ok=True)
+    launches(tag)
+    full_sets(tag)

@@ -406,4 +406,5 @@ def test_tensor_core_gemm_matches_fp32(M, N, K):
     e_tc = (out[2].double() - ref).abs().max().item()
     assert torch.isfinite(out[2]).all()
     assert e_ffma < 2e-6, e_ffma
-    assert e_tc < 2e-6, (e_tc, e_ffma)          # a single TF32 pass would be ~1e-3 here
+    assert e_tc < 3e-6, (e_tc, e_ffma)          # a single TF32 pass would be ~1e-3 here
+    print(f'gemm M={M} N={N} K={K}: max |err| ffma {e_ffma:.2e}  tf32x3 {e_tc:.2e}')
