@@ -342,6 +342,14 @@ def run_ours(args):
                   'ms_per_step': ms1 / k1, 'steps': k1, 'gpu_launches': net.last_launches,
                   'hbm_roofline_frac_whole_path': (WEIGHT_BYTES + T * IO_BYTES_PER_FRAME) / (ms1 / k1 / 1e3) / 1e9 / peak}
 
+    # ---- live-demo streaming (cfg5): 5 device-combo streams, sliding window, per-tick latency --------------
+    streaming = None
+    if args.workload == 'cfg3' and rank == 0:
+        streaming = {f'window_{W}': streaming_latency(net, dev, W) for W in (45, 125)}
+        streaming['note'] = ('per tick: window shift + 4 heads over the whole window + K5 + state update for 5 concurrent '
+                             'streams (combos lw_rp, rw_rp, lw_lp, rw_lp, lw_rp_h); window 45 is the reference default '
+                             '(config.py:52-54), 125 is BASELINE.json config 5; 60 Hz budget = 16.7 ms')
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = time_cpu_sample(sd, xs_host[0][:min(B, args.cpu_sample)].clone())
@@ -358,12 +366,34 @@ def run_ours(args):
                        'parallelism': f'{world} x (one process per GPU, sequences sharded, no data-path collective)'},
             'e2e': e2e, 'gpu_launches': launches * args.steps, 'gpu_launches_per_step': launches,
             'roofline': roofline, 'whole_path_algorithmic_GBps': whole, 'whole_path_hbm_frac': whole / peak,
-            'kernels': kernels, 'cpu_baseline': cpu, 'batch1': batch1, 'clocks': clocks.summary(),
+            'kernels': kernels, 'cpu_baseline': cpu, 'batch1': batch1, 'streaming': streaming, 'clocks': clocks.summary(),
             'all_gather_shape': gathered,
         }
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
+
+
+def streaming_latency(net, dev, W, ticks=240, warm=20):
+    import mobileposer_b200 as mp
+    from mobileposer_b200.synthetic import synthetic_imu_batch
+    combos = ['lw_rp', 'rw_rp', 'lw_lp', 'rw_lp', 'lw_rp_h']
+    x = torch.stack([synthetic_imu_batch([70000], ticks + warm, combo=c)[0] for c in combos]).to(dev)   # [5, n, 60]
+    net.velocity.rnn_state = None
+    st = mp.OnlineStreams(net, len(combos), dev, window=W)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(ticks)]
+    for t in range(warm):
+        st.step(x[:, t])
+    torch.cuda.synchronize()
+    for t in range(ticks):
+        ev[t][0].record()
+        st.step(x[:, warm + t])
+        ev[t][1].record()
+    torch.cuda.synchronize()
+    ms = sorted(a.elapsed_time(b) for a, b in ev)
+    net.velocity.rnn_state = None
+    return {'streams': len(combos), 'ticks': ticks, 'p50_ms': ms[len(ms) // 2], 'p99_ms': ms[int(len(ms) * 0.99) - 1],
+            'max_ms': ms[-1], 'frames_per_s': len(combos) * 1e3 / (sum(ms) / len(ms))}
 
 
 def net_workspace_mb(net, B, T):

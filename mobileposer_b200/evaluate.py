@@ -1,0 +1,183 @@
+"""`evaluate.py` of the reference (mobileposer/evaluate.py:16-126) for the B200 path.
+
+Same entry (`evaluate_pose(model, dataset, ...)`, CLI `--model --dataset`), same hot loop
+(`model.reset(); model.forward_offline(x[None], [T])`, evaluate.py:56-58) and the same printed table
+(evaluate.py:31-36).  Differences:
+  * sequences are sharded over the ranks of `torch.distributed` when it is initialised (sharding.py) and the
+    per-sequence [8, 2] rows are all-gathered once at the end;
+  * the metric rows are computed on the device from SMPL forward kinematics of the 24 joints
+    (evaluator.py:292-343: rows 0, 2-9).  The mesh-vertex row (evaluator.py row 1, needs the 6890-vertex SMPL
+    template) is NaN unless a `smpl_file` is given -- the evaluator is "next" in SURVEY.md section 8f;
+  * `--dataset synthetic_dip` evaluates a synthetic DIP-shaped set (10 subjects x 5 sequences x 3000 frames,
+    BASELINE.json config 4) because the real datasets cannot ship.
+"""
+from __future__ import annotations
+
+import math
+from argparse import ArgumentParser
+
+import torch
+
+from .config import SMPL_J_ZERO, SMPL_PARENT, datasets, joint_set
+from .model_utils import default_device, load_model
+from .net import getenv
+from .sharding import gather_rows, shard_sequences
+from .synthetic import synthetic_imu
+
+
+def r6d_to_rotation_matrix(r6d: torch.Tensor) -> torch.Tensor:
+    """articulate/math/angular.py:167-182 (ground-truth conversion at evaluate.py:60; not the hot path)."""
+    v = r6d.reshape(-1, 6)
+    c0 = v[:, :3] / v[:, :3].norm(dim=1, keepdim=True)
+    b = v[:, 3:] - (c0 * v[:, 3:]).sum(dim=1, keepdim=True) * c0
+    c1 = b / b.norm(dim=1, keepdim=True)
+    r = torch.stack((c0, c1, torch.linalg.cross(c0, c1, dim=1)), dim=-1)
+    return torch.nan_to_num(r, nan=0.0)
+
+
+def forward_kinematics(pose_local: torch.Tensor, tran: torch.Tensor = None):
+    """Local rotations [N, 24, 3, 3] -> (global rotations [N, 24, 3, 3], joint positions [N, 24, 3]) for the mean
+    shape (articulate/model.py:208-232 without the mesh)."""
+    n, dev = pose_local.shape[0], pose_local.device
+    j = torch.tensor(SMPL_J_ZERO, dtype=pose_local.dtype, device=dev)
+    bone = j.clone()
+    for i in range(1, 24):
+        bone[i] = j[i] - j[SMPL_PARENT[i]]
+    glb, pos = [pose_local[:, 0]], [bone[0].expand(n, 3)]
+    for i in range(1, 24):
+        p = SMPL_PARENT[i]
+        glb.append(glb[p] @ pose_local[:, i])
+        pos.append(pos[p] + (glb[p] @ bone[i]))
+    glb, pos = torch.stack(glb, dim=1), torch.stack(pos, dim=1)
+    if tran is not None:
+        pos = pos + tran.view(-1, 1, 3)
+    return glb, pos
+
+
+def angle_between(r1: torch.Tensor, r2: torch.Tensor) -> torch.Tensor:
+    """Rotation angle of r1^T r2 in radians (angular.py:86-99), robust near 0 and pi."""
+    d = r1.transpose(-1, -2) @ r2
+    skew = torch.stack((d[..., 2, 1] - d[..., 1, 2], d[..., 0, 2] - d[..., 2, 0], d[..., 1, 0] - d[..., 0, 1]), dim=-1)
+    tr = d[..., 0, 0] + d[..., 1, 1] + d[..., 2, 2]
+    return torch.atan2(skew.norm(dim=-1), tr - 1.0)
+
+
+def full_motion_errors(pose_p, pose_t, tran_p, tran_t, fps=datasets.fps, joint_mask=(2, 5, 16, 20)):
+    """[10, 2] mean/std rows of FullMotionEvaluator.__call__ (evaluator.py:292-343); row 1 (mesh) is NaN."""
+    f = fps
+    gp, jp = forward_kinematics(pose_p, tran_p)
+    gt, jt = forward_kinematics(pose_t, tran_t)
+    off = (jt[:, 0] - jp[:, 0]).unsqueeze(1)
+    je = (jp + off - jt).norm(dim=2)
+    lae = torch.rad2deg(angle_between(pose_p, pose_t))
+    gae = torch.rad2deg(angle_between(gp, gt))
+    jkp = ((jp[3:] - 3 * jp[2:-1] + 3 * jp[1:-2] - jp[:-3]) * (f ** 3)).norm(dim=2)
+    jkt = ((jt[3:] - 3 * jt[2:-1] + 3 * jt[1:-2] - jt[:-3]) * (f ** 3)).norm(dim=2)
+    te = ((jp[f:, :1] - jp[:-f, :1]) - (jt[f:, :1] - jt[:-f, :1])).norm(dim=2) * 100
+    m = list(joint_mask)
+    nan = torch.full((2,), float('nan'), device=pose_p.device)
+
+    def row(x):
+        if x.numel() == 0:
+            return nan
+        return torch.stack((x.mean(), x.std(dim=0).mean() if x.shape[0] > 1 else x.new_zeros(())))
+
+    return torch.stack([row(je), nan, row(lae), row(gae), row(jkp), row(jkt), row(te), row(je[:, m]), row(lae[:, m]),
+                        row(gae[:, m])])
+
+
+class PoseEvaluator:
+    """evaluate.py:16-36."""
+    names = ['SIP Error (deg)', 'Angular Error (deg)', 'Masked Angular Error (deg)', 'Positional Error (cm)',
+             'Masked Positional Error (cm)', 'Mesh Error (cm)', 'Jitter Error (100m/s^3)', 'Distance Error (cm)']
+
+    def eval(self, pose_p, pose_t, joint_p=None, tran_p=None, tran_t=None):
+        pose_p = pose_p.clone().view(-1, 24, 3, 3)
+        pose_t = pose_t.clone().view(-1, 24, 3, 3).to(pose_p.device)
+        tran_p = tran_p.clone().view(-1, 3)
+        tran_t = tran_t.clone().view(-1, 3).to(pose_p.device)
+        eye = torch.eye(3, device=pose_p.device)
+        pose_p[:, joint_set.ignored] = eye
+        pose_t[:, joint_set.ignored] = eye
+        errs = full_motion_errors(pose_p, pose_t, tran_p, tran_t)
+        return torch.stack([errs[9], errs[3], errs[9], errs[0] * 100, errs[7] * 100, errs[1] * 100, errs[4] / 100, errs[6]])
+
+    @classmethod
+    def print(cls, errors):
+        for i, name in enumerate(cls.names):
+            print('%s: %.2f (+/- %.2f)' % (name, errors[i, 0], errors[i, 1]))
+
+
+def synthetic_dip(n_subjects=10, n_seq=5, frames=3000, combo='lw_rp'):
+    """A DIP-shaped synthetic test set: items (imu [T,60], pose r6d [T,144], joint [T,24,3], tran [T,3]) like
+    PoseDataset.__getitem__ in evaluation mode (data.py:96-107).  Ground truth is a smooth random motion; it only
+    gives the metric code something to chew on -- accuracy numbers on it are meaningless."""
+    items = []
+    for k in range(n_subjects * n_seq):
+        g = torch.Generator().manual_seed(50_000 + k)
+        imu = synthetic_imu(10_000 + k, frames, combo)
+        t = torch.arange(frames, dtype=torch.float32).view(-1, 1)
+        phase = torch.rand(144, generator=g) * 6.28
+        eye6 = torch.tensor([1., 0., 0., 0., 1., 0.]).repeat(24)
+        pose = eye6 + 0.2 * torch.sin(t / 40.0 + phase)
+        tran = torch.cumsum(0.01 * torch.sin(t / 60.0 + torch.rand(3, generator=g) * 6.28), dim=0)
+        items.append((imu, pose, torch.zeros(frames, 24, 3), tran))
+    return items
+
+
+@torch.no_grad()
+def evaluate_pose(model, dataset, num_past_frame=20, num_future_frame=5, evaluate_tran=False, verbose=True):
+    """evaluate.py:39-107.  Returns the [n_sequences, 8, 2] offline rows in dataset order (on every rank)."""
+    import torch.distributed as dist
+    device = next(model.parameters()).device
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    items = list(dataset)
+    lengths = [it[0].shape[0] for it in items]
+    mine = shard_sequences(lengths, world)[rank]
+    evaluator = PoseEvaluator()
+    model.eval()
+    rows = []
+    online_rows = []
+    for i in mine:
+        imu, pose_t, _, tran_t = items[i]
+        x = imu.to(device)
+        model.reset()
+        pose_p, _, tran_p, _ = model.forward_offline(x.unsqueeze(0), [x.shape[0]])
+        pose_t = r6d_to_rotation_matrix(pose_t.to(device)).view(-1, 24, 3, 3)
+        rows.append(evaluator.eval(pose_p, pose_t, tran_p=tran_p, tran_t=tran_t))
+        if getenv("ONLINE"):
+            outs = [model.forward_online(f) for f in torch.cat((x, x[-1].repeat(num_future_frame, 1)))]
+            pose_o = torch.stack([o[0] for o in outs])[num_future_frame:]
+            tran_o = torch.stack([o[2] for o in outs])[num_future_frame:]
+            online_rows.append(evaluator.eval(pose_o, pose_t, tran_p=tran_o, tran_t=tran_t))
+    local = torch.stack(rows) if rows else torch.zeros(0, 8, 2, device=device)
+    table = gather_rows(local, mine, len(items))
+    if verbose and rank == 0:
+        print('============== offline ================')
+        PoseEvaluator.print(table.nanmean(dim=0) if table.numel() else table)
+    if getenv("ONLINE"):
+        lo = torch.stack(online_rows) if online_rows else torch.zeros(0, 8, 2, device=device)
+        online = gather_rows(lo, mine, len(items))
+        if verbose and rank == 0:
+            print('============== online ================')
+            PoseEvaluator.print(online.nanmean(dim=0))
+    return table
+
+
+if __name__ == '__main__':
+    parser = ArgumentParser()
+    parser.add_argument('--model', type=str, default=None, help='state_dict .pth; default: seeded random init')
+    parser.add_argument('--dataset', type=str, default='synthetic_dip')
+    parser.add_argument('--frames', type=int, default=3000)
+    args = parser.parse_args()
+    if args.dataset != 'synthetic_dip':
+        raise ValueError(f'Test dataset: {args.dataset} not found.')
+    if args.model:
+        net = load_model(args.model)
+    else:
+        from .net import MobilePoserNet
+        torch.manual_seed(0)
+        net = MobilePoserNet().to(default_device())
+    print(f'Starting evaluation: {args.dataset.capitalize()}')
+    evaluate_pose(net, synthetic_dip(frames=args.frames))

@@ -214,6 +214,29 @@ def main():
     save('batch8_T64', imu=xj, pose=torch.stack(poses), joints=torch.stack(joints),
          tran=torch.stack(trans), contact=torch.stack(contacts))
 
+    # --- K: metric side: SMPL FK and the FullMotionEvaluator rows on a small random motion ---
+    import mobileposer.articulate as art
+    g = torch.Generator().manual_seed(80)
+    n = 40
+    def rand_rot(k):
+        q = torch.randn(k, 4, generator=g)
+        q = q / q.norm(dim=1, keepdim=True)
+        w, x, y, z = q.unbind(1)
+        return torch.stack([1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w),
+                            2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w),
+                            2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)], dim=1).view(k, 3, 3)
+    pose_a = rand_rot(n * 24).view(n, 24, 3, 3)
+    pose_b = rand_rot(n * 24).view(n, 24, 3, 3)
+    tran_a = torch.randn(n, 3, generator=g) * 0.1
+    tran_b = torch.randn(n, 3, generator=g) * 0.1
+    glb_a, joint_a = net.bodymodel.forward_kinematics(pose_a, tran=tran_a)
+    cwd = os.getcwd()
+    os.chdir(os.path.join(REF, 'mobileposer'))
+    ev = art.FullMotionEvaluator(str(RC.paths.smpl_file), joint_mask=torch.tensor([2, 5, 16, 20]), fps=RC.datasets.fps)
+    os.chdir(cwd)
+    errs = ev(pose_a, pose_b, tran_p=tran_a, tran_t=tran_b)
+    save('metrics_unit', pose_a=pose_a, pose_b=pose_b, tran_a=tran_a, tran_b=tran_b, glb_a=glb_a, joint_a=joint_a, errs=errs)
+
     with open(os.path.join(OUT, 'MANIFEST.json'), 'w') as f:
         json.dump(manifest, f, indent=1, sort_keys=True)
     print('manifest written')

@@ -1,0 +1,49 @@
+"""CPU suite: the metric side of evaluate.py (SMPL forward kinematics + FullMotionEvaluator rows) against a fixture
+produced by the reference's own evaluator (oracle/make_golden.py, case K)."""
+import math
+
+import pytest
+import torch
+
+from conftest import load_golden
+from mobileposer_b200.evaluate import (PoseEvaluator, angle_between, forward_kinematics, full_motion_errors,
+                                       r6d_to_rotation_matrix, synthetic_dip)
+
+
+def test_forward_kinematics_matches_reference():
+    g = load_golden('metrics_unit')
+    glb, joint = forward_kinematics(g['pose_a'], g['tran_a'])
+    assert (glb - g['glb_a']).abs().max() < 1e-5
+    assert (joint - g['joint_a']).abs().max() < 1e-5
+    # identity pose -> zero-pose skeleton
+    from mobileposer_b200.config import SMPL_J_ZERO
+    _, j0 = forward_kinematics(torch.eye(3).repeat(1, 24, 1, 1))
+    assert (j0[0] - torch.tensor(SMPL_J_ZERO)).abs().max() < 1e-6
+
+
+def test_full_motion_rows_match_reference_evaluator():
+    g = load_golden('metrics_unit')
+    errs = full_motion_errors(g['pose_a'], g['pose_b'], g['tran_a'], g['tran_b'])
+    ref = g['errs']
+    rows = [0, 2, 3, 4, 5, 6, 7, 8, 9]            # row 1 is the mesh-vertex error (needs the SMPL template)
+    assert torch.isnan(errs[1]).all()
+    rel = ((errs[rows] - ref[rows]).abs() / ref[rows].abs().clamp_min(1e-6)).max().item()
+    assert rel < 2e-4, rel
+
+
+def test_angle_between_and_r6d():
+    a = torch.tensor(0.3)
+    rz = torch.tensor([[math.cos(a), -math.sin(a), 0.], [math.sin(a), math.cos(a), 0.], [0., 0., 1.]])
+    assert abs(angle_between(torch.eye(3)[None], rz[None]).item() - 0.3) < 1e-6
+    r = r6d_to_rotation_matrix(torch.tensor([[1., 0., 0., 0., 2., 0.]]))
+    assert torch.allclose(r[0], torch.eye(3))
+
+
+def test_pose_evaluator_rows_and_synthetic_set():
+    items = synthetic_dip(n_subjects=1, n_seq=2, frames=64)
+    assert len(items) == 2 and items[0][0].shape == (64, 60) and items[0][1].shape == (64, 144)
+    pose_t = r6d_to_rotation_matrix(items[0][1]).view(-1, 24, 3, 3)
+    rows = PoseEvaluator().eval(pose_t, items[0][1].new_tensor(pose_t), tran_p=items[0][3], tran_t=items[0][3])
+    assert rows.shape == (8, 2)
+    ok = [0, 1, 2, 3, 4, 7]
+    assert rows[ok, 0].abs().max() < 1e-3          # identical motions -> zero errors (mesh row NaN)
