@@ -100,13 +100,14 @@ __device__ __forceinline__ f32x2 ffma2(f32x2 a, float b, f32x2 c) {
 //   hbuf   [2][C][NB][UC]  h_t of every sequence of the tile, double buffered by step parity; the slice
 //                          written by source CTA `src` is contiguous so it travels as ONE bulk copy
 //   hstage [2][NB][UC]     this CTA's new slice, source of the bulk copies
-//   cbuf   [NB][UC]        cell state of the owned units
+//   cbuf   [2][UC][NB]     cell state of the owned units, double buffered by step parity (no read/write hazard
+//                          inside a step, so the sequence-group loop has no warp barrier and can be unrolled)
 //   lens   [NB] int, goff [NB] uint32 (element offset of sequence b in gin), yoff [NB] uint32 (same for y)
 //   bars   [2] uint64      mbarriers, one per hbuf parity
 template <int H, int C>
 __host__ __device__ inline size_t rec_smem_bytes(int NB) {
-    return sizeof(float) * ((size_t)2 * NB * H + (size_t)2 * NB * RecCfg<H, C>::UC + (size_t)NB * RecCfg<H, C>::UC) +
-           sizeof(int) * 3 * NB + 2 * sizeof(unsigned long long) + 16;
+    return sizeof(float) * ((size_t)2 * NB * H + (size_t)2 * NB * RecCfg<H, C>::UC + (size_t)2 * NB * RecCfg<H, C>::UC) +
+           sizeof(int) * 4 * NB + 2 * sizeof(unsigned long long) + 16;
 }
 
 // sigmoid(x) (k = 1) or tanh(x) (k = 2) from ONE exponential, branch free:  E = exp(-k x),
@@ -144,12 +145,13 @@ __global__ void __launch_bounds__(RecCfg<H, C>::THREADS, 1) lstm_rec_kernel(cons
     const int SRC = NB * UC;                  // floats in one source CTA's slice of hbuf
     float* hbuf = reinterpret_cast<float*>(smem_raw);
     float* hstage = hbuf + (size_t)2 * NB * H;
-    float* cbuf = hstage + (size_t)2 * NB * UC;          // [UC][NB]
-    int* lens = reinterpret_cast<int*>(cbuf + (size_t)NB * UC);
+    float* cbuf = hstage + (size_t)2 * NB * UC;          // [2][UC][NB]
+    int* lens = reinterpret_cast<int*>(cbuf + (size_t)2 * NB * UC);
     uint32_t* goff = reinterpret_cast<uint32_t*>(lens + NB);
     uint32_t* yoff = goff + NB;
+    int* glen = reinterpret_cast<int*>(yoff + NB);       // [NB/4] longest sequence of each group of 4
     unsigned long long* bars =
-        reinterpret_cast<unsigned long long*>((reinterpret_cast<uintptr_t>(yoff + NB) + 15) & ~uintptr_t(15));
+        reinterpret_cast<unsigned long long*>((reinterpret_cast<uintptr_t>(glen + NB) + 15) & ~uintptr_t(15));
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int rank = (C > 1) ? (int)cluster_ctarank() : 0;
@@ -204,6 +206,15 @@ __global__ void __launch_bounds__(RecCfg<H, C>::THREADS, 1) lstm_rec_kernel(cons
         const int u = i / NB, b = i - u * NB;
         cbuf[i] = (p.c0 && b < nb) ? p.c0[((size_t)dir * p.B + b_begin + b) * H + rank * UC + u] : 0.f;
     }
+    for (int i = tid; i < NB / 4; i += THREADS) {
+        int m = 0;
+        for (int q = 0; q < 4; ++q) {
+            const int b = i * 4 + q;
+            const int l = (b < nb) ? (p.lengths ? min(max(p.lengths[b_begin + b], 0), p.T) : p.T) : 0;
+            m = max(m, l);
+        }
+        glen[i] = m;
+    }
     const uint32_t bar0 = smem_u32(&bars[0]), bar1 = bar0 + 8;
     if (C > 1 && tid == 0) {
         mbar_init(bar0, 1);
@@ -227,6 +238,8 @@ __global__ void __launch_bounds__(RecCfg<H, C>::THREADS, 1) lstm_rec_kernel(cons
     // one step ahead on the latency path, one sequence group ahead on the throughput path
     float gi_next = 0.f;
     const int len0 = lens[0];
+    float c_reg = cbuf[u_local];              // latency path: the unit's cell state stays in a register
+    int g_hi = ((nb + 3) / 4) * 4;            // throughput path: sequences [0, g_hi) may still be active
     if constexpr (BG == 1) {
         if (len0 > 0) gi_next = __ldg(p.gin + ((size_t)b_begin * p.T + (dir ? len0 - 1 : 0)) * G4 + gcol);
     } else {
@@ -240,13 +253,7 @@ __global__ void __launch_bounds__(RecCfg<H, C>::THREADS, 1) lstm_rec_kernel(cons
         if constexpr (C > 1) {
             if (s > 0) mbar_wait(par ? bar1 : bar0, ((s - 1) >> 1) & 1);
             if (tid == 0 && send) {
-                int nsend = nb;
-                if (BG == 4 && !p.bulk) {
-                    nsend = 0;
-                    for (int i = 0; i < nb; ++i) nsend += (lens[i] > s);
-                } else if (BG == 4) {
-                    nsend = NB;
-                }
+                const int nsend = (BG == 4) ? NB : nb;     // throughput path: whole staged slices travel
                 mbar_arrive_expect_tx(par ? bar0 : bar1, (uint32_t)nsend * H * sizeof(float));
             }
         }
@@ -282,8 +289,8 @@ __global__ void __launch_bounds__(RecCfg<H, C>::THREADS, 1) lstm_rec_kernel(cons
             tot += __shfl_xor_sync(0xffffffffu, tot, 2);
             tot += __shfl_xor_sync(0xffffffffu, tot, 1);
             float c_new, h_new;
-            lstm_cell(tot + gi, gate, lane, cbuf[u_local], c_new, h_new);
-            __syncwarp();
+            lstm_cell(tot + gi, gate, lane, c_reg, c_new, h_new);
+            c_reg = c_new;
             if (send) {
                 if constexpr (C == 1) {
                     if ((lane & 15) == 0) hnext[unit] = h_new;
@@ -294,7 +301,6 @@ __global__ void __launch_bounds__(RecCfg<H, C>::THREADS, 1) lstm_rec_kernel(cons
                 }
             }
             if ((lane & 15) == 0) {
-                cbuf[u_local] = c_new;
                 p.y[((size_t)b_begin * p.T + t) * Y2 + dir * H + unit] = h_new;
                 if (s == len0 - 1) {
                     if (p.hn) p.hn[((size_t)dir * p.B + b_begin) * H + unit] = h_new;
@@ -302,24 +308,28 @@ __global__ void __launch_bounds__(RecCfg<H, C>::THREADS, 1) lstm_rec_kernel(cons
                 }
             }
         } else {
-            // ---------------- throughput path: groups of 4 sequences; after the reduce lane q owns sequence g0+q
-            for (int g0 = 0; g0 < nb; g0 += 4) {
+            // ---------------- throughput path: groups of 4 sequences; after the reduce lane q owns sequence g0+q.
+            // The body is straight-line (stores are predicated, the cell state is double buffered) so that two
+            // groups can be unrolled together and the scheduler overlaps the reduce / activation latency chain of
+            // one with the FFMA2 stream of the other -- with 4 warps per scheduler the kernel is latency bound
+            // otherwise (ncu: issue slots 53 % busy, FMA pipe 50 %).
+            while (g_hi > 0 && glen[g_hi / 4 - 1] <= s) g_hi -= 4;     // trailing groups that have finished
+            const float* ccur = cbuf + (size_t)par * NB * UC;
+            float* cnxt = cbuf + (size_t)(par ^ 1) * NB * UC;
+#pragma unroll 2
+            for (int g0 = 0; g0 < g_hi; g0 += 4) {
                 const int b = g0 + qn;
                 const int len = lens[b];
                 const bool active = s < len;
                 const int t = dir ? len - 1 - s : s;
                 const float gi = gi_next;
                 {   // prefetch the gate pre-activation of the NEXT group (or of group 0 of the next step)
-                    const bool wrap = (g0 + 4 >= nb);
+                    const bool wrap = (g0 + 4 >= g_hi);
                     const int bn = wrap ? qn : b + 4;
                     const int sn = wrap ? s + 1 : s;
                     const int ln = lens[bn];
                     if (sn < ln) gi_next = __ldg(p.gin + (goff[bn] + (uint32_t)(dir ? ln - 1 - sn : sn) * (uint32_t)G4 + (uint32_t)gcol_l));
                 }
-                int glen = 0;
-#pragma unroll
-                for (int q = 0; q < 4; ++q) glen = max(glen, lens[g0 + q]);   // lens[>=nb] == 0, NB % 4 == 0
-                if (s >= glen) continue;
                 f32x2 acc2[R / 2 * 4];
 #pragma unroll
                 for (int a = 0; a < R / 2 * 4; ++a) acc2[a] = 0ull;
@@ -349,38 +359,26 @@ __global__ void __launch_bounds__(RecCfg<H, C>::THREADS, 1) lstm_rec_kernel(cons
                 // (row, sequence) -> lane bits: lane = unit_in_warp*16 + gate*4 + q
                 const float tot = reduce_scatter<R * 4>(acc, KQ / 2);
                 float c_new, h_new;
-                lstm_cell(tot + gi, gate, lane, cbuf[u_local * NB + b], c_new, h_new);
-                __syncwarp();
-                if (active) {
-                    if (gate == 0) {
-                        cbuf[u_local * NB + b] = c_new;
-                        p.y[yoff[b] + (uint32_t)t * (uint32_t)Y2 + (uint32_t)unit] = h_new;
-                        if (s == len - 1) {
-                            if (p.hn) p.hn[((size_t)dir * p.B + b_begin + b) * H + unit] = h_new;
-                            if (p.cn) p.cn[((size_t)dir * p.B + b_begin + b) * H + unit] = c_new;
-                        }
-                    }
+                lstm_cell(tot + gi, gate, lane, ccur[u_local * NB + b], c_new, h_new);
+                const bool owner = active && gate == 0;
+                if (owner) {
+                    cnxt[u_local * NB + b] = c_new;
+                    p.y[yoff[b] + (uint32_t)t * (uint32_t)Y2 + (uint32_t)unit] = h_new;
                     if (send) {
-                        if constexpr (C == 1) {
-                            if (gate == 0) hnext[b * UC + u_local] = h_new;
-                        } else {
-                            if (!p.bulk) {
-                                // the 4 gate lanes of (unit, sequence) hold h_new; gate lane g feeds CTAs g, g+4, ..
-                                for (int r = gate; r < C; r += 4)
-                                    st_async_f32(mapa_u32(smem_u32(hnext + rank * SRC + b * UC + u_local), r), h_new,
-                                                 mapa_u32(par ? bar0 : bar1, r));
-                            } else if (gate == 0) {
-                                hst[b * UC + u_local] = h_new;
-                            }
-                        }
+                        if constexpr (C == 1) hnext[b * UC + u_local] = h_new;
+                        else hst[b * UC + u_local] = h_new;
                     }
+                }
+                if (owner && s == len - 1) {
+                    if (p.hn) p.hn[((size_t)dir * p.B + b_begin + b) * H + unit] = h_new;
+                    if (p.cn) p.cn[((size_t)dir * p.B + b_begin + b) * H + unit] = c_new;
                 }
             }
         }
 
         if constexpr (C == 1) {
             __syncthreads();
-        } else if (BG == 4 && p.bulk && send) {
+        } else if (BG == 4 && send) {
             // staged slice -> every CTA of the cluster: ONE contiguous NB*UC*4-byte bulk copy per destination
             fence_proxy_async_smem();
             __syncthreads();

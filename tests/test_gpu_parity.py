@@ -222,7 +222,7 @@ def test_batch_equals_independent_reference_calls(net, oracle):
     dict(MP_REC_IMPL='simple'),                          # debug kernel
     dict(MP_REC_NB=1, MP_REC_SEND='bulk'),               # latency path with bulk sends
     dict(MP_REC_NB=4),                                   # throughput path, bulk sends
-    dict(MP_REC_NB=4, MP_REC_SEND='stasync'),            # throughput path, st.async sends
+    dict(MP_REC_NB=12),                                  # odd number of sequence groups (unroll remainder)
     dict(MP_REC_NB=8),
     dict(MP_REC_NB=3),                                   # latency path, several sequences per cluster
 ])
