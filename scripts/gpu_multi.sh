@@ -1,0 +1,6 @@
+# N-GPU check of bench.py exactly as the driver launches it (torchrun, NCCL), plus the reference arm under torchrun.
+set -x
+mkdir -p gpurun_out
+N=${1:-2}
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 10 --warmup 3 > gpurun_out/bench_n$N.json 2> gpurun_out/bench_n$N.err; echo "bench n=$N exit $?"; cat gpurun_out/bench_n$N.json | cut -c1-400; tail -5 gpurun_out/bench_n$N.err
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 bench.py --impl reference --gpus $N --steps 3 --warmup 1 > gpurun_out/bench_ref_n$N.json 2> gpurun_out/bench_ref_n$N.err; echo "ref n=$N exit $?"; cat gpurun_out/bench_ref_n$N.json | cut -c1-300
