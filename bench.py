@@ -202,7 +202,7 @@ def run_reference(args):
         'e2e': {'value': fps, 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(json.dumps(line))
 
 
 def workload_name(w, B):
@@ -369,7 +369,7 @@ def run_ours(args):
             'kernels': kernels, 'cpu_baseline': cpu, 'batch1': batch1, 'streaming': streaming, 'clocks': clocks.summary(),
             'all_gather_shape': gathered,
         }
-        print(json.dumps(line), flush=True)
+        emit(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
 
@@ -418,9 +418,39 @@ def load_traffic(kernel):
         return None
 
 
+class StdoutGuard:
+    """The driver wants ONE JSON line on stdout; NCCL / torchrun children chat there too (e.g. 'NCCL version ...').
+    Route everything written to fd 1 to stderr for the duration of the run and keep the real stdout for the line."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.real = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def emit(self, line):
+        os.write(self.real, (line + '\n').encode())
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.real, 1)
+        os.close(self.real)
+
+
+OUT = None
+
+
+def emit(line):
+    if OUT is not None:
+        OUT.emit(line)
+    else:
+        print(line, flush=True)
+
+
 if __name__ == '__main__':
     a = parse_args()
-    if a.impl == 'reference':
-        run_reference(a)
-    else:
-        run_ours(a)
+    with StdoutGuard() as OUT:
+        if a.impl == 'reference':
+            run_reference(a)
+        else:
+            run_ours(a)
