@@ -73,6 +73,7 @@ struct mp_rnn {
     float* bsum[2] = {nullptr, nullptr};   // [dirs*4H]         b_ih + b_hh
     float4* whh_pack[2] = {nullptr, nullptr};
     float* whh_t[2] = {nullptr, nullptr};
+    float* whh_raw[2] = {nullptr, nullptr};  // [dirs][4H, H] torch layout
 };
 
 struct mp_net {
@@ -162,12 +163,13 @@ int mp_rnn_create(mp_rnn_t** out, const mp_rnn_weights_t* w, mp_stream_t stream_
     auto take = [&](size_t floats) { size_t o = off; off = align_up(off + floats * sizeof(float)); return o; };
     const size_t o_w1 = take((size_t)H * r->n_in), o_b1 = take(H);
     const size_t o_w2 = take((size_t)r->n_out * dirs * H), o_b2 = take(r->n_out);
-    size_t o_wih[2], o_bs[2], o_pk[2], o_wt[2];
+    size_t o_wih[2], o_bs[2], o_pk[2], o_wt[2], o_raw[2];
     for (int l = 0; l < 2; ++l) {
         o_wih[l] = take((size_t)dirs * 4 * H * in_l[l]);
         o_bs[l] = take((size_t)dirs * 4 * H);
         o_pk[l] = take(whh_pack_float4s(H, dirs) * 4);
         o_wt[l] = take((size_t)dirs * 4 * H * H);
+        o_raw[l] = take((size_t)dirs * 4 * H * H);
     }
     cudaError_t e = cudaMalloc(&r->blob, off);
     if (e != cudaSuccess) {
@@ -194,6 +196,8 @@ int mp_rnn_create(mp_rnn_t** out, const mp_rnn_weights_t* w, mp_stream_t stream_
         r->bsum[l] = (float*)(base + o_bs[l]);
         r->whh_pack[l] = (float4*)(base + o_pk[l]);
         r->whh_t[l] = (float*)(base + o_wt[l]);
+        r->whh_raw[l] = (float*)(base + o_raw[l]);
+        for (int d = 0; d < dirs; ++d) copy(r->whh_raw[l] + (size_t)d * 4 * H * H, w->w_hh[l][d], (size_t)4 * H * H);
         const float* whh[2] = {w->w_hh[l][0], w->w_hh[l][dirs - 1]};
         for (int d = 0; d < dirs; ++d) {
             permute_wih_kernel<<<296, 256, 0, stream>>>(w->w_ih[l][d], r->wih[l] + (size_t)d * 4 * H * in_l[l], H, in_l[l]);
@@ -267,6 +271,7 @@ static int rnn_forward_impl(const mp_rnn_t* r, const float* xa, int32_t ka, cons
         MP_TRY(launch_gemm_bias_act(layer_in, in_w, nullptr, 0, r->wih[l], r->bsum[l], gin, (int)M, dirs * 4 * H, 0, stream));
         RecLayerArgs a;
         a.gin = gin; a.wpack = r->whh_pack[l]; a.wT = r->whh_t[l]; a.y = ybuf[l];
+        a.w_raw[0] = r->whh_raw[l]; a.w_raw[1] = r->whh_raw[l] + (size_t)(dirs - 1) * 4 * H * H;
         const size_t so = (size_t)l * dirs * B * H;
         a.h0 = h0 ? h0 + so : nullptr; a.c0 = c0 ? c0 + so : nullptr;
         a.hn = hn ? hn + so : nullptr; a.cn = cn ? cn + so : nullptr;

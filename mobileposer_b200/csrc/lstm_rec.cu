@@ -648,6 +648,7 @@ int launch_lstm_recurrence(const RecLayerArgs& a, cudaStream_t stream) {
         count_launch();
         return MP_OK;
     }
+    if (rec_tc_eligible(a)) return launch_lstm_recurrence_tc(a, stream);
     if (a.H == 256) return rec_cluster_size(256) == 16 ? launch_for<256, 16>(a, stream) : launch_for<256, 8>(a, stream);
     if (a.H == 64) return launch_for<64, 1>(a, stream);
     set_error("lstm: hidden size %d not built (64, 256)", a.H);

@@ -1,0 +1,433 @@
+// Tensor-core LSTM recurrence (H = 256, throughput path): the per-step product  G[4H/C x NB] = W_hh_slice . h^T
+// runs on tcgen05 with fp32-grade accuracy (3xTF32), W_hh resident in TENSOR MEMORY for the whole sequence.
+//
+// Same contract as lstm_rec_kernel<256, 8, 4> (lstm_rec.cu): one launch walks all T steps of one LSTM layer for a
+// tile of NB sequences per 8-CTA cluster; CTA `rank` owns hidden units [32 rank, 32 rank + 32) = 128 gate rows.
+// What changes is where the FLOPs go.  The FFMA kernel is bound by issue slots (reduce-scatter + activations
+// around every 256 FMAs); here the 128 x N x 256 product of a step is 96 UMMA instructions issued by one thread:
+//
+//   operands     A = W_hh slice [128 rows (row m = unit_local*4 + gate) x K = 256], split once at kernel start into
+//                    hi = w & 0xFFFFE000 and lo = rn_tf32(w - hi):
+//                      W_hi  -> TMEM columns [0, 256)            (lane = row, column = k; tcgen05.st)
+//                      W_lo  -> TMEM columns [384, 512) for k < 128, shared memory (K-major, 128B swizzle) for k >= 128
+//                B = h_t [N sequences x K = 256] as hi / lo, K-major 128B-swizzled in shared memory; K-block `r`
+//                    (32 floats) of every row is exactly the slice produced by cluster rank r, so a rank pushes its
+//                    new slice to a peer with ONE cp.async.bulk per array
+//                D = two fp32 accumulators in TMEM: main (W_hi h_hi) columns [256, 256+N), correction
+//                    (W_lo h_hi + W_hi h_lo) columns [256+N, 256+2N)
+//   per step     MMA warp: wait h_t complete -> 96 x tcgen05.mma.kind::tf32 (A from TMEM or smem) -> tcgen05.commit
+//                16 epilogue warps: wait commit -> tcgen05.ld both accumulators -> + gate pre-activation (gin) ->
+//                    sigmoid/tanh -> i/f/g/o gather by shuffle (the 4 gates of a unit are adjacent TMEM lanes) ->
+//                    cell update (c in registers) -> y store, hi/lo of h_{t+1} into the staging slice ->
+//                    bulk copies to all 8 CTAs (transaction bytes on their `h_full` mbarrier)
+//   h is single buffered: a rank may overwrite a peer's h only after that peer's MMAs of the step have finished, which
+//   every CTA announces with a remote mbarrier arrive on all peers' `h_free` barrier right after its commit lands.
+#include "mp_common.cuh"
+
+#include <cstdlib>
+#include <cstring>
+
+namespace mp {
+
+namespace {
+
+constexpr int TH = 256;
+constexpr int TCC = 8;            // cluster size
+constexpr int TUC = TH / TCC;     // 32 units per CTA
+constexpr int EPI_WARPS = 16;
+constexpr int RTC_THREADS = (EPI_WARPS + 1) * 32;
+constexpr uint32_t COL_WHI = 0, COL_D = 256, COL_WLO = 384;
+constexpr int WLO_TMEM_K = 128;                       // k < 128 of W_lo lives in TMEM
+constexpr uint32_t WLO_S_BYTES = (TH - WLO_TMEM_K) / 32 * 128 * 128;   // 4 K-blocks x 128 rows x 128 B = 64 KiB
+
+struct RecTcParams {
+    const float* gin;
+    const float* w0;      // raw torch W_hh [4H, H] of direction 0 / 1
+    const float* w1;
+    float* y;
+    const float* h0;
+    const float* c0;
+    float* hn;
+    float* cn;
+    const int32_t* lengths;
+    int B, T, dirs, NB;
+};
+
+__host__ __device__ inline size_t rec_tc_smem_bytes(int N) {
+    // W_lo half | H_hi | H_lo | staging [2 parity][2 arrays] | tables | barriers
+    return 1024 + WLO_S_BYTES + (size_t)2 * 8 * N * 128 + (size_t)4 * N * 128 + (size_t)3 * N * 4 + 64;
+}
+
+__device__ __forceinline__ uint32_t tf32_hi(float x) { return __float_as_uint(x) & 0xFFFFE000u; }
+__device__ __forceinline__ uint32_t tf32_lo(float x, uint32_t hi) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x - __uint_as_float(hi)));
+    return r;
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem desc]
+__device__ __forceinline__ void umma_ts(uint32_t d, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d),
+        "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc]
+__device__ __forceinline__ void umma_ss(uint32_t d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+// K-major operand, 128-byte rows, SWIZZLE_128B: 8-row groups 1024 B apart
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// byte offset of float `k32` (0..31) of row `row` inside one [rows x 128 B] K-block with the 128B swizzle
+__device__ __forceinline__ uint32_t sw128_off(int row, int k32) {
+    return (uint32_t)row * 128u + (uint32_t)((((k32 >> 2) ^ (row & 7)) << 4) | ((k32 & 3) << 2));
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+        "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+        "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]),
+        "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]),
+        "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, float* v) {
+    uint32_t a, b, c, d;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(taddr) : "memory");
+    v[0] = __uint_as_float(a); v[1] = __uint_as_float(b); v[2] = __uint_as_float(c); v[3] = __uint_as_float(d);
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t remote_bar) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote_bar) : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
+__device__ __forceinline__ float act_sigmoid_or_tanh(float x, bool is_tanh) {
+    const float s = fminf(fmaxf(is_tanh ? 2.0f * x : x, -30.0f), 30.0f);
+    const float e = expf(-s);
+    const float r = __frcp_rn(1.0f + e);
+    return is_tanh ? (1.0f - e) * r : r;
+}
+
+// N = padded sequence count of the tile (multiple of 16, <= 64); SPW = N / 4 sequences per epilogue warp
+template <int N>
+__global__ void __launch_bounds__(RTC_THREADS, 1) lstm_rec_tc_kernel(const RecTcParams p) {
+    constexpr int SPW = N / 4;
+    constexpr uint32_t HBYTES = 8u * N * 128u;            // one h array: 8 K-blocks x N rows x 128 B
+    constexpr uint32_t SLICE = (uint32_t)N * 128u;        // one K-block = one rank's slice
+    static_assert(N % 16 == 0 && N <= 64 && COL_D + 2 * N <= COL_WLO, "tile");
+
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    unsigned char* gen = smem_raw + (base - smem_u32(smem_raw));
+    const uint32_t s_wlo = base, s_hhi = s_wlo + WLO_S_BYTES, s_hlo = s_hhi + HBYTES, s_stg = s_hlo + HBYTES;
+    unsigned char* g_wlo = gen;
+    unsigned char* g_hhi = g_wlo + WLO_S_BYTES;
+    unsigned char* g_hlo = g_hhi + HBYTES;
+    unsigned char* g_stg = g_hlo + HBYTES;                // [par][arr][N rows][128 B]
+    int* lens = reinterpret_cast<int*>(g_stg + 4 * SLICE);
+    uint32_t* goff = reinterpret_cast<uint32_t*>(lens + N);
+    uint32_t* yoff = goff + N;
+    const uint32_t s_bars = s_stg + 4 * SLICE + 3 * N * 4;
+    const uint32_t bar_full = (s_bars + 7u) & ~7u, bar_mma = bar_full + 8, bar_free = bar_full + 16, tmem_slot = bar_full + 24;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int rank = (int)cluster_ctarank();
+    const int tile = blockIdx.x / TCC, dir = blockIdx.y;
+    const int NB = p.NB;
+    const int b_begin = tile * NB;
+    const int nb = min(NB, p.B - b_begin);
+    const int G4 = p.dirs * 4 * TH, Y2 = p.dirs * TH;
+
+    if (tid == 0) {
+        mbar_init(bar_full, 1);
+        mbar_init(bar_mma, 1);
+        mbar_init(bar_free, TCC);
+        mbar_fence_init_cluster();
+    }
+    if (warp == EPI_WARPS) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    for (int i = tid; i < N; i += RTC_THREADS) {
+        lens[i] = (i < nb) ? (p.lengths ? min(max(p.lengths[b_begin + i], 0), p.T) : p.T) : 0;
+        goff[i] = (uint32_t)(b_begin + min(i, nb - 1)) * (uint32_t)p.T * (uint32_t)G4 + (uint32_t)(dir * 4 * TH + rank * TUC * 4);
+        yoff[i] = (uint32_t)(b_begin + min(i, nb - 1)) * (uint32_t)p.T * (uint32_t)Y2 + (uint32_t)(dir * TH + rank * TUC);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(gen + (tmem_slot - base));
+
+    // epilogue-thread coordinates: TMEM lane quarter, row m = unit_local*4 + gate, column (sequence) part
+    const int lq = warp & 3, part = (warp >> 2) & 3;
+    const int m = lq * 32 + lane, ul = m >> 2, gate = m & 3;
+    const uint32_t lane_base = (uint32_t)(lq * 32) << 16;
+
+    // ---- W_hh slice -> TMEM / shared memory as TF32 hi + lo (once) ---------------------------------------------
+    if (warp < EPI_WARPS) {
+        const float* wrow = (dir ? p.w1 : p.w0) + (size_t)(gate * TH + rank * TUC + ul) * TH;
+        for (int kc = part; kc < TH / 32; kc += 4) {
+            const int k0 = kc * 32;
+            uint32_t hi[32], lo[32];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float4 v = __ldg(reinterpret_cast<const float4*>(wrow + k0) + i);
+                hi[4 * i + 0] = tf32_hi(v.x); lo[4 * i + 0] = tf32_lo(v.x, hi[4 * i + 0]);
+                hi[4 * i + 1] = tf32_hi(v.y); lo[4 * i + 1] = tf32_lo(v.y, hi[4 * i + 1]);
+                hi[4 * i + 2] = tf32_hi(v.z); lo[4 * i + 2] = tf32_lo(v.z, hi[4 * i + 2]);
+                hi[4 * i + 3] = tf32_hi(v.w); lo[4 * i + 3] = tf32_lo(v.w, hi[4 * i + 3]);
+            }
+            tmem_st32(tmem + lane_base + COL_WHI + k0, hi);
+            if (k0 < WLO_TMEM_K) {
+                tmem_st32(tmem + lane_base + COL_WLO + k0, lo);
+            } else {
+                unsigned char* blk = g_wlo + (size_t)((k0 - WLO_TMEM_K) / 32) * (128 * 128);
+#pragma unroll
+                for (int c = 0; c < 8; ++c)
+                    *reinterpret_cast<uint4*>(blk + sw128_off(m, c * 4)) = make_uint4(lo[4 * c], lo[4 * c + 1], lo[4 * c + 2], lo[4 * c + 3]);
+            }
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
+    // ---- h_0 (hi / lo) for the whole tile, zeros in the padded rows ---------------------------------------------
+    for (int i = tid; i < N * (TH / 4); i += RTC_THREADS) {
+        const int n = i / (TH / 4), ch = i % (TH / 4);       // float4 chunk ch covers k = 4 ch .. 4 ch + 3
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.h0 && n < nb) v = __ldg(reinterpret_cast<const float4*>(p.h0 + ((size_t)dir * p.B + b_begin + n) * TH) + ch);
+        const uint32_t off = (uint32_t)(ch >> 3) * SLICE + sw128_off(n, (ch & 7) * 4);
+        uint4 h, l;
+        h.x = tf32_hi(v.x); h.y = tf32_hi(v.y); h.z = tf32_hi(v.z); h.w = tf32_hi(v.w);
+        l.x = tf32_lo(v.x, h.x); l.y = tf32_lo(v.y, h.y); l.z = tf32_lo(v.z, h.z); l.w = tf32_lo(v.w, h.w);
+        *reinterpret_cast<uint4*>(g_hhi + off) = h;
+        *reinterpret_cast<uint4*>(g_hlo + off) = l;
+    }
+    // cell state of this thread's (unit, sequences): every one of the 4 gate lanes of a unit keeps a copy
+    float cst[SPW];
+#pragma unroll
+    for (int j = 0; j < SPW; ++j) {
+        const int n = part * SPW + j;
+        cst[j] = (warp < EPI_WARPS && p.c0 && n < nb) ? p.c0[((size_t)dir * p.B + b_begin + n) * TH + rank * TUC + ul] : 0.f;
+    }
+    int maxlen = 0;
+    for (int i = 0; i < nb; ++i) maxlen = max(maxlen, lens[i]);
+
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+
+    // gate pre-activations of step 0 (gin columns are (unit, gate)-ordered: a warp reads 128 contiguous bytes)
+    float gi[SPW];
+#pragma unroll
+    for (int j = 0; j < SPW; ++j) {
+        const int n = part * SPW + j;
+        const int l = lens[n];
+        gi[j] = (warp < EPI_WARPS && l > 0) ? __ldg(p.gin + (goff[n] + (uint32_t)(dir ? l - 1 : 0) * (uint32_t)G4 + (uint32_t)(ul * 4 + gate))) : 0.f;
+    }
+
+    constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const uint32_t d_main = tmem + COL_D, d_corr = tmem + COL_D + N;
+
+    for (int s = 0; s < maxlen; ++s) {
+        const bool send = (s + 1 < maxlen);
+        const int par = s & 1;
+        if (warp == EPI_WARPS) {
+            // ================= MMA issuer =================
+            if (lane == 0) {
+                if (s > 0) mbar_wait(bar_full, (s - 1) & 1);
+                tc_fence_after();
+#pragma unroll 1
+                for (int ks = 0; ks < TH / 8; ++ks) {          // correction: W_lo . h_hi
+                    const uint64_t b = umma_desc_sw128(s_hhi + (ks >> 2) * SLICE + (ks & 3) * 32);
+                    if (ks < WLO_TMEM_K / 8) umma_ts(d_corr, tmem + COL_WLO + ks * 8, b, idesc, ks != 0);
+                    else umma_ss(d_corr, umma_desc_sw128(s_wlo + ((ks - WLO_TMEM_K / 8) >> 2) * (128 * 128) + (ks & 3) * 32), b, idesc, 1u);
+                }
+#pragma unroll 1
+                for (int ks = 0; ks < TH / 8; ++ks)            // correction: W_hi . h_lo
+                    umma_ts(d_corr, tmem + COL_WHI + ks * 8, umma_desc_sw128(s_hlo + (ks >> 2) * SLICE + (ks & 3) * 32), idesc, 1u);
+#pragma unroll 1
+                for (int ks = 0; ks < TH / 8; ++ks)            // main: W_hi . h_hi
+                    umma_ts(d_main, tmem + COL_WHI + ks * 8, umma_desc_sw128(s_hhi + (ks >> 2) * SLICE + (ks & 3) * 32), idesc, ks != 0);
+                tc_commit(bar_mma);
+            }
+            __syncwarp();
+        } else {
+            // ================= epilogue =================
+            if (tid == 0 && send) mbar_arrive_expect_tx(bar_full, 2u * TCC * SLICE);     // h_{s+1}: 8 ranks x (hi, lo)
+            mbar_wait(bar_mma, par);
+            tc_fence_after();
+            if (send && tid < TCC) mbar_arrive_remote(mapa_u32(bar_free, tid));          // my MMAs no longer read my h
+            float dm[SPW], dc[SPW];
+#pragma unroll
+            for (int q = 0; q < SPW / 4; ++q) {
+                tmem_ld4(d_main + lane_base + part * SPW + q * 4, dm + 4 * q);
+                tmem_ld4(d_corr + lane_base + part * SPW + q * 4, dc + 4 * q);
+            }
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            unsigned char* stg_hi = g_stg + (size_t)(par * 2 + 0) * SLICE;
+            unsigned char* stg_lo = g_stg + (size_t)(par * 2 + 1) * SLICE;
+#pragma unroll
+            for (int j = 0; j < SPW; ++j) {
+                const int n = part * SPW + j;
+                const int len = lens[n];
+                const bool active = s < len;
+                const int t = dir ? len - 1 - s : s;
+                const float pre = (dm[j] + dc[j]) + gi[j];
+                const float act = act_sigmoid_or_tanh(pre, gate == 2);
+                const int q0 = lane & ~3;
+                const float iv = __shfl_sync(0xffffffffu, act, q0);
+                const float fv = __shfl_sync(0xffffffffu, act, q0 | 1);
+                const float gv = __shfl_sync(0xffffffffu, act, q0 | 2);
+                const float ov = __shfl_sync(0xffffffffu, act, q0 | 3);
+                const float c_new = fmaf(fv, cst[j], iv * gv);
+                const float h_new = ov * act_sigmoid_or_tanh(c_new, true);
+                if (active) cst[j] = c_new;
+                // next step's gate pre-activation
+                if (s + 1 < len) gi[j] = __ldg(p.gin + (goff[n] + (uint32_t)(dir ? t - 1 : t + 1) * (uint32_t)G4 + (uint32_t)(ul * 4 + gate)));
+                if (gate == 0) {
+                    if (active) {
+                        p.y[yoff[n] + (uint32_t)t * (uint32_t)Y2 + (uint32_t)ul] = h_new;
+                        if (s == len - 1) {
+                            if (p.hn) p.hn[((size_t)dir * p.B + b_begin + n) * TH + rank * TUC + ul] = h_new;
+                            if (p.cn) p.cn[((size_t)dir * p.B + b_begin + n) * TH + rank * TUC + ul] = c_new;
+                        }
+                    }
+                    if (send) {
+                        const float hv = active ? h_new : 0.f;
+                        const uint32_t hh = tf32_hi(hv);
+                        const uint32_t off = sw128_off(n, ul);
+                        *reinterpret_cast<uint32_t*>(stg_hi + off) = hh;
+                        *reinterpret_cast<uint32_t*>(stg_lo + off) = tf32_lo(hv, hh);
+                    }
+                }
+            }
+            if (send) {
+                fence_proxy_async_smem();
+                named_bar_sync(1, EPI_WARPS * 32);
+                if (tid < 2 * TCC) {
+                    // every peer has finished the MMAs that read its h: the slices may land
+                    mbar_wait(bar_free, par);
+                    const int r = tid >> 1, arr = tid & 1;
+                    const uint32_t dst = (arr ? s_hlo : s_hhi) + (uint32_t)rank * SLICE;
+                    bulk_copy_s2c(mapa_u32(dst, r), s_stg + (uint32_t)(par * 2 + arr) * SLICE, SLICE, mapa_u32(bar_full, r));
+                }
+            }
+        }
+    }
+
+    // frames >= len of the layer output are zero (pad_packed_sequence, rnn.py:31)
+    for (int b = 0; b < nb; ++b) {
+        const int len = lens[b];
+        const int cnt = (p.T - len) * TUC;
+        for (int i = tid; i < cnt; i += RTC_THREADS) {
+            const int t = len + i / TUC, u = i % TUC;
+            p.y[yoff[b] + (uint32_t)t * (uint32_t)Y2 + (uint32_t)u] = 0.f;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == EPI_WARPS) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+}
+
+template <int N>
+int launch_tc_n(const RecTcParams& p, cudaStream_t stream) {
+    const size_t smem = rec_tc_smem_bytes(N);
+    auto kern = lstm_rec_tc_kernel<N>;
+    static bool configured = false;
+    if (!configured) {
+        MP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    const int n_tiles = (p.B + p.NB - 1) / p.NB;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(TCC * n_tiles, p.dirs, 1);
+    cfg.blockDim = dim3(RTC_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = TCC;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    MP_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, p));
+    count_launch();
+    return MP_OK;
+}
+
+int tc_cluster_slots() {
+    static int slots = 0;
+    if (slots > 0) return slots;
+    int n = 0;
+    auto kern = lstm_rec_tc_kernel<48>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rec_tc_smem_bytes(48));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(TCC * 64, 1, 1);
+    cfg.blockDim = dim3(RTC_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = rec_tc_smem_bytes(48);
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = TCC;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) {
+        cudaGetLastError();
+        n = 0;
+    }
+    slots = n > 0 ? n : 8;
+    return slots;
+}
+
+}  // namespace
+
+// Tensor-core recurrence for H = 256 when the batch is large enough to fill 16-wide MMA tiles.
+bool rec_tc_eligible(const RecLayerArgs& a) {
+    const char* v = getenv("MP_REC_IMPL");
+    if (v && (strcmp(v, "ffma") == 0 || strcmp(v, "simple") == 0)) return false;
+    if (a.H != TH || !a.w_raw[0]) return false;
+    const bool forced = v && strcmp(v, "tc") == 0;
+    return forced || a.B * a.dirs > 2 * tc_cluster_slots();
+}
+
+int launch_lstm_recurrence_tc(const RecLayerArgs& a, cudaStream_t stream) {
+    MP_REQUIRE((double)a.B * a.T * a.dirs * 4 * a.H < 4.0e9, "lstm_tc: B*T = %lld frames exceeds 32-bit gate buffer indexing", (long long)a.B * a.T);
+    const char* nbv = getenv("MP_REC_NB");
+    int NB = (nbv && *nbv) ? atoi(nbv) : 0;
+    if (NB <= 0) {
+        const int per = std::max(1, tc_cluster_slots() / a.dirs);
+        NB = (a.B + per - 1) / per;
+    }
+    NB = std::min(64, std::max(1, NB));
+    const int N = ((NB + 15) / 16) * 16;
+    // balance the tiles: same tile count, equal sizes
+    const int n_tiles = (a.B + NB - 1) / NB;
+    NB = (a.B + n_tiles - 1) / n_tiles;
+    RecTcParams p{a.gin, a.w_raw[0], a.w_raw[a.dirs - 1], a.y, a.h0, a.c0, a.hn, a.cn, a.lengths, a.B, a.T, a.dirs, NB};
+    ProfileScope prof("lstm_rec_tc_h256", 4.0 * ((double)a.dirs * 4 * a.H * a.H + (double)a.B * a.T * a.dirs * a.H), stream);
+    switch (N) {
+        case 16: return launch_tc_n<16>(p, stream);
+        case 32: return launch_tc_n<32>(p, stream);
+        case 48: return launch_tc_n<48>(p, stream);
+        default: return launch_tc_n<64>(p, stream);
+    }
+}
+
+}  // namespace mp

@@ -63,6 +63,7 @@ struct RecLayerArgs {
     const float* gin;     // [B, T, dirs*4H]  input projection + both biases
     const float4* wpack;  // packed W_hh for this layer (all dirs), see pack_whh
     const float* wT;      // [dirs][H][4H] transposed W_hh (debug kernel)
+    const float* w_raw[2];  // per direction: W_hh [4H, H] in torch layout (tensor-core kernel splits it itself)
     float* y;             // [B, T, dirs*H]
     const float* h0;      // [dirs, B, H] or null
     const float* c0;
@@ -72,6 +73,9 @@ struct RecLayerArgs {
     int B, T, H, dirs;
 };
 int launch_lstm_recurrence(const RecLayerArgs& a, cudaStream_t stream);
+// tcgen05 3xTF32 variant for H = 256 and large batches (lstm_rec_tc.cu)
+bool rec_tc_eligible(const RecLayerArgs& a);
+int launch_lstm_recurrence_tc(const RecLayerArgs& a, cudaStream_t stream);
 // number of float4 in the packed recurrent weights of one layer
 size_t whh_pack_float4s(int H, int dirs);
 // pack W_hh[dirs][4H,H] (device, torch layout) into the register-resident layout + transpose

@@ -225,6 +225,9 @@ def test_batch_equals_independent_reference_calls(net, oracle):
     dict(MP_REC_NB=12),                                  # odd number of sequence groups (unroll remainder)
     dict(MP_REC_NB=8),
     dict(MP_REC_NB=3),                                   # latency path, several sequences per cluster
+    dict(MP_REC_IMPL='tc'),                              # tcgen05 recurrence, several small tiles (N = 16)
+    dict(MP_REC_IMPL='tc', MP_REC_NB=11),                # tcgen05 recurrence, one ragged tile
+    dict(MP_REC_IMPL='ffma', MP_REC_NB=8),               # FFMA throughput path pinned
 ])
 def test_recurrence_variants_against_oracle(net, oracle, env, variant):
     from mobileposer_b200.synthetic import synthetic_imu_batch
