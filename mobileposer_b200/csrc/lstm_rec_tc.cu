@@ -51,6 +51,7 @@ struct RecTcParams {
     float* cn;
     const int32_t* lengths;
     int B, T, dirs, NB;
+    int dbg;   // MP_RTC_DBG bit mask (bring-up only): 1 skip MMAs, 2 skip W_lo-from-smem MMAs, 4 skip corrections
 };
 
 __host__ __device__ inline size_t rec_tc_smem_bytes(int N) {
@@ -170,6 +171,9 @@ __global__ void __launch_bounds__(RTC_THREADS, 1) lstm_rec_tc_kernel(const RecTc
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(gen + (tmem_slot - base));
+    bool bail = (p.dbg & 8) != 0;                        // bring-up checkpoints (MP_RTC_DBG): 8 after alloc,
+                                                         // 16 skip the TMEM weight stores, 32 exit before the time loop,
+                                                         // 64 skip the epilogue's TMEM loads, 128 skip the h exchange
 
     // epilogue-thread coordinates: TMEM lane quarter, row m = unit_local*4 + gate, column (sequence) part
     const int lq = warp & 3, part = (warp >> 2) & 3;
@@ -177,7 +181,7 @@ __global__ void __launch_bounds__(RTC_THREADS, 1) lstm_rec_tc_kernel(const RecTc
     const uint32_t lane_base = (uint32_t)(lq * 32) << 16;
 
     // ---- W_hh slice -> TMEM / shared memory as TF32 hi + lo (once) ---------------------------------------------
-    if (warp < EPI_WARPS) {
+    if (warp < EPI_WARPS && !bail) {
         const float* wrow = (dir ? p.w1 : p.w0) + (size_t)(gate * TH + rank * TUC + ul) * TH;
         for (int kc = part; kc < TH / 32; kc += 4) {
             const int k0 = kc * 32;
@@ -190,9 +194,9 @@ __global__ void __launch_bounds__(RTC_THREADS, 1) lstm_rec_tc_kernel(const RecTc
                 hi[4 * i + 2] = tf32_hi(v.z); lo[4 * i + 2] = tf32_lo(v.z, hi[4 * i + 2]);
                 hi[4 * i + 3] = tf32_hi(v.w); lo[4 * i + 3] = tf32_lo(v.w, hi[4 * i + 3]);
             }
-            tmem_st32(tmem + lane_base + COL_WHI + k0, hi);
+            if (!(p.dbg & 16)) tmem_st32(tmem + lane_base + COL_WHI + k0, hi);
             if (k0 < WLO_TMEM_K) {
-                tmem_st32(tmem + lane_base + COL_WLO + k0, lo);
+                if (!(p.dbg & 16)) tmem_st32(tmem + lane_base + COL_WLO + k0, lo);
             } else {
                 unsigned char* blk = g_wlo + (size_t)((k0 - WLO_TMEM_K) / 32) * (128 * 128);
 #pragma unroll
@@ -242,40 +246,51 @@ __global__ void __launch_bounds__(RTC_THREADS, 1) lstm_rec_tc_kernel(const RecTc
     constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     const uint32_t d_main = tmem + COL_D, d_corr = tmem + COL_D + N;
 
+    if (p.dbg & (8 | 32)) maxlen = 0;
+    const bool xchg = !(p.dbg & 128);
+    const bool do_free = !(p.dbg & 256), do_copy = !(p.dbg & 512);   // bring-up: isolate the handshake / the bulk copies
     for (int s = 0; s < maxlen; ++s) {
-        const bool send = (s + 1 < maxlen);
+        const bool send = xchg && (s + 1 < maxlen);
         const int par = s & 1;
         if (warp == EPI_WARPS) {
             // ================= MMA issuer =================
             if (lane == 0) {
-                if (s > 0) mbar_wait(bar_full, (s - 1) & 1);
+                if (s > 0 && xchg && do_copy && !(p.dbg & 4096)) mbar_wait(bar_full, (s - 1) & 1);
                 tc_fence_after();
+                if (!(p.dbg & 1)) {
 #pragma unroll 1
-                for (int ks = 0; ks < TH / 8; ++ks) {          // correction: W_lo . h_hi
+                for (int ks = 0; ks < ((p.dbg & 4) ? 0 : TH / 8); ++ks) {          // correction: W_lo . h_hi
                     const uint64_t b = umma_desc_sw128(s_hhi + (ks >> 2) * SLICE + (ks & 3) * 32);
                     if (ks < WLO_TMEM_K / 8) umma_ts(d_corr, tmem + COL_WLO + ks * 8, b, idesc, ks != 0);
-                    else umma_ss(d_corr, umma_desc_sw128(s_wlo + ((ks - WLO_TMEM_K / 8) >> 2) * (128 * 128) + (ks & 3) * 32), b, idesc, 1u);
+                    else if (!(p.dbg & 2)) umma_ss(d_corr, umma_desc_sw128(s_wlo + ((ks - WLO_TMEM_K / 8) >> 2) * (128 * 128) + (ks & 3) * 32), b, idesc, 1u);
                 }
 #pragma unroll 1
-                for (int ks = 0; ks < TH / 8; ++ks)            // correction: W_hi . h_lo
+                for (int ks = 0; ks < ((p.dbg & 4) ? 0 : TH / 8); ++ks)            // correction: W_hi . h_lo
                     umma_ts(d_corr, tmem + COL_WHI + ks * 8, umma_desc_sw128(s_hlo + (ks >> 2) * SLICE + (ks & 3) * 32), idesc, 1u);
 #pragma unroll 1
                 for (int ks = 0; ks < TH / 8; ++ks)            // main: W_hi . h_hi
                     umma_ts(d_main, tmem + COL_WHI + ks * 8, umma_desc_sw128(s_hhi + (ks >> 2) * SLICE + (ks & 3) * 32), idesc, ks != 0);
+                }
                 tc_commit(bar_mma);
             }
             __syncwarp();
         } else {
             // ================= epilogue =================
-            if (tid == 0 && send) mbar_arrive_expect_tx(bar_full, 2u * TCC * SLICE);     // h_{s+1}: 8 ranks x (hi, lo)
             mbar_wait(bar_mma, par);
             tc_fence_after();
-            if (send && tid < TCC) mbar_arrive_remote(mapa_u32(bar_free, tid));          // my MMAs no longer read my h
+            // h_{s+1} will arrive as 8 ranks x (hi, lo) slices.  Armed only now: MMA(s) has run, so the MMA thread has seen
+            // the previous phase of `bar_full` complete -- arming earlier could put two arrivals into one phase.
+            if (tid == 0 && send && do_copy) mbar_arrive_expect_tx(bar_full, (p.dbg & 1024) ? 2u * SLICE : 2u * TCC * SLICE);
+            if (send && do_free && tid < TCC) mbar_arrive_remote(mapa_u32(bar_free, tid));          // my MMAs no longer read my h
             float dm[SPW], dc[SPW];
 #pragma unroll
             for (int q = 0; q < SPW / 4; ++q) {
-                tmem_ld4(d_main + lane_base + part * SPW + q * 4, dm + 4 * q);
-                tmem_ld4(d_corr + lane_base + part * SPW + q * 4, dc + 4 * q);
+                if (p.dbg & 64) {
+                    for (int e = 0; e < 4; ++e) dm[4 * q + e] = dc[4 * q + e] = 0.f;
+                } else {
+                    tmem_ld4(d_main + lane_base + part * SPW + q * 4, dm + 4 * q);
+                    tmem_ld4(d_corr + lane_base + part * SPW + q * 4, dc + 4 * q);
+                }
             }
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             unsigned char* stg_hi = g_stg + (size_t)(par * 2 + 0) * SLICE;
@@ -320,10 +335,11 @@ __global__ void __launch_bounds__(RTC_THREADS, 1) lstm_rec_tc_kernel(const RecTc
                 named_bar_sync(1, EPI_WARPS * 32);
                 if (tid < 2 * TCC) {
                     // every peer has finished the MMAs that read its h: the slices may land
-                    mbar_wait(bar_free, par);
+                    if (do_free) mbar_wait(bar_free, par);
                     const int r = tid >> 1, arr = tid & 1;
-                    const uint32_t dst = (arr ? s_hlo : s_hhi) + (uint32_t)rank * SLICE;
-                    bulk_copy_s2c(mapa_u32(dst, r), s_stg + (uint32_t)(par * 2 + arr) * SLICE, SLICE, mapa_u32(bar_full, r));
+                    uint32_t dst = (arr ? s_hlo : s_hhi) + (uint32_t)rank * SLICE;
+                    if (p.dbg & 2048) dst = s_wlo + (uint32_t)(arr * TCC + rank) * SLICE;      // bring-up: harmless destination
+                    if (do_copy && (!(p.dbg & 1024) || r == rank)) bulk_copy_s2c(mapa_u32(dst, r), s_stg + (uint32_t)(par * 2 + arr) * SLICE, SLICE, mapa_u32(bar_full, r));
                 }
             }
         }
@@ -420,7 +436,9 @@ int launch_lstm_recurrence_tc(const RecLayerArgs& a, cudaStream_t stream) {
     // balance the tiles: same tile count, equal sizes
     const int n_tiles = (a.B + NB - 1) / NB;
     NB = (a.B + n_tiles - 1) / n_tiles;
-    RecTcParams p{a.gin, a.w_raw[0], a.w_raw[a.dirs - 1], a.y, a.h0, a.c0, a.hn, a.cn, a.lengths, a.B, a.T, a.dirs, NB};
+    const char* dbgv = getenv("MP_RTC_DBG");
+    RecTcParams p{a.gin, a.w_raw[0], a.w_raw[a.dirs - 1], a.y, a.h0, a.c0, a.hn, a.cn, a.lengths, a.B, a.T, a.dirs, NB,
+                  (dbgv && *dbgv) ? atoi(dbgv) : 0};
     ProfileScope prof("lstm_rec_tc_h256", 4.0 * ((double)a.dirs * 4 * a.H * a.H + (double)a.B * a.T * a.dirs * a.H), stream);
     switch (N) {
         case 16: return launch_tc_n<16>(p, stream);
