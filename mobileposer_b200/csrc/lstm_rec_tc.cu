@@ -51,7 +51,7 @@ struct RecTcParams {
     float* cn;
     const int32_t* lengths;
     int B, T, dirs, NB;
-    int dbg;   // MP_RTC_DBG bit mask (bring-up only): 1 skip MMAs, 2 skip W_lo-from-smem MMAs, 4 skip corrections
+    long long* ts;   // bring-up: per-step clock64 stamps of block (0,0) [step][8], or null (MP_RTC_TS)
 };
 
 __host__ __device__ inline size_t rec_tc_smem_bytes(int N) {
@@ -122,6 +122,11 @@ __device__ __forceinline__ float act_sigmoid_or_tanh(float x, bool is_tanh) {
     return is_tanh ? (1.0f - e) * r : r;
 }
 
+#define RTC_STAMP(slot)                                                                                  \
+    do {                                                                                                  \
+        if (p.ts && blockIdx.x == 0 && blockIdx.y == 0 && s < 64) p.ts[s * 8 + (slot)] = clock64();       \
+    } while (0)
+
 // N = padded sequence count of the tile (multiple of 16, <= 64); SPW = N / 4 sequences per epilogue warp
 template <int N>
 __global__ void __launch_bounds__(RTC_THREADS, 1) lstm_rec_tc_kernel(const RecTcParams p) {
@@ -171,9 +176,6 @@ __global__ void __launch_bounds__(RTC_THREADS, 1) lstm_rec_tc_kernel(const RecTc
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(gen + (tmem_slot - base));
-    bool bail = (p.dbg & 8) != 0;                        // bring-up checkpoints (MP_RTC_DBG): 8 after alloc,
-                                                         // 16 skip the TMEM weight stores, 32 exit before the time loop,
-                                                         // 64 skip the epilogue's TMEM loads, 128 skip the h exchange
 
     // epilogue-thread coordinates: TMEM lane quarter, row m = unit_local*4 + gate, column (sequence) part
     const int lq = warp & 3, part = (warp >> 2) & 3;
@@ -181,7 +183,7 @@ __global__ void __launch_bounds__(RTC_THREADS, 1) lstm_rec_tc_kernel(const RecTc
     const uint32_t lane_base = (uint32_t)(lq * 32) << 16;
 
     // ---- W_hh slice -> TMEM / shared memory as TF32 hi + lo (once) ---------------------------------------------
-    if (warp < EPI_WARPS && !bail) {
+    if (warp < EPI_WARPS) {
         const float* wrow = (dir ? p.w1 : p.w0) + (size_t)(gate * TH + rank * TUC + ul) * TH;
         for (int kc = part; kc < TH / 32; kc += 4) {
             const int k0 = kc * 32;
@@ -194,9 +196,9 @@ __global__ void __launch_bounds__(RTC_THREADS, 1) lstm_rec_tc_kernel(const RecTc
                 hi[4 * i + 2] = tf32_hi(v.z); lo[4 * i + 2] = tf32_lo(v.z, hi[4 * i + 2]);
                 hi[4 * i + 3] = tf32_hi(v.w); lo[4 * i + 3] = tf32_lo(v.w, hi[4 * i + 3]);
             }
-            if (!(p.dbg & 16)) tmem_st32(tmem + lane_base + COL_WHI + k0, hi);
+            tmem_st32(tmem + lane_base + COL_WHI + k0, hi);
             if (k0 < WLO_TMEM_K) {
-                if (!(p.dbg & 16)) tmem_st32(tmem + lane_base + COL_WLO + k0, lo);
+                tmem_st32(tmem + lane_base + COL_WLO + k0, lo);
             } else {
                 unsigned char* blk = g_wlo + (size_t)((k0 - WLO_TMEM_K) / 32) * (128 * 128);
 #pragma unroll
@@ -219,11 +221,12 @@ __global__ void __launch_bounds__(RTC_THREADS, 1) lstm_rec_tc_kernel(const RecTc
         *reinterpret_cast<uint4*>(g_hlo + off) = l;
     }
     // cell state of this thread's (unit, sequences): every one of the 4 gate lanes of a unit keeps a copy
-    float cst[SPW];
+    // cell state: lane `gate` of a unit's quad owns sequence 4*blk + gate of every block of 4 sequences
+    float cst[SPW / 4];
 #pragma unroll
-    for (int j = 0; j < SPW; ++j) {
-        const int n = part * SPW + j;
-        cst[j] = (warp < EPI_WARPS && p.c0 && n < nb) ? p.c0[((size_t)dir * p.B + b_begin + n) * TH + rank * TUC + ul] : 0.f;
+    for (int blk = 0; blk < SPW / 4; ++blk) {
+        const int n = blk * 16 + part * 4 + gate;
+        cst[blk] = (warp < EPI_WARPS && p.c0 && n < nb) ? p.c0[((size_t)dir * p.B + b_begin + n) * TH + rank * TUC + ul] : 0.f;
     }
     int maxlen = 0;
     for (int i = 0; i < nb; ++i) maxlen = max(maxlen, lens[i]);
@@ -238,7 +241,7 @@ __global__ void __launch_bounds__(RTC_THREADS, 1) lstm_rec_tc_kernel(const RecTc
     float gi[SPW];
 #pragma unroll
     for (int j = 0; j < SPW; ++j) {
-        const int n = part * SPW + j;
+        const int n = (j >> 2) * 16 + part * 4 + (j & 3);      // block j/4 of 16 sequences, this warp's 4 columns in it
         const int l = lens[n];
         gi[j] = (warp < EPI_WARPS && l > 0) ? __ldg(p.gin + (goff[n] + (uint32_t)(dir ? l - 1 : 0) * (uint32_t)G4 + (uint32_t)(ul * 4 + gate))) : 0.f;
     }
@@ -246,31 +249,36 @@ __global__ void __launch_bounds__(RTC_THREADS, 1) lstm_rec_tc_kernel(const RecTc
     constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     const uint32_t d_main = tmem + COL_D, d_corr = tmem + COL_D + N;
 
-    if (p.dbg & (8 | 32)) maxlen = 0;
-    const bool xchg = !(p.dbg & 128);
-    const bool do_free = !(p.dbg & 256), do_copy = !(p.dbg & 512);   // bring-up: isolate the handshake / the bulk copies
     for (int s = 0; s < maxlen; ++s) {
-        const bool send = xchg && (s + 1 < maxlen);
+        const bool send = (s + 1 < maxlen);
         const int par = s & 1;
         if (warp == EPI_WARPS) {
             // ================= MMA issuer =================
             if (lane == 0) {
-                if (s > 0 && xchg && do_copy && !(p.dbg & 4096)) mbar_wait(bar_full, (s - 1) & 1);
+                if (s > 0) mbar_wait(bar_full, (s - 1) & 1);
                 tc_fence_after();
-                if (!(p.dbg & 1)) {
-#pragma unroll 1
-                for (int ks = 0; ks < ((p.dbg & 4) ? 0 : TH / 8); ++ks) {          // correction: W_lo . h_hi
-                    const uint64_t b = umma_desc_sw128(s_hhi + (ks >> 2) * SLICE + (ks & 3) * 32);
-                    if (ks < WLO_TMEM_K / 8) umma_ts(d_corr, tmem + COL_WLO + ks * 8, b, idesc, ks != 0);
-                    else if (!(p.dbg & 2)) umma_ss(d_corr, umma_desc_sw128(s_wlo + ((ks - WLO_TMEM_K / 8) >> 2) * (128 * 128) + (ks & 3) * 32), b, idesc, 1u);
+                RTC_STAMP(0);
+                {
+                    // descriptors advance by compile-time constants (fully unrolled): one 64-bit add per operand, so the
+                    // single issuing thread spends ~5 instructions per UMMA instead of rebuilding descriptors
+                    const uint64_t bd_hi = umma_desc_sw128(s_hhi), bd_lo = umma_desc_sw128(s_hlo), ad_wlo = umma_desc_sw128(s_wlo);
+                    {
+#pragma unroll
+                        for (int ks = 0; ks < TH / 8; ++ks) {          // correction: W_lo . h_hi
+                            const uint64_t b = bd_hi + (uint64_t)(((ks >> 2) * SLICE + (ks & 3) * 32) >> 4);
+                            if (ks < WLO_TMEM_K / 8) umma_ts(d_corr, tmem + COL_WLO + ks * 8, b, idesc, ks != 0);
+                            else
+                                umma_ss(d_corr, ad_wlo + (uint64_t)((((ks - WLO_TMEM_K / 8) >> 2) * (128 * 128) + (ks & 3) * 32) >> 4), b, idesc, 1u);
+                        }
+#pragma unroll
+                        for (int ks = 0; ks < TH / 8; ++ks)            // correction: W_hi . h_lo
+                            umma_ts(d_corr, tmem + COL_WHI + ks * 8, bd_lo + (uint64_t)(((ks >> 2) * SLICE + (ks & 3) * 32) >> 4), idesc, 1u);
+                    }
+#pragma unroll
+                    for (int ks = 0; ks < TH / 8; ++ks)                // main: W_hi . h_hi
+                        umma_ts(d_main, tmem + COL_WHI + ks * 8, bd_hi + (uint64_t)(((ks >> 2) * SLICE + (ks & 3) * 32) >> 4), idesc, ks != 0);
                 }
-#pragma unroll 1
-                for (int ks = 0; ks < ((p.dbg & 4) ? 0 : TH / 8); ++ks)            // correction: W_hi . h_lo
-                    umma_ts(d_corr, tmem + COL_WHI + ks * 8, umma_desc_sw128(s_hlo + (ks >> 2) * SLICE + (ks & 3) * 32), idesc, 1u);
-#pragma unroll 1
-                for (int ks = 0; ks < TH / 8; ++ks)            // main: W_hi . h_hi
-                    umma_ts(d_main, tmem + COL_WHI + ks * 8, umma_desc_sw128(s_hhi + (ks >> 2) * SLICE + (ks & 3) * 32), idesc, ks != 0);
-                }
+                RTC_STAMP(1);
                 tc_commit(bar_mma);
             }
             __syncwarp();
@@ -280,68 +288,88 @@ __global__ void __launch_bounds__(RTC_THREADS, 1) lstm_rec_tc_kernel(const RecTc
             tc_fence_after();
             // h_{s+1} will arrive as 8 ranks x (hi, lo) slices.  Armed only now: MMA(s) has run, so the MMA thread has seen
             // the previous phase of `bar_full` complete -- arming earlier could put two arrivals into one phase.
-            if (tid == 0 && send && do_copy) mbar_arrive_expect_tx(bar_full, (p.dbg & 1024) ? 2u * SLICE : 2u * TCC * SLICE);
-            if (send && do_free && tid < TCC) mbar_arrive_remote(mapa_u32(bar_free, tid));          // my MMAs no longer read my h
+            if (tid == 0 && send) mbar_arrive_expect_tx(bar_full, 2u * TCC * SLICE);
+            if (tid == 0) RTC_STAMP(2);
+            if (send && tid < TCC) mbar_arrive_remote(mapa_u32(bar_free, tid));          // my MMAs no longer read my h
             float dm[SPW], dc[SPW];
 #pragma unroll
             for (int q = 0; q < SPW / 4; ++q) {
-                if (p.dbg & 64) {
-                    for (int e = 0; e < 4; ++e) dm[4 * q + e] = dc[4 * q + e] = 0.f;
-                } else {
-                    tmem_ld4(d_main + lane_base + part * SPW + q * 4, dm + 4 * q);
-                    tmem_ld4(d_corr + lane_base + part * SPW + q * 4, dc + 4 * q);
-                }
+                tmem_ld4(d_main + lane_base + q * 16 + part * 4, dm + 4 * q);
+                tmem_ld4(d_corr + lane_base + q * 16 + part * 4, dc + 4 * q);
             }
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (tid == 0) RTC_STAMP(3);
             unsigned char* stg_hi = g_stg + (size_t)(par * 2 + 0) * SLICE;
             unsigned char* stg_lo = g_stg + (size_t)(par * 2 + 1) * SLICE;
+            // Blocks of 4 sequences: every lane evaluates its gate for the 4 sequences, the quad (4 gate lanes of a unit)
+            // exchanges them, and lane g then owns sequence 4*blk + g: ONE cell update per lane instead of four redundant ones.
 #pragma unroll
-            for (int j = 0; j < SPW; ++j) {
-                const int n = part * SPW + j;
+            for (int blk = 0; blk < SPW / 4; ++blk) {
+                float a[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int j = blk * 4 + q;
+                    a[q] = act_sigmoid_or_tanh((dm[j] + dc[j]) + gi[j], gate == 2);
+                }
+                const int q0 = lane & ~3;
+                float iv = 0.f, fv = 0.f, gv = 0.f, ov = 0.f;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float i_q = __shfl_sync(0xffffffffu, a[q], q0);
+                    const float f_q = __shfl_sync(0xffffffffu, a[q], q0 | 1);
+                    const float g_q = __shfl_sync(0xffffffffu, a[q], q0 | 2);
+                    const float o_q = __shfl_sync(0xffffffffu, a[q], q0 | 3);
+                    if (q == gate) { iv = i_q; fv = f_q; gv = g_q; ov = o_q; }
+                }
+                // this lane's sequence of the block
+                const int n = blk * 16 + part * 4 + gate;
                 const int len = lens[n];
                 const bool active = s < len;
                 const int t = dir ? len - 1 - s : s;
-                const float pre = (dm[j] + dc[j]) + gi[j];
-                const float act = act_sigmoid_or_tanh(pre, gate == 2);
-                const int q0 = lane & ~3;
-                const float iv = __shfl_sync(0xffffffffu, act, q0);
-                const float fv = __shfl_sync(0xffffffffu, act, q0 | 1);
-                const float gv = __shfl_sync(0xffffffffu, act, q0 | 2);
-                const float ov = __shfl_sync(0xffffffffu, act, q0 | 3);
-                const float c_new = fmaf(fv, cst[j], iv * gv);
+                const float c_new = fmaf(fv, cst[blk], iv * gv);
                 const float h_new = ov * act_sigmoid_or_tanh(c_new, true);
-                if (active) cst[j] = c_new;
-                // next step's gate pre-activation
-                if (s + 1 < len) gi[j] = __ldg(p.gin + (goff[n] + (uint32_t)(dir ? t - 1 : t + 1) * (uint32_t)G4 + (uint32_t)(ul * 4 + gate)));
-                if (gate == 0) {
-                    if (active) {
-                        p.y[yoff[n] + (uint32_t)t * (uint32_t)Y2 + (uint32_t)ul] = h_new;
-                        if (s == len - 1) {
-                            if (p.hn) p.hn[((size_t)dir * p.B + b_begin + n) * TH + rank * TUC + ul] = h_new;
-                            if (p.cn) p.cn[((size_t)dir * p.B + b_begin + n) * TH + rank * TUC + ul] = c_new;
+                if (active) {
+                    cst[blk] = c_new;
+                    p.y[yoff[n] + (uint32_t)t * (uint32_t)Y2 + (uint32_t)ul] = h_new;
+                    if (s == len - 1) {
+                        if (p.hn) p.hn[((size_t)dir * p.B + b_begin + n) * TH + rank * TUC + ul] = h_new;
+                        if (p.cn) p.cn[((size_t)dir * p.B + b_begin + n) * TH + rank * TUC + ul] = c_new;
+                    }
+                }
+                if (send) {
+                    const float hv = active ? h_new : 0.f;
+                    const uint32_t hh = tf32_hi(hv);
+                    const uint32_t off = sw128_off(n, ul);
+                    *reinterpret_cast<uint32_t*>(stg_hi + off) = hh;
+                    *reinterpret_cast<uint32_t*>(stg_lo + off) = tf32_lo(hv, hh);
+                }
+                // next step's gate pre-activations of the block (this lane's gate, all 4 sequences)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int nq = blk * 16 + part * 4 + q;
+                    const int lq2 = lens[nq];
+                    if (s + 1 < lq2)
+                        gi[blk * 4 + q] = __ldg(p.gin + (goff[nq] + (uint32_t)(dir ? lq2 - 2 - s : s + 1) * (uint32_t)G4 + (uint32_t)(ul * 4 + gate)));
+                }
+                // rows [16 blk, 16 blk + 16) of the new slice are complete: ship them now, so the exchange of this block
+                // overlaps the activation work of the next one (only the last block's transfer is exposed)
+                if (send) {
+                    fence_proxy_async_smem();
+                    named_bar_sync(1, EPI_WARPS * 32);
+                    if (tid < 2 * TCC) {
+                        if (blk == 0) {
+                            if (tid == 0) RTC_STAMP(5);
+                            mbar_wait(bar_free, par);      // every peer has finished the MMAs that read its h
+                            if (tid == 0) RTC_STAMP(6);
                         }
-                    }
-                    if (send) {
-                        const float hv = active ? h_new : 0.f;
-                        const uint32_t hh = tf32_hi(hv);
-                        const uint32_t off = sw128_off(n, ul);
-                        *reinterpret_cast<uint32_t*>(stg_hi + off) = hh;
-                        *reinterpret_cast<uint32_t*>(stg_lo + off) = tf32_lo(hv, hh);
+                        const int r = tid >> 1, arr = tid & 1;
+                        const uint32_t chunk = 16u * 128u;
+                        bulk_copy_s2c(mapa_u32((arr ? s_hlo : s_hhi) + (uint32_t)rank * SLICE + blk * chunk, r),
+                                      s_stg + (uint32_t)(par * 2 + arr) * SLICE + blk * chunk, chunk, mapa_u32(bar_full, r));
                     }
                 }
             }
-            if (send) {
-                fence_proxy_async_smem();
-                named_bar_sync(1, EPI_WARPS * 32);
-                if (tid < 2 * TCC) {
-                    // every peer has finished the MMAs that read its h: the slices may land
-                    if (do_free) mbar_wait(bar_free, par);
-                    const int r = tid >> 1, arr = tid & 1;
-                    uint32_t dst = (arr ? s_hlo : s_hhi) + (uint32_t)rank * SLICE;
-                    if (p.dbg & 2048) dst = s_wlo + (uint32_t)(arr * TCC + rank) * SLICE;      // bring-up: harmless destination
-                    if (do_copy && (!(p.dbg & 1024) || r == rank)) bulk_copy_s2c(mapa_u32(dst, r), s_stg + (uint32_t)(par * 2 + arr) * SLICE, SLICE, mapa_u32(bar_full, r));
-                }
-            }
+            if (tid == 0) RTC_STAMP(4);
         }
     }
 
@@ -436,16 +464,33 @@ int launch_lstm_recurrence_tc(const RecLayerArgs& a, cudaStream_t stream) {
     // balance the tiles: same tile count, equal sizes
     const int n_tiles = (a.B + NB - 1) / NB;
     NB = (a.B + n_tiles - 1) / n_tiles;
-    const char* dbgv = getenv("MP_RTC_DBG");
-    RecTcParams p{a.gin, a.w_raw[0], a.w_raw[a.dirs - 1], a.y, a.h0, a.c0, a.hn, a.cn, a.lengths, a.B, a.T, a.dirs, NB,
-                  (dbgv && *dbgv) ? atoi(dbgv) : 0};
-    ProfileScope prof("lstm_rec_tc_h256", 4.0 * ((double)a.dirs * 4 * a.H * a.H + (double)a.B * a.T * a.dirs * a.H), stream);
-    switch (N) {
-        case 16: return launch_tc_n<16>(p, stream);
-        case 32: return launch_tc_n<32>(p, stream);
-        case 48: return launch_tc_n<48>(p, stream);
-        default: return launch_tc_n<64>(p, stream);
+    static long long* ts_dev = nullptr;
+    const bool want_ts = getenv("MP_RTC_TS") != nullptr;
+    if (want_ts && !ts_dev) {
+        cudaMalloc(&ts_dev, 64 * 8 * sizeof(long long));
+        cudaMemset(ts_dev, 0, 64 * 8 * sizeof(long long));
     }
+    RecTcParams p{a.gin, a.w_raw[0], a.w_raw[a.dirs - 1], a.y, a.h0, a.c0, a.hn, a.cn, a.lengths, a.B, a.T, a.dirs, NB,
+                  want_ts ? ts_dev : nullptr};
+    ProfileScope prof("lstm_rec_tc_h256", 4.0 * ((double)a.dirs * 4 * a.H * a.H + (double)a.B * a.T * a.dirs * a.H), stream);
+    int st;
+    switch (N) {
+        case 16: st = launch_tc_n<16>(p, stream); break;
+        case 32: st = launch_tc_n<32>(p, stream); break;
+        case 48: st = launch_tc_n<48>(p, stream); break;
+        default: st = launch_tc_n<64>(p, stream); break;
+    }
+    if (st == MP_OK && want_ts) {      // bring-up only: synchronous dump of the stamps of block (0,0)
+        long long h[64 * 8];
+        cudaStreamSynchronize(stream);
+        cudaMemcpy(h, ts_dev, sizeof(h), cudaMemcpyDeviceToHost);
+        fprintf(stderr, "[rtc ts] N=%d NB=%d B=%d\n", N, NB, a.B);
+        for (int s = 2; s < 8 && s < a.T - 1; ++s)
+            fprintf(stderr, "[rtc ts] s=%d  mma issue %lld | commit->epi %lld  tmem ld %lld  block0 %lld  free-wait %lld  blocks1.. %lld  tail->next mma %lld  step %lld\n", s,
+                    h[s * 8 + 1] - h[s * 8 + 0], h[s * 8 + 2] - h[s * 8 + 1], h[s * 8 + 3] - h[s * 8 + 2], h[s * 8 + 5] - h[s * 8 + 3],
+                    h[s * 8 + 6] - h[s * 8 + 5], h[s * 8 + 4] - h[s * 8 + 6], h[(s + 1) * 8 + 0] - h[s * 8 + 4], h[(s + 1) * 8 + 0] - h[s * 8 + 0]);
+    }
+    return st;
 }
 
 }  // namespace mp
