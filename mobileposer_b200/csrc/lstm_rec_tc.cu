@@ -35,7 +35,7 @@ constexpr int TH = 256;
 constexpr int TCC = 8;            // cluster size
 constexpr int TUC = TH / TCC;     // 32 units per CTA
 constexpr int EPI_WARPS = 16;
-constexpr int RTC_THREADS = (EPI_WARPS + 1) * 32;
+constexpr int RTC_THREADS = (EPI_WARPS + 2) * 32;   // 16 epilogue warps + MMA warp + copy warp
 constexpr uint32_t COL_WHI = 0, COL_D = 256, COL_WLO = 384;
 constexpr int WLO_TMEM_K = 128;                       // k < 128 of W_lo lives in TMEM
 constexpr uint32_t WLO_S_BYTES = (TH - WLO_TMEM_K) / 32 * 128 * 128;   // 4 K-blocks x 128 rows x 128 B = 64 KiB
@@ -56,7 +56,7 @@ struct RecTcParams {
 
 __host__ __device__ inline size_t rec_tc_smem_bytes(int N) {
     // W_lo half | H_hi | H_lo | staging [2 parity][2 arrays] | tables | barriers
-    return 1024 + WLO_S_BYTES + (size_t)2 * 8 * N * 128 + (size_t)4 * N * 128 + (size_t)3 * N * 4 + 64;
+    return 1024 + WLO_S_BYTES + (size_t)2 * 8 * N * 128 + (size_t)4 * N * 128 + (size_t)3 * N * 4 + 96;
 }
 
 __device__ __forceinline__ uint32_t tf32_hi(float x) { return __float_as_uint(x) & 0xFFFFE000u; }
@@ -113,6 +113,14 @@ __device__ __forceinline__ void tmem_ld4(uint32_t taddr, float* v) {
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t remote_bar) {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote_bar) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive_local(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
 __device__ __forceinline__ float act_sigmoid_or_tanh(float x, bool is_tanh) {
@@ -147,7 +155,8 @@ __global__ void __launch_bounds__(RTC_THREADS, 1) lstm_rec_tc_kernel(const RecTc
     uint32_t* goff = reinterpret_cast<uint32_t*>(lens + N);
     uint32_t* yoff = goff + N;
     const uint32_t s_bars = s_stg + 4 * SLICE + 3 * N * 4;
-    const uint32_t bar_full = (s_bars + 7u) & ~7u, bar_mma = bar_full + 8, bar_free = bar_full + 16, tmem_slot = bar_full + 24;
+    const uint32_t bar_full = (s_bars + 7u) & ~7u, bar_mma = bar_full + 8, bar_free = bar_full + 16, bar_chunk = bar_full + 24,
+                   tmem_slot = bar_full + 24 + 8 * 4;   // bar_chunk[0..3]: "rows [16 b, 16 b + 16) of the new slice are staged"
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int rank = (int)cluster_ctarank();
@@ -161,6 +170,7 @@ __global__ void __launch_bounds__(RTC_THREADS, 1) lstm_rec_tc_kernel(const RecTc
         mbar_init(bar_full, 1);
         mbar_init(bar_mma, 1);
         mbar_init(bar_free, TCC);
+        for (int b = 0; b < 4; ++b) mbar_init(bar_chunk + 8 * b, EPI_WARPS * 32);
         mbar_fence_init_cluster();
     }
     if (warp == EPI_WARPS) {
@@ -254,10 +264,14 @@ __global__ void __launch_bounds__(RTC_THREADS, 1) lstm_rec_tc_kernel(const RecTc
         const int par = s & 1;
         if (warp == EPI_WARPS) {
             // ================= MMA issuer =================
-            if (lane == 0) {
+            // The whole warp walks the (fully unrolled) issue sequence and one elected lane executes each tcgen05.mma:
+            // in warp-uniform control flow the descriptors live in uniform registers; under `if (lane == 0)` every
+            // UMMA was wrapped in an ELECT / R2UR / BRA.U.ANY loop (48 clk per issue, 4.6 k clk per step).
+            {
                 if (s > 0) mbar_wait(bar_full, (s - 1) & 1);
                 tc_fence_after();
-                RTC_STAMP(0);
+                const bool leader = elect_one();
+                if (leader) RTC_STAMP(0);
                 {
                     // descriptors advance by compile-time constants (fully unrolled): one 64-bit add per operand, so the
                     // single issuing thread spends ~5 instructions per UMMA instead of rebuilding descriptors
@@ -266,20 +280,38 @@ __global__ void __launch_bounds__(RTC_THREADS, 1) lstm_rec_tc_kernel(const RecTc
 #pragma unroll
                         for (int ks = 0; ks < TH / 8; ++ks) {          // correction: W_lo . h_hi
                             const uint64_t b = bd_hi + (uint64_t)(((ks >> 2) * SLICE + (ks & 3) * 32) >> 4);
-                            if (ks < WLO_TMEM_K / 8) umma_ts(d_corr, tmem + COL_WLO + ks * 8, b, idesc, ks != 0);
-                            else
+                            if (ks < WLO_TMEM_K / 8) { if (leader) umma_ts(d_corr, tmem + COL_WLO + ks * 8, b, idesc, ks != 0); }
+                            else if (leader)
                                 umma_ss(d_corr, ad_wlo + (uint64_t)((((ks - WLO_TMEM_K / 8) >> 2) * (128 * 128) + (ks & 3) * 32) >> 4), b, idesc, 1u);
                         }
 #pragma unroll
                         for (int ks = 0; ks < TH / 8; ++ks)            // correction: W_hi . h_lo
-                            umma_ts(d_corr, tmem + COL_WHI + ks * 8, bd_lo + (uint64_t)(((ks >> 2) * SLICE + (ks & 3) * 32) >> 4), idesc, 1u);
+                            if (leader) umma_ts(d_corr, tmem + COL_WHI + ks * 8, bd_lo + (uint64_t)(((ks >> 2) * SLICE + (ks & 3) * 32) >> 4), idesc, 1u);
                     }
 #pragma unroll
                     for (int ks = 0; ks < TH / 8; ++ks)                // main: W_hi . h_hi
-                        umma_ts(d_main, tmem + COL_WHI + ks * 8, bd_hi + (uint64_t)(((ks >> 2) * SLICE + (ks & 3) * 32) >> 4), idesc, ks != 0);
+                        if (leader) umma_ts(d_main, tmem + COL_WHI + ks * 8, bd_hi + (uint64_t)(((ks >> 2) * SLICE + (ks & 3) * 32) >> 4), idesc, ks != 0);
                 }
-                RTC_STAMP(1);
-                tc_commit(bar_mma);
+                if (leader) {
+                    RTC_STAMP(1);
+                    tc_commit(bar_mma);
+                }
+            }
+            __syncwarp();
+        } else if (warp == EPI_WARPS + 1) {
+            // ================= copy warp =================
+            // ships rows [16 b, 16 b + 16) of the new slice to all 8 CTAs as soon as the 16 epilogue warps have staged
+            // them, so the exchange overlaps the activation work of the following blocks and costs them no barrier
+            if (send && lane < 2 * TCC) {
+                const int r = lane >> 1, arr = lane & 1;
+                const uint32_t chunk = 16u * 128u;
+#pragma unroll 1
+                for (int blk = 0; blk < SPW / 4; ++blk) {
+                    mbar_wait(bar_chunk + 8 * blk, par);
+                    if (blk == 0) mbar_wait(bar_free, par);      // every peer has finished the MMAs that read its h
+                    bulk_copy_s2c(mapa_u32((arr ? s_hlo : s_hhi) + (uint32_t)rank * SLICE + blk * chunk, r),
+                                  s_stg + (uint32_t)(par * 2 + arr) * SLICE + blk * chunk, chunk, mapa_u32(bar_full, r));
+                }
             }
             __syncwarp();
         } else {
@@ -355,18 +387,7 @@ __global__ void __launch_bounds__(RTC_THREADS, 1) lstm_rec_tc_kernel(const RecTc
                 // overlaps the activation work of the next one (only the last block's transfer is exposed)
                 if (send) {
                     fence_proxy_async_smem();
-                    named_bar_sync(1, EPI_WARPS * 32);
-                    if (tid < 2 * TCC) {
-                        if (blk == 0) {
-                            if (tid == 0) RTC_STAMP(5);
-                            mbar_wait(bar_free, par);      // every peer has finished the MMAs that read its h
-                            if (tid == 0) RTC_STAMP(6);
-                        }
-                        const int r = tid >> 1, arr = tid & 1;
-                        const uint32_t chunk = 16u * 128u;
-                        bulk_copy_s2c(mapa_u32((arr ? s_hlo : s_hhi) + (uint32_t)rank * SLICE + blk * chunk, r),
-                                      s_stg + (uint32_t)(par * 2 + arr) * SLICE + blk * chunk, chunk, mapa_u32(bar_full, r));
-                    }
+                    mbar_arrive_local(bar_chunk + 8 * blk);      // non-blocking: the copy warp ships the chunk
                 }
             }
             if (tid == 0) RTC_STAMP(4);
@@ -486,9 +507,9 @@ int launch_lstm_recurrence_tc(const RecLayerArgs& a, cudaStream_t stream) {
         cudaMemcpy(h, ts_dev, sizeof(h), cudaMemcpyDeviceToHost);
         fprintf(stderr, "[rtc ts] N=%d NB=%d B=%d\n", N, NB, a.B);
         for (int s = 2; s < 8 && s < a.T - 1; ++s)
-            fprintf(stderr, "[rtc ts] s=%d  mma issue %lld | commit->epi %lld  tmem ld %lld  block0 %lld  free-wait %lld  blocks1.. %lld  tail->next mma %lld  step %lld\n", s,
-                    h[s * 8 + 1] - h[s * 8 + 0], h[s * 8 + 2] - h[s * 8 + 1], h[s * 8 + 3] - h[s * 8 + 2], h[s * 8 + 5] - h[s * 8 + 3],
-                    h[s * 8 + 6] - h[s * 8 + 5], h[s * 8 + 4] - h[s * 8 + 6], h[(s + 1) * 8 + 0] - h[s * 8 + 4], h[(s + 1) * 8 + 0] - h[s * 8 + 0]);
+            fprintf(stderr, "[rtc ts] s=%d  mma issue %lld | commit->epi %lld  tmem ld %lld  activations+staging %lld  tail->next mma %lld  step %lld\n", s,
+                    h[s * 8 + 1] - h[s * 8 + 0], h[s * 8 + 2] - h[s * 8 + 1], h[s * 8 + 3] - h[s * 8 + 2], h[s * 8 + 4] - h[s * 8 + 3],
+                    h[(s + 1) * 8 + 0] - h[s * 8 + 4], h[(s + 1) * 8 + 0] - h[s * 8 + 0]);
     }
     return st;
 }

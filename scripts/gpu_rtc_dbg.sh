@@ -1,5 +1,5 @@
 set -x
 mkdir -p gpurun_out
-for nb in 16 32 64; do
-MP_RTC_TS=1 MP_REC_IMPL=tc MP_REC_NB=$nb timeout 120 python scripts/rtc_debug.py 256 12 > gpurun_out/ts_$nb.log 2>&1; echo "ts nb=$nb exit $?"; grep -E "rtc ts|max" gpurun_out/ts_$nb.log | sed -n '1p;3p;$p' | cut -c1-330
-done
+MP_RTC_TS=1 MP_REC_IMPL=tc timeout 120 python scripts/rtc_debug.py 256 20 > gpurun_out/ts.log 2>&1; echo "ts exit $?"; grep -E "rtc ts|max" gpurun_out/ts.log | sed -n '1,4p;$p' | cut -c1-250
+MP_REC_IMPL=tc timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "variants or ragged or cfg3 or float64" > gpurun_out/pytest_rtc.log 2>&1; echo "tests exit $?"; tail -4 gpurun_out/pytest_rtc.log | cut -c1-300
+timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_rtc.json 2> gpurun_out/bench_rtc.err; echo "bench exit $?"; cut -c1-260 gpurun_out/bench_rtc.json; tail -3 gpurun_out/bench_rtc.err
