@@ -306,15 +306,28 @@ def run_ours(args):
     prof = _cabi.profile_collect()
     _cabi.check(lib.mp_profile_enable(0))
     peak, peak_src = measured_peak_gbs()
-    dom = prof.get('lstm_rec_h256', None)
+    # dominant kernel: the H=256 recurrence (tcgen05 variant for large batches, FFMA cluster kernel otherwise)
+    dom_name = max((k for k in prof if k.startswith('lstm_rec') and 'h64' not in k), key=lambda k: prof[k]['total_ms'], default=None)
+    dom = prof.get(dom_name)
     roofline = None
     if dom:
         gbs = dom['algorithmic_bytes'] / (dom['total_ms'] / 1e3) / 1e9
-        roofline = {'bound': 'hbm', 'kernel': 'lstm_rec_kernel<256,8,*>', 'achieved': gbs, 'peak': peak, 'unit': 'GB/s',
-                    'frac': gbs / peak, 'traffic': load_traffic('lstm_rec_h256'), 'peak_source': peak_src,
-                    'avg_launch_ms': dom['total_ms'] / dom['launches'],
+        # MACs of the recurrent product per launch: B*T*dirs*4H*H; 3 TF32 products each on the tensor-core variant
+        roofline = {'bound': 'hbm', 'kernel': {'lstm_rec_tc_h256': 'lstm_rec_tc_kernel<N> (tcgen05 3xTF32, W_hh in TMEM)',
+                                               'lstm_rec_h256': 'lstm_rec_kernel<256,8,*> (FFMA2, W_hh in registers)'}.get(dom_name, dom_name),
+                    'achieved': gbs, 'peak': peak, 'unit': 'GB/s', 'frac': gbs / peak, 'traffic': load_traffic(dom_name),
+                    'peak_source': peak_src, 'avg_launch_ms': dom['total_ms'] / dom['launches'],
                     'algorithmic_bytes_per_launch': dom['algorithmic_bytes'] / dom['launches'],
-                    'note': 'recurrence is serial in T: latency/FFMA-bound by construction, see DESIGN.md'}
+                    'launches_per_step': dom['launches'] / args.steps,
+                    'note': 'the recurrence is serial in T: bound by the per-step MMA + activation + DSMEM-exchange chain, not by '
+                            'HBM (DESIGN.md 4.1); the HBM fraction is the contract figure of the brief'}
+        if dom_name == 'lstm_rec_tc_h256':
+            tf = tensor_peak_tflops()
+            # every launch of this kernel type in the step: sum over layers of 3 (TF32 products) * 2 * B*T*dirs*4H*H flops
+            flops = 3 * 2 * sum_recurrent_macs(B, T) * args.steps
+            ach = flops / (dom['total_ms'] / 1e3) / 1e12
+            roofline['tensor'] = {'achieved_tflops_tf32x3': ach, 'peak_tflops_tf32': tf, 'frac': ach / tf if tf else None,
+                                  'peak_source': 'MEASURED_PEAKS.json bf16_tflops / 2 (TF32 runs at half the bf16 rate)'}
     whole = (WEIGHT_BYTES + B * T * IO_BYTES_PER_FRAME) / (ms / args.steps / 1e3) / 1e9
     kernels = {k: {'launches_per_step': v['launches'] / args.steps, 'ms_per_step': v['total_ms'] / args.steps,
                    'algorithmic_GBps': v['algorithmic_bytes'] / (v['total_ms'] / 1e3) / 1e9} for k, v in prof.items()}
@@ -394,6 +407,20 @@ def streaming_latency(net, dev, W, ticks=240, warm=20):
     net.velocity.rnn_state = None
     return {'streams': len(combos), 'ticks': ticks, 'p50_ms': ms[len(ms) // 2], 'p99_ms': ms[int(len(ms) * 0.99) - 1],
             'max_ms': ms[-1], 'frames_per_s': len(combos) * 1e3 / (sum(ms) / len(ms))}
+
+
+def tensor_peak_tflops():
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+            return float(json.load(f)['bf16_tflops']) / 2.0
+    except Exception:
+        return 1590.0 / 2.0
+
+
+def sum_recurrent_macs(B, T):
+    """W_hh h MACs of the H=256 layers per forward: joints and pose 2 layers x 2 directions, velocity 2 x 1."""
+    per_layer_dir = B * T * 4 * 256 * 256
+    return per_layer_dir * (4 + 4 + 2)
 
 
 def net_workspace_mb(net, B, T):
