@@ -56,7 +56,7 @@ struct RecTcParams {
 
 __host__ __device__ inline size_t rec_tc_smem_bytes(int N) {
     // W_lo half | H_hi | H_lo | staging [2 parity][2 arrays] | tables | barriers
-    return 1024 + WLO_S_BYTES + (size_t)2 * 8 * N * 128 + (size_t)4 * N * 128 + (size_t)3 * N * 4 + 96;
+    return 1024 + WLO_S_BYTES + (size_t)2 * 8 * N * 128 + (size_t)4 * N * 128 + (size_t)3 * N * 4 + 128;
 }
 
 __device__ __forceinline__ uint32_t tf32_hi(float x) { return __float_as_uint(x) & 0xFFFFE000u; }
@@ -155,8 +155,10 @@ __global__ void __launch_bounds__(RTC_THREADS, 1) lstm_rec_tc_kernel(const RecTc
     uint32_t* goff = reinterpret_cast<uint32_t*>(lens + N);
     uint32_t* yoff = goff + N;
     const uint32_t s_bars = s_stg + 4 * SLICE + 3 * N * 4;
-    const uint32_t bar_full = (s_bars + 7u) & ~7u, bar_mma = bar_full + 8, bar_free = bar_full + 16, bar_chunk = bar_full + 24,
-                   tmem_slot = bar_full + 24 + 8 * 4;   // bar_chunk[0..3]: "rows [16 b, 16 b + 16) of the new slice are staged"
+    // per sub-tile: bar_full[2] (h rows arrived), bar_mma[2] (MMAs committed), bar_free[2] (all peers' MMAs done);
+    // bar_chunk[0..3]: "rows [16 b, 16 b + 16) of the new slice are staged"
+    const uint32_t bar_full = (s_bars + 7u) & ~7u, bar_mma = bar_full + 16, bar_free = bar_full + 32, bar_chunk = bar_full + 48,
+                   tmem_slot = bar_full + 48 + 8 * 4;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int rank = (int)cluster_ctarank();
@@ -167,9 +169,11 @@ __global__ void __launch_bounds__(RTC_THREADS, 1) lstm_rec_tc_kernel(const RecTc
     const int G4 = p.dirs * 4 * TH, Y2 = p.dirs * TH;
 
     if (tid == 0) {
-        mbar_init(bar_full, 1);
-        mbar_init(bar_mma, 1);
-        mbar_init(bar_free, TCC);
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(bar_full + 8 * b, 1);
+            mbar_init(bar_mma + 8 * b, 1);
+            mbar_init(bar_free + 8 * b, TCC);
+        }
         for (int b = 0; b < 4; ++b) mbar_init(bar_chunk + 8 * b, EPI_WARPS * 32);
         mbar_fence_init_cluster();
     }
@@ -256,8 +260,14 @@ __global__ void __launch_bounds__(RTC_THREADS, 1) lstm_rec_tc_kernel(const RecTc
         gi[j] = (warp < EPI_WARPS && l > 0) ? __ldg(p.gin + (goff[n] + (uint32_t)(dir ? l - 1 : 0) * (uint32_t)G4 + (uint32_t)(ul * 4 + gate))) : 0.f;
     }
 
-    constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     const uint32_t d_main = tmem + COL_D, d_corr = tmem + COL_D + N;
+
+    // The tile is split into two sub-tiles of whole 16-sequence blocks that ping-pong through the step: while the
+    // epilogue warps run the activations of one sub-tile the tensor core already works on the other, and the exchange of
+    // a finished sub-tile hides behind both.  Each sub-tile has its own full / mma / free barriers.
+    constexpr int NBLK = N / 16;
+    constexpr int NSUB = NBLK >= 2 ? 2 : 1;
+    constexpr int BLK_A = (NBLK + 1) / 2;
 
     for (int s = 0; s < maxlen; ++s) {
         const bool send = (s + 1 < maxlen);
@@ -267,34 +277,36 @@ __global__ void __launch_bounds__(RTC_THREADS, 1) lstm_rec_tc_kernel(const RecTc
             // The whole warp walks the (fully unrolled) issue sequence and one elected lane executes each tcgen05.mma:
             // in warp-uniform control flow the descriptors live in uniform registers; under `if (lane == 0)` every
             // UMMA was wrapped in an ELECT / R2UR / BRA.U.ANY loop (48 clk per issue, 4.6 k clk per step).
-            {
-                if (s > 0) mbar_wait(bar_full, (s - 1) & 1);
+            const bool leader = elect_one();
+#pragma unroll
+            for (int sub = 0; sub < NSUB; ++sub) {
+                const int blk0 = sub == 0 ? 0 : BLK_A;
+                const int nblk = sub == 0 ? BLK_A : NBLK - BLK_A;
+                const uint32_t row0 = 16u * blk0;                       // first sequence row / accumulator column of the sub-tile
+                const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)((16 * nblk) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+                if (s > 0) mbar_wait(bar_full + 8 * sub, (s - 1) & 1);
                 tc_fence_after();
-                const bool leader = elect_one();
-                if (leader) RTC_STAMP(0);
-                {
-                    // descriptors advance by compile-time constants (fully unrolled): one 64-bit add per operand, so the
-                    // single issuing thread spends ~5 instructions per UMMA instead of rebuilding descriptors
-                    const uint64_t bd_hi = umma_desc_sw128(s_hhi), bd_lo = umma_desc_sw128(s_hlo), ad_wlo = umma_desc_sw128(s_wlo);
-                    {
+                if (leader && sub == 0) RTC_STAMP(0);
+                // descriptors advance by compile-time constants (fully unrolled): one 64-bit add per operand
+                const uint64_t bd_hi = umma_desc_sw128(s_hhi + row0 * 128u), bd_lo = umma_desc_sw128(s_hlo + row0 * 128u),
+                               ad_wlo = umma_desc_sw128(s_wlo);
+                const uint32_t dm_ = d_main + row0, dc_ = d_corr + row0;
 #pragma unroll
-                        for (int ks = 0; ks < TH / 8; ++ks) {          // correction: W_lo . h_hi
-                            const uint64_t b = bd_hi + (uint64_t)(((ks >> 2) * SLICE + (ks & 3) * 32) >> 4);
-                            if (ks < WLO_TMEM_K / 8) { if (leader) umma_ts(d_corr, tmem + COL_WLO + ks * 8, b, idesc, ks != 0); }
-                            else if (leader)
-                                umma_ss(d_corr, ad_wlo + (uint64_t)((((ks - WLO_TMEM_K / 8) >> 2) * (128 * 128) + (ks & 3) * 32) >> 4), b, idesc, 1u);
-                        }
-#pragma unroll
-                        for (int ks = 0; ks < TH / 8; ++ks)            // correction: W_hi . h_lo
-                            if (leader) umma_ts(d_corr, tmem + COL_WHI + ks * 8, bd_lo + (uint64_t)(((ks >> 2) * SLICE + (ks & 3) * 32) >> 4), idesc, 1u);
-                    }
-#pragma unroll
-                    for (int ks = 0; ks < TH / 8; ++ks)                // main: W_hi . h_hi
-                        if (leader) umma_ts(d_main, tmem + COL_WHI + ks * 8, bd_hi + (uint64_t)(((ks >> 2) * SLICE + (ks & 3) * 32) >> 4), idesc, ks != 0);
+                for (int ks = 0; ks < TH / 8; ++ks) {          // correction: W_lo . h_hi
+                    const uint64_t b = bd_hi + (uint64_t)(((ks >> 2) * SLICE + (ks & 3) * 32) >> 4);
+                    if (ks < WLO_TMEM_K / 8) { if (leader) umma_ts(dc_, tmem + COL_WLO + ks * 8, b, idesc, ks != 0); }
+                    else if (leader)
+                        umma_ss(dc_, ad_wlo + (uint64_t)((((ks - WLO_TMEM_K / 8) >> 2) * (128 * 128) + (ks & 3) * 32) >> 4), b, idesc, 1u);
                 }
+#pragma unroll
+                for (int ks = 0; ks < TH / 8; ++ks)            // correction: W_hi . h_lo
+                    if (leader) umma_ts(dc_, tmem + COL_WHI + ks * 8, bd_lo + (uint64_t)(((ks >> 2) * SLICE + (ks & 3) * 32) >> 4), idesc, 1u);
+#pragma unroll
+                for (int ks = 0; ks < TH / 8; ++ks)            // main: W_hi . h_hi
+                    if (leader) umma_ts(dm_, tmem + COL_WHI + ks * 8, bd_hi + (uint64_t)(((ks >> 2) * SLICE + (ks & 3) * 32) >> 4), idesc, ks != 0);
                 if (leader) {
-                    RTC_STAMP(1);
-                    tc_commit(bar_mma);
+                    if (sub == NSUB - 1) RTC_STAMP(1);
+                    tc_commit(bar_mma + 8 * sub);
                 }
             }
             __syncwarp();
@@ -305,89 +317,93 @@ __global__ void __launch_bounds__(RTC_THREADS, 1) lstm_rec_tc_kernel(const RecTc
             if (send && lane < 2 * TCC) {
                 const int r = lane >> 1, arr = lane & 1;
                 const uint32_t chunk = 16u * 128u;
-#pragma unroll 1
-                for (int blk = 0; blk < SPW / 4; ++blk) {
+#pragma unroll
+                for (int blk = 0; blk < NBLK; ++blk) {
+                    const int sub = blk < BLK_A ? 0 : 1;
                     mbar_wait(bar_chunk + 8 * blk, par);
-                    if (blk == 0) mbar_wait(bar_free, par);      // every peer has finished the MMAs that read its h
+                    if (blk == 0 || blk == BLK_A) mbar_wait(bar_free + 8 * sub, par);   // every peer's MMAs on this sub-tile are done
                     bulk_copy_s2c(mapa_u32((arr ? s_hlo : s_hhi) + (uint32_t)rank * SLICE + blk * chunk, r),
-                                  s_stg + (uint32_t)(par * 2 + arr) * SLICE + blk * chunk, chunk, mapa_u32(bar_full, r));
+                                  s_stg + (uint32_t)(par * 2 + arr) * SLICE + blk * chunk, chunk, mapa_u32(bar_full + 8 * sub, r));
                 }
             }
             __syncwarp();
         } else {
             // ================= epilogue =================
-            mbar_wait(bar_mma, par);
-            tc_fence_after();
-            // h_{s+1} will arrive as 8 ranks x (hi, lo) slices.  Armed only now: MMA(s) has run, so the MMA thread has seen
-            // the previous phase of `bar_full` complete -- arming earlier could put two arrivals into one phase.
-            if (tid == 0 && send) mbar_arrive_expect_tx(bar_full, 2u * TCC * SLICE);
-            if (tid == 0) RTC_STAMP(2);
-            if (send && tid < TCC) mbar_arrive_remote(mapa_u32(bar_free, tid));          // my MMAs no longer read my h
-            float dm[SPW], dc[SPW];
-#pragma unroll
-            for (int q = 0; q < SPW / 4; ++q) {
-                tmem_ld4(d_main + lane_base + q * 16 + part * 4, dm + 4 * q);
-                tmem_ld4(d_corr + lane_base + q * 16 + part * 4, dc + 4 * q);
-            }
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            if (tid == 0) RTC_STAMP(3);
             unsigned char* stg_hi = g_stg + (size_t)(par * 2 + 0) * SLICE;
             unsigned char* stg_lo = g_stg + (size_t)(par * 2 + 1) * SLICE;
-            // Blocks of 4 sequences: every lane evaluates its gate for the 4 sequences, the quad (4 gate lanes of a unit)
-            // exchanges them, and lane g then owns sequence 4*blk + g: ONE cell update per lane instead of four redundant ones.
 #pragma unroll
-            for (int blk = 0; blk < SPW / 4; ++blk) {
-                float a[4];
+            for (int sub = 0; sub < NSUB; ++sub) {
+                const int blk0 = sub == 0 ? 0 : BLK_A;
+                const int nblk = sub == 0 ? BLK_A : NBLK - BLK_A;
+                mbar_wait(bar_mma + 8 * sub, par);
+                tc_fence_after();
+                // h_{s+1} of this sub-tile will arrive as 8 ranks x (hi, lo) x nblk chunks.  Armed only now: MMA(s) has run,
+                // so the MMA warp has seen the previous phase of the barrier complete -- arming earlier could put two
+                // arrivals into one phase.
+                if (tid == 0 && send) mbar_arrive_expect_tx(bar_full + 8 * sub, 2u * TCC * (uint32_t)nblk * 16u * 128u);
+                if (tid == 0 && sub == 0) RTC_STAMP(2);
+                if (send && tid < TCC) mbar_arrive_remote(mapa_u32(bar_free + 8 * sub, tid));     // my MMAs no longer read these rows
+                float dm[4 * (NBLK - NBLK / 2)], dc[4 * (NBLK - NBLK / 2)];
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int j = blk * 4 + q;
-                    a[q] = act_sigmoid_or_tanh((dm[j] + dc[j]) + gi[j], gate == 2);
+                for (int q = 0; q < nblk; ++q) {
+                    tmem_ld4(d_main + lane_base + (blk0 + q) * 16 + part * 4, dm + 4 * q);
+                    tmem_ld4(d_corr + lane_base + (blk0 + q) * 16 + part * 4, dc + 4 * q);
                 }
-                const int q0 = lane & ~3;
-                float iv = 0.f, fv = 0.f, gv = 0.f, ov = 0.f;
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (tid == 0 && sub == 0) RTC_STAMP(3);
+                // Blocks of 4 sequences per lane quad: every lane evaluates its gate for the 4 sequences, the quad (4 gate
+                // lanes of a unit) exchanges them, and lane g then owns sequence 4*blk + g: ONE cell update per lane.
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const float i_q = __shfl_sync(0xffffffffu, a[q], q0);
-                    const float f_q = __shfl_sync(0xffffffffu, a[q], q0 | 1);
-                    const float g_q = __shfl_sync(0xffffffffu, a[q], q0 | 2);
-                    const float o_q = __shfl_sync(0xffffffffu, a[q], q0 | 3);
-                    if (q == gate) { iv = i_q; fv = f_q; gv = g_q; ov = o_q; }
-                }
-                // this lane's sequence of the block
-                const int n = blk * 16 + part * 4 + gate;
-                const int len = lens[n];
-                const bool active = s < len;
-                const int t = dir ? len - 1 - s : s;
-                const float c_new = fmaf(fv, cst[blk], iv * gv);
-                const float h_new = ov * act_sigmoid_or_tanh(c_new, true);
-                if (active) {
-                    cst[blk] = c_new;
-                    p.y[yoff[n] + (uint32_t)t * (uint32_t)Y2 + (uint32_t)ul] = h_new;
-                    if (s == len - 1) {
-                        if (p.hn) p.hn[((size_t)dir * p.B + b_begin + n) * TH + rank * TUC + ul] = h_new;
-                        if (p.cn) p.cn[((size_t)dir * p.B + b_begin + n) * TH + rank * TUC + ul] = c_new;
+                for (int bq = 0; bq < nblk; ++bq) {
+                    const int blk = blk0 + bq;
+                    float a[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) a[q] = act_sigmoid_or_tanh((dm[bq * 4 + q] + dc[bq * 4 + q]) + gi[blk * 4 + q], gate == 2);
+                    const int q0 = lane & ~3;
+                    float iv = 0.f, fv = 0.f, gv = 0.f, ov = 0.f;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const float i_q = __shfl_sync(0xffffffffu, a[q], q0);
+                        const float f_q = __shfl_sync(0xffffffffu, a[q], q0 | 1);
+                        const float g_q = __shfl_sync(0xffffffffu, a[q], q0 | 2);
+                        const float o_q = __shfl_sync(0xffffffffu, a[q], q0 | 3);
+                        if (q == gate) { iv = i_q; fv = f_q; gv = g_q; ov = o_q; }
                     }
-                }
-                if (send) {
-                    const float hv = active ? h_new : 0.f;
-                    const uint32_t hh = tf32_hi(hv);
-                    const uint32_t off = sw128_off(n, ul);
-                    *reinterpret_cast<uint32_t*>(stg_hi + off) = hh;
-                    *reinterpret_cast<uint32_t*>(stg_lo + off) = tf32_lo(hv, hh);
-                }
-                // next step's gate pre-activations of the block (this lane's gate, all 4 sequences)
+                    // this lane's sequence of the block
+                    const int n = blk * 16 + part * 4 + gate;
+                    const int len = lens[n];
+                    const bool active = s < len;
+                    const int t = dir ? len - 1 - s : s;
+                    const float c_new = fmaf(fv, cst[blk], iv * gv);
+                    const float h_new = ov * act_sigmoid_or_tanh(c_new, true);
+                    if (active) {
+                        cst[blk] = c_new;
+                        p.y[yoff[n] + (uint32_t)t * (uint32_t)Y2 + (uint32_t)ul] = h_new;
+                        if (s == len - 1) {
+                            if (p.hn) p.hn[((size_t)dir * p.B + b_begin + n) * TH + rank * TUC + ul] = h_new;
+                            if (p.cn) p.cn[((size_t)dir * p.B + b_begin + n) * TH + rank * TUC + ul] = c_new;
+                        }
+                    }
+                    if (send) {
+                        const float hv = active ? h_new : 0.f;
+                        const uint32_t hh = tf32_hi(hv);
+                        const uint32_t off = sw128_off(n, ul);
+                        *reinterpret_cast<uint32_t*>(stg_hi + off) = hh;
+                        *reinterpret_cast<uint32_t*>(stg_lo + off) = tf32_lo(hv, hh);
+                    }
+                    // next step's gate pre-activations of the block (this lane's gate, all 4 sequences)
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int nq = blk * 16 + part * 4 + q;
-                    const int lq2 = lens[nq];
-                    if (s + 1 < lq2)
-                        gi[blk * 4 + q] = __ldg(p.gin + (goff[nq] + (uint32_t)(dir ? lq2 - 2 - s : s + 1) * (uint32_t)G4 + (uint32_t)(ul * 4 + gate)));
-                }
-                // rows [16 blk, 16 blk + 16) of the new slice are complete: ship them now, so the exchange of this block
-                // overlaps the activation work of the next one (only the last block's transfer is exposed)
-                if (send) {
-                    fence_proxy_async_smem();
-                    mbar_arrive_local(bar_chunk + 8 * blk);      // non-blocking: the copy warp ships the chunk
+                    for (int q = 0; q < 4; ++q) {
+                        const int nq = blk * 16 + part * 4 + q;
+                        const int lq2 = lens[nq];
+                        if (s + 1 < lq2)
+                            gi[blk * 4 + q] = __ldg(p.gin + (goff[nq] + (uint32_t)(dir ? lq2 - 2 - s : s + 1) * (uint32_t)G4 + (uint32_t)(ul * 4 + gate)));
+                    }
+                    // rows [16 blk, 16 blk + 16) of the new slice are staged: hand them to the copy warp (non-blocking)
+                    if (send) {
+                        fence_proxy_async_smem();
+                        mbar_arrive_local(bar_chunk + 8 * blk);
+                    }
                 }
             }
             if (tid == 0) RTC_STAMP(4);
