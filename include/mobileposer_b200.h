@@ -132,6 +132,44 @@ int mp_online_push_frame(const float* win_in, float* win_out, const float* frame
 int mp_online_reset(mp_online_state_t* state, int32_t S, int32_t full, mp_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * K8: kinematic-physics optimizer behind the PHYSICS hook       [net.py:66-69,157-169,211-217]
+ * The reference imports `dynamics.PhysicsOptimizer`, a module that is NOT in its tree (its rbdl
+ * dependency is neither vendored nor pinned): PARITY UNPINNED.  The algorithm is defined by this
+ * repository (float64 statement: oracle/physics_port.py) behind the hook's
+ * signature  optimize_frame(pose, jvel, contact, acc) -> (pose, tran) / reset_states().
+ * ---------------------------------------------------------------------------------------- */
+typedef struct mp_physics_params {
+    float w_vel;     /* weight of the joint-velocity consistency rows (24 joints)            */
+    float w_contact; /* weight of a stance foot's stationarity rows at contact probability >= 0.9 */
+    float damping;   /* Marquardt damping of the 45 rotational unknowns, relative to diag(J^T W J) */
+    float damping_abs; /* absolute part of the damping (> 0; joints without leverage stay SPD)  */
+    float fps;       /* datasets.fps (config.py:89)                                           */
+    float vel_scale; /* amass.vel_scale (config.py:83): raw velocity head -> m/s (net.py:162)  */
+    float floor_y;   /* floor height in the zero-pose root frame (net.py:49)                  */
+} mp_physics_params_t;
+/* Per-skeleton state carried between calls (reset_states() = zero it): root position [3],
+ * started flag, previous world joint positions [24,3], padding.                              */
+#define MP_PHYSICS_STATE_FLOATS 80
+/* Batched optimize_frame: B skeletons (one warp each) walk their T frames in sequence.
+ *   pose [B,T,24,3,3] local rotations (K5), vel [B,T,72] RAW velocity-head output, contact
+ *   [B,T,2] logits, lengths [B] or NULL, state [B, MP_PHYSICS_STATE_FLOATS] (read and written),
+ *   pose_out [B,T,24,3,3] (may alias pose), tran_out [B,T,3] or NULL.  Frames >= lengths[b]
+ *   pass through.  The online tick is the T = 1 case with the state kept by the caller.       */
+int mp_physics_optimize(const float* pose, const float* vel, const float* contact, const int32_t* lengths,
+                        float* state, int32_t B, int32_t T, const mp_physics_params_t* params,
+                        float* pose_out, float* tran_out, mp_stream_t stream);
+/* Test hook: same call, additionally dumps the normal equations of frame `dbg_frame`
+ * (49 x 49 lower triangle in elimination order, row 48 = right-hand side) and the solution [48]
+ * into dbg [B, 49*49 + 48].                                                                   */
+int mp_physics_optimize_debug(const float* pose, const float* vel, const float* contact, const int32_t* lengths,
+                              float* state, int32_t B, int32_t T, const mp_physics_params_t* params,
+                              float* pose_out, float* tran_out, float* dbg, int32_t dbg_frame, mp_stream_t stream);
+/* SMPL forward kinematics of the optimizer (ParametricModel.forward_kinematics with shape=None,
+ * calc_mesh=False, articulate/model.py:208-232): pose [n,24,3,3] local -> global rotations
+ * [n,24,3,3] and root-relative joint positions [n,24,3].                                      */
+int mp_physics_fk(const float* pose, int64_t n_frames, float* global_rot, float* joint_pos, mp_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * Whole net = MobilePoserNet.forward / forward_offline           [net.py:101-171]
  * ---------------------------------------------------------------------------------------- */
 /* The net borrows the four heads (they must outlive it). */

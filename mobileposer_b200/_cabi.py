@@ -37,6 +37,15 @@ class ProfileEntry(C.Structure):
 
 ONLINE_STATE_BYTES = 64   # sizeof(mp_online_state_t)
 
+
+class PhysicsParams(C.Structure):
+    """struct mp_physics_params."""
+    _fields_ = [('w_vel', C.c_float), ('w_contact', C.c_float), ('damping', C.c_float), ('damping_abs', C.c_float), ('fps', C.c_float),
+                ('vel_scale', C.c_float), ('floor_y', C.c_float)]
+
+
+PHYSICS_STATE_FLOATS = 80   # MP_PHYSICS_STATE_FLOATS
+
 # name -> (restype, argtypes); must list every symbol the header declares (tests/test_cabi.py)
 SIGNATURES = {
     'mp_abi_version': (C.c_int, []),
@@ -55,6 +64,11 @@ SIGNATURES = {
                                C.c_int32, c_stream]),
     'mp_pose_reduced_global_to_full': (C.c_int, [c_float_p, C.c_int64, c_float_p, c_stream]),
     'mp_tran_offline': (C.c_int, [c_float_p, c_float_p, c_float_p, c_int_p, C.c_int32, C.c_int32, c_float_p, c_stream]),
+    'mp_physics_optimize': (C.c_int, [c_float_p, c_float_p, c_float_p, c_int_p, c_float_p, C.c_int32, C.c_int32,
+                                      C.POINTER(PhysicsParams), c_float_p, c_float_p, c_stream]),
+    'mp_physics_optimize_debug': (C.c_int, [c_float_p, c_float_p, c_float_p, c_int_p, c_float_p, C.c_int32, C.c_int32,
+                                            C.POINTER(PhysicsParams), c_float_p, c_float_p, c_float_p, C.c_int32, c_stream]),
+    'mp_physics_fk': (C.c_int, [c_float_p, C.c_int64, c_float_p, c_float_p, c_stream]),
     'mp_online_update': (C.c_int, [C.c_void_p, c_float_p, c_float_p, c_float_p, c_float_p, C.c_int32, C.c_int32,
                                    C.c_int32, c_float_p, c_float_p, c_float_p, c_stream]),
     'mp_online_push_frame': (C.c_int, [c_float_p, c_float_p, c_float_p, C.c_int32, C.c_int32, C.c_int32, c_stream]),

@@ -312,6 +312,21 @@ int mp_tran_offline(const float* joints, const float* vel, const float* contact,
                     int32_t T, float* tran, mp_stream_t stream) {
     return launch_tran_offline(joints, vel, contact, lengths, B, T, tran, (cudaStream_t)stream);
 }
+int mp_physics_optimize(const float* pose, const float* vel, const float* contact, const int32_t* lengths, float* state,
+                        int32_t B, int32_t T, const mp_physics_params_t* params, float* pose_out, float* tran_out,
+                        mp_stream_t stream) {
+    return launch_physics_optimize(pose, vel, contact, lengths, state, B, T, params, pose_out, tran_out, nullptr, -1,
+                                   (cudaStream_t)stream);
+}
+int mp_physics_optimize_debug(const float* pose, const float* vel, const float* contact, const int32_t* lengths,
+                              float* state, int32_t B, int32_t T, const mp_physics_params_t* params, float* pose_out,
+                              float* tran_out, float* dbg, int32_t dbg_frame, mp_stream_t stream) {
+    return launch_physics_optimize(pose, vel, contact, lengths, state, B, T, params, pose_out, tran_out, dbg, dbg_frame,
+                                   (cudaStream_t)stream);
+}
+int mp_physics_fk(const float* pose, int64_t n_frames, float* global_rot, float* joint_pos, mp_stream_t stream) {
+    return launch_physics_fk(pose, n_frames, global_rot, joint_pos, (cudaStream_t)stream);
+}
 int mp_online_update(mp_online_state_t* state, const float* pose, const float* joints, const float* vel,
                      const float* contact, int32_t S, int32_t W, int32_t frame_idx, float* pose_out, float* root_out,
                      float* contact_out, mp_stream_t stream) {

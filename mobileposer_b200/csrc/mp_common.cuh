@@ -93,6 +93,12 @@ int launch_online_reset(mp_online_state_t* st, int S, int full, cudaStream_t str
 int launch_online_push(const float* win_in, float* win_out, const float* frame, int S, int W, int cold,
                        cudaStream_t stream);
 
+// K8 (physics.cu)
+int launch_physics_optimize(const float* pose, const float* vel, const float* contact, const int32_t* lengths, float* state,
+                            int B, int T, const mp_physics_params_t* prm, float* pose_out, float* tran_out, float* dbg,
+                            int dbg_frame, cudaStream_t stream);
+int launch_physics_fk(const float* pose, int64_t n, float* glb, float* pos, cudaStream_t stream);
+
 // ---- PTX helpers (clusters, mbarrier, distributed shared memory) ---------------------------
 #ifdef __CUDACC__
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {

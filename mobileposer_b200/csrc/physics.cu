@@ -1,0 +1,476 @@
+// K8: kinematic-physics optimizer behind the reference's PHYSICS hook -- one warp per skeleton.
+//
+// Reference interface (relative to /root/reference/mobileposer): models/net.py:66-69 (`PhysicsOptimizer(debug=False)`,
+// `reset_states()`), net.py:157-169 and 211-217 (`optimize_frame(pose, jvel, contact, acc) -> (pose, tran)`).  The module
+// behind that hook (`dynamics`) is NOT in the reference tree and its dependency rbdl is neither vendored nor pinned
+// (SURVEY.md F2): PARITY UNPINNED.  The algorithm is defined by this repository (float64 statement in
+// oracle/physics_port.py); only its SMPL forward kinematics is pinned to the reference (articulate/model.py:208-232).
+//
+// Per frame (sequential in time, state = root position p + previous world joint positions q_prev):
+//   FK of the network pose -> G_j, P_j;   e_j = q_prev_j + jvel_j/fps - (p + P_j);   ec_f = q_prev_f - (p + P_f)
+//   min  w_vel sum_j |J_j dth + d - e_j|^2 + sum_f wc_f |J_f dth + d - ec_f|^2 + sum_i (damping H_ii + damping_abs) dth_i^2
+//        (45 rotational + 3 translational unknowns; H = J^T W J: Marquardt's diagonal scaling)
+//   R_k <- R_k exp([dth_k]x);  floor clamp on d_y;  p += d;  q_prev <- p + FK(new pose)
+//
+// Mapping: lane = joint for FK / residuals / the rotation update (parents by warp shuffle, level by level), the
+// normal equations are assembled from SUBTREE MOMENTS instead of an explicit Jacobian -- column (k, a) of joint j is
+// G_k[:,a] x (P_j - P_k), so every 3x3 block of J^T W J between an ancestor k1 and a descendant k2 is a function of
+// G_k1, G_k2, P_k2 - P_k1 and the weighted moments (sum c r, sum c r r^T) of k2's subtree -- and solved by an envelope
+// Cholesky in shared memory: unknowns are ordered leaves-first (elimination tree = kinematic tree) so the factor has
+// no fill outside the ancestor blocks; the right-hand side rides along as row 48.  No cuBLAS / cuSolver.
+// HBM traffic per frame and skeleton: 864 B pose in + 288 B velocity + 8 B contact, 864 B pose + 12 B tran out.
+#include "mp_common.cuh"
+
+#include <mutex>
+
+namespace mp {
+
+namespace {
+
+constexpr int NJ = 24, NOPT = 15, NX = 48, LDH = 49;
+constexpr int MAX_PAIRS = 64;
+
+struct PhysTables {
+    int parent[NJ];
+    int depth[NJ];
+    unsigned desc[NJ];          // bit j set: j is k or a descendant of k
+    float bone[NJ][3];          // J[j] - J[parent[j]] of the zero pose (articulate/model.py:77-92, shape=None)
+    int ord[NOPT];              // elimination order (leaves first)
+    int slot[NJ];               // joint -> slot in `ord` or -1
+    int npair;
+    unsigned char pair_a[MAX_PAIRS], pair_d[MAX_PAIRS];   // (ancestor-or-self slot, deeper slot)
+    int env[LDH];               // first column of each row's envelope
+};
+
+__constant__ PhysTables c_tab;
+
+// zero-pose joints J - J[0] as float32 (mobileposer_b200/config.py:SMPL_J_ZERO; tests compare FK against the reference)
+const float kJZero[NJ][3] = {
+    {0.0f, 0.0f, 0.0f},
+    {0.058581352f, -0.08228004f, -0.017664082f},
+    {-0.060309727f, -0.09051329f, -0.013542531f},
+    {0.004439451f, 0.12440355f, -0.03838522f},
+    {0.10203278f, -0.46874952f, -0.009627081f},
+    {-0.103566356f, -0.47420114f, -0.018385574f},
+    {0.008927891f, 0.26235995f, -0.0115648955f},
+    {0.08724245f, -0.8956239f, -0.047055073f},
+    {-0.08451081f, -0.8942467f, -0.052947246f},
+    {0.0066633024f, 0.31839234f, -0.008709848f},
+    {0.1282968f, -0.95590985f, 0.074987344f},
+    {-0.11935069f, -0.95635235f, 0.07737604f},
+    {-0.006726882f, 0.53002787f, -0.042177428f},
+    {0.07836577f, 0.43239203f, -0.02760802f},
+    {-0.076290354f, 0.4308647f, -0.032417234f},
+    {0.0033863292f, 0.61896527f, 0.008232435f},
+    {0.20128717f, 0.47759712f, -0.04665402f},
+    {-0.18951866f, 0.47771794f, -0.040889304f},
+    {0.45661905f, 0.4619481f, -0.06960051f},
+    {-0.44964615f, 0.46334866f, -0.07215803f},
+    {0.7223283f, 0.4746462f, -0.07697524f},
+    {-0.7187546f, 0.47014236f, -0.0781848f},
+    {0.80901885f, 0.46401018f, -0.09256954f},
+    {-0.80750835f, 0.4614908f, -0.088291876f},
+};
+const int kParent[NJ] = {-1, 0, 0, 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 9, 9, 12, 13, 14, 16, 17, 18, 19, 20, 21};
+// joint_set.reduced without the root (config.py:134), deepest joints first, one kinematic chain after the other
+const int kOrd[NOPT] = {15, 12, 18, 16, 13, 19, 17, 14, 9, 6, 3, 4, 1, 5, 2};
+
+PhysTables build_tables() {
+    PhysTables t = {};
+    for (int j = 0; j < NJ; ++j) {
+        t.parent[j] = kParent[j];
+        t.depth[j] = kParent[j] < 0 ? 0 : t.depth[kParent[j]] + 1;
+        for (int a = 0; a < 3; ++a) t.bone[j][a] = kJZero[j][a] - (kParent[j] < 0 ? 0.f : kJZero[kParent[j]][a]);
+        t.slot[j] = -1;
+    }
+    for (int j = 0; j < NJ; ++j)
+        for (int k = j; k >= 0; k = kParent[k]) t.desc[k] |= 1u << j;
+    for (int i = 0; i < NOPT; ++i) {
+        t.ord[i] = kOrd[i];
+        t.slot[kOrd[i]] = i;
+    }
+    // pairs (ancestor-or-self, deeper); the envelope of a row starts at the first slot that is a descendant of its joint
+    int first_desc[NOPT];
+    for (int i = 0; i < NOPT; ++i) first_desc[i] = i;
+    for (int d = 0; d < NOPT; ++d)
+        for (int a = 0; a < NOPT; ++a)
+            if ((t.desc[kOrd[a]] >> kOrd[d]) & 1u) {
+                t.pair_a[t.npair] = (unsigned char)a;
+                t.pair_d[t.npair] = (unsigned char)d;
+                ++t.npair;
+                if (d < first_desc[a]) first_desc[a] = d;
+            }
+    int lo = NX;
+    for (int i = 0; i < NOPT; ++i) {
+        for (int a = 0; a < 3; ++a) t.env[3 * i + a] = 3 * first_desc[i];
+        if (3 * first_desc[i] < lo) lo = 3 * first_desc[i];
+    }
+    for (int r = 45; r < LDH; ++r) t.env[r] = 0;     // translation rows and the right-hand side couple with everything
+    return t;
+}
+
+int upload_tables() {
+    static std::mutex mu;
+    static bool done[64] = {};
+    int dev = 0;
+    MP_CUDA_TRY(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(mu);
+    if (dev < 64 && done[dev]) return MP_OK;
+    const PhysTables t = build_tables();
+    MP_REQUIRE(t.npair <= MAX_PAIRS, "physics: pair table overflow (%d)", t.npair);
+    MP_CUDA_TRY(cudaMemcpyToSymbol(c_tab, &t, sizeof(t)));
+    if (dev < 64) done[dev] = true;
+    return MP_OK;
+}
+
+struct PhysParams {
+    const float* pose;       // [B, T, 24, 9] local rotations (K5 output)
+    const float* vel;        // [B, T, 72]    raw velocity-head output
+    const float* contact;    // [B, T, 2]     logits
+    const int32_t* lengths;  // [B] or null
+    float* state;            // [B, 80]: p[3], started, q_prev[72], pad[4]
+    float* pose_out;         // [B, T, 24, 9] (may alias pose)
+    float* tran_out;         // [B, T, 3] or null
+    float* dbg;              // [B, 49*49 + 48] normal equations (+ rhs row) and solution of frame dbg_frame, or null
+    int B, T, dbg_frame;
+    float jvel_dt;           // vel_scale / fps: raw velocity -> displacement per frame
+    float w_vel, w_contact, damping, damping_abs, floor_y;
+};
+
+// lane = joint: global rotation and root-relative position by walking the tree one level per shuffle round
+__device__ __forceinline__ void warp_fk(const float (&R)[9], int j, bool isj, int par, int depth, const float (&bone)[3], float (&G)[9],
+                                        float (&P)[3]) {
+#pragma unroll
+    for (int i = 0; i < 9; ++i) G[i] = R[i];
+    P[0] = P[1] = P[2] = 0.f;
+#pragma unroll 1
+    for (int lvl = 1; lvl <= 8; ++lvl) {
+        float Gp[9], Pp[3];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) Gp[i] = __shfl_sync(0xffffffffu, G[i], par);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) Pp[i] = __shfl_sync(0xffffffffu, P[i], par);
+        if (isj && depth == lvl) {
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) G[r * 3 + c] = fmaf(Gp[r * 3 + 2], R[6 + c], fmaf(Gp[r * 3 + 1], R[3 + c], Gp[r * 3] * R[c]));
+                P[r] = Pp[r] + fmaf(Gp[r * 3 + 2], bone[2], fmaf(Gp[r * 3 + 1], bone[1], Gp[r * 3] * bone[0]));
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ float sincf_stable(float x) { return fabsf(x) < 1e-3f ? 1.f - x * x * (1.f / 6.f) : sinf(x) / x; }
+
+__device__ __forceinline__ float phys_prob_to_weight(float logit) {
+    const float p = 1.f / (1.f + expf(-logit));
+    return (fminf(fmaxf(p, 0.5f), 0.9f) - 0.5f) / 0.4f;       // net.py:90-91
+}
+
+__global__ void __launch_bounds__(32) physics_optimize_kernel(const PhysParams p) {
+    __shared__ float sG[NJ * 9];
+    __shared__ float sP[NJ * 3];
+    __shared__ float sC[NJ];
+    __shared__ float sS[NJ * 3];
+    __shared__ float sS1[NJ * 3];
+    __shared__ float sS2[NJ * 6];
+    __shared__ float sT1[NJ * 3];
+    __shared__ float sH[LDH * LDH];
+    __shared__ float sX[NX];
+
+    const int lane = threadIdx.x;
+    const int b = blockIdx.x;
+    if (b >= p.B) return;
+    const bool isj = lane < NJ;
+    const int j = isj ? lane : 0;
+    const int par = c_tab.parent[j] < 0 ? 0 : c_tab.parent[j];
+    const int depth = c_tab.depth[j];
+    const float bone[3] = {c_tab.bone[j][0], c_tab.bone[j][1], c_tab.bone[j][2]};
+    const int slot = isj ? c_tab.slot[j] : -1;
+    const unsigned desc = c_tab.desc[j];
+    const int len = p.lengths ? min(max(p.lengths[b], 0), p.T) : p.T;
+
+    float* st = p.state + (size_t)b * 80;
+    float px = st[0], py = st[1], pz = st[2];
+    bool started = st[3] != 0.f;
+    float q[3] = {0.f, 0.f, 0.f};
+    if (isj) { q[0] = st[4 + j * 3]; q[1] = st[5 + j * 3]; q[2] = st[6 + j * 3]; }
+
+    for (int i = lane; i < LDH * LDH; i += 32) sH[i] = 0.f;
+
+    const float* pose_b = p.pose + (size_t)b * p.T * 216;
+    const float* vel_b = p.vel + (size_t)b * p.T * 72;
+    const float* con_b = p.contact + (size_t)b * p.T * 2;
+    float* out_b = p.pose_out + (size_t)b * p.T * 216;
+
+    // frame 0 inputs; inside the loop the loads of frame t+1 are issued before the work of frame t
+    float Rn[9], vn[3], cn0 = 0.f, cn1 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) Rn[i] = (isj && len > 0) ? __ldg(pose_b + j * 9 + i) : (i % 4 == 0 ? 1.f : 0.f);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) vn[i] = (isj && len > 0) ? __ldg(vel_b + j * 3 + i) : 0.f;
+    if (len > 0) { cn0 = __ldg(con_b); cn1 = __ldg(con_b + 1); }
+
+    for (int t = 0; t < len; ++t) {
+        float R[9], jv[3];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) R[i] = Rn[i];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) jv[i] = vn[i] * p.jvel_dt;
+        const float c0 = cn0, c1 = cn1;
+        if (t + 1 < len) {
+            if (isj) {
+#pragma unroll
+                for (int i = 0; i < 9; ++i) Rn[i] = __ldg(pose_b + (size_t)(t + 1) * 216 + j * 9 + i);
+#pragma unroll
+                for (int i = 0; i < 3; ++i) vn[i] = __ldg(vel_b + (size_t)(t + 1) * 72 + j * 3 + i);
+            }
+            cn0 = __ldg(con_b + (size_t)(t + 1) * 2);
+            cn1 = __ldg(con_b + (size_t)(t + 1) * 2 + 1);
+        }
+
+        float G[9], P[3];
+        warp_fk(R, j, isj, par, depth, bone, G, P);
+
+        float Rout[9];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) Rout[i] = R[i];
+        float dx = 0.f, dy = 0.f, dz = 0.f;
+
+        if (started) {
+            // ---- residuals and weights (lane = joint) ----------------------------------------------------------
+            const float wcl = p.w_contact * phys_prob_to_weight(c0), wcr = p.w_contact * phys_prob_to_weight(c1);
+            const float wc = (j == 10) ? wcl : ((j == 11) ? wcr : 0.f);
+            const float wx = px + P[0], wy = py + P[1], wz = pz + P[2];
+            const float cj = isj ? p.w_vel + wc : 0.f;
+            float s[3];
+            s[0] = isj ? p.w_vel * (q[0] + jv[0] - wx) + wc * (q[0] - wx) : 0.f;
+            s[1] = isj ? p.w_vel * (q[1] + jv[1] - wy) + wc * (q[1] - wy) : 0.f;
+            s[2] = isj ? p.w_vel * (q[2] + jv[2] - wz) + wc * (q[2] - wz) : 0.f;
+            if (isj) {
+#pragma unroll
+                for (int i = 0; i < 9; ++i) sG[j * 9 + i] = G[i];
+#pragma unroll
+                for (int i = 0; i < 3; ++i) { sP[j * 3 + i] = P[i]; sS[j * 3 + i] = s[i]; }
+                sC[j] = cj;
+            }
+            float c_tot = cj, s_tot[3] = {s[0], s[1], s[2]};
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                c_tot += __shfl_xor_sync(0xffffffffu, c_tot, o);
+#pragma unroll
+                for (int i = 0; i < 3; ++i) s_tot[i] += __shfl_xor_sync(0xffffffffu, s_tot[i], o);
+            }
+            __syncwarp();
+
+            // ---- subtree moments about the joint's own position (lanes of the optimised joints) ----------------
+            if (slot >= 0) {
+                float S1[3] = {0.f, 0.f, 0.f}, S2[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, T1[3] = {0.f, 0.f, 0.f};
+                for (int d = j + 1; d < NJ; ++d) {
+                    if (!((desc >> d) & 1u)) continue;
+                    const float rx = sP[d * 3] - P[0], ry = sP[d * 3 + 1] - P[1], rz = sP[d * 3 + 2] - P[2];
+                    const float cd = sC[d], sx = sS[d * 3], sy = sS[d * 3 + 1], sz = sS[d * 3 + 2];
+                    S1[0] = fmaf(cd, rx, S1[0]); S1[1] = fmaf(cd, ry, S1[1]); S1[2] = fmaf(cd, rz, S1[2]);
+                    S2[0] = fmaf(cd * rx, rx, S2[0]); S2[1] = fmaf(cd * rx, ry, S2[1]); S2[2] = fmaf(cd * rx, rz, S2[2]);
+                    S2[3] = fmaf(cd * ry, ry, S2[3]); S2[4] = fmaf(cd * ry, rz, S2[4]); S2[5] = fmaf(cd * rz, rz, S2[5]);
+                    T1[0] += ry * sz - rz * sy; T1[1] += rz * sx - rx * sz; T1[2] += rx * sy - ry * sx;
+                }
+#pragma unroll
+                for (int i = 0; i < 3; ++i) { sS1[j * 3 + i] = S1[i]; sT1[j * 3 + i] = T1[i]; }
+#pragma unroll
+                for (int i = 0; i < 6; ++i) sS2[j * 6 + i] = S2[i];
+            }
+            __syncwarp();
+
+            // ---- normal equations: rotation-rotation blocks of ancestor-related joint pairs --------------------
+            const int nitem = c_tab.npair * 9;
+            for (int it = lane; it < nitem; it += 32) {
+                const int pr = it / 9, a1 = (it % 9) / 3, a2 = it % 3;
+                const int ia = c_tab.pair_a[pr], id = c_tab.pair_d[pr];
+                const int ka = c_tab.ord[ia], kd = c_tab.ord[id];
+                const float g1x = sG[ka * 9 + a1], g1y = sG[ka * 9 + 3 + a1], g1z = sG[ka * 9 + 6 + a1];
+                const float g2x = sG[kd * 9 + a2], g2y = sG[kd * 9 + 3 + a2], g2z = sG[kd * 9 + 6 + a2];
+                const float ex = sP[kd * 3] - sP[ka * 3], ey = sP[kd * 3 + 1] - sP[ka * 3 + 1], ez = sP[kd * 3 + 2] - sP[ka * 3 + 2];
+                const float m1x = sS1[kd * 3], m1y = sS1[kd * 3 + 1], m1z = sS1[kd * 3 + 2];
+                const float* M = sS2 + kd * 6;     // xx xy xz yy yz zz
+                const float tr = M[0] + M[3] + M[5] + (ex * m1x + ey * m1y + ez * m1z);
+                // g2^T S2 g1
+                const float tx = M[0] * g1x + M[1] * g1y + M[2] * g1z, ty = M[1] * g1x + M[3] * g1y + M[4] * g1z,
+                            tz = M[2] * g1x + M[4] * g1y + M[5] * g1z;
+                const float quad = g2x * tx + g2y * ty + g2z * tz + (g2x * ex + g2y * ey + g2z * ez) * (m1x * g1x + m1y * g1y + m1z * g1z);
+                float v = (g1x * g2x + g1y * g2y + g1z * g2z) * tr - quad;
+                const int r = 3 * ia + a1, c = 3 * id + a2;
+                if (r == c) v = fmaf(v, p.damping, v) + p.damping_abs;      // Marquardt scaling of the rotational unknowns
+                // lower triangle only: slots of descendants come first, so (row, col) = (ancestor, descendant); inside a
+                // diagonal block both orders appear as separate items with the same value
+                if (r >= c) sH[r * LDH + c] = v;
+            }
+            // rotation-translation blocks, translation block, right-hand side (row 48)
+            for (int it = lane; it < NOPT * 3; it += 32) {
+                const int i = it / 3, a = it % 3, k = c_tab.ord[i];
+                const float gx = sG[k * 9 + a], gy = sG[k * 9 + 3 + a], gz = sG[k * 9 + 6 + a];
+                const float mx = sS1[k * 3], my = sS1[k * 3 + 1], mz = sS1[k * 3 + 2];
+                sH[45 * LDH + it] = gy * mz - gz * my;
+                sH[46 * LDH + it] = gz * mx - gx * mz;
+                sH[47 * LDH + it] = gx * my - gy * mx;
+                sH[48 * LDH + it] = gx * sT1[k * 3] + gy * sT1[k * 3 + 1] + gz * sT1[k * 3 + 2];
+            }
+            if (lane < 3) {
+                sH[(45 + lane) * LDH + 45] = lane == 0 ? c_tot : 0.f;
+                sH[(45 + lane) * LDH + 46] = lane == 1 ? c_tot : 0.f;
+                sH[(45 + lane) * LDH + 47] = lane == 2 ? c_tot : 0.f;
+                sH[48 * LDH + 45 + lane] = s_tot[lane];
+            }
+            __syncwarp();
+            if (p.dbg && t == p.dbg_frame) {
+                float* dbg = p.dbg + (size_t)b * (LDH * LDH + NX);
+                for (int i = lane; i < LDH * LDH; i += 32) dbg[i] = sH[i];
+            }
+
+            // ---- envelope Cholesky, left looking; lane l owns rows k + l and k + 32 + l of column k; row 48 = rhs -----
+#pragma unroll 1
+            for (int k = 0; k < NX; ++k) {
+                const int fk = c_tab.env[k];
+                const int i1 = k + lane, i2 = k + 32 + lane;
+                const bool h1 = i1 < LDH, h2 = i2 < LDH;
+                const float* rk = sH + k * LDH;
+                const float* r1 = sH + (h1 ? i1 : k) * LDH;
+                const float* r2 = sH + (h2 ? i2 : k) * LDH;
+                float a1 = r1[k], a2 = r2[k];
+                for (int m = fk; m < k; ++m) {
+                    const float lk = rk[m];
+                    a1 = fmaf(-r1[m], lk, a1);
+                    a2 = fmaf(-r2[m], lk, a2);
+                }
+                const float diag = __shfl_sync(0xffffffffu, a1, 0);
+                const float inv = rsqrtf(diag);
+                if (lane == 0) {
+                    sH[k * LDH + k] = inv;                  // the diagonal keeps 1 / L_kk
+                } else if (h1) {
+                    sH[i1 * LDH + k] = a1 * inv;
+                }
+                if (h2) sH[i2 * LDH + k] = a2 * inv;
+                __syncwarp();
+            }
+            // ---- back substitution L^T x = y (y = row 48); lane l owns x_l and x_{l+32} ---------------------------
+            float y1 = sH[48 * LDH + lane], y2 = (lane < NX - 32) ? sH[48 * LDH + 32 + lane] : 0.f;
+#pragma unroll 1
+            for (int i = NX - 1; i >= 0; --i) {
+                const float yi = __shfl_sync(0xffffffffu, i >= 32 ? y2 : y1, i & 31);
+                const float xi = yi * sH[i * LDH + i];
+                if (lane == (i & 31)) { if (i >= 32) y2 = xi; else y1 = xi; }
+                const float* ri = sH + i * LDH;
+                if (lane < i) y1 = fmaf(-ri[lane], xi, y1);
+                if (lane + 32 < i) y2 = fmaf(-ri[lane + 32], xi, y2);
+            }
+            sX[lane] = y1;
+            if (lane < NX - 32) sX[32 + lane] = y2;
+            __syncwarp();
+            if (p.dbg && t == p.dbg_frame) {
+                float* dbg = p.dbg + (size_t)b * (LDH * LDH + NX) + LDH * LDH;
+                for (int i = lane; i < NX; i += 32) dbg[i] = sX[i];
+            }
+
+            // ---- rotation update of the optimised joints (lane = joint) ----------------------------------------
+            if (slot >= 0) {
+                const float w0 = sX[3 * slot], w1 = sX[3 * slot + 1], w2 = sX[3 * slot + 2];
+                const float th2 = w0 * w0 + w1 * w1 + w2 * w2, th = sqrtf(th2);
+                const float A = sincf_stable(th), hb = sincf_stable(0.5f * th), Bc = 0.5f * hb * hb;
+                // E = (1 - B th^2) I + A [w]x + B w w^T
+                const float e0 = 1.f - Bc * th2;
+                const float E[9] = {e0 + Bc * w0 * w0, Bc * w0 * w1 - A * w2, Bc * w0 * w2 + A * w1,
+                                    Bc * w0 * w1 + A * w2, e0 + Bc * w1 * w1, Bc * w1 * w2 - A * w0,
+                                    Bc * w0 * w2 - A * w1, Bc * w1 * w2 + A * w0, e0 + Bc * w2 * w2};
+#pragma unroll
+                for (int r = 0; r < 3; ++r)
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) Rout[r * 3 + c] = fmaf(R[r * 3 + 2], E[6 + c], fmaf(R[r * 3 + 1], E[3 + c], R[r * 3] * E[c]));
+            }
+            dx = sX[45]; dy = sX[46]; dz = sX[47];
+            __syncwarp();
+            warp_fk(Rout, j, isj, par, depth, bone, G, P);
+        }
+
+        // ---- floor clamp (net.py:148-153's rule on the optimiser's own root), integration, state -----------------
+        const float fl = __shfl_sync(0xffffffffu, P[1], 10), fr = __shfl_sync(0xffffffffu, P[1], 11);
+        const float foot_y = fminf(fl, fr) + py + dy;
+        if (foot_y < p.floor_y) dy += p.floor_y - foot_y;
+        px += dx; py += dy; pz += dz;
+        q[0] = px + P[0]; q[1] = py + P[1]; q[2] = pz + P[2];
+        started = true;
+
+        if (isj) {
+            float* dst = out_b + (size_t)t * 216 + j * 9;
+#pragma unroll
+            for (int i = 0; i < 9; ++i) dst[i] = Rout[i];
+        }
+        if (p.tran_out && lane < 3) p.tran_out[((size_t)b * p.T + t) * 3 + lane] = lane == 0 ? px : (lane == 1 ? py : pz);
+    }
+
+    // frames past the sequence's length pass through (pose) / hold the last root position (tran)
+    for (int t = len; t < p.T; ++t) {
+        if (isj && p.pose_out != p.pose) {
+#pragma unroll
+            for (int i = 0; i < 9; ++i) out_b[(size_t)t * 216 + j * 9 + i] = pose_b[(size_t)t * 216 + j * 9 + i];
+        }
+        if (p.tran_out && lane < 3) p.tran_out[((size_t)b * p.T + t) * 3 + lane] = lane == 0 ? px : (lane == 1 ? py : pz);
+    }
+
+    if (lane == 0) { st[0] = px; st[1] = py; st[2] = pz; st[3] = started ? 1.f : 0.f; }
+    if (isj) { st[4 + j * 3] = q[0]; st[5 + j * 3] = q[1]; st[6 + j * 3] = q[2]; }
+}
+
+__global__ void physics_fk_kernel(const float* __restrict__ pose, long long n, float* __restrict__ glb, float* __restrict__ pos) {
+    const int lane = threadIdx.x & 31;
+    const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const bool isj = lane < NJ;
+    const int j = isj ? lane : 0;
+    const int par = c_tab.parent[j] < 0 ? 0 : c_tab.parent[j];
+    const int depth = c_tab.depth[j];
+    const float bone[3] = {c_tab.bone[j][0], c_tab.bone[j][1], c_tab.bone[j][2]};
+    for (long long f = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; f < n; f += warps) {
+        float R[9], G[9], P[3];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) R[i] = isj ? __ldg(pose + f * 216 + j * 9 + i) : 0.f;
+        warp_fk(R, j, isj, par, depth, bone, G, P);
+        if (isj) {
+#pragma unroll
+            for (int i = 0; i < 9; ++i) glb[f * 216 + j * 9 + i] = G[i];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) pos[f * 72 + j * 3 + i] = P[i];
+        }
+    }
+}
+
+}  // namespace
+
+int launch_physics_optimize(const float* pose, const float* vel, const float* contact, const int32_t* lengths, float* state,
+                            int B, int T, const mp_physics_params_t* prm, float* pose_out, float* tran_out, float* dbg,
+                            int dbg_frame, cudaStream_t stream) {
+    MP_REQUIRE(pose && vel && contact && state && pose_out && prm, "physics: null pointer");
+    MP_REQUIRE(B > 0 && T > 0, "physics: B = %d, T = %d", B, T);
+    MP_REQUIRE(prm->damping >= 0.f && prm->damping_abs > 0.f && prm->w_vel > 0.f && prm->w_contact >= 0.f && prm->fps > 0.f,
+               "physics: w_vel, damping_abs and fps must be positive, damping and w_contact non-negative");
+    MP_TRY(upload_tables());
+    PhysParams p{pose, vel, contact, lengths, state, pose_out, tran_out, dbg, B, T, dbg_frame, prm->vel_scale / prm->fps,
+                 prm->w_vel, prm->w_contact, prm->damping, prm->damping_abs, prm->floor_y};
+    // algorithmic bytes: pose in + out, velocity, contact, translation
+    ProfileScope prof("k8_physics", (double)B * T * (864.0 * 2 + 288 + 8 + 12), stream);
+    physics_optimize_kernel<<<B, 32, 0, stream>>>(p);
+    MP_CUDA_TRY(cudaGetLastError());
+    count_launch();
+    return MP_OK;
+}
+
+int launch_physics_fk(const float* pose, int64_t n, float* glb, float* pos, cudaStream_t stream) {
+    MP_REQUIRE(pose && glb && pos && n > 0, "physics_fk: bad arguments");
+    MP_TRY(upload_tables());
+    const int blocks = (int)std::min<int64_t>((n + 7) / 8, 148 * 8);
+    physics_fk_kernel<<<blocks, 256, 0, stream>>>(pose, n, glb, pos);
+    MP_CUDA_TRY(cudaGetLastError());
+    count_launch();
+    return MP_OK;
+}
+
+}  // namespace mp

@@ -82,11 +82,12 @@ class MobilePoserNet(nn.Module):
         self.imu = None
         self.reuse_outputs = False        # True: return views of the static buffers (no clone)
 
+        # net.py:66-69.  The reference imports `dynamics.PhysicsOptimizer`, a module that is not in its tree
+        # (SURVEY.md F2); here the hook is served by mobileposer_b200.dynamics (parity unpinned).
+        self.dynamics_optimizer = None
+        self.last_physics_tran = None
         if getenv("PHYSICS"):
-            # net.py:66-69: the reference imports a module that is not in its tree
-            from dynamics import PhysicsOptimizer
-            self.dynamics_optimizer = PhysicsOptimizer(debug=False)
-            self.dynamics_optimizer.reset_states()
+            self.enable_physics()
 
         self._net = None
         self._net_key = None
@@ -121,6 +122,15 @@ class MobilePoserNet(nn.Module):
             self._close_net()
         except Exception:
             pass
+
+    def enable_physics(self, on: bool = True, **params):
+        """PHYSICS=1 without the environment variable; `params` go to dynamics.PhysicsOptimizer."""
+        if on:
+            from .dynamics import PhysicsOptimizer
+            self.dynamics_optimizer = PhysicsOptimizer(debug=False, **params)
+            self.dynamics_optimizer.reset_states()
+        else:
+            self.dynamics_optimizer = None
 
     def set_graph(self, enabled: bool):
         _cabi.check(_cabi.lib().mp_net_set_graph(self._net_handle(), int(enabled)), 'mp_net_set_graph')
@@ -240,8 +250,17 @@ class MobilePoserNet(nn.Module):
         if tmax < s.T:
             raise RuntimeError('padded length must equal max(input_lengths)')
         pose, joints, tran, contact = self._out(s.pose), self._out(s.joints), self._out(s.tran), self._out(s.contact)
-        if getenv("PHYSICS"):
-            raise NotImplementedError('PHYSICS=1: the reference optimizer module `dynamics` is not part of its tree')
+        if self.dynamics_optimizer is not None:
+            # net.py:157-169: per-frame optimize_frame over the sequence, here B skeletons x T frames in one launch;
+            # the optimizer's translation is discarded like the reference does (`pose, _ = ...`).  B == 1 keeps the
+            # reference's state carry between calls (reset_states() is only called by the constructor, net.py:69);
+            # batched sequences start from a fresh state each (same convention as the velocity state, F6).
+            if B > 1:
+                self.dynamics_optimizer.reset_states()
+            lens = s.lengths if min(self._lengths(input_lengths, B, s.T)) < s.T else None
+            pose_opt, self.last_physics_tran = self.dynamics_optimizer.optimize_sequences(
+                s.pose.view(B, s.T, 24, 3, 3), s.vel, s.contact, lens, out=pose.view(B, s.T, 24, 9))
+            pose = pose_opt.view(B * s.T, 24, 3, 3)
         if B == 1:
             return pose, joints, tran[0], contact[0]
         return pose, joints, tran, contact
@@ -259,6 +278,8 @@ class MobilePoserNet(nn.Module):
         st = self._online_state(1, data.device)
         pose, joints, root, contact = st.step(data.reshape(1, 60))
         self.imu = st.window[0]
+        if self.dynamics_optimizer is not None:
+            return pose[0].view(24, 3, 3), joints[0], root[0].clone(), contact[0]      # net.py:216-217
         return pose[0].view(24, 9), joints[0], root[0].clone(), contact[0]
 
     @torch.no_grad()
@@ -331,6 +352,11 @@ class OnlineStreams:
                                              s.vel.data_ptr(), s.contact.data_ptr(), self.S, self.W, self.P,
                                              self.pose.data_ptr(), self.root.data_ptr(), self.contact.data_ptr(), stream),
                         'mp_online_update')
+            if net.dynamics_optimizer is not None:
+                # net.py:211-217: optimize the tick's frame (joint velocity of frame P times vel_scale); tran discarded
+                net.dynamics_optimizer.optimize_sequences(self.pose.view(self.S, 1, 24, 3, 3), s.vel[:, self.P:self.P + 1],
+                                                          self.contact.view(self.S, 1, 2), None,
+                                                          out=self.pose.view(self.S, 1, 24, 9))
         return self.pose, s.joints if net.reuse_outputs else s.joints.clone(), self.root, self.contact.clone()
 
 
