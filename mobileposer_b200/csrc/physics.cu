@@ -27,7 +27,8 @@ namespace mp {
 
 namespace {
 
-constexpr int NJ = 24, NOPT = 15, NX = 48, LDH = 49;
+constexpr int NJ = 24, NOPT = 15, NX = 48, NROW = 49, LDH = 52;   // 49 rows (row 48 = rhs), 16-byte aligned row stride
+constexpr int NITEM_MAX = 512;
 constexpr int MAX_PAIRS = 64;
 
 struct PhysTables {
@@ -39,7 +40,7 @@ struct PhysTables {
     int slot[NJ];               // joint -> slot in `ord` or -1
     int npair;
     unsigned char pair_a[MAX_PAIRS], pair_d[MAX_PAIRS];   // (ancestor-or-self slot, deeper slot)
-    int env[LDH];               // first column of each row's envelope
+    int env[NROW];              // first column of each row's envelope
 };
 
 __constant__ PhysTables c_tab;
@@ -105,7 +106,7 @@ PhysTables build_tables() {
         for (int a = 0; a < 3; ++a) t.env[3 * i + a] = 3 * first_desc[i];
         if (3 * first_desc[i] < lo) lo = 3 * first_desc[i];
     }
-    for (int r = 45; r < LDH; ++r) t.env[r] = 0;     // translation rows and the right-hand side couple with everything
+    for (int r = 45; r < NROW; ++r) t.env[r] = 0;     // translation rows and the right-hand side couple with everything
     return t;
 }
 
@@ -143,7 +144,7 @@ __device__ __forceinline__ void warp_fk(const float (&R)[9], int j, bool isj, in
 #pragma unroll
     for (int i = 0; i < 9; ++i) G[i] = R[i];
     P[0] = P[1] = P[2] = 0.f;
-#pragma unroll 1
+#pragma unroll
     for (int lvl = 1; lvl <= 8; ++lvl) {
         float Gp[9], Pp[3];
 #pragma unroll
@@ -176,8 +177,10 @@ __global__ void __launch_bounds__(32) physics_optimize_kernel(const PhysParams p
     __shared__ float sS1[NJ * 3];
     __shared__ float sS2[NJ * 6];
     __shared__ float sT1[NJ * 3];
-    __shared__ float sH[LDH * LDH];
+    __shared__ __align__(16) float sH[NROW * LDH];
     __shared__ float sX[NX];
+    __shared__ uint32_t sItem[NITEM_MAX];     // rotation-rotation entries: ka | kd<<5 | a1<<10 | a2<<12 | row<<14 | col<<20 | valid<<31
+    __shared__ int sOrd[NOPT];
 
     const int lane = threadIdx.x;
     const int b = blockIdx.x;
@@ -197,7 +200,18 @@ __global__ void __launch_bounds__(32) physics_optimize_kernel(const PhysParams p
     float q[3] = {0.f, 0.f, 0.f};
     if (isj) { q[0] = st[4 + j * 3]; q[1] = st[5 + j * 3]; q[2] = st[6 + j * 3]; }
 
-    for (int i = lane; i < LDH * LDH; i += 32) sH[i] = 0.f;
+    for (int i = lane; i < NROW * LDH; i += 32) sH[i] = 0.f;
+    // entry descriptors of the rotation-rotation blocks (the constant tables are indexed per lane: read them once)
+    const int nitem = c_tab.npair * 9;
+    for (int it = lane; it < nitem; it += 32) {
+        const int pr = it / 9, a1 = (it % 9) / 3, a2 = it % 3;
+        const int ia = c_tab.pair_a[pr], id = c_tab.pair_d[pr];
+        const int r = 3 * ia + a1, c = 3 * id + a2;
+        sItem[it] = (uint32_t)c_tab.ord[ia] | ((uint32_t)c_tab.ord[id] << 5) | ((uint32_t)a1 << 10) | ((uint32_t)a2 << 12) |
+                    ((uint32_t)r << 14) | ((uint32_t)c << 20) | (r >= c ? 0x80000000u : 0u);
+    }
+    if (lane < NOPT) sOrd[lane] = c_tab.ord[lane];
+    __syncwarp();
 
     const float* pose_b = p.pose + (size_t)b * p.T * 216;
     const float* vel_b = p.vel + (size_t)b * p.T * 72;
@@ -267,8 +281,9 @@ __global__ void __launch_bounds__(32) physics_optimize_kernel(const PhysParams p
             // ---- subtree moments about the joint's own position (lanes of the optimised joints) ----------------
             if (slot >= 0) {
                 float S1[3] = {0.f, 0.f, 0.f}, S2[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, T1[3] = {0.f, 0.f, 0.f};
-                for (int d = j + 1; d < NJ; ++d) {
-                    if (!((desc >> d) & 1u)) continue;
+#pragma unroll 2
+                for (unsigned rest = desc & ~(1u << j); rest; rest &= rest - 1) {
+                    const int d = __ffs(rest) - 1;
                     const float rx = sP[d * 3] - P[0], ry = sP[d * 3 + 1] - P[1], rz = sP[d * 3 + 2] - P[2];
                     const float cd = sC[d], sx = sS[d * 3], sy = sS[d * 3 + 1], sz = sS[d * 3 + 2];
                     S1[0] = fmaf(cd, rx, S1[0]); S1[1] = fmaf(cd, ry, S1[1]); S1[2] = fmaf(cd, rz, S1[2]);
@@ -284,11 +299,11 @@ __global__ void __launch_bounds__(32) physics_optimize_kernel(const PhysParams p
             __syncwarp();
 
             // ---- normal equations: rotation-rotation blocks of ancestor-related joint pairs --------------------
-            const int nitem = c_tab.npair * 9;
+#pragma unroll 2
             for (int it = lane; it < nitem; it += 32) {
-                const int pr = it / 9, a1 = (it % 9) / 3, a2 = it % 3;
-                const int ia = c_tab.pair_a[pr], id = c_tab.pair_d[pr];
-                const int ka = c_tab.ord[ia], kd = c_tab.ord[id];
+                const uint32_t ds = sItem[it];
+                const int ka = ds & 31, kd = (ds >> 5) & 31, a1 = (ds >> 10) & 3, a2 = (ds >> 12) & 3;
+                const int r = (ds >> 14) & 63, c = (ds >> 20) & 63;
                 const float g1x = sG[ka * 9 + a1], g1y = sG[ka * 9 + 3 + a1], g1z = sG[ka * 9 + 6 + a1];
                 const float g2x = sG[kd * 9 + a2], g2y = sG[kd * 9 + 3 + a2], g2z = sG[kd * 9 + 6 + a2];
                 const float ex = sP[kd * 3] - sP[ka * 3], ey = sP[kd * 3 + 1] - sP[ka * 3 + 1], ez = sP[kd * 3 + 2] - sP[ka * 3 + 2];
@@ -300,15 +315,14 @@ __global__ void __launch_bounds__(32) physics_optimize_kernel(const PhysParams p
                             tz = M[2] * g1x + M[4] * g1y + M[5] * g1z;
                 const float quad = g2x * tx + g2y * ty + g2z * tz + (g2x * ex + g2y * ey + g2z * ez) * (m1x * g1x + m1y * g1y + m1z * g1z);
                 float v = (g1x * g2x + g1y * g2y + g1z * g2z) * tr - quad;
-                const int r = 3 * ia + a1, c = 3 * id + a2;
                 if (r == c) v = fmaf(v, p.damping, v) + p.damping_abs;      // Marquardt scaling of the rotational unknowns
                 // lower triangle only: slots of descendants come first, so (row, col) = (ancestor, descendant); inside a
                 // diagonal block both orders appear as separate items with the same value
-                if (r >= c) sH[r * LDH + c] = v;
+                if (ds >> 31) sH[r * LDH + c] = v;
             }
             // rotation-translation blocks, translation block, right-hand side (row 48)
             for (int it = lane; it < NOPT * 3; it += 32) {
-                const int i = it / 3, a = it % 3, k = c_tab.ord[i];
+                const int i = it / 3, a = it % 3, k = sOrd[i];
                 const float gx = sG[k * 9 + a], gy = sG[k * 9 + 3 + a], gz = sG[k * 9 + 6 + a];
                 const float mx = sS1[k * 3], my = sS1[k * 3 + 1], mz = sS1[k * 3 + 2];
                 sH[45 * LDH + it] = gy * mz - gz * my;
@@ -324,51 +338,95 @@ __global__ void __launch_bounds__(32) physics_optimize_kernel(const PhysParams p
             }
             __syncwarp();
             if (p.dbg && t == p.dbg_frame) {
-                float* dbg = p.dbg + (size_t)b * (LDH * LDH + NX);
-                for (int i = lane; i < LDH * LDH; i += 32) dbg[i] = sH[i];
+                float* dbg = p.dbg + (size_t)b * (NROW * NROW + NX);
+                for (int i = lane; i < NROW * NROW; i += 32) dbg[i] = sH[(i / NROW) * LDH + i % NROW];
             }
 
-            // ---- envelope Cholesky, left looking; lane l owns rows k + l and k + 32 + l of column k; row 48 = rhs -----
+            // ---- envelope Cholesky, left looking, one joint (3 columns) per round; lane l owns rows c0 + l and c0 + 32 + l,
+            //      so lanes 0..2 hold the diagonal block; row 48 = right-hand side.  Rows are read 4 columns at a time.
 #pragma unroll 1
-            for (int k = 0; k < NX; ++k) {
-                const int fk = c_tab.env[k];
-                const int i1 = k + lane, i2 = k + 32 + lane;
-                const bool h1 = i1 < LDH, h2 = i2 < LDH;
-                const float* rk = sH + k * LDH;
-                const float* r1 = sH + (h1 ? i1 : k) * LDH;
-                const float* r2 = sH + (h2 ? i2 : k) * LDH;
-                float a1 = r1[k], a2 = r2[k];
-                for (int m = fk; m < k; ++m) {
-                    const float lk = rk[m];
-                    a1 = fmaf(-r1[m], lk, a1);
-                    a2 = fmaf(-r2[m], lk, a2);
+            for (int K = 0; K < NX / 3; ++K) {
+                const int c0 = 3 * K;
+                const int m_begin = c_tab.env[c0] & ~3;
+                const int i1 = c0 + lane, i2 = c0 + 32 + lane;
+                const bool h1 = i1 < NROW, h2 = i2 < NROW;
+                const float* rk = sH + c0 * LDH;
+                const float* r1 = sH + (h1 ? i1 : c0) * LDH;
+                const float* r2 = sH + (h2 ? i2 : c0) * LDH;
+                float a1[3] = {r1[c0], r1[c0 + 1], r1[c0 + 2]}, a2[3] = {r2[c0], r2[c0 + 1], r2[c0 + 2]};
+#pragma unroll 2
+                for (int m = m_begin; m < c0; m += 4) {
+                    const float4 u = *reinterpret_cast<const float4*>(r1 + m), w = *reinterpret_cast<const float4*>(r2 + m);
+                    float4 k0 = *reinterpret_cast<const float4*>(rk + m), k1 = *reinterpret_cast<const float4*>(rk + LDH + m),
+                           k2 = *reinterpret_cast<const float4*>(rk + 2 * LDH + m);
+                    if (m + 4 > c0) {      // the last chunk reaches into the not yet factored columns: drop them
+                        if (m + 1 >= c0) { k0.y = 0.f; k1.y = 0.f; k2.y = 0.f; }
+                        if (m + 2 >= c0) { k0.z = 0.f; k1.z = 0.f; k2.z = 0.f; }
+                        k0.w = 0.f; k1.w = 0.f; k2.w = 0.f;
+                    }
+                    a1[0] = fmaf(-u.x, k0.x, a1[0]); a1[0] = fmaf(-u.y, k0.y, a1[0]); a1[0] = fmaf(-u.z, k0.z, a1[0]); a1[0] = fmaf(-u.w, k0.w, a1[0]);
+                    a1[1] = fmaf(-u.x, k1.x, a1[1]); a1[1] = fmaf(-u.y, k1.y, a1[1]); a1[1] = fmaf(-u.z, k1.z, a1[1]); a1[1] = fmaf(-u.w, k1.w, a1[1]);
+                    a1[2] = fmaf(-u.x, k2.x, a1[2]); a1[2] = fmaf(-u.y, k2.y, a1[2]); a1[2] = fmaf(-u.z, k2.z, a1[2]); a1[2] = fmaf(-u.w, k2.w, a1[2]);
+                    a2[0] = fmaf(-w.x, k0.x, a2[0]); a2[0] = fmaf(-w.y, k0.y, a2[0]); a2[0] = fmaf(-w.z, k0.z, a2[0]); a2[0] = fmaf(-w.w, k0.w, a2[0]);
+                    a2[1] = fmaf(-w.x, k1.x, a2[1]); a2[1] = fmaf(-w.y, k1.y, a2[1]); a2[1] = fmaf(-w.z, k1.z, a2[1]); a2[1] = fmaf(-w.w, k1.w, a2[1]);
+                    a2[2] = fmaf(-w.x, k2.x, a2[2]); a2[2] = fmaf(-w.y, k2.y, a2[2]); a2[2] = fmaf(-w.z, k2.z, a2[2]); a2[2] = fmaf(-w.w, k2.w, a2[2]);
                 }
-                const float diag = __shfl_sync(0xffffffffu, a1, 0);
-                const float inv = rsqrtf(diag);
-                if (lane == 0) {
-                    sH[k * LDH + k] = inv;                  // the diagonal keeps 1 / L_kk
-                } else if (h1) {
-                    sH[i1 * LDH + k] = a1 * inv;
+                // 3 x 3 diagonal block (rows of lanes 0, 1, 2), factored redundantly by every lane
+                const float d00 = __shfl_sync(0xffffffffu, a1[0], 0);
+                const float d10 = __shfl_sync(0xffffffffu, a1[0], 1), d11 = __shfl_sync(0xffffffffu, a1[1], 1);
+                const float d20 = __shfl_sync(0xffffffffu, a1[0], 2), d21 = __shfl_sync(0xffffffffu, a1[1], 2),
+                            d22 = __shfl_sync(0xffffffffu, a1[2], 2);
+                const float v0 = rsqrtf(d00);
+                const float l10 = d10 * v0, l20 = d20 * v0;
+                const float v1 = rsqrtf(fmaf(-l10, l10, d11));
+                const float l21 = fmaf(-l20, l10, d21) * v1;
+                const float v2 = rsqrtf(fmaf(-l21, l21, fmaf(-l20, l20, d22)));
+                if (lane == 0) {       // the diagonal keeps 1 / L_kk
+                    sH[c0 * LDH + c0] = v0;
+                    sH[(c0 + 1) * LDH + c0] = l10; sH[(c0 + 1) * LDH + c0 + 1] = v1;
+                    sH[(c0 + 2) * LDH + c0] = l20; sH[(c0 + 2) * LDH + c0 + 1] = l21; sH[(c0 + 2) * LDH + c0 + 2] = v2;
                 }
-                if (h2) sH[i2 * LDH + k] = a2 * inv;
+                if (lane >= 3 && h1) {
+                    const float x0 = a1[0] * v0, x1 = fmaf(-x0, l10, a1[1]) * v1, x2 = fmaf(-x1, l21, fmaf(-x0, l20, a1[2])) * v2;
+                    float* w1 = sH + i1 * LDH + c0;
+                    w1[0] = x0; w1[1] = x1; w1[2] = x2;
+                }
+                if (h2) {
+                    const float x0 = a2[0] * v0, x1 = fmaf(-x0, l10, a2[1]) * v1, x2 = fmaf(-x1, l21, fmaf(-x0, l20, a2[2])) * v2;
+                    float* w2 = sH + i2 * LDH + c0;
+                    w2[0] = x0; w2[1] = x1; w2[2] = x2;
+                }
                 __syncwarp();
             }
-            // ---- back substitution L^T x = y (y = row 48); lane l owns x_l and x_{l+32} ---------------------------
+            // ---- back substitution L^T x = y (y = row 48), one joint per round; lane l owns x_l and x_{l+32} --------------
             float y1 = sH[48 * LDH + lane], y2 = (lane < NX - 32) ? sH[48 * LDH + 32 + lane] : 0.f;
 #pragma unroll 1
-            for (int i = NX - 1; i >= 0; --i) {
-                const float yi = __shfl_sync(0xffffffffu, i >= 32 ? y2 : y1, i & 31);
-                const float xi = yi * sH[i * LDH + i];
-                if (lane == (i & 31)) { if (i >= 32) y2 = xi; else y1 = xi; }
-                const float* ri = sH + i * LDH;
-                if (lane < i) y1 = fmaf(-ri[lane], xi, y1);
-                if (lane + 32 < i) y2 = fmaf(-ri[lane + 32], xi, y2);
+            for (int K = NX / 3 - 1; K >= 0; --K) {
+                const int c0 = 3 * K;
+                const float* rk = sH + c0 * LDH;
+                const float v0 = rk[c0], l10 = rk[LDH + c0], v1 = rk[LDH + c0 + 1], l20 = rk[2 * LDH + c0], l21 = rk[2 * LDH + c0 + 1],
+                            v2 = rk[2 * LDH + c0 + 2];
+                const float u0 = rk[lane], u1 = rk[LDH + lane], u2 = rk[2 * LDH + lane];            // columns l < c0 of the 3 rows
+                const float w0 = rk[(lane + 32) % LDH], w1 = rk[LDH + (lane + 32) % LDH], w2 = rk[2 * LDH + (lane + 32) % LDH];
+                const float yk0 = __shfl_sync(0xffffffffu, c0 >= 32 ? y2 : y1, c0 & 31);
+                const float yk1 = __shfl_sync(0xffffffffu, c0 + 1 >= 32 ? y2 : y1, (c0 + 1) & 31);
+                const float yk2 = __shfl_sync(0xffffffffu, c0 + 2 >= 32 ? y2 : y1, (c0 + 2) & 31);
+                const float x2 = yk2 * v2;
+                const float x1 = fmaf(-l21, x2, yk1) * v1;
+                const float x0 = fmaf(-l20, x2, fmaf(-l10, x1, yk0)) * v0;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const float xc = c == 0 ? x0 : (c == 1 ? x1 : x2);
+                    if (lane == ((c0 + c) & 31)) { if (c0 + c >= 32) y2 = xc; else y1 = xc; }
+                }
+                if (lane < c0) y1 = fmaf(-u2, x2, fmaf(-u1, x1, fmaf(-u0, x0, y1)));
+                if (lane + 32 < c0) y2 = fmaf(-w2, x2, fmaf(-w1, x1, fmaf(-w0, x0, y2)));
             }
             sX[lane] = y1;
             if (lane < NX - 32) sX[32 + lane] = y2;
             __syncwarp();
             if (p.dbg && t == p.dbg_frame) {
-                float* dbg = p.dbg + (size_t)b * (LDH * LDH + NX) + LDH * LDH;
+                float* dbg = p.dbg + (size_t)b * (NROW * NROW + NX) + NROW * NROW;
                 for (int i = lane; i < NX; i += 32) dbg[i] = sX[i];
             }
 
