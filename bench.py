@@ -4,7 +4,8 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg3|cfg2]
 
 Workloads (BASELINE.json configs):
-  cfg3 (default): MobilePoserNet 4 heads + kinematic tail (K5) + translation (K6) = forward_offline on a batch
+  cfg3 (default): MobilePoserNet 4 heads + kinematic tail (K5) + translation (K6) + the PHYSICS-hook optimizer (K8,
+                  --physics off to leave it out like the reference's default PHYSICS=0) = forward_offline on a batch
                   of 256 sequences x 300 frames per GPU (weak scaling: every rank gets its own 256 sequences);
   cfg2:           the same path at batch 1 (one 300-frame window), also reported inside the cfg3 line as "batch1".
 A "step" is one forward_offline pass over the batch.  `value` = frames/s with inputs resident in HBM,
@@ -47,6 +48,8 @@ def parse_args():
     ap.add_argument('--batch', type=int, default=0, help='override sequences per GPU')
     ap.add_argument('--cpu-sample', type=int, default=32, help='sequences in the CPU-baseline sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--physics', default='auto', choices=['auto', 'on', 'off'],
+                    help='K8 optimizer behind the PHYSICS hook (auto: on for cfg3, which names it; off for cfg2)')
     return ap.parse_args()
 
 
@@ -118,29 +121,39 @@ def dist_env():
 
 
 # ------------------------------------------------------------------------------------------------------
-def cpu_reference_pass(oracle, x, lens):
+def physics_on(args):
+    return args.physics == 'on' or (args.physics == 'auto' and args.workload == 'cfg3')
+
+
+def cpu_reference_pass(oracle, x, lens, physics=False):
     """The reference's CPU path for a batch: batched net.forward (net.py:101-119) + the per-sequence
-    translation tail of forward_offline (net.py:125-154)."""
+    translation tail of forward_offline (net.py:125-154) + (physics) the PHYSICS-hook loop of net.py:157-169 as the
+    compiled float64 statement of K8 (oracle/physics_port.c, one OpenMP thread per sequence)."""
     from oracle.torch_port import offline_translation
     oracle.vel_state = None
     pose, joints, vel, contact = oracle.forward(x, lens)
-    vel = vel.view(x.shape[0], x.shape[1], 72)
+    B, T = x.shape[0], x.shape[1]
+    vel = vel.view(B, T, 72)
     trans = [offline_translation(joints[b, :L], vel[b, :L], contact[b, :L]) for b, L in enumerate(lens)]
+    if physics:
+        from oracle.physics_c import PhysicsOptimizerC
+        pose_opt, _ = PhysicsOptimizerC(B=B).optimize_sequences(pose.view(B, T, 24, 3, 3).numpy(), vel.numpy(), contact.numpy(), lens)
+        pose = torch.from_numpy(pose_opt)
     return pose, joints, trans, contact
 
 
-def time_cpu_sample(sd, x_sample, budget_s=20.0, min_passes=2):
+def time_cpu_sample(sd, x_sample, budget_s=20.0, min_passes=2, physics=False):
     """frames/s of the oracle port on this box's host cores for a bounded sample; returns the cpu_baseline dict."""
     from oracle.torch_port import OraclePoser
     oracle = OraclePoser(sd)
     B, T = x_sample.shape[0], x_sample.shape[1]
     lens = [T] * B
     with torch.no_grad():
-        cpu_reference_pass(oracle, x_sample[:2], lens[:2])      # warm-up (MKL thread pools)
+        cpu_reference_pass(oracle, x_sample[:2], lens[:2], physics)      # warm-up (MKL thread pools)
         t0 = time.perf_counter()
         passes = 0
         while passes < min_passes or (time.perf_counter() - t0 < budget_s * 0.6 and passes < 50):
-            cpu_reference_pass(oracle, x_sample, lens)
+            cpu_reference_pass(oracle, x_sample, lens, physics)
             passes += 1
         dt_batched = (time.perf_counter() - t0) / passes
         # the reference's own evaluate.py call pattern: one sequence at a time (forward_offline, B = 1)
@@ -148,7 +161,10 @@ def time_cpu_sample(sd, x_sample, budget_s=20.0, min_passes=2):
         n1 = 0
         while n1 < 2 or (time.perf_counter() - t1 < budget_s * 0.3 and n1 < B):
             oracle.vel_state = None
-            oracle.forward_offline(x_sample[n1 % B:n1 % B + 1], [T])
+            if physics:
+                cpu_reference_pass(oracle, x_sample[n1 % B:n1 % B + 1], [T], True)
+            else:
+                oracle.forward_offline(x_sample[n1 % B:n1 % B + 1], [T])
             n1 += 1
         dt_single = (time.perf_counter() - t1) / n1
     fps_batched, fps_single = B * T / dt_batched, T / dt_single
@@ -156,6 +172,7 @@ def time_cpu_sample(sd, x_sample, budget_s=20.0, min_passes=2):
         'value': max(fps_batched, fps_single), 'unit': 'frames/s', 'cores': torch.get_num_threads(),
         'host_cpus': os.cpu_count(), 'kind': 'port',
         'sample': (f'{B} of the workload\'s sequences x {T} frames: batched forward + per-sequence translation tail '
+                   + ('+ K8 (C float64 port, OpenMP) ' if physics else '') +
                    f'= {fps_batched:.0f} frames/s ({passes} passes); evaluate.py-style one sequence at a time '
                    f'(forward_offline, B=1) = {fps_single:.0f} frames/s ({n1} sequences); torch {torch.__version__} CPU'),
         'batched_fps': fps_batched, 'single_sequence_fps': fps_single,
@@ -183,32 +200,35 @@ def run_reference(args):
     oracle = OraclePoser(sd)
     lens = [T_FRAMES] * Bs
     with torch.no_grad():
+        phys = physics_on(args)
         for _ in range(args.warmup):
-            cpu_reference_pass(oracle, x, lens)
+            cpu_reference_pass(oracle, x, lens, phys)
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            cpu_reference_pass(oracle, x, lens)
+            cpu_reference_pass(oracle, x, lens, phys)
         dt = time.perf_counter() - t0
     fps = Bs * T_FRAMES * args.steps / dt
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': fps, 'unit': 'frames/s', 'n_gpus': args.gpus,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': dt / args.steps * 1e3, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': workload_name(args.workload, B), 'sample': f'{Bs} sequences x {T_FRAMES} frames per step',
+        'config': {'workload': workload_name(args.workload, B, phys), 'sample': f'{Bs} sequences x {T_FRAMES} frames per step',
                    'combo': 'lw_rp', 'weights': 'torch.manual_seed(0) default init'},
         'cpu_baseline': {'value': fps, 'unit': 'frames/s', 'cores': torch.get_num_threads(), 'host_cpus': os.cpu_count(),
                          'kind': 'port', 'sample': f'{Bs} sequences x {T_FRAMES} frames per step, batched forward + '
-                                                   f'per-sequence translation tail, torch {torch.__version__} CPU'},
+                                                   f'per-sequence translation tail' + (' + K8 (C float64 port, OpenMP)' if phys else '') +
+                                                   f', torch {torch.__version__} CPU'},
         'e2e': {'value': fps, 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
     emit(json.dumps(line))
 
 
-def workload_name(w, B):
+def workload_name(w, B, physics=False):
     if w == 'cfg3':
-        return (f'cfg3: MobilePoserNet 4 heads + kinematic tail + translation (forward_offline), batch={B} sequences x '
-                f'{T_FRAMES} frames per GPU, combo lw_rp')
+        return (f'cfg3: MobilePoserNet 4 heads + kinematic tail + translation (forward_offline)'
+                + (' + physics-hook optimizer K8 (parity unpinned: the reference module is absent)' if physics else '')
+                + f', batch={B} sequences x {T_FRAMES} frames per GPU, combo lw_rp')
     return f'cfg2: full MobilePoserNet forward_offline, batch={B}, {T_FRAMES}-frame window, combo lw_rp'
 
 
@@ -258,6 +278,8 @@ def run_ours(args):
     net = net.to(dev)
     net.reuse_outputs = True
     lens = [T] * B
+    phys = physics_on(args)
+    net.enable_physics(phys)
 
     # several distinct input sets so a step never finds its inputs in L2 from the previous step
     n_sets = 8 if B > 1 else 64
@@ -274,6 +296,13 @@ def run_ours(args):
     launches = net.last_launches
     frames_per_step = B * T * world
     value = frames_per_step * args.steps / (ms / 1e3)
+    without_physics = None
+    if phys:      # the reference's default path (PHYSICS=0), for comparison with the pinned-parity number
+        net.enable_physics(False)
+        ms0 = timed_device_steps(step, args.steps, args.warmup, dist)
+        without_physics = {'value': frames_per_step * args.steps / (ms0 / 1e3), 'unit': 'frames/s', 'ms_per_step': ms0 / args.steps,
+                           'gpu_launches_per_step': net.last_launches}
+        net.enable_physics(True)
 
     # ---- e2e: host buffers through the C ABI, copies inside the timed region ------------------------
     host = mp.HostOffline(net, B, T)
@@ -342,6 +371,7 @@ def run_ours(args):
         gathered = list(out.shape)
 
     # ---- batch-1 latency configuration (cfg2) on rank 0's GPU, every rank a replica --------------------
+    net.enable_physics(False)      # cfg2 / cfg5 do not name the optimizer
     batch1 = None
     if args.workload == 'cfg3':
         x1 = [synthetic_imu_batch([90000 + rank * 64 + i], T).to(dev) for i in range(16)]
@@ -365,21 +395,21 @@ def run_ours(args):
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu = time_cpu_sample(sd, xs_host[0][:min(B, args.cpu_sample)].clone())
+        cpu = time_cpu_sample(sd, xs_host[0][:min(B, args.cpu_sample)].clone(), physics=phys)
 
     if rank == 0:
         line = {
             'metric': METRIC, 'value': value, 'unit': 'frames/s', 'n_gpus': world, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': workload_name(args.workload, B), 'frames_per_step': frames_per_step,
+            'config': {'workload': workload_name(args.workload, B, phys), 'frames_per_step': frames_per_step,
                        'weights': 'torch.manual_seed(0) default init (bit-identical to the reference init)',
                        'l2': f'{n_sets} distinct resident input sets rotate between steps; per-step intermediates '
                              f'({net_workspace_mb(net, B, T):.0f} MB) exceed the 126 MB L2',
                        'parallelism': f'{world} x (one process per GPU, sequences sharded, no data-path collective)'},
             'e2e': e2e, 'gpu_launches': launches * args.steps, 'gpu_launches_per_step': launches,
             'roofline': roofline, 'whole_path_algorithmic_GBps': whole, 'whole_path_hbm_frac': whole / peak,
-            'kernels': kernels, 'cpu_baseline': cpu, 'batch1': batch1, 'streaming': streaming, 'clocks': clocks.summary(),
+            'kernels': kernels, 'without_physics': without_physics, 'cpu_baseline': cpu, 'batch1': batch1, 'streaming': streaming, 'clocks': clocks.summary(),
             'all_gather_shape': gathered,
         }
         emit(json.dumps(line))

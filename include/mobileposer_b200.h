@@ -177,6 +177,10 @@ int mp_net_create(mp_net_t** out, const mp_rnn_t* joints, const mp_rnn_t* pose,
                   const mp_rnn_t* foot_contact, const mp_rnn_t* velocity);
 void mp_net_destroy(mp_net_t* net);
 size_t mp_net_workspace_bytes(const mp_net_t* net, int32_t B, int32_t T);
+/* PHYSICS hook inside the net (net.py:157-169): with non-NULL params every mp_net_forward that computes the
+ * translation (tran != NULL, i.e. forward_offline) finishes with K8 over the pose, in place, each sequence from a
+ * fresh optimizer state; NULL switches it off (default).  Parity unpinned, see mp_physics_optimize.            */
+int mp_net_set_physics(mp_net_t* net, const mp_physics_params_t* params);
 /* 1 = replay the forward as a cached CUDA graph keyed on (pointers, B, T) (default 1). */
 int mp_net_set_graph(mp_net_t* net, int32_t enabled);
 

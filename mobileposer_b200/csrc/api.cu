@@ -81,6 +81,9 @@ struct mp_net {
     cudaStream_t s_foot = nullptr, s_vel = nullptr, s_cap = nullptr;
     cudaEvent_t ev_joints = nullptr, ev_foot = nullptr, ev_vel = nullptr;
     int graph_enabled = 1;
+    int physics_on = 0;              // K8 tail of forward_offline (mp_net_set_physics)
+    uint64_t physics_epoch = 0;      // bumps whenever the parameters change: part of the graph key
+    mp_physics_params_t phys = {};
     struct Entry {
         std::vector<uintptr_t> key;
         cudaGraphExec_t exec = nullptr;
@@ -382,13 +385,26 @@ void mp_net_destroy(mp_net_t* n) {
     delete n;
 }
 
+int mp_net_set_physics(mp_net_t* n, const mp_physics_params_t* params) {
+    MP_REQUIRE(n, "net_set_physics: null");
+    if (!params) {
+        n->physics_on = 0;
+        return MP_OK;
+    }
+    MP_TRY(physics_prepare());
+    n->phys = *params;
+    n->physics_on = 1;
+    ++n->physics_epoch;
+    return MP_OK;
+}
+
 int mp_net_set_graph(mp_net_t* n, int32_t enabled) {
     MP_REQUIRE(n, "net_set_graph: null");
     n->graph_enabled = enabled ? 1 : 0;
     return MP_OK;
 }
 
-static void net_ws_layout(const mp_net* n, int B, int T, size_t off[5], size_t* total) {
+static void net_ws_layout(const mp_net* n, int B, int T, size_t off[6], size_t* total) {
     size_t o = 0;
     const mp_rnn* heads[4] = {n->joints, n->pose, n->foot, n->vel};
     for (int i = 0; i < 4; ++i) {
@@ -397,12 +413,14 @@ static void net_ws_layout(const mp_net* n, int B, int T, size_t off[5], size_t* 
     }
     off[4] = o;   // r6d [B*T, 96]
     o = align_up(o + (size_t)B * T * 96 * sizeof(float));
+    off[5] = o;   // K8 state [B, MP_PHYSICS_STATE_FLOATS]
+    o = align_up(o + (size_t)B * MP_PHYSICS_STATE_FLOATS * sizeof(float));
     *total = o;
 }
 
 size_t mp_net_workspace_bytes(const mp_net_t* n, int32_t B, int32_t T) {
     if (!n || B <= 0 || T <= 0) return 0;
-    size_t off[5], total;
+    size_t off[6], total;
     net_ws_layout(n, B, T, off, &total);
     return total;
 }
@@ -417,7 +435,7 @@ struct NetArgs {
 // Enqueue the whole forward: joints on `s`, then pose(+K5) on `s`, foot_contact and velocity on the
 // net's side streams (forked after joints, joined before K6).          net.py:101-119,125-154
 static int net_enqueue(mp_net* n, const NetArgs& a, cudaStream_t s) {
-    size_t off[5], total;
+    size_t off[6], total;
     net_ws_layout(n, a.B, a.T, off, &total);
     char* ws = (char*)a.ws;
     auto wsz = [&](int i) { return (i < 3 ? off[i + 1] : off[4]) - off[i]; };
@@ -440,6 +458,13 @@ static int net_enqueue(mp_net* n, const NetArgs& a, cudaStream_t s) {
     MP_CUDA_TRY(cudaStreamWaitEvent(s, n->ev_foot, 0));
     MP_CUDA_TRY(cudaStreamWaitEvent(s, n->ev_vel, 0));
     if (a.tran) MP_TRY(launch_tran_offline(a.joints, a.vel, a.contact, a.lengths, a.B, a.T, a.tran, s));
+    if (a.tran && n->physics_on) {
+        // net.py:157-169: the PHYSICS hook rewrites the pose in place (its translation is discarded); every sequence
+        // of the batch starts from a fresh optimizer state
+        float* st = (float*)(ws + off[5]);
+        MP_CUDA_TRY(cudaMemsetAsync(st, 0, (size_t)a.B * MP_PHYSICS_STATE_FLOATS * sizeof(float), s));
+        MP_TRY(launch_physics_optimize(a.pose, a.vel, a.contact, a.lengths, st, a.B, a.T, &n->phys, a.pose, nullptr, nullptr, -1, s));
+    }
     return MP_OK;
 }
 
@@ -462,7 +487,7 @@ int mp_net_forward(mp_net_t* n, const float* imu, int32_t B, int32_t T, const in
     std::vector<uintptr_t> key = {(uintptr_t)imu, (uintptr_t)B, (uintptr_t)T, (uintptr_t)lengths, (uintptr_t)vel_h0,
                                   (uintptr_t)vel_c0, (uintptr_t)vel_hn, (uintptr_t)vel_cn, (uintptr_t)pose,
                                   (uintptr_t)joints, (uintptr_t)vel, (uintptr_t)contact, (uintptr_t)tran,
-                                  (uintptr_t)workspace};
+                                  (uintptr_t)workspace, (uintptr_t)(n->physics_on ? n->physics_epoch : 0)};
     mp_net::Entry* hit = nullptr;
     for (auto& en : n->cache)
         if (en.key == key) hit = &en;

@@ -98,6 +98,7 @@ int launch_physics_optimize(const float* pose, const float* vel, const float* co
                             int B, int T, const mp_physics_params_t* prm, float* pose_out, float* tran_out, float* dbg,
                             int dbg_frame, cudaStream_t stream);
 int launch_physics_fk(const float* pose, int64_t n, float* glb, float* pos, cudaStream_t stream);
+int physics_prepare();   // uploads the constant tables of the current device (must not happen inside a graph capture)
 
 // ---- PTX helpers (clusters, mbarrier, distributed shared memory) ---------------------------
 #ifdef __CUDACC__

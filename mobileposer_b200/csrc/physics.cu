@@ -521,6 +521,8 @@ int launch_physics_optimize(const float* pose, const float* vel, const float* co
     return MP_OK;
 }
 
+int physics_prepare() { return upload_tables(); }
+
 int launch_physics_fk(const float* pose, int64_t n, float* glb, float* pos, cudaStream_t stream) {
     MP_REQUIRE(pose && glb && pos && n > 0, "physics_fk: bad arguments");
     MP_TRY(upload_tables());

@@ -19,7 +19,7 @@ import torch
 import torch.nn as nn
 
 from . import _cabi
-from .config import (FLOOR_Y, SMPL_J_ZERO, SMPL_PARENT, joint_set, model_config)
+from .config import (FLOOR_Y, SMPL_J_ZERO, SMPL_PARENT, amass, joint_set, model_config)
 from .modules import FootContact, Joints, Poser, Velocity, _require_cuda, _f32c, current_stream_ptr
 
 
@@ -91,6 +91,7 @@ class MobilePoserNet(nn.Module):
 
         self._net = None
         self._net_key = None
+        self._net_physics = None
         self._slots = {}
         self._online = None
         self.last_launches = 0
@@ -109,7 +110,22 @@ class MobilePoserNet(nn.Module):
                 _cabi.check(_cabi.lib().mp_net_create(C.byref(out), *handles), 'mp_net_create')
             self._net, self._net_key = out.value, handles
             self._slots = {}
+            self._net_physics = None
         return self._net
+
+    def _sync_net_physics(self, inline: bool):
+        """Switch the in-graph K8 tail of mp_net_forward on (batched forward_offline) or off."""
+        net = self._net_handle()
+        want = None
+        if inline and self.dynamics_optimizer is not None:
+            prm = _cabi.PhysicsParams.from_buffer_copy(self.dynamics_optimizer.params)
+            prm.vel_scale = amass.vel_scale
+            want = bytes(prm)
+        if want != self._net_physics:
+            arg = C.byref(_cabi.PhysicsParams.from_buffer_copy(want)) if want is not None else None
+            with torch.cuda.device(self._device()):
+                _cabi.check(_cabi.lib().mp_net_set_physics(net, arg), 'mp_net_set_physics')
+            self._net_physics = want
 
     def _close_net(self):
         if self._net is not None:
@@ -182,7 +198,7 @@ class MobilePoserNet(nn.Module):
         return lens
 
     @torch.no_grad()
-    def _run(self, batch, input_lengths, want_tran, carry_velocity):
+    def _run(self, batch, input_lengths, want_tran, carry_velocity, physics_inline=False):
         """One fused mp_net_forward; returns the slot holding the results."""
         _require_cuda(batch, 'input batch')
         lib = _cabi.lib()
@@ -193,6 +209,7 @@ class MobilePoserNet(nn.Module):
         dev = x.device
         lens = self._lengths(input_lengths, B, T)
         net = self._net_handle()
+        self._sync_net_physics(physics_inline)
         s = self._slot(B, T, dev)
         s.imu.copy_(x)
         ragged = min(lens) < T
@@ -246,21 +263,18 @@ class MobilePoserNet(nn.Module):
         if input_lengths is None:
             raise ValueError('forward_offline needs input_lengths (every reference caller passes them)')
         B = imu.shape[0]
-        s, tmax = self._run(imu, input_lengths, want_tran=True, carry_velocity=(B == 1))
+        # batched sequences: K8 runs inside the net's graph (fresh optimizer state per sequence, F6 convention)
+        s, tmax = self._run(imu, input_lengths, want_tran=True, carry_velocity=(B == 1), physics_inline=(B > 1))
         if tmax < s.T:
             raise RuntimeError('padded length must equal max(input_lengths)')
         pose, joints, tran, contact = self._out(s.pose), self._out(s.joints), self._out(s.tran), self._out(s.contact)
-        if self.dynamics_optimizer is not None:
-            # net.py:157-169: per-frame optimize_frame over the sequence, here B skeletons x T frames in one launch;
-            # the optimizer's translation is discarded like the reference does (`pose, _ = ...`).  B == 1 keeps the
-            # reference's state carry between calls (reset_states() is only called by the constructor, net.py:69);
-            # batched sequences start from a fresh state each (same convention as the velocity state, F6).
-            if B > 1:
-                self.dynamics_optimizer.reset_states()
-            lens = s.lengths if min(self._lengths(input_lengths, B, s.T)) < s.T else None
+        if self.dynamics_optimizer is not None and B == 1:
+            # net.py:157-169: per-frame optimize_frame over the sequence, here one launch; the optimizer's translation is
+            # discarded like the reference does (`pose, _ = ...`).  B == 1 keeps the reference's state carry between calls
+            # (reset_states() is only called by the constructor, net.py:69).
             pose_opt, self.last_physics_tran = self.dynamics_optimizer.optimize_sequences(
-                s.pose.view(B, s.T, 24, 3, 3), s.vel, s.contact, lens, out=pose.view(B, s.T, 24, 9))
-            pose = pose_opt.view(B * s.T, 24, 3, 3)
+                s.pose.view(1, s.T, 24, 3, 3), s.vel, s.contact, None, out=pose.view(1, s.T, 24, 9))
+            pose = pose_opt.view(s.T, 24, 3, 3)
         if B == 1:
             return pose, joints, tran[0], contact[0]
         return pose, joints, tran, contact
@@ -390,6 +404,7 @@ class HostOffline:
             lens = self.net._lengths(input_lengths, self.B, self.T)
             self.lengths.copy_(torch.tensor(lens, dtype=torch.int32))
             lens_ptr = self.lengths.data_ptr()
+        self.net._sync_net_physics(True)
         with torch.cuda.device(self.dev):
             _cabi.check(_cabi.lib().mp_net_forward_offline_host(
                 self.net._net_handle(), imu_host.data_ptr(), self.B, self.T, lens_ptr, self.pose.data_ptr(),

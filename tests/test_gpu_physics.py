@@ -142,3 +142,30 @@ def test_forward_offline_with_physics_hook(seeded_state_dict, oracle):
     for b, L in enumerate(lens):
         assert max_angle(pose[b, :L], torch.from_numpy(ref_pose[b, :L])) <= ANGLE_TOL
     assert max_angle(pose[0], p0.view(2, 48, 24, 3, 3)[0]) > 1e-3       # the hook did something
+
+
+def test_forward_offline_b1_carries_the_optimizer_state(seeded_state_dict):
+    """B == 1 is the reference's own call pattern: reset_states() only runs in the constructor (net.py:69), so the
+    optimizer state of one forward_offline call is the initial state of the next."""
+    import mobileposer_b200 as mp
+    from mobileposer_b200.synthetic import synthetic_imu_batch
+    net = mp.MobilePoserNet()
+    net.load_state_dict(seeded_state_dict)
+    net = net.to(DEV).eval()
+    xs = [synthetic_imu_batch([9], 30).to(DEV), synthetic_imu_batch([10], 24).to(DEV)]
+    net.enable_physics()
+    got = []
+    for x in xs:
+        net.velocity.rnn_state = None
+        got.append(net.forward_offline(x, [x.shape[1]])[0])
+    net.enable_physics(False)
+    port = pp.PhysicsOptimizerPort(B=1)
+    for x, pose in zip(xs, got):
+        T = x.shape[1]
+        net.velocity.rnn_state = None
+        p0, _, _, c0 = net.forward_offline(x, [T])
+        net.velocity.rnn_state = None
+        vel = net.forward(x, [T])[2]
+        ref, _ = port.optimize_sequences(p0.view(1, T, 24, 3, 3).cpu().numpy(), vel.view(1, T, 72).cpu().numpy(),
+                                         c0.view(1, T, 2).cpu().numpy())
+        assert max_angle(pose.view(T, 24, 3, 3), torch.from_numpy(ref[0])) <= ANGLE_TOL

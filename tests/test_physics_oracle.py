@@ -78,3 +78,13 @@ def test_floor_clamp_and_ragged_lengths():
         assert feet_y[b, :L].min() >= pp.FLOOR_Y - 1e-12
         assert np.array_equal(pose[b, L:], R[b, L:].astype(np.float64))      # frames past the length pass through
     assert np.linalg.norm(pose.reshape(-1, 3, 3) @ pose.reshape(-1, 3, 3).transpose(0, 2, 1) - np.eye(3), axis=(1, 2)).max() < 1e-6    # the inputs are float32 rotations
+
+
+def test_c_port_matches_numpy_port():
+    """oracle/physics_port.c (what bench.py's CPU arm times) == oracle/physics_port.py, ragged batch included."""
+    from oracle.physics_c import PhysicsOptimizerC
+    R, vel, contact = synthetic_motion(4, 50, seed=13)
+    lens = [50, 50, 33, 2]
+    ref_pose, ref_tran = pp.PhysicsOptimizerPort(B=4).optimize_sequences(R, vel, contact, lens)
+    pose, tran = PhysicsOptimizerC(B=4).optimize_sequences(R, vel, contact, lens)
+    assert np.abs(pose - ref_pose).max() < 5e-7 and np.abs(tran - ref_tran).max() < 5e-7
