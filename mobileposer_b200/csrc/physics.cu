@@ -28,7 +28,6 @@ namespace mp {
 namespace {
 
 constexpr int NJ = 24, NOPT = 15, NX = 48, NROW = 49, LDH = 52;   // 49 rows (row 48 = rhs), 16-byte aligned row stride
-constexpr int NITEM_MAX = 512;
 constexpr int MAX_PAIRS = 64;
 
 struct PhysTables {
@@ -138,26 +137,36 @@ struct PhysParams {
     float w_vel, w_contact, damping, damping_abs, floor_y;
 };
 
-// lane = joint: global rotation and root-relative position by walking the tree one level per shuffle round
-__device__ __forceinline__ void warp_fk(const float (&R)[9], int j, bool isj, int par, int depth, const float (&bone)[3], float (&G)[9],
-                                        float (&P)[3]) {
+// lane = joint: global rotation and root-relative position by pointer jumping.  After round r a lane holds the
+// transform from its 2^r-th ancestor's frame (the world once the pointer has run past the root) down to itself:
+// 4 rounds cover the 9 links of the deepest chain, against 8 rounds of a level-by-level walk.  `jump` packs the
+// lane's 1st, 2nd, 4th and 8th ancestor (255 = past the root), one byte each.
+__device__ __forceinline__ void warp_fk(const float (&R)[9], bool isj, unsigned jump, const float (&bone)[3], float (&G)[9], float (&P)[3]) {
 #pragma unroll
     for (int i = 0; i < 9; ++i) G[i] = R[i];
-    P[0] = P[1] = P[2] = 0.f;
 #pragma unroll
-    for (int lvl = 1; lvl <= 8; ++lvl) {
-        float Gp[9], Pp[3];
+    for (int i = 0; i < 3; ++i) P[i] = bone[i];
 #pragma unroll
-        for (int i = 0; i < 9; ++i) Gp[i] = __shfl_sync(0xffffffffu, G[i], par);
+    for (int r = 0; r < 4; ++r) {
+        const unsigned a = (jump >> (8 * r)) & 255u;
+        const int src = a == 255u ? 0 : (int)a;
+        float Ga[9], Pa[3];
 #pragma unroll
-        for (int i = 0; i < 3; ++i) Pp[i] = __shfl_sync(0xffffffffu, P[i], par);
-        if (isj && depth == lvl) {
+        for (int i = 0; i < 9; ++i) Ga[i] = __shfl_sync(0xffffffffu, G[i], src);
 #pragma unroll
-            for (int r = 0; r < 3; ++r) {
+        for (int i = 0; i < 3; ++i) Pa[i] = __shfl_sync(0xffffffffu, P[i], src);
+        if (isj && a != 255u) {
+            float Gn[9], Pn[3];
 #pragma unroll
-                for (int c = 0; c < 3; ++c) G[r * 3 + c] = fmaf(Gp[r * 3 + 2], R[6 + c], fmaf(Gp[r * 3 + 1], R[3 + c], Gp[r * 3] * R[c]));
-                P[r] = Pp[r] + fmaf(Gp[r * 3 + 2], bone[2], fmaf(Gp[r * 3 + 1], bone[1], Gp[r * 3] * bone[0]));
+            for (int rr = 0; rr < 3; ++rr) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) Gn[rr * 3 + c] = fmaf(Ga[rr * 3 + 2], G[6 + c], fmaf(Ga[rr * 3 + 1], G[3 + c], Ga[rr * 3] * G[c]));
+                Pn[rr] = Pa[rr] + fmaf(Ga[rr * 3 + 2], P[2], fmaf(Ga[rr * 3 + 1], P[1], Ga[rr * 3] * P[0]));
             }
+#pragma unroll
+            for (int i = 0; i < 9; ++i) G[i] = Gn[i];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) P[i] = Pn[i];
         }
     }
 }
@@ -179,7 +188,7 @@ __global__ void __launch_bounds__(32) physics_optimize_kernel(const PhysParams p
     __shared__ float sT1[NJ * 3];
     __shared__ __align__(16) float sH[NROW * LDH];
     __shared__ float sX[NX];
-    __shared__ uint32_t sItem[NITEM_MAX];     // rotation-rotation entries: ka | kd<<5 | a1<<10 | a2<<12 | row<<14 | col<<20 | valid<<31
+    __shared__ uint32_t sItem[MAX_PAIRS];     // rotation-rotation blocks: joint a | joint d << 5 | slot a << 10 | slot d << 14
     __shared__ int sOrd[NOPT];
 
     const int lane = threadIdx.x;
@@ -187,8 +196,14 @@ __global__ void __launch_bounds__(32) physics_optimize_kernel(const PhysParams p
     if (b >= p.B) return;
     const bool isj = lane < NJ;
     const int j = isj ? lane : 0;
-    const int par = c_tab.parent[j] < 0 ? 0 : c_tab.parent[j];
-    const int depth = c_tab.depth[j];
+    unsigned jump = 0;
+    {
+        for (int r = 0, step = 1; r < 4; ++r, step *= 2) {       // 1st, 2nd, 4th, 8th ancestor of the lane's joint
+            int q = j;
+            for (int sidx = 0; sidx < step && q >= 0; ++sidx) q = c_tab.parent[q];
+            jump |= (unsigned)(q < 0 ? 255 : q) << (8 * r);
+        }
+    }
     const float bone[3] = {c_tab.bone[j][0], c_tab.bone[j][1], c_tab.bone[j][2]};
     const int slot = isj ? c_tab.slot[j] : -1;
     const unsigned desc = c_tab.desc[j];
@@ -201,14 +216,11 @@ __global__ void __launch_bounds__(32) physics_optimize_kernel(const PhysParams p
     if (isj) { q[0] = st[4 + j * 3]; q[1] = st[5 + j * 3]; q[2] = st[6 + j * 3]; }
 
     for (int i = lane; i < NROW * LDH; i += 32) sH[i] = 0.f;
-    // entry descriptors of the rotation-rotation blocks (the constant tables are indexed per lane: read them once)
-    const int nitem = c_tab.npair * 9;
-    for (int it = lane; it < nitem; it += 32) {
-        const int pr = it / 9, a1 = (it % 9) / 3, a2 = it % 3;
+    // pair descriptors of the rotation-rotation blocks (the constant tables are indexed per lane: read them once)
+    const int npair = c_tab.npair;
+    for (int pr = lane; pr < npair; pr += 32) {
         const int ia = c_tab.pair_a[pr], id = c_tab.pair_d[pr];
-        const int r = 3 * ia + a1, c = 3 * id + a2;
-        sItem[it] = (uint32_t)c_tab.ord[ia] | ((uint32_t)c_tab.ord[id] << 5) | ((uint32_t)a1 << 10) | ((uint32_t)a2 << 12) |
-                    ((uint32_t)r << 14) | ((uint32_t)c << 20) | (r >= c ? 0x80000000u : 0u);
+        sItem[pr] = (uint32_t)c_tab.ord[ia] | ((uint32_t)c_tab.ord[id] << 5) | ((uint32_t)ia << 10) | ((uint32_t)id << 14);
     }
     if (lane < NOPT) sOrd[lane] = c_tab.ord[lane];
     __syncwarp();
@@ -245,7 +257,7 @@ __global__ void __launch_bounds__(32) physics_optimize_kernel(const PhysParams p
         }
 
         float G[9], P[3];
-        warp_fk(R, j, isj, par, depth, bone, G, P);
+        warp_fk(R, isj, jump, bone, G, P);
 
         float Rout[9];
 #pragma unroll
@@ -299,26 +311,37 @@ __global__ void __launch_bounds__(32) physics_optimize_kernel(const PhysParams p
             __syncwarp();
 
             // ---- normal equations: rotation-rotation blocks of ancestor-related joint pairs --------------------
-#pragma unroll 2
-            for (int it = lane; it < nitem; it += 32) {
-                const uint32_t ds = sItem[it];
-                const int ka = ds & 31, kd = (ds >> 5) & 31, a1 = (ds >> 10) & 3, a2 = (ds >> 12) & 3;
-                const int r = (ds >> 14) & 63, c = (ds >> 20) & 63;
-                const float g1x = sG[ka * 9 + a1], g1y = sG[ka * 9 + 3 + a1], g1z = sG[ka * 9 + 6 + a1];
-                const float g2x = sG[kd * 9 + a2], g2y = sG[kd * 9 + 3 + a2], g2z = sG[kd * 9 + 6 + a2];
+            // one lane per (ancestor-or-self a, descendant d) pair: entry (i, k) of the 3 x 3 block is
+            //   g2_k . [ tr g1_i - S2 g1_i - e (S1 . g1_i) ],   g1_i / g2_k = columns of G_a / G_d, e = P_d - P_a,
+            //   S1, S2 = moments of d's subtree about P_d, tr = trace(S2) + e . S1
+            for (int pr = lane; pr < npair; pr += 32) {
+                const uint32_t ds = sItem[pr];
+                const int ka = ds & 31, kd = (ds >> 5) & 31, ia = (ds >> 10) & 15, id = (ds >> 14) & 15;
+                float Ga[9], Gd[9];
+#pragma unroll
+                for (int i = 0; i < 9; ++i) { Ga[i] = sG[ka * 9 + i]; Gd[i] = sG[kd * 9 + i]; }
                 const float ex = sP[kd * 3] - sP[ka * 3], ey = sP[kd * 3 + 1] - sP[ka * 3 + 1], ez = sP[kd * 3 + 2] - sP[ka * 3 + 2];
                 const float m1x = sS1[kd * 3], m1y = sS1[kd * 3 + 1], m1z = sS1[kd * 3 + 2];
                 const float* M = sS2 + kd * 6;     // xx xy xz yy yz zz
-                const float tr = M[0] + M[3] + M[5] + (ex * m1x + ey * m1y + ez * m1z);
-                // g2^T S2 g1
-                const float tx = M[0] * g1x + M[1] * g1y + M[2] * g1z, ty = M[1] * g1x + M[3] * g1y + M[4] * g1z,
-                            tz = M[2] * g1x + M[4] * g1y + M[5] * g1z;
-                const float quad = g2x * tx + g2y * ty + g2z * tz + (g2x * ex + g2y * ey + g2z * ez) * (m1x * g1x + m1y * g1y + m1z * g1z);
-                float v = (g1x * g2x + g1y * g2y + g1z * g2z) * tr - quad;
-                if (r == c) v = fmaf(v, p.damping, v) + p.damping_abs;      // Marquardt scaling of the rotational unknowns
-                // lower triangle only: slots of descendants come first, so (row, col) = (ancestor, descendant); inside a
-                // diagonal block both orders appear as separate items with the same value
-                if (ds >> 31) sH[r * LDH + c] = v;
+                const float mxx = M[0], mxy = M[1], mxz = M[2], myy = M[3], myz = M[4], mzz = M[5];
+                const float tr = mxx + myy + mzz + (ex * m1x + ey * m1y + ez * m1z);
+                float* dst = sH + (3 * ia) * LDH + 3 * id;
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    const float gx = Ga[i], gy = Ga[3 + i], gz = Ga[6 + i];
+                    const float sg = m1x * gx + m1y * gy + m1z * gz;
+                    const float nx = tr * gx - (mxx * gx + mxy * gy + mxz * gz) - ex * sg;
+                    const float ny = tr * gy - (mxy * gx + myy * gy + myz * gz) - ey * sg;
+                    const float nz = tr * gz - (mxz * gx + myz * gy + mzz * gz) - ez * sg;
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        float v = Gd[k] * nx + Gd[3 + k] * ny + Gd[6 + k] * nz;
+                        if (ia == id && i == k) v = fmaf(v, p.damping, v) + p.damping_abs;      // Marquardt scaling
+                        // lower triangle only: descendants come first in the elimination order, so (row, col) =
+                        // (ancestor, descendant); inside a diagonal block keep i >= k
+                        if (ia != id || i >= k) dst[i * LDH + k] = v;
+                    }
+                }
             }
             // rotation-translation blocks, translation block, right-hand side (row 48)
             for (int it = lane; it < NOPT * 3; it += 32) {
@@ -350,13 +373,14 @@ __global__ void __launch_bounds__(32) physics_optimize_kernel(const PhysParams p
                 const int m_begin = c_tab.env[c0] & ~3;
                 const int i1 = c0 + lane, i2 = c0 + 32 + lane;
                 const bool h1 = i1 < NROW, h2 = i2 < NROW;
+                const bool any2 = c0 + 32 < NROW;            // warp-uniform: the second row set exists at all
                 const float* rk = sH + c0 * LDH;
                 const float* r1 = sH + (h1 ? i1 : c0) * LDH;
                 const float* r2 = sH + (h2 ? i2 : c0) * LDH;
                 float a1[3] = {r1[c0], r1[c0 + 1], r1[c0 + 2]}, a2[3] = {r2[c0], r2[c0 + 1], r2[c0 + 2]};
 #pragma unroll 2
                 for (int m = m_begin; m < c0; m += 4) {
-                    const float4 u = *reinterpret_cast<const float4*>(r1 + m), w = *reinterpret_cast<const float4*>(r2 + m);
+                    const float4 u = *reinterpret_cast<const float4*>(r1 + m);
                     float4 k0 = *reinterpret_cast<const float4*>(rk + m), k1 = *reinterpret_cast<const float4*>(rk + LDH + m),
                            k2 = *reinterpret_cast<const float4*>(rk + 2 * LDH + m);
                     if (m + 4 > c0) {      // the last chunk reaches into the not yet factored columns: drop them
@@ -367,9 +391,12 @@ __global__ void __launch_bounds__(32) physics_optimize_kernel(const PhysParams p
                     a1[0] = fmaf(-u.x, k0.x, a1[0]); a1[0] = fmaf(-u.y, k0.y, a1[0]); a1[0] = fmaf(-u.z, k0.z, a1[0]); a1[0] = fmaf(-u.w, k0.w, a1[0]);
                     a1[1] = fmaf(-u.x, k1.x, a1[1]); a1[1] = fmaf(-u.y, k1.y, a1[1]); a1[1] = fmaf(-u.z, k1.z, a1[1]); a1[1] = fmaf(-u.w, k1.w, a1[1]);
                     a1[2] = fmaf(-u.x, k2.x, a1[2]); a1[2] = fmaf(-u.y, k2.y, a1[2]); a1[2] = fmaf(-u.z, k2.z, a1[2]); a1[2] = fmaf(-u.w, k2.w, a1[2]);
-                    a2[0] = fmaf(-w.x, k0.x, a2[0]); a2[0] = fmaf(-w.y, k0.y, a2[0]); a2[0] = fmaf(-w.z, k0.z, a2[0]); a2[0] = fmaf(-w.w, k0.w, a2[0]);
-                    a2[1] = fmaf(-w.x, k1.x, a2[1]); a2[1] = fmaf(-w.y, k1.y, a2[1]); a2[1] = fmaf(-w.z, k1.z, a2[1]); a2[1] = fmaf(-w.w, k1.w, a2[1]);
-                    a2[2] = fmaf(-w.x, k2.x, a2[2]); a2[2] = fmaf(-w.y, k2.y, a2[2]); a2[2] = fmaf(-w.z, k2.z, a2[2]); a2[2] = fmaf(-w.w, k2.w, a2[2]);
+                    if (any2) {
+                        const float4 w = *reinterpret_cast<const float4*>(r2 + m);
+                        a2[0] = fmaf(-w.x, k0.x, a2[0]); a2[0] = fmaf(-w.y, k0.y, a2[0]); a2[0] = fmaf(-w.z, k0.z, a2[0]); a2[0] = fmaf(-w.w, k0.w, a2[0]);
+                        a2[1] = fmaf(-w.x, k1.x, a2[1]); a2[1] = fmaf(-w.y, k1.y, a2[1]); a2[1] = fmaf(-w.z, k1.z, a2[1]); a2[1] = fmaf(-w.w, k1.w, a2[1]);
+                        a2[2] = fmaf(-w.x, k2.x, a2[2]); a2[2] = fmaf(-w.y, k2.y, a2[2]); a2[2] = fmaf(-w.z, k2.z, a2[2]); a2[2] = fmaf(-w.w, k2.w, a2[2]);
+                    }
                 }
                 // 3 x 3 diagonal block (rows of lanes 0, 1, 2), factored redundantly by every lane
                 const float d00 = __shfl_sync(0xffffffffu, a1[0], 0);
@@ -447,7 +474,7 @@ __global__ void __launch_bounds__(32) physics_optimize_kernel(const PhysParams p
             }
             dx = sX[45]; dy = sX[46]; dz = sX[47];
             __syncwarp();
-            warp_fk(Rout, j, isj, par, depth, bone, G, P);
+            warp_fk(Rout, isj, jump, bone, G, P);
         }
 
         // ---- floor clamp (net.py:148-153's rule on the optimiser's own root), integration, state -----------------
@@ -484,14 +511,20 @@ __global__ void physics_fk_kernel(const float* __restrict__ pose, long long n, f
     const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
     const bool isj = lane < NJ;
     const int j = isj ? lane : 0;
-    const int par = c_tab.parent[j] < 0 ? 0 : c_tab.parent[j];
-    const int depth = c_tab.depth[j];
+    unsigned jump = 0;
+    {
+        for (int r = 0, step = 1; r < 4; ++r, step *= 2) {       // 1st, 2nd, 4th, 8th ancestor of the lane's joint
+            int q = j;
+            for (int sidx = 0; sidx < step && q >= 0; ++sidx) q = c_tab.parent[q];
+            jump |= (unsigned)(q < 0 ? 255 : q) << (8 * r);
+        }
+    }
     const float bone[3] = {c_tab.bone[j][0], c_tab.bone[j][1], c_tab.bone[j][2]};
     for (long long f = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; f < n; f += warps) {
         float R[9], G[9], P[3];
 #pragma unroll
         for (int i = 0; i < 9; ++i) R[i] = isj ? __ldg(pose + f * 216 + j * 9 + i) : 0.f;
-        warp_fk(R, j, isj, par, depth, bone, G, P);
+        warp_fk(R, isj, jump, bone, G, P);
         if (isj) {
 #pragma unroll
             for (int i = 0; i < 9; ++i) glb[f * 216 + j * 9 + i] = G[i];
