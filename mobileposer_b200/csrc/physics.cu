@@ -27,7 +27,10 @@ namespace mp {
 
 namespace {
 
-constexpr int NJ = 24, NOPT = 15, NX = 48, NROW = 49, LDH = 52;   // 49 rows (row 48 = rhs), 16-byte aligned row stride
+constexpr int NJ = 24, NOPT = 15, NX = 48, NROW = 49, NBLK = 16;
+// 49 rows (row 48 = right-hand side); every block of 3 unknowns owns 4 columns (the 4th stays zero) so that a block is one
+// 16-byte read of a row; row stride 68 floats = 17 x 16 B keeps the 8 lanes of a quarter warp on distinct bank groups
+constexpr int LDH = 68;
 constexpr int MAX_PAIRS = 64;
 
 struct PhysTables {
@@ -40,6 +43,8 @@ struct PhysTables {
     int npair;
     unsigned char pair_a[MAX_PAIRS], pair_d[MAX_PAIRS];   // (ancestor-or-self slot, deeper slot)
     int env[NROW];              // first column of each row's envelope
+    int first_blk[NBLK];        // first block of a block row's envelope
+    unsigned char rowmap[NBLK][32];   // rows a lane works on in block column K: own 3, ancestors', translation, rhs; 255 = idle
 };
 
 __constant__ PhysTables c_tab;
@@ -106,6 +111,19 @@ PhysTables build_tables() {
         if (3 * first_desc[i] < lo) lo = 3 * first_desc[i];
     }
     for (int r = 45; r < NROW; ++r) t.env[r] = 0;     // translation rows and the right-hand side couple with everything
+    for (int K = 0; K < NBLK; ++K) {
+        t.first_blk[K] = K == 15 ? 0 : first_desc[K];
+        int n = 0;
+        for (int l = 0; l < 32; ++l) t.rowmap[K][l] = 255;
+        for (int r = 0; r < 3; ++r) t.rowmap[K][n++] = (unsigned char)(3 * K + r);
+        if (K < 15) {
+            for (int a = K + 1; a < NOPT; ++a)
+                if ((t.desc[kOrd[a]] >> kOrd[K]) & 1u)
+                    for (int r = 0; r < 3; ++r) t.rowmap[K][n++] = (unsigned char)(3 * a + r);
+            for (int r = 45; r < 48; ++r) t.rowmap[K][n++] = (unsigned char)r;
+        }
+        t.rowmap[K][n++] = 48;
+    }
     return t;
 }
 
@@ -190,6 +208,7 @@ __global__ void __launch_bounds__(32) physics_optimize_kernel(const PhysParams p
     __shared__ float sX[NX];
     __shared__ uint32_t sItem[MAX_PAIRS];     // rotation-rotation blocks: joint a | joint d << 5 | slot a << 10 | slot d << 14
     __shared__ int sOrd[NOPT];
+    __shared__ unsigned char sRow[NBLK * 32];
 
     const int lane = threadIdx.x;
     const int b = blockIdx.x;
@@ -223,6 +242,7 @@ __global__ void __launch_bounds__(32) physics_optimize_kernel(const PhysParams p
         sItem[pr] = (uint32_t)c_tab.ord[ia] | ((uint32_t)c_tab.ord[id] << 5) | ((uint32_t)ia << 10) | ((uint32_t)id << 14);
     }
     if (lane < NOPT) sOrd[lane] = c_tab.ord[lane];
+    for (int i = lane; i < NBLK * 32; i += 32) sRow[i] = c_tab.rowmap[i / 32][i % 32];
     __syncwarp();
 
     const float* pose_b = p.pose + (size_t)b * p.T * 216;
@@ -325,7 +345,7 @@ __global__ void __launch_bounds__(32) physics_optimize_kernel(const PhysParams p
                 const float* M = sS2 + kd * 6;     // xx xy xz yy yz zz
                 const float mxx = M[0], mxy = M[1], mxz = M[2], myy = M[3], myz = M[4], mzz = M[5];
                 const float tr = mxx + myy + mzz + (ex * m1x + ey * m1y + ez * m1z);
-                float* dst = sH + (3 * ia) * LDH + 3 * id;
+                float* dst = sH + (3 * ia) * LDH + 4 * id;
 #pragma unroll
                 for (int i = 0; i < 3; ++i) {
                     const float gx = Ga[i], gy = Ga[3 + i], gz = Ga[6 + i];
@@ -348,93 +368,86 @@ __global__ void __launch_bounds__(32) physics_optimize_kernel(const PhysParams p
                 const int i = it / 3, a = it % 3, k = sOrd[i];
                 const float gx = sG[k * 9 + a], gy = sG[k * 9 + 3 + a], gz = sG[k * 9 + 6 + a];
                 const float mx = sS1[k * 3], my = sS1[k * 3 + 1], mz = sS1[k * 3 + 2];
-                sH[45 * LDH + it] = gy * mz - gz * my;
-                sH[46 * LDH + it] = gz * mx - gx * mz;
-                sH[47 * LDH + it] = gx * my - gy * mx;
-                sH[48 * LDH + it] = gx * sT1[k * 3] + gy * sT1[k * 3 + 1] + gz * sT1[k * 3 + 2];
+                const int col = 4 * i + a;
+                sH[45 * LDH + col] = gy * mz - gz * my;
+                sH[46 * LDH + col] = gz * mx - gx * mz;
+                sH[47 * LDH + col] = gx * my - gy * mx;
+                sH[48 * LDH + col] = gx * sT1[k * 3] + gy * sT1[k * 3 + 1] + gz * sT1[k * 3 + 2];
             }
             if (lane < 3) {
-                sH[(45 + lane) * LDH + 45] = lane == 0 ? c_tot : 0.f;
-                sH[(45 + lane) * LDH + 46] = lane == 1 ? c_tot : 0.f;
-                sH[(45 + lane) * LDH + 47] = lane == 2 ? c_tot : 0.f;
-                sH[48 * LDH + 45 + lane] = s_tot[lane];
+                sH[(45 + lane) * LDH + 60] = lane == 0 ? c_tot : 0.f;
+                sH[(45 + lane) * LDH + 61] = lane == 1 ? c_tot : 0.f;
+                sH[(45 + lane) * LDH + 62] = lane == 2 ? c_tot : 0.f;
+                sH[48 * LDH + 60 + lane] = s_tot[lane];
             }
             __syncwarp();
             if (p.dbg && t == p.dbg_frame) {
                 float* dbg = p.dbg + (size_t)b * (NROW * NROW + NX);
-                for (int i = lane; i < NROW * NROW; i += 32) dbg[i] = sH[(i / NROW) * LDH + i % NROW];
+                for (int i = lane; i < NROW * NROW; i += 32) {      // compact 49 x 49 view of the padded storage
+                    const int c = i % NROW;
+                    dbg[i] = c < NX ? sH[(i / NROW) * LDH + 4 * (c / 3) + c % 3] : 0.f;
+                }
             }
 
-            // ---- envelope Cholesky, left looking, one joint (3 columns) per round; lane l owns rows c0 + l and c0 + 32 + l,
-            //      so lanes 0..2 hold the diagonal block; row 48 = right-hand side.  Rows are read 4 columns at a time.
+            // ---- envelope Cholesky, left looking, one joint (block of 3 unknowns) per round.  Lane l works on row
+            //      rowmap[K][l] of block column K: lanes 0..2 hold the diagonal block, then the rows of the joint's ancestors,
+            //      the translation rows and the right-hand side (row 48) -- never more than 22 rows.  A block of a row is
+            //      one 16-byte read; the dot products run over the blocks of the joint's descendants only (the envelope).
 #pragma unroll 1
-            for (int K = 0; K < NX / 3; ++K) {
+            for (int K = 0; K < NBLK; ++K) {
                 const int c0 = 3 * K;
-                const int m_begin = c_tab.env[c0] & ~3;
-                const int i1 = c0 + lane, i2 = c0 + 32 + lane;
-                const bool h1 = i1 < NROW, h2 = i2 < NROW;
-                const bool any2 = c0 + 32 < NROW;            // warp-uniform: the second row set exists at all
+                const int i1 = sRow[K * 32 + lane];
+                const bool h1 = i1 != 255;
                 const float* rk = sH + c0 * LDH;
                 const float* r1 = sH + (h1 ? i1 : c0) * LDH;
-                const float* r2 = sH + (h2 ? i2 : c0) * LDH;
-                float a1[3] = {r1[c0], r1[c0 + 1], r1[c0 + 2]}, a2[3] = {r2[c0], r2[c0 + 1], r2[c0 + 2]};
+                const float4 ini = *reinterpret_cast<const float4*>(r1 + 4 * K);
+                float a0 = ini.x, a1 = ini.y, a2 = ini.z;
 #pragma unroll 2
-                for (int m = m_begin; m < c0; m += 4) {
+                for (int m = 4 * c_tab.first_blk[K]; m < 4 * K; m += 4) {
                     const float4 u = *reinterpret_cast<const float4*>(r1 + m);
-                    float4 k0 = *reinterpret_cast<const float4*>(rk + m), k1 = *reinterpret_cast<const float4*>(rk + LDH + m),
-                           k2 = *reinterpret_cast<const float4*>(rk + 2 * LDH + m);
-                    if (m + 4 > c0) {      // the last chunk reaches into the not yet factored columns: drop them
-                        if (m + 1 >= c0) { k0.y = 0.f; k1.y = 0.f; k2.y = 0.f; }
-                        if (m + 2 >= c0) { k0.z = 0.f; k1.z = 0.f; k2.z = 0.f; }
-                        k0.w = 0.f; k1.w = 0.f; k2.w = 0.f;
-                    }
-                    a1[0] = fmaf(-u.x, k0.x, a1[0]); a1[0] = fmaf(-u.y, k0.y, a1[0]); a1[0] = fmaf(-u.z, k0.z, a1[0]); a1[0] = fmaf(-u.w, k0.w, a1[0]);
-                    a1[1] = fmaf(-u.x, k1.x, a1[1]); a1[1] = fmaf(-u.y, k1.y, a1[1]); a1[1] = fmaf(-u.z, k1.z, a1[1]); a1[1] = fmaf(-u.w, k1.w, a1[1]);
-                    a1[2] = fmaf(-u.x, k2.x, a1[2]); a1[2] = fmaf(-u.y, k2.y, a1[2]); a1[2] = fmaf(-u.z, k2.z, a1[2]); a1[2] = fmaf(-u.w, k2.w, a1[2]);
-                    if (any2) {
-                        const float4 w = *reinterpret_cast<const float4*>(r2 + m);
-                        a2[0] = fmaf(-w.x, k0.x, a2[0]); a2[0] = fmaf(-w.y, k0.y, a2[0]); a2[0] = fmaf(-w.z, k0.z, a2[0]); a2[0] = fmaf(-w.w, k0.w, a2[0]);
-                        a2[1] = fmaf(-w.x, k1.x, a2[1]); a2[1] = fmaf(-w.y, k1.y, a2[1]); a2[1] = fmaf(-w.z, k1.z, a2[1]); a2[1] = fmaf(-w.w, k1.w, a2[1]);
-                        a2[2] = fmaf(-w.x, k2.x, a2[2]); a2[2] = fmaf(-w.y, k2.y, a2[2]); a2[2] = fmaf(-w.z, k2.z, a2[2]); a2[2] = fmaf(-w.w, k2.w, a2[2]);
-                    }
+                    const float4 k0 = *reinterpret_cast<const float4*>(rk + m), k1 = *reinterpret_cast<const float4*>(rk + LDH + m),
+                                 k2 = *reinterpret_cast<const float4*>(rk + 2 * LDH + m);
+                    a0 = fmaf(-u.x, k0.x, a0); a1 = fmaf(-u.x, k1.x, a1); a2 = fmaf(-u.x, k2.x, a2);
+                    a0 = fmaf(-u.y, k0.y, a0); a1 = fmaf(-u.y, k1.y, a1); a2 = fmaf(-u.y, k2.y, a2);
+                    a0 = fmaf(-u.z, k0.z, a0); a1 = fmaf(-u.z, k1.z, a1); a2 = fmaf(-u.z, k2.z, a2);
                 }
                 // 3 x 3 diagonal block (rows of lanes 0, 1, 2), factored redundantly by every lane
-                const float d00 = __shfl_sync(0xffffffffu, a1[0], 0);
-                const float d10 = __shfl_sync(0xffffffffu, a1[0], 1), d11 = __shfl_sync(0xffffffffu, a1[1], 1);
-                const float d20 = __shfl_sync(0xffffffffu, a1[0], 2), d21 = __shfl_sync(0xffffffffu, a1[1], 2),
-                            d22 = __shfl_sync(0xffffffffu, a1[2], 2);
+                const float d00 = __shfl_sync(0xffffffffu, a0, 0);
+                const float d10 = __shfl_sync(0xffffffffu, a0, 1), d11 = __shfl_sync(0xffffffffu, a1, 1);
+                const float d20 = __shfl_sync(0xffffffffu, a0, 2), d21 = __shfl_sync(0xffffffffu, a1, 2),
+                            d22 = __shfl_sync(0xffffffffu, a2, 2);
                 const float v0 = rsqrtf(d00);
                 const float l10 = d10 * v0, l20 = d20 * v0;
                 const float v1 = rsqrtf(fmaf(-l10, l10, d11));
                 const float l21 = fmaf(-l20, l10, d21) * v1;
                 const float v2 = rsqrtf(fmaf(-l21, l21, fmaf(-l20, l20, d22)));
-                if (lane == 0) {       // the diagonal keeps 1 / L_kk
-                    sH[c0 * LDH + c0] = v0;
-                    sH[(c0 + 1) * LDH + c0] = l10; sH[(c0 + 1) * LDH + c0 + 1] = v1;
-                    sH[(c0 + 2) * LDH + c0] = l20; sH[(c0 + 2) * LDH + c0 + 1] = l21; sH[(c0 + 2) * LDH + c0 + 2] = v2;
+                float4 out;
+                if (lane >= 3) {
+                    out.x = a0 * v0;
+                    out.y = fmaf(-out.x, l10, a1) * v1;
+                    out.z = fmaf(-out.y, l21, fmaf(-out.x, l20, a2)) * v2;
+                } else {              // the diagonal keeps 1 / L_kk
+                    out.x = lane == 0 ? v0 : (lane == 1 ? l10 : l20);
+                    out.y = lane == 0 ? 0.f : (lane == 1 ? v1 : l21);
+                    out.z = lane == 2 ? v2 : 0.f;
                 }
-                if (lane >= 3 && h1) {
-                    const float x0 = a1[0] * v0, x1 = fmaf(-x0, l10, a1[1]) * v1, x2 = fmaf(-x1, l21, fmaf(-x0, l20, a1[2])) * v2;
-                    float* w1 = sH + i1 * LDH + c0;
-                    w1[0] = x0; w1[1] = x1; w1[2] = x2;
-                }
-                if (h2) {
-                    const float x0 = a2[0] * v0, x1 = fmaf(-x0, l10, a2[1]) * v1, x2 = fmaf(-x1, l21, fmaf(-x0, l20, a2[2])) * v2;
-                    float* w2 = sH + i2 * LDH + c0;
-                    w2[0] = x0; w2[1] = x1; w2[2] = x2;
-                }
+                out.w = 0.f;
+                if (h1) *reinterpret_cast<float4*>(sH + i1 * LDH + 4 * K) = out;
                 __syncwarp();
             }
             // ---- back substitution L^T x = y (y = row 48), one joint per round; lane l owns x_l and x_{l+32} --------------
-            float y1 = sH[48 * LDH + lane], y2 = (lane < NX - 32) ? sH[48 * LDH + 32 + lane] : 0.f;
+            const int col1 = 4 * (lane / 3) + lane % 3, col2 = 4 * ((lane + 32) / 3) + (lane + 32) % 3;
+            float y1 = sH[48 * LDH + col1], y2 = (lane < NX - 32) ? sH[48 * LDH + col2] : 0.f;
 #pragma unroll 1
-            for (int K = NX / 3 - 1; K >= 0; --K) {
+            for (int K = NBLK - 1; K >= 0; --K) {
                 const int c0 = 3 * K;
                 const float* rk = sH + c0 * LDH;
-                const float v0 = rk[c0], l10 = rk[LDH + c0], v1 = rk[LDH + c0 + 1], l20 = rk[2 * LDH + c0], l21 = rk[2 * LDH + c0 + 1],
-                            v2 = rk[2 * LDH + c0 + 2];
-                const float u0 = rk[lane], u1 = rk[LDH + lane], u2 = rk[2 * LDH + lane];            // columns l < c0 of the 3 rows
-                const float w0 = rk[(lane + 32) % LDH], w1 = rk[LDH + (lane + 32) % LDH], w2 = rk[2 * LDH + (lane + 32) % LDH];
+                const float4 dg0 = *reinterpret_cast<const float4*>(rk + 4 * K), dg1 = *reinterpret_cast<const float4*>(rk + LDH + 4 * K),
+                             dg2 = *reinterpret_cast<const float4*>(rk + 2 * LDH + 4 * K);
+                const float v0 = dg0.x, l10 = dg1.x, v1 = dg1.y, l20 = dg2.x, l21 = dg2.y, v2 = dg2.z;
+                const float u0 = rk[col1], u1 = rk[LDH + col1], u2 = rk[2 * LDH + col1];            // columns l < c0 of the 3 rows
+                const int cw = lane < NX - 32 ? col2 : 0;
+                const float w0 = rk[cw], w1 = rk[LDH + cw], w2 = rk[2 * LDH + cw];
                 const float yk0 = __shfl_sync(0xffffffffu, c0 >= 32 ? y2 : y1, c0 & 31);
                 const float yk1 = __shfl_sync(0xffffffffu, c0 + 1 >= 32 ? y2 : y1, (c0 + 1) & 31);
                 const float yk2 = __shfl_sync(0xffffffffu, c0 + 2 >= 32 ? y2 : y1, (c0 + 2) & 31);
