@@ -13,12 +13,14 @@ ap = argparse.ArgumentParser()
 ap.add_argument('--batch', type=int, default=256)
 ap.add_argument('--frames', type=int, default=300)
 ap.add_argument('--passes', type=int, default=2)
+ap.add_argument('--physics', action='store_true', help='PHYSICS hook on (K8 at the end of every pass)')
 a = ap.parse_args()
 
 torch.manual_seed(0)
 net = mp.MobilePoserNet().eval().to('cuda:0')
 net.set_graph(False)
 net.reuse_outputs = True
+net.enable_physics(a.physics)
 x = synthetic_imu_batch(list(range(a.batch)), a.frames).to('cuda:0')
 for _ in range(a.passes):
     net.velocity.rnn_state = None
