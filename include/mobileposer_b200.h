@@ -197,6 +197,14 @@ int mp_net_forward(mp_net_t* net, const float* imu, int32_t B, int32_t T, const 
  * pose/joints/tran/contact, then a stream synchronise.  `dev_io` is device staging of at least
  * mp_net_host_staging_bytes(B,T).  Used for the end-to-end number of bench.py.               */
 size_t mp_net_host_staging_bytes(int32_t B, int32_t T);
+/* The same without the final synchronise: everything (H2D, forward, D2H) is enqueued on `stream` and the call
+ * returns; the host buffers are valid once the stream has drained.  Two nets (mp_net_create on the same heads), each
+ * with its own staging / workspace / stream, give a depth-2 software pipeline over batches: the copies of one batch
+ * overlap the kernels of the next.                                                                */
+int mp_net_enqueue_offline_host(mp_net_t* net, const float* imu_host, int32_t B, int32_t T,
+                                const int32_t* lengths_host, float* pose_host, float* joints_host,
+                                float* tran_host, float* contact_host, void* dev_io,
+                                void* workspace, size_t workspace_bytes, mp_stream_t stream);
 int mp_net_forward_offline_host(mp_net_t* net, const float* imu_host, int32_t B, int32_t T,
                                 const int32_t* lengths_host, float* pose_host, float* joints_host,
                                 float* tran_host, float* contact_host, void* dev_io,

@@ -82,6 +82,9 @@ SIGNATURES = {
                                  c_float_p, c_float_p, c_float_p, c_float_p, c_float_p, c_float_p, c_float_p,
                                  C.c_void_p, C.c_size_t, c_stream]),
     'mp_net_host_staging_bytes': (C.c_size_t, [C.c_int32, C.c_int32]),
+    'mp_net_enqueue_offline_host': (C.c_int, [C.c_void_p, c_float_p, C.c_int32, C.c_int32, c_int_p, c_float_p,
+                                              c_float_p, c_float_p, c_float_p, C.c_void_p, C.c_void_p, C.c_size_t,
+                                              c_stream]),
     'mp_net_forward_offline_host': (C.c_int, [C.c_void_p, c_float_p, C.c_int32, C.c_int32, c_int_p, c_float_p,
                                               c_float_p, c_float_p, c_float_p, C.c_void_p, C.c_void_p, C.c_size_t,
                                               c_stream]),

@@ -553,7 +553,7 @@ size_t mp_net_host_staging_bytes(int32_t B, int32_t T) {
     return total;
 }
 
-int mp_net_forward_offline_host(mp_net_t* n, const float* imu_host, int32_t B, int32_t T, const int32_t* lengths_host,
+int mp_net_enqueue_offline_host(mp_net_t* n, const float* imu_host, int32_t B, int32_t T, const int32_t* lengths_host,
                                 float* pose_host, float* joints_host, float* tran_host, float* contact_host, void* dev_io,
                                 void* workspace, size_t workspace_bytes, mp_stream_t stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
@@ -576,7 +576,15 @@ int mp_net_forward_offline_host(mp_net_t* n, const float* imu_host, int32_t B, i
     MP_CUDA_TRY(cudaMemcpyAsync(joints_host, d_joints, F * 72 * 4, cudaMemcpyDeviceToHost, stream));
     MP_CUDA_TRY(cudaMemcpyAsync(tran_host, d_tran, F * 3 * 4, cudaMemcpyDeviceToHost, stream));
     MP_CUDA_TRY(cudaMemcpyAsync(contact_host, d_contact, F * 2 * 4, cudaMemcpyDeviceToHost, stream));
-    MP_CUDA_TRY(cudaStreamSynchronize(stream));
+    return MP_OK;
+}
+
+int mp_net_forward_offline_host(mp_net_t* n, const float* imu_host, int32_t B, int32_t T, const int32_t* lengths_host,
+                                float* pose_host, float* joints_host, float* tran_host, float* contact_host, void* dev_io,
+                                void* workspace, size_t workspace_bytes, mp_stream_t stream_) {
+    MP_TRY(mp_net_enqueue_offline_host(n, imu_host, B, T, lengths_host, pose_host, joints_host, tran_host, contact_host, dev_io,
+                                       workspace, workspace_bytes, stream_));
+    MP_CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream_));
     return MP_OK;
 }
 

@@ -375,39 +375,105 @@ class OnlineStreams:
 
 
 class HostOffline:
-    """forward_offline through HOST buffers: one C-ABI call does H2D of the IMU batch, the whole forward, D2H of
-    (pose, joints, tran, contact) and a stream synchronise (mp_net_forward_offline_host).  Fresh velocity state per
-    call.  Buffers (device staging, workspace, pinned outputs) are allocated once for a fixed (B, T)."""
+    """forward_offline through HOST buffers: H2D of the IMU batch, the whole forward, D2H of (pose, joints, tran,
+    contact), all enqueued by one C-ABI call (mp_net_enqueue_offline_host) on this object's own stream.  Fresh velocity
+    (and optimizer) state per call.  Every HostOffline owns its `mp_net` handle (side streams, graph cache), device
+    staging, workspace and pinned outputs for a fixed (B, T), so two of them form a depth-2 pipeline over batches:
+
+        a.submit(x0); b.submit(x1); a.wait() -> a.pose ...; a.submit(x2); b.wait() ...
+
+    `run()` = submit + wait (one batch at a time, what evaluate.py's loop does)."""
 
     def __init__(self, net: MobilePoserNet, B: int, T: int, device=None):
         lib = _cabi.lib()
         self.net, self.B, self.T = net, B, T
         self.dev = device or net._device()
-        handle = net._net_handle()
+        heads = (net.joints.joints, net.pose.pose, net.foot_contact.footcontact, net.velocity.vel)
+        self._heads_key = tuple(h.packed_handle() for h in heads)
+        out = C.c_void_p()
         with torch.cuda.device(self.dev):
+            _cabi.check(lib.mp_net_create(C.byref(out), *self._heads_key), 'mp_net_create')
+            self.handle = out.value
+            self.stream = torch.cuda.Stream(self.dev)
             self.staging = torch.empty(lib.mp_net_host_staging_bytes(B, T), device=self.dev, dtype=torch.uint8)
-            self.ws_bytes = lib.mp_net_workspace_bytes(handle, B, T)
+            self.ws_bytes = lib.mp_net_workspace_bytes(self.handle, B, T)
             self.ws = torch.empty(self.ws_bytes, device=self.dev, dtype=torch.uint8)
+        self._physics = None
         self.pose = torch.empty(B * T, 24, 3, 3).pin_memory()
         self.joints = torch.empty(B, T, 72).pin_memory()
         self.tran = torch.empty(B, T, 3).pin_memory()
         self.contact = torch.empty(B, T, 2).pin_memory()
         self.lengths = torch.empty(B, dtype=torch.int32).pin_memory()
 
-    def run(self, imu_host: torch.Tensor, input_lengths=None):
+    def __del__(self):
+        try:
+            if self.handle is not None:
+                self.stream.synchronize()
+                _cabi.lib().mp_net_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    def _sync_physics(self):
+        opt = self.net.dynamics_optimizer
+        want = None
+        if opt is not None:
+            prm = _cabi.PhysicsParams.from_buffer_copy(opt.params)
+            prm.vel_scale = amass.vel_scale
+            want = bytes(prm)
+        if want != self._physics:
+            arg = C.byref(_cabi.PhysicsParams.from_buffer_copy(want)) if want is not None else None
+            with torch.cuda.device(self.dev):
+                _cabi.check(_cabi.lib().mp_net_set_physics(self.handle, arg), 'mp_net_set_physics')
+            self._physics = want
+
+    def submit(self, imu_host: torch.Tensor, input_lengths=None):
+        """Enqueue one batch; returns immediately.  `imu_host` must stay untouched until wait()."""
         if imu_host.is_cuda or imu_host.dtype != torch.float32 or not imu_host.is_contiguous():
-            raise ValueError('HostOffline.run expects a contiguous float32 host tensor')
+            raise ValueError('HostOffline expects a contiguous float32 host tensor')
         if tuple(imu_host.shape) != (self.B, self.T, 60):
             raise ValueError(f'expected {(self.B, self.T, 60)}, got {tuple(imu_host.shape)}')
+        heads = (self.net.joints.joints, self.net.pose.pose, self.net.foot_contact.footcontact, self.net.velocity.vel)
+        if tuple(h.packed_handle() for h in heads) != self._heads_key:
+            raise RuntimeError('the parameters of the net changed after this HostOffline was built; build a new one')
         lens_ptr = None
         if input_lengths is not None:
             lens = self.net._lengths(input_lengths, self.B, self.T)
             self.lengths.copy_(torch.tensor(lens, dtype=torch.int32))
             lens_ptr = self.lengths.data_ptr()
-        self.net._sync_net_physics(True)
+        self._sync_physics()
         with torch.cuda.device(self.dev):
-            _cabi.check(_cabi.lib().mp_net_forward_offline_host(
-                self.net._net_handle(), imu_host.data_ptr(), self.B, self.T, lens_ptr, self.pose.data_ptr(),
+            _cabi.check(_cabi.lib().mp_net_enqueue_offline_host(
+                self.handle, imu_host.data_ptr(), self.B, self.T, lens_ptr, self.pose.data_ptr(),
                 self.joints.data_ptr(), self.tran.data_ptr(), self.contact.data_ptr(), self.staging.data_ptr(),
-                self.ws.data_ptr(), self.ws_bytes, current_stream_ptr(self.dev)), 'mp_net_forward_offline_host')
+                self.ws.data_ptr(), self.ws_bytes, self.stream.cuda_stream), 'mp_net_enqueue_offline_host')
+
+    def submit_device(self, imu_dev: torch.Tensor):
+        """The same batch step with device-resident input and outputs (no copies): mp_net_forward on this object's
+        stream into its own device buffers (`d_pose`, `d_joints`, `d_tran`, `d_contact`, valid after wait())."""
+        _require_cuda(imu_dev, 'input batch')
+        if tuple(imu_dev.shape) != (self.B, self.T, 60) or imu_dev.dtype != torch.float32 or not imu_dev.is_contiguous():
+            raise ValueError(f'expected a contiguous float32 {(self.B, self.T, 60)} device tensor')
+        if not hasattr(self, 'd_pose'):
+            f32 = dict(device=self.dev, dtype=torch.float32)
+            B, T = self.B, self.T
+            self.d_pose, self.d_joints = torch.empty(B * T, 24, 3, 3, **f32), torch.empty(B, T, 72, **f32)
+            self.d_vel, self.d_contact, self.d_tran = torch.empty(B, T, 72, **f32), torch.empty(B, T, 2, **f32), torch.empty(B, T, 3, **f32)
+            self.d_hn, self.d_cn = torch.empty(2, B, 256, **f32), torch.empty(2, B, 256, **f32)
+            torch.cuda.current_stream(self.dev).synchronize()
+        self._sync_physics()
+        with torch.cuda.device(self.dev):
+            _cabi.check(_cabi.lib().mp_net_forward(
+                self.handle, imu_dev.data_ptr(), self.B, self.T, None, None, None, self.d_hn.data_ptr(), self.d_cn.data_ptr(),
+                self.d_pose.data_ptr(), self.d_joints.data_ptr(), self.d_vel.data_ptr(), self.d_contact.data_ptr(),
+                self.d_tran.data_ptr(), self.ws.data_ptr(), self.ws_bytes, self.stream.cuda_stream), 'mp_net_forward')
+        self.last_launches = int(_cabi.lib().mp_launch_count())
+
+    def wait(self):
+        """Block until the submitted batch is on the host; -> (pose [B*T,24,3,3], joints, tran, contact) pinned tensors."""
+        self.stream.synchronize()
         return self.pose, self.joints, self.tran, self.contact
+
+    def run(self, imu_host: torch.Tensor, input_lengths=None):
+        self.submit(imu_host, input_lengths)
+        return self.wait()

@@ -368,6 +368,36 @@ def test_host_buffer_entry_matches_device_entry(net):
         assert torch.equal(tran_h[b, :L], tran[b, :L].cpu())
 
 
+def test_pipelined_host_batches_equal_one_at_a_time(net):
+    """Two HostOffline objects as a depth-2 pipeline (bench.py's e2e): results are bit-identical to submit + wait per batch,
+    with and without the physics hook inside the graph."""
+    import mobileposer_b200 as mp
+    from mobileposer_b200.synthetic import synthetic_imu_batch
+    xs = [synthetic_imu_batch([200 + 4 * i + k for k in range(4)], 32).pin_memory() for i in range(5)]
+    try:
+        for physics in (False, True):
+            net.enable_physics(physics)
+            solo = mp.HostOffline(net, 4, 32)
+            want = [tuple(t.clone() for t in solo.run(x)) for x in xs]
+            pipe = [mp.HostOffline(net, 4, 32), mp.HostOffline(net, 4, 32)]
+            got = [None] * len(xs)
+            for i, x in enumerate(xs):
+                h = pipe[i % 2]
+                if i >= 2:
+                    got[i - 2] = tuple(t.clone() for t in h.wait())
+                h.submit(x)
+            for i in (len(xs) - 2, len(xs) - 1):
+                got[i] = tuple(t.clone() for t in pipe[i % 2].wait())
+            for w, g in zip(want, got):
+                assert all(torch.equal(a, b) for a, b in zip(w, g))
+            if physics:
+                net.enable_physics(False)
+                plain = solo.run(xs[0])[0]
+                assert not torch.equal(plain, want[0][0])          # the hook really ran inside the graph
+    finally:
+        net.enable_physics(False)
+
+
 def test_float64_arbitration(net, oracle, seeded_state_dict):
     """Both fp32 implementations against a float64 evaluation of the same equations (oracle/np_port.py): the CUDA
     path must be as close to the exact answer as the reference's own CPU path is (it cannot be asked to be closer
