@@ -30,6 +30,14 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# The CPU arm (--impl reference) uses every host core.  torchrun exports OMP_NUM_THREADS=1 to its children, and the
+# OpenMP / oneDNN pools read it when torch is imported: fix the environment and re-exec before that happens.
+if 'reference' in sys.argv and os.environ.get('MP_BENCH_REEXEC') != '1':
+    _n = str(os.cpu_count() or 1)
+    if os.environ.get('OMP_NUM_THREADS', _n) != _n or os.environ.get('MKL_NUM_THREADS', _n) != _n:
+        os.environ.update(OMP_NUM_THREADS=_n, MKL_NUM_THREADS=_n, MP_BENCH_REEXEC='1')
+        os.execv(sys.executable, [sys.executable] + sys.argv)
+
 import torch
 
 T_FRAMES = 300
@@ -125,6 +133,15 @@ def physics_on(args):
     return args.physics == 'on' or (args.physics == 'auto' and args.workload == 'cfg3')
 
 
+def use_all_host_threads():
+    """The CPU arm uses every host core; torchrun exports OMP_NUM_THREADS=1 to its children, undo that here."""
+    n = os.cpu_count() or 1
+    torch.set_num_threads(n)
+    from oracle.physics_c import set_threads
+    set_threads(n)
+    return n
+
+
 def cpu_reference_pass(oracle, x, lens, physics=False):
     """The reference's CPU path for a batch: batched net.forward (net.py:101-119) + the per-sequence
     translation tail of forward_offline (net.py:125-154) + (physics) the PHYSICS-hook loop of net.py:157-169 as the
@@ -145,6 +162,7 @@ def cpu_reference_pass(oracle, x, lens, physics=False):
 def time_cpu_sample(sd, x_sample, budget_s=20.0, min_passes=2, physics=False):
     """frames/s of the oracle port on this box's host cores for a bounded sample; returns the cpu_baseline dict."""
     from oracle.torch_port import OraclePoser
+    use_all_host_threads()
     oracle = OraclePoser(sd)
     B, T = x_sample.shape[0], x_sample.shape[1]
     lens = [T] * B
@@ -193,6 +211,7 @@ def run_reference(args):
         return
     from mobileposer_b200.synthetic import synthetic_imu_batch
     from oracle.torch_port import OraclePoser
+    use_all_host_threads()
     B = (args.batch or (256 if args.workload == 'cfg3' else 1))
     Bs = min(B, args.cpu_sample)
     _, sd = seeded_state_dict()

@@ -26,7 +26,14 @@ def lib():
         _lib = C.CDLL(_build.build())
         _lib.mp_oracle_physics_optimize.restype = C.c_int
         _lib.mp_oracle_physics_optimize.argtypes = [C.c_void_p] * 5 + [C.c_int32, C.c_int32, C.POINTER(_Params)] + [C.c_void_p] * 3
+        _lib.mp_oracle_set_threads.restype = None
+        _lib.mp_oracle_set_threads.argtypes = [C.c_int32]
     return _lib
+
+
+def set_threads(n: int):
+    """OpenMP threads of the C port (torchrun sets OMP_NUM_THREADS=1 for its children)."""
+    lib().mp_oracle_set_threads(int(n))
 
 
 class PhysicsOptimizerC:

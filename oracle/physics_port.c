@@ -10,6 +10,7 @@
  *   gcc -O3 -fopenmp -shared -fPIC -o oracle/_build/libphysics_port.so oracle/physics_port.c -lm      (oracle/build.py)
  */
 #include <math.h>
+#include <omp.h>
 #include <stdint.h>
 #include <string.h>
 
@@ -162,6 +163,11 @@ static void optimize_frame(const mp_oracle_physics_params_t* prm, const double* 
     for (int i = 0; i < NJ * 9; ++i) pose_out[i] = (float)Rn[i];
     if (tran_out)
         for (int r = 0; r < 3; ++r) tran_out[r] = (float)p[r];
+}
+
+/* torchrun exports OMP_NUM_THREADS=1 to its children; the CPU arm of bench.py asks for the host's cores explicitly. */
+void mp_oracle_set_threads(int32_t n) {
+    if (n > 0) omp_set_num_threads(n);
 }
 
 /* pose [B,T,24,9] f32, vel [B,T,72] raw velocity head, contact [B,T,2] logits, lengths [B] or NULL,
