@@ -72,6 +72,9 @@ __device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t smem_addr) {
     return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | (1ull << 16) | ((uint64_t)(512 >> 4) << 32) | (1ull << 46) | (4ull << 61);
 }
 
+// NARROW = false: full 256-column tiles, everything about the tile is a compile-time constant (the runtime-width variant
+// costs the wide projections 45%: 12.9 ms against 8.8 ms per cfg3 step)
+template <bool NARROW>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
                    const float* __restrict__ bias, float* __restrict__ C, int M, int N, int K) {
@@ -89,6 +92,11 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int n0 = blockIdx.x * TC_BN, m0 = blockIdx.y * TC_BM;
     const int KB = K / TC_BK;
+    // narrow outputs (linear2: N = 72 / 96, one column tile): the W box has n_mma = N rounded up to 16 rows (TMA zero-fills
+    // the few rows past the end, the transaction counts the whole box), the MMAs span n_mma columns, the epilogue masks its
+    // stores.  (A full 256-row box over a 72-row tensor works too but is 6x slower: 1.8 ms against 0.3 ms for the FFMA kernel.)
+    const int n_valid = NARROW ? min(TC_BN, N - n0) : TC_BN;
+    const int n_mma = NARROW ? (n_valid + 15) & ~15 : TC_BN;
 
     if (tid == 0) {
         for (int s = 0; s < TC_STAGES; ++s) {
@@ -113,7 +121,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             for (int kb = 0; kb < KB; ++kb) {
                 const int s = kb % TC_STAGES;
                 if (kb >= TC_STAGES) mbar_wait(bar_free(s), ((kb / TC_STAGES) - 1) & 1);
-                mbar_arrive_expect_tx(bar_full(s), A_TILE + W_TILE);
+                mbar_arrive_expect_tx(bar_full(s), A_TILE + (uint32_t)n_mma * (TC_BK * 4));
                 const uint32_t st = base + s * STAGE_BYTES;
                 tma_load_2d(st, &map_a, kb * TC_BK, m0, bar_full(s));
                 tma_load_2d(st + 2 * A_TILE, &map_w, kb * TC_BK, n0, bar_full(s));
@@ -121,8 +129,8 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            // instruction descriptor: D = f32, A = B = tf32, both K-major, N = 256, M = 128
-            constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+            // instruction descriptor: D = f32, A = B = tf32, both K-major, N = n_mma (256 for full tiles), M = 128
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n_mma >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
             for (int kb = 0; kb < KB; ++kb) {
                 const int s = kb % TC_STAGES;
                 mbar_wait(bar_split(s), (kb / TC_STAGES) & 1);
@@ -172,7 +180,8 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
 #pragma unroll
             for (int i = 0; i < (int)(A_TILE / 16 / 128); ++i) split(a_hi, a_lo, t + i * 128);
 #pragma unroll
-            for (int i = 0; i < (int)(W_TILE / 16 / 128); ++i) split(w_hi, w_lo, t + i * 128);
+            for (int i = 0; i < (int)(W_TILE / 16 / 128); ++i)
+                if (!NARROW || (t + i * 128) * 16 < n_mma * (TC_BK * 4)) split(w_hi, w_lo, t + i * 128);      // 64-byte rows: only the rows the MMAs read
             fence_proxy_async_smem();
             mbar_arrive(bar_split(s));
         }
@@ -181,7 +190,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         tcgen05_fence_after();
         const int wq = warp & 3;                         // TMEM lane quarter this warp may read
         const int row = m0 + wq * 32 + lane;
-        for (int c0 = 0; c0 < TC_BN; c0 += 32) {
+        for (int c0 = 0; c0 < n_valid; c0 += 32) {
             uint32_t v[32];
             const uint32_t taddr = tmem + ((uint32_t)(wq * 32) << 16) + (uint32_t)c0;
             asm volatile(
@@ -213,6 +222,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                 const float4* b4 = reinterpret_cast<const float4*>(bias + n0 + c0);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
+                    if (NARROW && c0 + 4 * j >= n_valid) break;          // N is a multiple of 4: whole float4s are valid or not
                     const float4 b = __ldg(b4 + j);
                     float4 o;
                     o.x = __uint_as_float(v[4 * j + 0]) + b.x;
@@ -274,25 +284,35 @@ bool gemm_tc_eligible(int M, int N, int K) {
     const char* v = getenv("MP_GEMM");
     if (v && strcmp(v, "ffma") == 0) return false;
     const int min_m = (v && strcmp(v, "tc") == 0) ? 1 : 2048;
-    return M >= min_m && N % TC_BN == 0 && K % TC_BK == 0 && K >= TC_BK;
+    // Narrow outputs (linear2, N = 72 / 96) run 2.5x faster here in isolation (0.12 ms against 0.31 ms for the FFMA kernel at
+    // M = 76800, K = 512) but make the whole step 1.6 ms SLOWER: a CTA of this kernel owns all 512 TMEM columns and 195 KB of
+    // shared memory, so it cannot share an SM with the recurrence clusters of the other heads the way the FFMA kernel does
+    // (and it fragments the GPCs those clusters need).  They stay on the FFMA kernel unless MP_GEMM=tc asks otherwise.
+    const bool narrow_ok = v && strcmp(v, "tc") == 0 && N < TC_BN && N % 4 == 0 && N >= 16;
+    return M >= min_m && (N % TC_BN == 0 || narrow_ok) && K % TC_BK == 0 && K >= TC_BK;
 }
 
 int launch_gemm_tf32x3(const float* A, const float* W, const float* bias, float* C, int M, int N, int K, cudaStream_t stream) {
     MP_REQUIRE(A && W && bias && C && M > 0, "gemm_tc: bad arguments");
-    MP_REQUIRE(N % TC_BN == 0 && K % TC_BK == 0, "gemm_tc: N=%d must be a multiple of %d and K=%d of %d", N, TC_BN, K, TC_BK);
+    MP_REQUIRE((N % TC_BN == 0 || (N < TC_BN && N % 4 == 0 && N >= 16)) && K % TC_BK == 0,
+               "gemm_tc: N=%d must be a multiple of %d (or of 4, in [16, %d)) and K=%d of %d", N, TC_BN, TC_BN, K, TC_BK);
     MP_REQUIRE(((uintptr_t)A & 15) == 0 && ((uintptr_t)W & 15) == 0 && ((uintptr_t)C & 15) == 0 && ((uintptr_t)bias & 15) == 0,
                "gemm_tc: pointers must be 16-byte aligned");
     alignas(64) CUtensorMap map_a, map_w;
     MP_TRY(make_map(&map_a, A, M, K, TC_BM));
-    MP_TRY(make_map(&map_w, W, N, K, TC_BN));
+    MP_TRY(make_map(&map_w, W, N, K, N % TC_BN == 0 ? TC_BN : ((N + 15) & ~15)));
     static bool configured = false;
     if (!configured) {
-        MP_CUDA_TRY(cudaFuncSetAttribute(gemm_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
+        MP_CUDA_TRY(cudaFuncSetAttribute(gemm_tf32x3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
+        MP_CUDA_TRY(cudaFuncSetAttribute(gemm_tf32x3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
         configured = true;
     }
     ProfileScope prof("gemm_tf32x3", 4.0 * ((double)N * K + N + (double)M * K + (double)M * N), stream);
-    dim3 grid(N / TC_BN, (M + TC_BM - 1) / TC_BM);
-    gemm_tf32x3_kernel<<<grid, TC_THREADS, TC_SMEM, stream>>>(map_a, map_w, bias, C, M, N, K);
+    dim3 grid((N + TC_BN - 1) / TC_BN, (M + TC_BM - 1) / TC_BM);
+    if (N % TC_BN == 0)
+        gemm_tf32x3_kernel<false><<<grid, TC_THREADS, TC_SMEM, stream>>>(map_a, map_w, bias, C, M, N, K);
+    else
+        gemm_tf32x3_kernel<true><<<grid, TC_THREADS, TC_SMEM, stream>>>(map_a, map_w, bias, C, M, N, K);
     MP_CUDA_TRY(cudaGetLastError());
     count_launch();
     return MP_OK;

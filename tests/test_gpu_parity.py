@@ -419,7 +419,8 @@ def test_float64_arbitration(net, oracle, seeded_state_dict):
     assert e_gpu <= 3.0 * e_ref + 5e-8, (e_ref, e_gpu)
 
 
-@pytest.mark.parametrize('M,N,K', [(128, 256, 16), (300, 256, 64), (4096, 2048, 256), (5000, 1024, 512), (2500, 512, 128)])
+@pytest.mark.parametrize('M,N,K', [(128, 256, 16), (300, 256, 64), (4096, 2048, 256), (5000, 1024, 512), (2500, 512, 128),
+                                   (3000, 72, 512), (2100, 96, 512), (700, 72, 256), (4100, 200, 64), (130, 16, 32)])
 def test_tensor_core_gemm_matches_fp32(M, N, K):
     """tcgen05 3xTF32 input projection (gemm_tc.cu) against the FFMA kernel and a float64 product."""
     from mobileposer_b200 import _cabi
