@@ -56,6 +56,7 @@ def parse_args():
     ap.add_argument('--batch', type=int, default=0, help='override sequences per GPU')
     ap.add_argument('--cpu-sample', type=int, default=32, help='sequences in the CPU-baseline sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--depth', type=int, default=0, help='batches in flight per GPU (pipeline over steps); default 4 for cfg3, 1 for the latency configuration cfg2')
     ap.add_argument('--physics', default='auto', choices=['auto', 'on', 'off'],
                     help='K8 optimizer behind the PHYSICS hook (auto: on for cfg3, which names it; off for cfg2)')
     return ap.parse_args()
@@ -319,10 +320,11 @@ def run_ours(args):
     # `value`: K steps, inputs resident in HBM, two batches in flight (depth-2 pipeline over batches: two net handles on two
     # streams, step i+1 is enqueued while step i runs, so the tail of one batch -- K8, the small GEMMs, the SMs the cluster
     # kernels leave idle -- overlaps the head of the next).  The one-batch-at-a-time figure is reported beside it.
-    pipes = [mp.HostOffline(net, B, T), mp.HostOffline(net, B, T)]
+    D = args.depth if args.depth > 0 else (4 if args.workload == 'cfg3' else 1)
+    pipes = [mp.HostOffline(net, B, T) for _ in range(D)]
 
     def pipe_step(i):
-        pipes[i % 2].submit_device(xs[i % n_sets])
+        pipes[i % D].submit_device(xs[i % n_sets])
 
     with ClockSampler(local) as clocks:
         ms_seq = timed_device_steps(step, args.steps, args.warmup, dist)
@@ -345,7 +347,7 @@ def run_ours(args):
     # (a) one batch at a time (evaluate.py's loop: submit + wait);  (b) depth-2 pipeline over batches: two HostOffline
     # objects (own net handle, stream, staging, pinned outputs), batch i+1 is submitted before batch i is awaited, so
     # the copies of one batch overlap the kernels of the next.  Every step still moves its own inputs and results.
-    hosts = [mp.HostOffline(net, B, T), mp.HostOffline(net, B, T)]
+    hosts = [mp.HostOffline(net, B, T) for _ in range(D)]
 
     def e2e_time(pipelined):
         def body(n, off):
@@ -354,10 +356,11 @@ def run_ours(args):
                     hosts[0].run(xs_host[(off + i) % n_sets], None)
                 return
             for i in range(n):
-                h = hosts[i % 2]
+                h = hosts[i % D]
                 h.wait()                                   # the slot's previous batch is on the host
                 h.submit(xs_host[(off + i) % n_sets], None)
-            hosts[0].wait(); hosts[1].wait()
+            for h in hosts:
+                h.wait()
         body(max(3, args.warmup), 0)
         torch.cuda.synchronize()
         if dist is not None:
@@ -376,7 +379,7 @@ def run_ours(args):
     e2e_s = e2e_time(True)
     e2e = {'value': frames_per_step * args.steps / e2e_s, 'unit': 'frames/s', 'h2d_bytes_per_step': B * T * 60 * 4,
            'd2h_bytes_per_step': B * T * (216 + 72 + 3 + 2) * 4, 'ms_per_step': e2e_s / args.steps * 1e3,
-           'how': 'depth-2 pipeline over batches through mp_net_enqueue_offline_host (HostOffline.submit / wait): pinned host imu '
+           'how': f'depth-{D} pipeline over batches through mp_net_enqueue_offline_host (HostOffline.submit / wait): pinned host imu '
                   'in, pose/joints/tran/contact out to pinned host memory, every step',
            'one_batch_at_a_time': {'value': frames_per_step * args.steps / e2e_sync_s, 'unit': 'frames/s',
                                    'ms_per_step': e2e_sync_s / args.steps * 1e3}}
@@ -462,7 +465,7 @@ def run_ours(args):
                        'l2': f'{n_sets} distinct resident input sets rotate between steps; per-step intermediates '
                              f'({net_workspace_mb(net, B, T):.0f} MB) exceed the 126 MB L2',
                        'parallelism': f'{world} x (one process per GPU, sequences sharded, no data-path collective); '
-                                      f'two batches in flight per GPU (depth-2 pipeline over steps)'},
+                                      f'{D} batches in flight per GPU (pipeline over steps)'},
             'e2e': e2e, 'gpu_launches': launches * args.steps, 'gpu_launches_per_step': launches,
             'roofline': roofline, 'whole_path_algorithmic_GBps': whole, 'whole_path_hbm_frac': whole / peak,
             'kernels': kernels, 'one_batch_at_a_time': sequential, 'without_physics': without_physics, 'cpu_baseline': cpu, 'batch1': batch1, 'streaming': streaming, 'clocks': clocks.summary(),

@@ -35,17 +35,26 @@ KEEP = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum
 
 
 def launches(tag):
-    path = os.path.join(SRC, 'launches.csv')
-    if not os.path.exists(path):
-        return
-    lines = [l for l in open(path) if not l.startswith('==')]
-    rows = list(csv.DictReader(lines))
-    with open(os.path.join(OUT, f'{tag}_launches.csv'), 'w', newline='') as f:
-        w = csv.writer(f)
-        w.writerow(['id', 'kernel', 'grid', 'block', 'duration_ns'])
-        for r in rows:
-            w.writerow([r['ID'], r['Kernel Name'].replace('mp::<unnamed>::', ''), r['Grid Size'], r['Block Size'], r['Metric Value']])
-    print('wrote', f'{tag}_launches.csv', len(rows), 'launches')
+    """launches.csv: two eager passes (scripts/prof_one.py); launches_bench.csv: the bench.py command itself."""
+    for src, dst in (('launches.csv', f'{tag}_launches.csv'), ('launches_bench.csv', f'{tag}_launches_bench.csv')):
+        path = os.path.join(SRC, src)
+        if not os.path.exists(path):
+            continue
+        lines = [l for l in open(path) if not l.startswith('==')]
+        rows = list(csv.DictReader(lines))
+        share = {}
+        with open(os.path.join(OUT, dst), 'w', newline='') as f:
+            w = csv.writer(f)
+            w.writerow(['id', 'kernel', 'grid', 'block', 'duration_ns'])
+            for r in rows:
+                name = r['Kernel Name'].replace('mp::<unnamed>::', '')
+                w.writerow([r['ID'], name, r['Grid Size'], r['Block Size'], r['Metric Value']])
+                key = name.split('(')[0].replace('void ', '')
+                share[key] = share.get(key, 0.0) + float(r['Metric Value'])
+        tot = sum(share.values()) or 1.0
+        print('wrote', dst, len(rows), 'launches; time share by kernel:')
+        for k, v in sorted(share.items(), key=lambda kv: -kv[1])[:10]:
+            print(f'    {100 * v / tot:5.1f}%  {k[:90]}')
 
 
 def full_sets(tag):
