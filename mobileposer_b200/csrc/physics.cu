@@ -400,7 +400,8 @@ __global__ void __launch_bounds__(32) physics_optimize_kernel(const PhysParams p
                 const bool h1 = i1 != 255;
                 const float* rk = sH + c0 * LDH;
                 const float* r1 = sH + (h1 ? i1 : c0) * LDH;
-                const float4 ini = *reinterpret_cast<const float4*>(r1 + 4 * K);
+                // idle lanes must not touch the diagonal block lane 0 rewrites below (warp-synchronous, but racecheck is right to ask)
+                const float4 ini = h1 ? *reinterpret_cast<const float4*>(r1 + 4 * K) : make_float4(1.f, 0.f, 0.f, 0.f);
                 float a0 = ini.x, a1 = ini.y, a2 = ini.z;
 #pragma unroll 2
                 for (int m = 4 * c_tab.first_blk[K]; m < 4 * K; m += 4) {
