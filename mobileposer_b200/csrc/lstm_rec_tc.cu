@@ -126,7 +126,12 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volat
 __device__ __forceinline__ float act_sigmoid_or_tanh(float x, bool is_tanh) {
     const float s = fminf(fmaxf(is_tanh ? 2.0f * x : x, -30.0f), 30.0f);
     const float e = expf(-s);
-    const float r = __frcp_rn(1.0f + e);
+    // 1 / (1 + e): MUFU reciprocal + one Newton step (<= 1 ulp; 1 + e is in [1, 1e13], no special cases) -- the correctly
+    // rounded __frcp_rn cost as many instructions as expf itself (ncu: 15 % of the kernel's instructions)
+    const float d = 1.0f + e;
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d));
+    r = fmaf(fmaf(-d, r, 1.0f), r, r);
     return is_tanh ? (1.0f - e) * r : r;
 }
 
@@ -251,13 +256,29 @@ __global__ void __launch_bounds__(RTC_THREADS, 1) lstm_rec_tc_kernel(const RecTc
     cluster_sync_all();
     tc_fence_after();
 
-    // gate pre-activations of step 0 (gin columns are (unit, gate)-ordered: a warp reads 128 contiguous bytes)
+    // gate pre-activations of step 0 (gin columns are (unit, gate)-ordered: a warp reads 128 contiguous bytes); go[j] is
+    // the running offset of the NEXT frame of sequence j (one add per step instead of rebuilding it from the tables)
     float gi[SPW];
+    uint32_t go[SPW];
+    const uint32_t dG4 = dir ? (uint32_t)(-G4) : (uint32_t)G4;
 #pragma unroll
     for (int j = 0; j < SPW; ++j) {
         const int n = (j >> 2) * 16 + part * 4 + (j & 3);      // block j/4 of 16 sequences, this warp's 4 columns in it
         const int l = lens[n];
-        gi[j] = (warp < EPI_WARPS && l > 0) ? __ldg(p.gin + (goff[n] + (uint32_t)(dir ? l - 1 : 0) * (uint32_t)G4 + (uint32_t)(ul * 4 + gate))) : 0.f;
+        go[j] = goff[n] + (uint32_t)(dir ? max(l - 1, 0) : 0) * (uint32_t)G4 + (uint32_t)(ul * 4 + gate);
+        gi[j] = (warp < EPI_WARPS && l > 0) ? __ldg(p.gin + go[j]) : 0.f;
+        go[j] += dG4;
+    }
+    // this lane's own sequence of every block: length, staging offset, running output offset
+    int len_own[SPW / 4];
+    uint32_t so[SPW / 4], yo[SPW / 4];
+    const uint32_t dY2 = dir ? (uint32_t)(-Y2) : (uint32_t)Y2;
+#pragma unroll
+    for (int blk = 0; blk < SPW / 4; ++blk) {
+        const int n = blk * 16 + part * 4 + gate;
+        len_own[blk] = lens[n];
+        so[blk] = sw128_off(n, ul);
+        yo[blk] = yoff[n] + (uint32_t)(dir ? max(len_own[blk] - 1, 0) : 0) * (uint32_t)Y2 + (uint32_t)ul;
     }
 
     const uint32_t d_main = tmem + COL_D, d_corr = tmem + COL_D + N;
@@ -359,45 +380,39 @@ __global__ void __launch_bounds__(RTC_THREADS, 1) lstm_rec_tc_kernel(const RecTc
                     float a[4];
 #pragma unroll
                     for (int q = 0; q < 4; ++q) a[q] = act_sigmoid_or_tanh((dm[bq * 4 + q] + dc[bq * 4 + q]) + gi[blk * 4 + q], gate == 2);
-                    const int q0 = lane & ~3;
-                    float iv = 0.f, fv = 0.f, gv = 0.f, ov = 0.f;
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const float i_q = __shfl_sync(0xffffffffu, a[q], q0);
-                        const float f_q = __shfl_sync(0xffffffffu, a[q], q0 | 1);
-                        const float g_q = __shfl_sync(0xffffffffu, a[q], q0 | 2);
-                        const float o_q = __shfl_sync(0xffffffffu, a[q], q0 | 3);
-                        if (q == gate) { iv = i_q; fv = f_q; gv = g_q; ov = o_q; }
-                    }
+                    // 4 x 4 transpose inside the gate quad (lanes = gates i, f, g, o of one unit; registers = the 4 sequences):
+                    // two butterfly rounds, 4 shuffles instead of 16
+                    const bool b0 = lane & 1, b1 = lane & 2;
+                    const float r0 = __shfl_xor_sync(0xffffffffu, b0 ? a[0] : a[1], 1), r1 = __shfl_xor_sync(0xffffffffu, b0 ? a[2] : a[3], 1);
+                    const float u0 = b0 ? r0 : a[0], u1 = b0 ? a[1] : r0, u2 = b0 ? r1 : a[2], u3 = b0 ? a[3] : r1;
+                    const float q0 = __shfl_xor_sync(0xffffffffu, b1 ? u0 : u2, 2), q1 = __shfl_xor_sync(0xffffffffu, b1 ? u1 : u3, 2);
+                    const float iv = b1 ? q0 : u0, fv = b1 ? q1 : u1, gv = b1 ? u2 : q0, ov = b1 ? u3 : q1;
                     // this lane's sequence of the block
                     const int n = blk * 16 + part * 4 + gate;
-                    const int len = lens[n];
+                    const int len = len_own[blk];
                     const bool active = s < len;
-                    const int t = dir ? len - 1 - s : s;
                     const float c_new = fmaf(fv, cst[blk], iv * gv);
                     const float h_new = ov * act_sigmoid_or_tanh(c_new, true);
                     if (active) {
                         cst[blk] = c_new;
-                        p.y[yoff[n] + (uint32_t)t * (uint32_t)Y2 + (uint32_t)ul] = h_new;
+                        p.y[yo[blk]] = h_new;
                         if (s == len - 1) {
                             if (p.hn) p.hn[((size_t)dir * p.B + b_begin + n) * TH + rank * TUC + ul] = h_new;
                             if (p.cn) p.cn[((size_t)dir * p.B + b_begin + n) * TH + rank * TUC + ul] = c_new;
                         }
                     }
+                    yo[blk] += dY2;
                     if (send) {
                         const float hv = active ? h_new : 0.f;
                         const uint32_t hh = tf32_hi(hv);
-                        const uint32_t off = sw128_off(n, ul);
-                        *reinterpret_cast<uint32_t*>(stg_hi + off) = hh;
-                        *reinterpret_cast<uint32_t*>(stg_lo + off) = tf32_lo(hv, hh);
+                        *reinterpret_cast<uint32_t*>(stg_hi + so[blk]) = hh;
+                        *reinterpret_cast<uint32_t*>(stg_lo + so[blk]) = tf32_lo(hv, hh);
                     }
                     // next step's gate pre-activations of the block (this lane's gate, all 4 sequences)
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
-                        const int nq = blk * 16 + part * 4 + q;
-                        const int lq2 = lens[nq];
-                        if (s + 1 < lq2)
-                            gi[blk * 4 + q] = __ldg(p.gin + (goff[nq] + (uint32_t)(dir ? lq2 - 2 - s : s + 1) * (uint32_t)G4 + (uint32_t)(ul * 4 + gate)));
+                        if (s + 1 < lens[blk * 16 + part * 4 + q]) gi[blk * 4 + q] = __ldg(p.gin + go[blk * 4 + q]);
+                        go[blk * 4 + q] += dG4;
                     }
                     // rows [16 blk, 16 blk + 16) of the new slice are staged: hand them to the copy warp (non-blocking)
                     if (send) {

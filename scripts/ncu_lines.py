@@ -12,7 +12,8 @@ tot = 0
 lines = []
 for r in rows[3:]:
     if len(r) >= 8 and r[0].isdigit():
-        s, inst = int(r[6] or 0), int(r[7] or 0)
+        num = lambda v: int(v) if v.strip().lstrip('-').isdigit() else 0
+        s, inst = num(r[6]), num(r[7])
         lines.append((int(r[0]), r[1][:110], s, inst))
         tot += s
 print('total samples', tot)
