@@ -121,10 +121,12 @@ __device__ __forceinline__ bool elect_one() {
     asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
     return pred != 0;
 }
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
 __device__ __forceinline__ float act_sigmoid_or_tanh(float x, bool is_tanh) {
     const float s = fminf(fmaxf(is_tanh ? 2.0f * x : x, -30.0f), 30.0f);
+    // expf, not ex2.approx on s log2(e): the MUFU form is as accurate for a sigmoid (measured: max |tc - ffma| 8.2e-8 either way)
+    // and 9 instructions shorter, but an A/B on the same box showed no difference (1.50 ms per launch both): after the
+    // reciprocal / transpose / offset diet the epilogue is bound by its dependent chains, not by issue slots.
     const float e = expf(-s);
     // 1 / (1 + e): MUFU reciprocal + one Newton step (<= 1 ulp; 1 + e is in [1, 1e13], no special cases) -- the correctly
     // rounded __frcp_rn cost as many instructions as expf itself (ncu: 15 % of the kernel's instructions)
