@@ -376,6 +376,10 @@ __global__ void __launch_bounds__(RTC_THREADS, 1) lstm_rec_tc_kernel(const RecTc
                 if (tid == 0 && sub == 0) RTC_STAMP(3);
                 // Blocks of 4 sequences per lane quad: every lane evaluates its gate for the 4 sequences, the quad (4 gate
                 // lanes of a unit) exchanges them, and lane g then owns sequence 4*blk + g: ONE cell update per lane.
+                // Phase 1 is register-only for all blocks of the sub-tile, so their dependent chains (activation -> transpose ->
+                // cell -> tanh) interleave; the stores, fences and barrier arrivals (compiler barriers) come after, per block.
+                constexpr int MAXB = NBLK - NBLK / 2;
+                float c_nw[MAXB], h_nw[MAXB];
 #pragma unroll
                 for (int bq = 0; bq < nblk; ++bq) {
                     const int blk = blk0 + bq;
@@ -389,12 +393,17 @@ __global__ void __launch_bounds__(RTC_THREADS, 1) lstm_rec_tc_kernel(const RecTc
                     const float u0 = b0 ? r0 : a[0], u1 = b0 ? a[1] : r0, u2 = b0 ? r1 : a[2], u3 = b0 ? a[3] : r1;
                     const float q0 = __shfl_xor_sync(0xffffffffu, b1 ? u0 : u2, 2), q1 = __shfl_xor_sync(0xffffffffu, b1 ? u1 : u3, 2);
                     const float iv = b1 ? q0 : u0, fv = b1 ? q1 : u1, gv = b1 ? u2 : q0, ov = b1 ? u3 : q1;
+                    c_nw[bq] = fmaf(fv, cst[blk], iv * gv);
+                    h_nw[bq] = ov * act_sigmoid_or_tanh(c_nw[bq], true);
+                }
+#pragma unroll
+                for (int bq = 0; bq < nblk; ++bq) {
+                    const int blk = blk0 + bq;
                     // this lane's sequence of the block
                     const int n = blk * 16 + part * 4 + gate;
                     const int len = len_own[blk];
                     const bool active = s < len;
-                    const float c_new = fmaf(fv, cst[blk], iv * gv);
-                    const float h_new = ov * act_sigmoid_or_tanh(c_new, true);
+                    const float c_new = c_nw[bq], h_new = h_nw[bq];
                     if (active) {
                         cst[blk] = c_new;
                         p.y[yo[blk]] = h_new;
@@ -409,17 +418,15 @@ __global__ void __launch_bounds__(RTC_THREADS, 1) lstm_rec_tc_kernel(const RecTc
                         const uint32_t hh = tf32_hi(hv);
                         *reinterpret_cast<uint32_t*>(stg_hi + so[blk]) = hh;
                         *reinterpret_cast<uint32_t*>(stg_lo + so[blk]) = tf32_lo(hv, hh);
+                        // rows [16 blk, 16 blk + 16) of the new slice are staged: hand them to the copy warp (non-blocking)
+                        fence_proxy_async_smem();
+                        mbar_arrive_local(bar_chunk + 8 * blk);
                     }
                     // next step's gate pre-activations of the block (this lane's gate, all 4 sequences)
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
                         if (s + 1 < lens[blk * 16 + part * 4 + q]) gi[blk * 4 + q] = __ldg(p.gin + go[blk * 4 + q]);
                         go[blk * 4 + q] += dG4;
-                    }
-                    // rows [16 blk, 16 blk + 16) of the new slice are staged: hand them to the copy warp (non-blocking)
-                    if (send) {
-                        fence_proxy_async_smem();
-                        mbar_arrive_local(bar_chunk + 8 * blk);
                     }
                 }
             }
