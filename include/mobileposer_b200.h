@@ -89,6 +89,17 @@ int mp_gemm_bias(const float* A, const float* W, const float* bias, float* C, in
                  int32_t relu, int32_t mode, mp_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Input assembly (the step right before the heads).
+ *   PoseDataset._process_file_data / _process_combo_data          [data.py:60-61,69-76]
+ *   DataLoader._get_imu + smooth_avg                              [loader.py:39-49, utils/model_utils.py:28-37]
+ * acc [T, slots_in, 3] and ori [T, slots_in, 3, 3] are the raw per-slot streams (slots_in >= 5, the first 5 are used);
+ * combo_masks_host[c] has bit s set when slot s is worn in combo c (amass.combos, config.py:60-73; HOST array, <= 16
+ * entries).  imu_out [n_combos, T, 60] = per combo cat(acc / acc_scale [15], ori [45]) with the other slots zeroed;
+ * smooth != 0 additionally applies the viewer's 3-tap moving average to the scaled accelerations.                    */
+int mp_imu_assemble(const float* acc, const float* ori, int64_t T, int32_t slots_in, const int32_t* combo_masks_host,
+                    int32_t n_combos, float acc_scale, int32_t smooth, float* imu_out, mp_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * Kinematic tail.
  * ---------------------------------------------------------------------------------------- */
 /* MobilePoserNet._reduced_global_to_full                         [net.py:93-99]

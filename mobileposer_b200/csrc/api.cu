@@ -70,6 +70,7 @@ struct mp_rnn {
     void* blob = nullptr;
     float *w1 = nullptr, *b1 = nullptr, *w2 = nullptr, *b2 = nullptr;
     float* wih[2] = {nullptr, nullptr};    // [dirs*4H, In_l]   both directions stacked on N
+    float* wih_split[2] = {nullptr, nullptr};   // [2 * dirs*4H, In_l]: TF32 hi rows, then lo rows (tensor-core projection), or null
     float* bsum[2] = {nullptr, nullptr};   // [dirs*4H]         b_ih + b_hh
     float4* whh_pack[2] = {nullptr, nullptr};
     float* whh_t[2] = {nullptr, nullptr};
@@ -166,9 +167,10 @@ int mp_rnn_create(mp_rnn_t** out, const mp_rnn_weights_t* w, mp_stream_t stream_
     auto take = [&](size_t floats) { size_t o = off; off = align_up(off + floats * sizeof(float)); return o; };
     const size_t o_w1 = take((size_t)H * r->n_in), o_b1 = take(H);
     const size_t o_w2 = take((size_t)r->n_out * dirs * H), o_b2 = take(r->n_out);
-    size_t o_wih[2], o_bs[2], o_pk[2], o_wt[2], o_raw[2];
+    size_t o_wih[2], o_bs[2], o_pk[2], o_wt[2], o_raw[2], o_split[2];
     for (int l = 0; l < 2; ++l) {
         o_wih[l] = take((size_t)dirs * 4 * H * in_l[l]);
+        o_split[l] = take((size_t)2 * dirs * 4 * H * in_l[l]);
         o_bs[l] = take((size_t)dirs * 4 * H);
         o_pk[l] = take(whh_pack_float4s(H, dirs) * 4);
         o_wt[l] = take((size_t)dirs * 4 * H * H);
@@ -207,6 +209,12 @@ int mp_rnn_create(mp_rnn_t** out, const mp_rnn_weights_t* w, mp_stream_t stream_
             bias_sum_permute_kernel<<<(4 * H + 255) / 256, 256, 0, stream>>>(w->b_ih[l][d], w->b_hh[l][d], r->bsum[l] + (size_t)d * 4 * H, H);
         }
         if (st == MP_OK) st = launch_pack_whh(whh, H, dirs, r->whh_pack[l], r->whh_t[l], stream);
+        // pre-split copy of the (permuted, stacked) W_ih for the tensor-core projection: the shapes it accepts are N % 256 == 0
+        // and K % 16 == 0 (gemm_tc_eligible); the H = 64 head (N = 512, K = 64 / 128) qualifies too
+        if (st == MP_OK && (dirs * 4 * H) % 256 == 0 && in_l[l] % 16 == 0) {
+            r->wih_split[l] = (float*)(base + o_split[l]);
+            st = launch_split_weights(r->wih[l], (size_t)dirs * 4 * H * in_l[l], r->wih_split[l], stream);
+        }
     }
     if (st == MP_OK && cudaStreamSynchronize(stream) != cudaSuccess) {
         set_error("rnn_create: packing failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -271,7 +279,10 @@ static int rnn_forward_impl(const mp_rnn_t* r, const float* xa, int32_t ka, cons
     int in_w = H;
     for (int l = 0; l < 2; ++l) {
         // hoisted input projection of both directions                        rnn.py:27 (W_ih x + b_ih + b_hh)
-        MP_TRY(launch_gemm_bias_act(layer_in, in_w, nullptr, 0, r->wih[l], r->bsum[l], gin, (int)M, dirs * 4 * H, 0, stream));
+        if (r->wih_split[l] && gemm_tc_eligible((int)M, dirs * 4 * H, in_w) && !getenv("MP_GEMM_NOSPLIT"))
+            MP_TRY(launch_gemm_tf32x3_presplit(layer_in, r->wih_split[l], r->bsum[l], gin, (int)M, dirs * 4 * H, in_w, stream));
+        else
+            MP_TRY(launch_gemm_bias_act(layer_in, in_w, nullptr, 0, r->wih[l], r->bsum[l], gin, (int)M, dirs * 4 * H, 0, stream));
         RecLayerArgs a;
         a.gin = gin; a.wpack = r->whh_pack[l]; a.wT = r->whh_t[l]; a.y = ybuf[l];
         a.w_raw[0] = r->whh_raw[l]; a.w_raw[1] = r->whh_raw[l] + (size_t)(dirs - 1) * 4 * H * H;
@@ -314,6 +325,10 @@ int mp_pose_reduced_global_to_full(const float* r6d, int64_t n_frames, float* po
 int mp_tran_offline(const float* joints, const float* vel, const float* contact, const int32_t* lengths, int32_t B,
                     int32_t T, float* tran, mp_stream_t stream) {
     return launch_tran_offline(joints, vel, contact, lengths, B, T, tran, (cudaStream_t)stream);
+}
+int mp_imu_assemble(const float* acc, const float* ori, int64_t T, int32_t slots_in, const int32_t* combo_masks_host, int32_t n_combos,
+                    float acc_scale, int32_t smooth, float* imu_out, mp_stream_t stream) {
+    return launch_imu_assemble(acc, ori, T, slots_in, combo_masks_host, n_combos, acc_scale, smooth, imu_out, (cudaStream_t)stream);
 }
 int mp_physics_optimize(const float* pose, const float* vel, const float* contact, const int32_t* lengths, float* state,
                         int32_t B, int32_t T, const mp_physics_params_t* params, float* pose_out, float* tran_out,

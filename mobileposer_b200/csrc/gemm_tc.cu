@@ -74,7 +74,10 @@ __device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t smem_addr) {
 
 // NARROW = false: full 256-column tiles, everything about the tile is a compile-time constant (the runtime-width variant
 // costs the wide projections 45%: 12.9 ms against 8.8 ms per cfg3 step)
-template <bool NARROW>
+// PRESPLIT = true: W arrives already split (rows [0, N) = hi, rows [N, 2N) = lo of a [2N, K] array made once when the head
+// is packed): the producer fetches both halves and the splitter warps only touch A -- a third of their shared-memory traffic,
+// which is what bounds this kernel (per slab: 24 KB landed + 72 KB split traffic + 72 KB operand fetch against 768 clk of MMA)
+template <bool NARROW, bool PRESPLIT>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
                    const float* __restrict__ bias, float* __restrict__ C, int M, int N, int K) {
@@ -121,10 +124,11 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             for (int kb = 0; kb < KB; ++kb) {
                 const int s = kb % TC_STAGES;
                 if (kb >= TC_STAGES) mbar_wait(bar_free(s), ((kb / TC_STAGES) - 1) & 1);
-                mbar_arrive_expect_tx(bar_full(s), A_TILE + (uint32_t)n_mma * (TC_BK * 4));
+                mbar_arrive_expect_tx(bar_full(s), A_TILE + (PRESPLIT ? 2u : 1u) * (uint32_t)n_mma * (TC_BK * 4));
                 const uint32_t st = base + s * STAGE_BYTES;
                 tma_load_2d(st, &map_a, kb * TC_BK, m0, bar_full(s));
                 tma_load_2d(st + 2 * A_TILE, &map_w, kb * TC_BK, n0, bar_full(s));
+                if (PRESPLIT) tma_load_2d(st + 2 * A_TILE + W_TILE, &map_w, kb * TC_BK, N + n0, bar_full(s));
             }
         }
     } else if (warp == 1) {
@@ -180,7 +184,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
 #pragma unroll
             for (int i = 0; i < (int)(A_TILE / 16 / 128); ++i) split(a_hi, a_lo, t + i * 128);
 #pragma unroll
-            for (int i = 0; i < (int)(W_TILE / 16 / 128); ++i)
+            for (int i = 0; i < (int)(PRESPLIT ? 0 : W_TILE / 16 / 128); ++i)
                 if (!NARROW || (t + i * 128) * 16 < n_mma * (TC_BK * 4)) split(w_hi, w_lo, t + i * 128);      // 64-byte rows: only the rows the MMAs read
             fence_proxy_async_smem();
             mbar_arrive(bar_split(s));
@@ -292,7 +296,7 @@ bool gemm_tc_eligible(int M, int N, int K) {
     return M >= min_m && (N % TC_BN == 0 || narrow_ok) && K % TC_BK == 0 && K >= TC_BK;
 }
 
-int launch_gemm_tf32x3(const float* A, const float* W, const float* bias, float* C, int M, int N, int K, cudaStream_t stream) {
+static int launch_gemm_tc_impl(const float* A, const float* W, const float* bias, float* C, int M, int N, int K, bool presplit, cudaStream_t stream) {
     MP_REQUIRE(A && W && bias && C && M > 0, "gemm_tc: bad arguments");
     MP_REQUIRE((N % TC_BN == 0 || (N < TC_BN && N % 4 == 0 && N >= 16)) && K % TC_BK == 0,
                "gemm_tc: N=%d must be a multiple of %d (or of 4, in [16, %d)) and K=%d of %d", N, TC_BN, TC_BN, K, TC_BK);
@@ -300,21 +304,51 @@ int launch_gemm_tf32x3(const float* A, const float* W, const float* bias, float*
                "gemm_tc: pointers must be 16-byte aligned");
     alignas(64) CUtensorMap map_a, map_w;
     MP_TRY(make_map(&map_a, A, M, K, TC_BM));
-    MP_TRY(make_map(&map_w, W, N, K, N % TC_BN == 0 ? TC_BN : ((N + 15) & ~15)));
+    MP_REQUIRE(!presplit || N % TC_BN == 0, "gemm_tc: pre-split weights need N=%d to be a multiple of %d", N, TC_BN);
+    MP_TRY(make_map(&map_w, W, presplit ? 2 * N : N, K, N % TC_BN == 0 ? TC_BN : ((N + 15) & ~15)));
     static bool configured = false;
     if (!configured) {
-        MP_CUDA_TRY(cudaFuncSetAttribute(gemm_tf32x3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
-        MP_CUDA_TRY(cudaFuncSetAttribute(gemm_tf32x3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
+        MP_CUDA_TRY(cudaFuncSetAttribute(gemm_tf32x3_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
+        MP_CUDA_TRY(cudaFuncSetAttribute(gemm_tf32x3_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
+        MP_CUDA_TRY(cudaFuncSetAttribute(gemm_tf32x3_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
         configured = true;
     }
     ProfileScope prof("gemm_tf32x3", 4.0 * ((double)N * K + N + (double)M * K + (double)M * N), stream);
     dim3 grid((N + TC_BN - 1) / TC_BN, (M + TC_BM - 1) / TC_BM);
-    if (N % TC_BN == 0)
-        gemm_tf32x3_kernel<false><<<grid, TC_THREADS, TC_SMEM, stream>>>(map_a, map_w, bias, C, M, N, K);
+    if (presplit)
+        gemm_tf32x3_kernel<false, true><<<grid, TC_THREADS, TC_SMEM, stream>>>(map_a, map_w, bias, C, M, N, K);
+    else if (N % TC_BN == 0)
+        gemm_tf32x3_kernel<false, false><<<grid, TC_THREADS, TC_SMEM, stream>>>(map_a, map_w, bias, C, M, N, K);
     else
-        gemm_tf32x3_kernel<true><<<grid, TC_THREADS, TC_SMEM, stream>>>(map_a, map_w, bias, C, M, N, K);
+        gemm_tf32x3_kernel<true, false><<<grid, TC_THREADS, TC_SMEM, stream>>>(map_a, map_w, bias, C, M, N, K);
     MP_CUDA_TRY(cudaGetLastError());
     count_launch();
+    return MP_OK;
+}
+
+int launch_gemm_tf32x3(const float* A, const float* W, const float* bias, float* C, int M, int N, int K, cudaStream_t stream) {
+    return launch_gemm_tc_impl(A, W, bias, C, M, N, K, false, stream);
+}
+
+// W_split [2N, K]: rows [0, N) = TF32 hi parts, rows [N, 2N) = TF32-rounded lo parts of W (launch_split_weights)
+int launch_gemm_tf32x3_presplit(const float* A, const float* W_split, const float* bias, float* C, int M, int N, int K, cudaStream_t stream) {
+    return launch_gemm_tc_impl(A, W_split, bias, C, M, N, K, true, stream);
+}
+
+namespace {
+__global__ void split_weights_kernel(const float* __restrict__ w, size_t n, float* __restrict__ out) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float x = w[i];
+        const uint32_t hi = __float_as_uint(x) & 0xFFFFE000u;
+        out[i] = __uint_as_float(hi);
+        out[n + i] = __uint_as_float(tf32_rna(x - __uint_as_float(hi)));      // same rounding as the in-kernel splitter
+    }
+}
+}  // namespace
+
+int launch_split_weights(const float* W, size_t n, float* W_split, cudaStream_t stream) {
+    split_weights_kernel<<<296, 256, 0, stream>>>(W, n, W_split);
+    MP_CUDA_TRY(cudaGetLastError());
     return MP_OK;
 }
 

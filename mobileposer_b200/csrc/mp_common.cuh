@@ -56,6 +56,10 @@ int launch_gemm_bias_act(const float* A1, int K1, const float* A2, int K2, const
 bool gemm_tc_eligible(int M, int N, int K);
 int launch_gemm_tf32x3(const float* A, const float* W, const float* bias, float* C, int M, int N, int K,
                        cudaStream_t stream);
+// the same with W given as [2N, K] = (hi rows, lo rows), split once by launch_split_weights
+int launch_gemm_tf32x3_presplit(const float* A, const float* W_split, const float* bias, float* C, int M, int N, int K,
+                                cudaStream_t stream);
+int launch_split_weights(const float* W, size_t n, float* W_split, cudaStream_t stream);
 int launch_gemm_ffma(const float* A1, int K1, const float* A2, int K2, const float* W, const float* bias, float* C,
                      int M, int N, int relu, cudaStream_t stream);
 
@@ -92,6 +96,10 @@ int launch_online_update(mp_online_state_t* st, const float* pose, const float* 
 int launch_online_reset(mp_online_state_t* st, int S, int full, cudaStream_t stream);
 int launch_online_push(const float* win_in, float* win_out, const float* frame, int S, int W, int cold,
                        cudaStream_t stream);
+
+// N2 (inputs.cu)
+int launch_imu_assemble(const float* acc, const float* ori, int64_t T, int slots_in, const int32_t* masks_host, int n_combos,
+                        float acc_scale, int smooth, float* out, cudaStream_t stream);
 
 // K8 (physics.cu)
 int launch_physics_optimize(const float* pose, const float* vel, const float* contact, const int32_t* lengths, float* state,
