@@ -79,6 +79,7 @@ SIGNATURES = {
     'mp_net_destroy': (None, [C.c_void_p]),
     'mp_net_workspace_bytes': (C.c_size_t, [C.c_void_p, C.c_int32, C.c_int32]),
     'mp_net_set_graph': (C.c_int, [C.c_void_p, C.c_int32]),
+    'mp_net_set_rec_tile': (C.c_int, [C.c_void_p, C.c_int32]),
     'mp_net_set_physics': (C.c_int, [C.c_void_p, C.POINTER(PhysicsParams)]),
     'mp_net_forward': (C.c_int, [C.c_void_p, c_float_p, C.c_int32, C.c_int32, c_int_p, c_float_p, c_float_p,
                                  c_float_p, c_float_p, c_float_p, c_float_p, c_float_p, c_float_p, c_float_p,

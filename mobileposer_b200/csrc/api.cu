@@ -82,6 +82,7 @@ struct mp_net {
     cudaStream_t s_foot = nullptr, s_vel = nullptr, s_cap = nullptr;
     cudaEvent_t ev_joints = nullptr, ev_foot = nullptr, ev_vel = nullptr;
     int graph_enabled = 1;
+    int rec_tile = 0;                // sequences per cluster tile of the tensor-core recurrence (mp_net_set_rec_tile), 0 = auto
     int physics_on = 0;              // K8 tail of forward_offline (mp_net_set_physics)
     uint64_t physics_epoch = 0;      // bumps whenever the parameters change: part of the graph key
     mp_physics_params_t phys = {};
@@ -254,7 +255,7 @@ size_t mp_rnn_workspace_bytes(const mp_rnn_t* r, int32_t B, int32_t T) {
 
 static int rnn_forward_impl(const mp_rnn_t* r, const float* xa, int32_t ka, const float* xb, int32_t kb, int32_t B, int32_t T,
                             const int32_t* lengths, const float* h0, const float* c0, float* hn, float* cn, float* y,
-                            void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+                            void* workspace, size_t workspace_bytes, cudaStream_t stream, int tile_hint = 0) {
     MP_REQUIRE(r && xa && y && workspace, "rnn_forward: null argument");
     MP_REQUIRE(B > 0 && T > 0, "rnn_forward: empty batch (B=%d T=%d)", B, T);
     MP_REQUIRE(ka + kb == r->n_in, "rnn_forward: input width %d+%d != n_input %d", ka, kb, r->n_in);
@@ -290,6 +291,7 @@ static int rnn_forward_impl(const mp_rnn_t* r, const float* xa, int32_t ka, cons
         a.h0 = h0 ? h0 + so : nullptr; a.c0 = c0 ? c0 + so : nullptr;
         a.hn = hn ? hn + so : nullptr; a.cn = cn ? cn + so : nullptr;
         a.lengths = lengths; a.B = B; a.T = T; a.H = H; a.dirs = dirs;
+        a.tile_hint = tile_hint;
         MP_TRY(launch_lstm_recurrence(a, stream));
         layer_in = ybuf[l];
         in_w = dirs * H;
@@ -413,6 +415,12 @@ int mp_net_set_physics(mp_net_t* n, const mp_physics_params_t* params) {
     return MP_OK;
 }
 
+int mp_net_set_rec_tile(mp_net_t* n, int32_t sequences_per_tile) {
+    MP_REQUIRE(n && sequences_per_tile >= 0 && sequences_per_tile <= 64, "net_set_rec_tile: 0 (auto) .. 64");
+    n->rec_tile = sequences_per_tile;
+    return MP_OK;
+}
+
 int mp_net_set_graph(mp_net_t* n, int32_t enabled) {
     MP_REQUIRE(n, "net_set_graph: null");
     n->graph_enabled = enabled ? 1 : 0;
@@ -456,19 +464,19 @@ static int net_enqueue(mp_net* n, const NetArgs& a, cudaStream_t s) {
     auto wsz = [&](int i) { return (i < 3 ? off[i + 1] : off[4]) - off[i]; };
     float* r6d = (float*)(ws + off[4]);
     MP_TRY(rnn_forward_impl(n->joints, a.imu, 60, nullptr, 0, a.B, a.T, a.lengths, nullptr, nullptr, nullptr, nullptr,
-                          a.joints, ws + off[0], wsz(0), s));
+                          a.joints, ws + off[0], wsz(0), s, n->rec_tile));
     MP_CUDA_TRY(cudaEventRecord(n->ev_joints, s));
     MP_CUDA_TRY(cudaStreamWaitEvent(n->s_foot, n->ev_joints, 0));
     MP_CUDA_TRY(cudaStreamWaitEvent(n->s_vel, n->ev_joints, 0));
     // velocity first on its own stream: it is the longest side branch (unidirectional, 2 x T steps)
     MP_TRY(rnn_forward_impl(n->vel, a.joints, 72, a.imu, 60, a.B, a.T, a.lengths, a.vel_h0, a.vel_c0, a.vel_hn, a.vel_cn,
-                          a.vel, ws + off[3], wsz(3), n->s_vel));
+                          a.vel, ws + off[3], wsz(3), n->s_vel, n->rec_tile));
     MP_CUDA_TRY(cudaEventRecord(n->ev_vel, n->s_vel));
     MP_TRY(rnn_forward_impl(n->foot, a.joints, 72, a.imu, 60, a.B, a.T, a.lengths, nullptr, nullptr, nullptr, nullptr,
-                          a.contact, ws + off[2], wsz(2), n->s_foot));
+                          a.contact, ws + off[2], wsz(2), n->s_foot, n->rec_tile));
     MP_CUDA_TRY(cudaEventRecord(n->ev_foot, n->s_foot));
     MP_TRY(rnn_forward_impl(n->pose, a.joints, 72, a.imu, 60, a.B, a.T, a.lengths, nullptr, nullptr, nullptr, nullptr, r6d,
-                          ws + off[1], wsz(1), s));
+                          ws + off[1], wsz(1), s, n->rec_tile));
     MP_TRY(launch_reduced_global_to_full(r6d, (int64_t)a.B * a.T, a.pose, s));
     MP_CUDA_TRY(cudaStreamWaitEvent(s, n->ev_foot, 0));
     MP_CUDA_TRY(cudaStreamWaitEvent(s, n->ev_vel, 0));
@@ -502,7 +510,7 @@ int mp_net_forward(mp_net_t* n, const float* imu, int32_t B, int32_t T, const in
     std::vector<uintptr_t> key = {(uintptr_t)imu, (uintptr_t)B, (uintptr_t)T, (uintptr_t)lengths, (uintptr_t)vel_h0,
                                   (uintptr_t)vel_c0, (uintptr_t)vel_hn, (uintptr_t)vel_cn, (uintptr_t)pose,
                                   (uintptr_t)joints, (uintptr_t)vel, (uintptr_t)contact, (uintptr_t)tran,
-                                  (uintptr_t)workspace, (uintptr_t)(n->physics_on ? n->physics_epoch : 0)};
+                                  (uintptr_t)workspace, (uintptr_t)(n->physics_on ? n->physics_epoch : 0), (uintptr_t)n->rec_tile};
     mp_net::Entry* hit = nullptr;
     for (auto& en : n->cache)
         if (en.key == key) hit = &en;

@@ -515,7 +515,7 @@ bool rec_tc_eligible(const RecLayerArgs& a) {
 int launch_lstm_recurrence_tc(const RecLayerArgs& a, cudaStream_t stream) {
     MP_REQUIRE((double)a.B * a.T * a.dirs * 4 * a.H < 4.0e9, "lstm_tc: B*T = %lld frames exceeds 32-bit gate buffer indexing", (long long)a.B * a.T);
     const char* nbv = getenv("MP_REC_NB");
-    int NB = (nbv && *nbv) ? atoi(nbv) : 0;
+    int NB = (nbv && *nbv) ? atoi(nbv) : a.tile_hint;
     if (NB <= 0) {
         const int per = std::max(1, tc_cluster_slots() / a.dirs);
         NB = (a.B + per - 1) / per;

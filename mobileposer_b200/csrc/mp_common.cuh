@@ -75,6 +75,7 @@ struct RecLayerArgs {
     float* cn;
     const int32_t* lengths;  // [B] or null
     int B, T, H, dirs;
+    int tile_hint = 0;    // sequences per cluster tile of the tensor-core recurrence; 0 = one wave covering the batch
 };
 int launch_lstm_recurrence(const RecLayerArgs& a, cudaStream_t stream);
 // tcgen05 3xTF32 variant for H = 256 and large batches (lstm_rec_tc.cu)

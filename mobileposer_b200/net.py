@@ -384,7 +384,10 @@ class HostOffline:
 
     `run()` = submit + wait (one batch at a time, what evaluate.py's loop does)."""
 
-    def __init__(self, net: MobilePoserNet, B: int, T: int, device=None):
+    def __init__(self, net: MobilePoserNet, B: int, T: int, device=None, rec_tile: int = 64):
+        """rec_tile: sequences per cluster tile of the tensor-core recurrence (mp_net_set_rec_tile).  These objects are the
+        throughput path (several batches in flight), so the default is the fullest tile; 0 = the latency policy of a
+        single forward."""
         lib = _cabi.lib()
         self.net, self.B, self.T = net, B, T
         self.dev = device or net._device()
@@ -394,6 +397,7 @@ class HostOffline:
         with torch.cuda.device(self.dev):
             _cabi.check(lib.mp_net_create(C.byref(out), *self._heads_key), 'mp_net_create')
             self.handle = out.value
+            _cabi.check(lib.mp_net_set_rec_tile(self.handle, int(rec_tile)), 'mp_net_set_rec_tile')
             self.stream = torch.cuda.Stream(self.dev)
             self.staging = torch.empty(lib.mp_net_host_staging_bytes(B, T), device=self.dev, dtype=torch.uint8)
             self.ws_bytes = lib.mp_net_workspace_bytes(self.handle, B, T)
