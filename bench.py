@@ -332,9 +332,9 @@ def run_ours(args):
     launches = net.last_launches
     frames_per_step = B * T * world
     value = frames_per_step * args.steps / (ms / 1e3)
-    sequential = {'value': frames_per_step * args.steps / (ms_seq / 1e3), 'unit': 'frames/s', 'ms_per_step': ms_seq / args.steps,
-                  'how': 'one batch at a time (MobilePoserNet.forward_offline in a loop, one stream)'}
     del pipes
+    sequential = {'value': frames_per_step * args.steps / (ms_seq / 1e3), 'unit': 'frames/s', 'ms_per_step': ms_seq / args.steps,
+                  'how': 'one batch at a time (MobilePoserNet.forward_offline in a loop, one stream, latency tile policy)'}
     without_physics = None
     if phys:      # the reference's default path (PHYSICS=0), for comparison with the pinned-parity number
         net.enable_physics(False)
@@ -386,12 +386,17 @@ def run_ours(args):
     del hosts
 
     # ---- per-kernel durations (CUDA events on the launching streams), same steps, graphs bypassed ----
+    # (through one pipeline slot, i.e. with the tile policy of the headline number; one batch at a time so that a kernel's
+    #  duration is its own and not its wait for SMs held by another batch)
     lib = _cabi.lib()
+    prof_pipe = mp.HostOffline(net, B, T)
     _cabi.check(lib.mp_profile_enable(1))
     for i in range(args.steps):
-        step(i)
+        prof_pipe.submit_device(xs[i % n_sets])
+        prof_pipe.wait()
     prof = _cabi.profile_collect()
     _cabi.check(lib.mp_profile_enable(0))
+    del prof_pipe
     peak, peak_src = measured_peak_gbs()
     # dominant kernel: the H=256 recurrence (tcgen05 variant for large batches, FFMA cluster kernel otherwise)
     dom_name = max((k for k in prof if k.startswith('lstm_rec') and 'h64' not in k), key=lambda k: prof[k]['total_ms'], default=None)

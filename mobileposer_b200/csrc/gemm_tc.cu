@@ -168,6 +168,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             uint4* a_lo = a_hi + A_TILE / 16;
             uint4* w_hi = a_hi + 2 * A_TILE / 16;
             uint4* w_lo = w_hi + W_TILE / 16;
+            constexpr bool WRITE_HI = false;
             auto split = [](uint4* hi_p, uint4* lo_p, int i) {
                 const uint4 v = hi_p[i];
                 uint4 h, l;
@@ -178,7 +179,10 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                 l.y = tf32_rna(__uint_as_float(v.y) - __uint_as_float(h.y));
                 l.z = tf32_rna(__uint_as_float(v.z) - __uint_as_float(h.z));
                 l.w = tf32_rna(__uint_as_float(v.w) - __uint_as_float(h.w));
-                hi_p[i] = h;
+                // `hi` is not written back: kind::tf32 reads fp32 words and drops the low 13 mantissa bits itself, which is exactly
+                // hi = x & 0xFFFFE000 -- the raw slab IS the hi operand (test_tensor_core_gemm_matches_fp32 would see 1e-4 instead
+                // of 1e-6 if the tensor core rounded instead of truncating)
+                if (WRITE_HI) hi_p[i] = h;
                 lo_p[i] = l;
             };
 #pragma unroll

@@ -6,10 +6,10 @@ timeout 300 python __graft_entry__.py --smoke > gpurun_out/smoke.log 2>&1; echo 
 timeout 900 python bench.py --steps 20 --warmup 5 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench exit $?"; cut -c1-300 gpurun_out/bench.json; tail -3 gpurun_out/bench.err
 timeout 600 python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; echo "ref exit $?"; cut -c1-300 gpurun_out/bench_ref.json
 timeout 600 python bench.py --workload cfg2 --steps 100 --warmup 10 --no-cpu-baseline > gpurun_out/bench_cfg2.json 2> gpurun_out/bench_cfg2.err; echo "cfg2 exit $?"; cut -c1-200 gpurun_out/bench_cfg2.json
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 120 --csv --log-file gpurun_out/launches.csv python scripts/prof_one.py --batch 256 --passes 2 --physics > gpurun_out/prof_list.log 2>&1; echo "ncu list exit $?"
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 120 --csv --log-file gpurun_out/launches.csv python scripts/prof_one.py --batch 256 --passes 2 --physics --tile 64 > gpurun_out/prof_list.log 2>&1; echo "ncu list exit $?"
 # the launch list of the bench command itself (first 400 launches: warm-up + timed steps of the one-batch-at-a-time loop)
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_bench.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/prof_list_bench.log 2>&1; echo "ncu bench list exit $?"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:lstm_rec_tc -c 1 -o gpurun_out/prof_rec_tc_b256 python scripts/prof_one.py --batch 256 --passes 1 > gpurun_out/prof_a.log 2>&1; echo "ncu rec_tc exit $?"
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:lstm_rec_tc -c 1 -o gpurun_out/prof_rec_tc_b256 python scripts/prof_one.py --batch 256 --passes 1 --tile 64 > gpurun_out/prof_a.log 2>&1; echo "ncu rec_tc exit $?"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemm_tf32x3 -s 1 -c 1 -o gpurun_out/prof_gemm_tc python scripts/prof_one.py --batch 256 --passes 1 > gpurun_out/prof_b.log 2>&1; echo "ncu gemm exit $?"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:lstm_rec_kernel -c 1 -o gpurun_out/prof_rec_b1 python scripts/prof_one.py --batch 1 --passes 1 > gpurun_out/prof_c.log 2>&1; echo "ncu rec b1 exit $?"
 MP_REC_IMPL=ffma timeout 900 ncu --set full --clock-control none --import-source on -k regex:lstm_rec_kernel -c 1 -o gpurun_out/prof_rec_b256 python scripts/prof_one.py --batch 256 --passes 1 > gpurun_out/prof_d.log 2>&1; echo "ncu rec ffma exit $?"

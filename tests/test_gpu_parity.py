@@ -398,6 +398,24 @@ def test_pipelined_host_batches_equal_one_at_a_time(net):
         net.enable_physics(False)
 
 
+def test_recurrence_tile_policy_does_not_change_results(net):
+    """mp_net_set_rec_tile only regroups sequences into clusters: every sequence is one MMA column whatever the tile, so
+    16 / 40 / 64 sequences per cluster and the one-wave default give bit-identical outputs (B = 70 takes the tcgen05 path)."""
+    import mobileposer_b200 as mp
+    from mobileposer_b200.synthetic import synthetic_imu_batch
+    x = synthetic_imu_batch(list(range(300, 370)), 20).to(DEV)
+    outs = []
+    for tile in (0, 16, 40, 64):
+        slot = mp.HostOffline(net, 70, 20, rec_tile=tile)
+        slot.submit_device(x)
+        slot.wait()
+        outs.append([t.clone() for t in (slot.d_pose, slot.d_joints, slot.d_tran, slot.d_contact)])
+    for o in outs[1:]:
+        assert all(torch.equal(a, b) for a, b in zip(outs[0], o))
+    ref = net.forward_offline(x, [20] * 70)
+    assert torch.equal(ref[0], outs[0][0]) and torch.equal(ref[2], outs[0][2])
+
+
 def test_float64_arbitration(net, oracle, seeded_state_dict):
     """Both fp32 implementations against a float64 evaluation of the same equations (oracle/np_port.py): the CUDA
     path must be as close to the exact answer as the reference's own CPU path is (it cannot be asked to be closer
