@@ -192,11 +192,11 @@ size_t mp_net_workspace_bytes(const mp_net_t* net, int32_t B, int32_t T);
  * translation (tran != NULL, i.e. forward_offline) finishes with K8 over the pose, in place, each sequence from a
  * fresh optimizer state; NULL switches it off (default).  Parity unpinned, see mp_physics_optimize.            */
 int mp_net_set_physics(mp_net_t* net, const mp_physics_params_t* params);
-/* Tile policy of the tensor-core recurrence (H = 256, large batches).  0 (default): the tile is sized so that ONE wave of
- * resident clusters covers the batch -- lowest latency for a single forward (cfg3: 37 sequences per cluster, 14 clusters).
- * n > 0: n sequences per cluster (<= 64) -- fewer, fuller clusters: a step of the recurrence costs about the same for 37 or
- * 64 sequences, so the SM time per sequence drops and concurrent forwards (other heads, other batches in flight) get the
- * SMs: +20 % throughput with 4 batches in flight, -25 % for one forward alone.                                      */
+/* Tile policy of the tensor-core recurrence (H = 256, batches large enough for it).  A step of that kernel costs about the
+ * same for 16 or 64 sequences per cluster, so fuller clusters mean less SM time per sequence and more SMs for whatever runs
+ * beside them (the other heads, other batches in flight).  0 (default) = auto: 64 sequences per cluster from 128 sequences
+ * up, one wave of clusters covering the batch below; n > 0: n sequences per cluster (<= 64); -1: always one wave (cfg3:
+ * 14 clusters of 37 -- 16.3 ms per forward against 14.2 ms with clusters of 64).  Results do not depend on it.        */
 int mp_net_set_rec_tile(mp_net_t* net, int32_t sequences_per_tile);
 /* 1 = replay the forward as a cached CUDA graph keyed on (pointers, B, T) (default 1). */
 int mp_net_set_graph(mp_net_t* net, int32_t enabled);

@@ -516,7 +516,17 @@ int launch_lstm_recurrence_tc(const RecLayerArgs& a, cudaStream_t stream) {
     MP_REQUIRE((double)a.B * a.T * a.dirs * 4 * a.H < 4.0e9, "lstm_tc: B*T = %lld frames exceeds 32-bit gate buffer indexing", (long long)a.B * a.T);
     const char* nbv = getenv("MP_REC_NB");
     int NB = (nbv && *nbv) ? atoi(nbv) : a.tile_hint;
-    if (NB <= 0) {
+    if (NB == 0) {
+        // auto: a step of this kernel costs about the same for 16 or 64 sequences per cluster (ncu, cfg3: 1.49 ms with 14
+        // clusters of 37, 1.45 ms with 8 clusters of 64), so large batches take the fullest tile and leave the other SMs to
+        // whatever runs beside them (the other heads, other batches); small batches spread over one wave of clusters
+        if (a.B >= 128) {
+            NB = 64;
+        } else {
+            const int per = std::max(1, tc_cluster_slots() / a.dirs);
+            NB = (a.B + per - 1) / per;
+        }
+    } else if (NB < 0) {      // -1: the one-wave policy whatever the batch (lowest occupancy per cluster)
         const int per = std::max(1, tc_cluster_slots() / a.dirs);
         NB = (a.B + per - 1) / per;
     }

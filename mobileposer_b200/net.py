@@ -81,6 +81,7 @@ class MobilePoserNet(nn.Module):
         self.rnn_state = None
         self.imu = None
         self.reuse_outputs = False        # True: return views of the static buffers (no clone)
+        self.rec_tile = int(os.environ.get('MP_NET_TILE', 0))   # mp_net_set_rec_tile policy of this module's own net handle
 
         # net.py:66-69.  The reference imports `dynamics.PhysicsOptimizer`, a module that is not in its tree
         # (SURVEY.md F2); here the hook is served by mobileposer_b200.dynamics (parity unpinned).
@@ -111,6 +112,7 @@ class MobilePoserNet(nn.Module):
             self._net, self._net_key = out.value, handles
             self._slots = {}
             self._net_physics = None
+            _cabi.check(_cabi.lib().mp_net_set_rec_tile(self._net, int(self.rec_tile)), 'mp_net_set_rec_tile')
         return self._net
 
     def _sync_net_physics(self, inline: bool):
@@ -384,10 +386,8 @@ class HostOffline:
 
     `run()` = submit + wait (one batch at a time, what evaluate.py's loop does)."""
 
-    def __init__(self, net: MobilePoserNet, B: int, T: int, device=None, rec_tile: int = 64):
-        """rec_tile: sequences per cluster tile of the tensor-core recurrence (mp_net_set_rec_tile).  These objects are the
-        throughput path (several batches in flight), so the default is the fullest tile; 0 = the latency policy of a
-        single forward."""
+    def __init__(self, net: MobilePoserNet, B: int, T: int, device=None, rec_tile: int = 0):
+        """rec_tile: mp_net_set_rec_tile policy of this slot's net handle (0 = auto)."""
         lib = _cabi.lib()
         self.net, self.B, self.T = net, B, T
         self.dev = device or net._device()

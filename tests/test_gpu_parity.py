@@ -405,7 +405,7 @@ def test_recurrence_tile_policy_does_not_change_results(net):
     from mobileposer_b200.synthetic import synthetic_imu_batch
     x = synthetic_imu_batch(list(range(300, 370)), 20).to(DEV)
     outs = []
-    for tile in (0, 16, 40, 64):
+    for tile in (0, -1, 16, 40, 64):
         slot = mp.HostOffline(net, 70, 20, rec_tile=tile)
         slot.submit_device(x)
         slot.wait()
