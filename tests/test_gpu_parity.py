@@ -260,6 +260,37 @@ def test_recurrence_variants_against_oracle(net, oracle, env, variant):
         assert argmax_equal(contact[b, :L], o_contact[b, :L])
 
 
+def test_large_ragged_batch_on_the_64_sequence_tiles(net, oracle, env):
+    """B = 150 >= 128 takes the automatic 64-sequences-per-cluster policy (3 tiles of 50, N = 64): ragged lengths, carried
+    velocity state, against the oracle and against the FFMA path."""
+    from mobileposer_b200.synthetic import synthetic_imu_batch
+    g = torch.Generator().manual_seed(17)
+    B, T = 150, 24
+    lens = [int(v) for v in torch.randint(1, T + 1, (B,), generator=g)]
+    lens[0] = T
+    x = synthetic_imu_batch(list(range(500, 500 + B)), T)
+    for b, L in enumerate(lens):
+        x[b, L:] = 0
+    oracle.vel_state = None
+    o_pose, o_joints, o_vel, o_contact = oracle.forward(x, lens)
+    oracle.vel_state = None
+    net.set_graph(False)
+    try:
+        net.velocity.rnn_state = None
+        pose, joints, vel, contact = net.forward(x.to(DEV), lens)
+        net.velocity.rnn_state = None
+        env(MP_REC_IMPL='ffma')
+        pose_f, joints_f, vel_f, contact_f = net.forward(x.to(DEV), lens)
+    finally:
+        net.set_graph(True)
+        net.velocity.rnn_state = None
+    assert max_abs(joints, o_joints) <= VALUE_TOL and max_abs(vel, o_vel) <= VALUE_TOL and max_abs(contact, o_contact) <= VALUE_TOL
+    assert angle_excess(pose, o_pose, reference_r6d(oracle, x, lens))[0] <= 1.0
+    assert max_abs(joints, joints_f) <= 2e-6 and max_abs(vel, vel_f) <= 2e-6 and max_abs(contact, contact_f) <= 2e-6
+    for b, L in enumerate(lens):
+        assert argmax_equal(contact[b, :L], o_contact[b, :L])
+
+
 def test_rnn_module_surface(net, oracle):
     """RNN.forward(x, seq_lengths, h) return convention incl. the sequence-first case (rnn.py:15)."""
     from oracle.torch_port import _Head  # noqa: F401
