@@ -180,6 +180,16 @@ int mp_physics_optimize_debug(const float* pose, const float* vel, const float* 
  * [n,24,3,3] and root-relative joint positions [n,24,3].                                      */
 int mp_physics_fk(const float* pose, int64_t n_frames, float* global_rot, float* joint_pos, mp_stream_t stream);
 
+/* Metric side of evaluate.py (the part that needs no mesh): per-frame errors between a predicted and a
+ * true motion, FullMotionEvaluator.__call__ [articulate/evaluator.py:316-327] with shape = None:
+ *   pose_p / pose_t [n,24,3,3] local rotations, tran_p / tran_t [n,3] or NULL ->
+ *   joint_p / joint_t [n,24,3] world joint positions (forward kinematics + translation),
+ *   je [n,24] root-aligned joint position error (m), lae / gae [n,24] local / global joint angle error (degrees).
+ * The jerk and translation-drift rows and the mean / std reductions are slices of these outputs (host side, torch).   */
+int mp_eval_frame_errors(const float* pose_p, const float* pose_t, const float* tran_p, const float* tran_t,
+                         int64_t n_frames, float* joint_p, float* joint_t, float* je, float* lae, float* gae,
+                         mp_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * Whole net = MobilePoserNet.forward / forward_offline           [net.py:101-171]
  * ---------------------------------------------------------------------------------------- */

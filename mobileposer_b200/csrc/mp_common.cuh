@@ -107,7 +107,10 @@ int launch_physics_optimize(const float* pose, const float* vel, const float* co
                             int B, int T, const mp_physics_params_t* prm, float* pose_out, float* tran_out, float* dbg,
                             int dbg_frame, cudaStream_t stream);
 int launch_physics_fk(const float* pose, int64_t n, float* glb, float* pos, cudaStream_t stream);
-int physics_prepare();   // uploads the constant tables of the current device (must not happen inside a graph capture)
+int physics_prepare();
+// N1 (physics.cu: shares the SMPL tables and the warp FK)
+int launch_eval_frame_errors(const float* pose_p, const float* pose_t, const float* tran_p, const float* tran_t, int64_t n,
+                             float* joint_p, float* joint_t, float* je, float* lae, float* gae, cudaStream_t stream);   // uploads the constant tables of the current device (must not happen inside a graph capture)
 
 // ---- PTX helpers (clusters, mbarrier, distributed shared memory) ---------------------------
 #ifdef __CUDACC__

@@ -548,7 +548,81 @@ __global__ void physics_fk_kernel(const float* __restrict__ pose, long long n, f
     }
 }
 
+// ---- N1 (metric side, evaluator.py:292-343): per-frame errors between two motions -------------------------------------
+// One warp per frame, lane = joint: SMPL forward kinematics of both poses (same pointer-jumping FK as K8), world joint
+// positions, root-aligned joint position error, local and global joint angle errors in degrees.  The frame-to-frame rows
+// (jerk, translation drift) and the mean / std reductions are cheap slices of these outputs and stay in torch.
+__device__ __forceinline__ float rot_angle_deg(const float (&A)[9], const float (&B)[9]) {
+    // angle of A^T B (angular.py:86-99): d[a][b] = sum_k A[k][a] B[k][b]; trace = 1 + 2 cos, |skew| = 2 sin
+    float tr = 0.f;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) tr = fmaf(A[i], B[i], tr);
+    const float d21 = A[2] * B[1] + A[5] * B[4] + A[8] * B[7], d12 = A[1] * B[2] + A[4] * B[5] + A[7] * B[8];
+    const float d02 = A[0] * B[2] + A[3] * B[5] + A[6] * B[8], d20 = A[2] * B[0] + A[5] * B[3] + A[8] * B[6];
+    const float d10 = A[1] * B[0] + A[4] * B[3] + A[7] * B[6], d01 = A[0] * B[1] + A[3] * B[4] + A[6] * B[7];
+    const float sx = d21 - d12, sy = d02 - d20, sz = d10 - d01;
+    return atan2f(sqrtf(sx * sx + sy * sy + sz * sz), tr - 1.0f) * 57.29577951308232f;
+}
+
+__global__ void __launch_bounds__(256) eval_frame_errors_kernel(const float* __restrict__ pose_p, const float* __restrict__ pose_t,
+                                                                const float* __restrict__ tran_p, const float* __restrict__ tran_t,
+                                                                long long n, float* __restrict__ joint_p, float* __restrict__ joint_t,
+                                                                float* __restrict__ je, float* __restrict__ lae, float* __restrict__ gae) {
+    const int lane = threadIdx.x & 31;
+    const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const bool isj = lane < NJ;
+    const int j = isj ? lane : 0;
+    unsigned jump = 0;
+    for (int r = 0, step = 1; r < 4; ++r, step *= 2) {
+        int q = j;
+        for (int sidx = 0; sidx < step && q >= 0; ++sidx) q = c_tab.parent[q];
+        jump |= (unsigned)(q < 0 ? 255 : q) << (8 * r);
+    }
+    const float bone[3] = {c_tab.bone[j][0], c_tab.bone[j][1], c_tab.bone[j][2]};
+    for (long long f = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; f < n; f += warps) {
+        float Rp[9], Rt[9], Gp[9], Gt[9], Pp[3], Pt[3];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) {
+            Rp[i] = isj ? __ldg(pose_p + f * 216 + j * 9 + i) : 0.f;
+            Rt[i] = isj ? __ldg(pose_t + f * 216 + j * 9 + i) : 0.f;
+        }
+        warp_fk(Rp, isj, jump, bone, Gp, Pp);
+        warp_fk(Rt, isj, jump, bone, Gt, Pt);
+        float off[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            Pp[i] += tran_p ? __ldg(tran_p + f * 3 + i) : 0.f;
+            Pt[i] += tran_t ? __ldg(tran_t + f * 3 + i) : 0.f;
+            off[i] = __shfl_sync(0xffffffffu, Pt[i] - Pp[i], 0);          // align the roots (evaluator.py:322)
+        }
+        if (isj) {
+            const float ex = Pp[0] + off[0] - Pt[0], ey = Pp[1] + off[1] - Pt[1], ez = Pp[2] + off[2] - Pt[2];
+            je[f * NJ + j] = sqrtf(ex * ex + ey * ey + ez * ez);
+            lae[f * NJ + j] = rot_angle_deg(Rp, Rt);
+            gae[f * NJ + j] = rot_angle_deg(Gp, Gt);
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                joint_p[f * 72 + j * 3 + i] = Pp[i];
+                joint_t[f * 72 + j * 3 + i] = Pt[i];
+            }
+        }
+    }
+}
+
 }  // namespace
+
+int launch_eval_frame_errors(const float* pose_p, const float* pose_t, const float* tran_p, const float* tran_t, int64_t n,
+                             float* joint_p, float* joint_t, float* je, float* lae, float* gae, cudaStream_t stream) {
+    MP_REQUIRE(pose_p && pose_t && joint_p && joint_t && je && lae && gae && n > 0, "eval_frame_errors: bad arguments");
+    MP_TRY(upload_tables());
+    // algorithmic bytes: two poses in, two joint sets + three error planes out
+    ProfileScope prof("n1_frame_errors", (double)n * (2 * 864.0 + 24 + 2 * 288 + 3 * 96), stream);
+    const int blocks = (int)std::min<int64_t>((n + 7) / 8, 148 * 8);
+    eval_frame_errors_kernel<<<blocks, 256, 0, stream>>>(pose_p, pose_t, tran_p, tran_t, n, joint_p, joint_t, je, lae, gae);
+    MP_CUDA_TRY(cudaGetLastError());
+    count_launch();
+    return MP_OK;
+}
 
 int launch_physics_optimize(const float* pose, const float* vel, const float* contact, const int32_t* lengths, float* state,
                             int B, int T, const mp_physics_params_t* prm, float* pose_out, float* tran_out, float* dbg,

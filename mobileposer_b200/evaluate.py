@@ -62,15 +62,38 @@ def angle_between(r1: torch.Tensor, r2: torch.Tensor) -> torch.Tensor:
     return torch.atan2(skew.norm(dim=-1), tr - 1.0)
 
 
+def frame_errors_cuda(pose_p, pose_t, tran_p, tran_t):
+    """mp_eval_frame_errors: -> (joint_p [n,24,3], joint_t [n,24,3], je [n,24], lae [n,24], gae [n,24])."""
+    from . import _cabi
+    from .modules import _f32c, current_stream_ptr
+    pose_p, pose_t = _f32c(pose_p).view(-1, 24, 3, 3), _f32c(pose_t).view(-1, 24, 3, 3)
+    n, dev = pose_p.shape[0], pose_p.device
+    tp = _f32c(tran_p).view(n, 3) if tran_p is not None else None
+    tt = _f32c(tran_t).view(n, 3) if tran_t is not None else None
+    jp, jt = torch.empty(n, 24, 3, device=dev), torch.empty(n, 24, 3, device=dev)
+    je, lae, gae = (torch.empty(n, 24, device=dev) for _ in range(3))
+    with torch.cuda.device(dev):
+        _cabi.check(_cabi.lib().mp_eval_frame_errors(pose_p.data_ptr(), pose_t.data_ptr(), tp.data_ptr() if tp is not None else None,
+                                                     tt.data_ptr() if tt is not None else None, n, jp.data_ptr(), jt.data_ptr(),
+                                                     je.data_ptr(), lae.data_ptr(), gae.data_ptr(), current_stream_ptr(dev)),
+                    'mp_eval_frame_errors')
+    return jp, jt, je, lae, gae
+
+
 def full_motion_errors(pose_p, pose_t, tran_p, tran_t, fps=datasets.fps, joint_mask=(2, 5, 16, 20)):
     """[10, 2] mean/std rows of FullMotionEvaluator.__call__ (evaluator.py:292-343); row 1 (mesh) is NaN."""
     f = fps
-    gp, jp = forward_kinematics(pose_p, tran_p)
-    gt, jt = forward_kinematics(pose_t, tran_t)
-    off = (jt[:, 0] - jp[:, 0]).unsqueeze(1)
-    je = (jp + off - jt).norm(dim=2)
-    lae = torch.rad2deg(angle_between(pose_p, pose_t))
-    gae = torch.rad2deg(angle_between(gp, gt))
+    if pose_p.is_cuda:
+        # the per-frame part (two forward kinematics, joint / local-angle / global-angle errors) is one kernel
+        jp, jt, je, lae, gae = frame_errors_cuda(pose_p, pose_t, tran_p, tran_t)
+    else:
+        # CPU tensors: the torch statement of the same rows (what tests/test_evaluate.py pins to the reference's evaluator)
+        gp, jp = forward_kinematics(pose_p, tran_p)
+        gt, jt = forward_kinematics(pose_t, tran_t)
+        off = (jt[:, 0] - jp[:, 0]).unsqueeze(1)
+        je = (jp + off - jt).norm(dim=2)
+        lae = torch.rad2deg(angle_between(pose_p, pose_t))
+        gae = torch.rad2deg(angle_between(gp, gt))
     jkp = ((jp[3:] - 3 * jp[2:-1] + 3 * jp[1:-2] - jp[:-3]) * (f ** 3)).norm(dim=2)
     jkt = ((jt[3:] - 3 * jt[2:-1] + 3 * jt[1:-2] - jt[:-3]) * (f ** 3)).norm(dim=2)
     te = ((jp[f:, :1] - jp[:-f, :1]) - (jt[f:, :1] - jt[:-f, :1])).norm(dim=2) * 100
