@@ -169,3 +169,32 @@ def test_forward_offline_b1_carries_the_optimizer_state(seeded_state_dict):
         ref, _ = port.optimize_sequences(p0.view(1, T, 24, 3, 3).cpu().numpy(), vel.view(1, T, 72).cpu().numpy(),
                                          c0.view(1, T, 2).cpu().numpy())
         assert max_angle(pose.view(T, 24, 3, 3), torch.from_numpy(ref[0])) <= ANGLE_TOL
+
+
+def test_forward_online_with_the_physics_hook(seeded_state_dict):
+    """net.py:211-217: the online tick ends with optimize_frame on the tick's frame (T = 1 launches with the optimizer state
+    kept on the device between ticks): [24, 3, 3] rotations, equal to the optimizer applied to the hook-less online outputs."""
+    import mobileposer_b200 as mp
+    from mobileposer_b200.synthetic import synthetic_imu
+    x = synthetic_imu(31, 12).to(DEV)
+
+    def run(physics):
+        net = mp.MobilePoserNet()
+        net.load_state_dict(seeded_state_dict)
+        net = net.to(DEV).eval()
+        net.enable_physics(physics)
+        out = []
+        for t in range(x.shape[0]):
+            pose, _, root, contact = net.forward_online(x[t])
+            vel_p = net._slots[next(iter(net._slots))].vel[0, net.num_past_frames].clone()
+            out.append((pose.clone().view(24, 3, 3), root.clone(), contact.clone(), vel_p))
+        return out
+
+    plain, hooked = run(False), run(True)
+    port = pp.PhysicsOptimizerPort(B=1)
+    for (p0, r0, c0, v0), (p1, r1, c1, _) in zip(plain, hooked):
+        assert torch.equal(r0, r1) and torch.equal(c0, c1)              # translation and contact are not touched (net.py:215)
+        ref, _ = port.optimize_sequences(p0.view(1, 1, 24, 3, 3).cpu().numpy(), v0.view(1, 1, 72).cpu().numpy(),
+                                         c0.view(1, 1, 2).cpu().numpy())
+        assert max_angle(p1, torch.from_numpy(ref[0, 0])) <= ANGLE_TOL
+    assert max_angle(hooked[-1][0], plain[-1][0]) > 1e-4                # the hook did something by the last tick
