@@ -56,7 +56,7 @@ def parse_args():
     ap.add_argument('--batch', type=int, default=0, help='override sequences per GPU')
     ap.add_argument('--cpu-sample', type=int, default=32, help='sequences in the CPU-baseline sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--depth', type=int, default=0, help='batches in flight per GPU (pipeline over steps); default 4 for cfg3, 1 for the latency configuration cfg2')
+    ap.add_argument('--depth', type=int, default=0, help='batches in flight per GPU (pipeline over steps); default 6 for cfg3, 1 for the latency configuration cfg2')
     ap.add_argument('--physics', default='auto', choices=['auto', 'on', 'off'],
                     help='K8 optimizer behind the PHYSICS hook (auto: on for cfg3, which names it; off for cfg2)')
     return ap.parse_args()
@@ -320,7 +320,7 @@ def run_ours(args):
     # `value`: K steps, inputs resident in HBM, two batches in flight (depth-2 pipeline over batches: two net handles on two
     # streams, step i+1 is enqueued while step i runs, so the tail of one batch -- K8, the small GEMMs, the SMs the cluster
     # kernels leave idle -- overlaps the head of the next).  The one-batch-at-a-time figure is reported beside it.
-    D = args.depth if args.depth > 0 else (4 if args.workload == 'cfg3' else 1)
+    D = args.depth if args.depth > 0 else (6 if args.workload == 'cfg3' else 1)
     pipes = [mp.HostOffline(net, B, T) for _ in range(D)]
 
     def pipe_step(i):
