@@ -1,4 +1,5 @@
-"""Isolated timing of mp_gemm_bias (mode 1 = FFMA, 2 = tcgen05 3xTF32) for the shapes of the cfg3 step."""
+"""Isolated timing of mp_gemm_bias (mode 1 = FFMA, 2 = tcgen05 3xTF32) for the shapes of the cfg3 step.
+A/B switches of the FFMA kernel (read once per process): MP_GEMM_FFMA2=0 (plain FFMA), MP_GEMM_WIDE=1 (128-wide tile for every N)."""
 import os
 import sys
 
@@ -9,13 +10,16 @@ from mobileposer_b200 import _cabi
 
 lib = _cabi.lib()
 M = 76800
-for N, K in [(72, 512), (96, 512), (72, 256), (2048, 512), (2048, 256), (1024, 256)]:
+shapes = [(72, 512), (96, 512), (72, 256), (64, 132), (2, 128), (256, 60), (256, 132)]
+if '--all' in sys.argv:
+    shapes += [(2048, 512), (2048, 256), (1024, 256)]
+for N, K in shapes:
     A = torch.randn(M, K, device='cuda')
     W = torch.randn(N, K, device='cuda') / K ** 0.5
     b = torch.randn(N, device='cuda')
     C = torch.empty(M, N, device='cuda')
     s = torch.cuda.current_stream().cuda_stream
-    for mode in (1, 2):
+    for mode in ((1, 2) if (N % 256 == 0 and K % 16 == 0) or os.environ.get('MP_GEMM') == 'tc' and N % 4 == 0 and N >= 16 and K % 16 == 0 else (1,)):
         for _ in range(3):
             _cabi.check(lib.mp_gemm_bias(A.data_ptr(), W.data_ptr(), b.data_ptr(), C.data_ptr(), M, N, K, 0, mode, s))
         torch.cuda.synchronize()

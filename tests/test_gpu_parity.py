@@ -495,6 +495,31 @@ def test_tensor_core_gemm_matches_fp32(M, N, K):
     assert e_tc < 1e-6, (e_tc, e_ffma)         # a single TF32 pass would be ~5e-4 on this scale
 
 
+@pytest.mark.parametrize('M,N,K,relu', [(19000, 72, 512, 0), (19001, 96, 256, 0), (20000, 64, 132, 1), (19003, 256, 60, 1),
+                                        (19000, 2, 128, 0), (19002, 8, 64, 1), (1500, 2, 128, 0), (19000, 68, 64, 0),
+                                        (19000, 70, 64, 1), (19000, 100, 128, 0), (76800, 72, 512, 0)])
+def test_ffma_gemm_tiles_match_float64(M, N, K, relu):
+    """Every tile shape of the fp32 FFMA GEMM (gemm.cu: 128x128, 128x96, 128x72, 128x64 packed-FFMA2 tiles and the
+    one-warp-per-row kernel for N <= 8) against a float64 product, ragged M / N edges and the ReLU epilogue included."""
+    from mobileposer_b200 import _cabi
+    lib = _cabi.lib()
+    g = torch.Generator().manual_seed(7 * M + N + K)
+    A = (torch.randn(M, K, generator=g) * 0.7).to(DEV)
+    W = (torch.randn(N, K, generator=g) / K ** 0.5).to(DEV)
+    bias = torch.randn(N, generator=g).to(DEV)
+    C = torch.full((M + 1, N), float('nan'), device=DEV)      # one guard row: nothing may be written past M
+    _cabi.check(lib.mp_gemm_bias(A.data_ptr(), W.data_ptr(), bias.data_ptr(), C.data_ptr(), M, N, K, relu, 1,
+                                 torch.cuda.current_stream().cuda_stream))
+    assert torch.isnan(C[M]).all()
+    ref = A.double() @ W.double().t() + bias.double()
+    scale = A.double().abs() @ W.double().abs().t() + bias.double().abs()
+    if relu:
+        ref = ref.clamp_min(0.0)
+    err = ((C[:M].double() - ref).abs() / scale).max().item()
+    assert torch.isfinite(C[:M]).all()
+    assert err < 4e-7, err
+
+
 def test_evaluate_pose_entry(net):
     """evaluate.py drop-in: same loop as evaluate.py:56-58, rows gathered in dataset order."""
     from mobileposer_b200.evaluate import evaluate_pose, synthetic_dip
