@@ -190,6 +190,16 @@ int mp_eval_frame_errors(const float* pose_p, const float* pose_t, const float* 
                          int64_t n_frames, float* joint_p, float* joint_t, float* je, float* lae, float* gae,
                          mp_stream_t stream);
 
+/* Translation-error windows of evaluate_pose(..., evaluate_tran=True) [evaluate.py:66-92], S sequences
+ * per call: tran_p / tran_t [S,T,3] predicted / true root translation (padded to T frames), lengths [S] device ints or NULL ->
+ *   err [S,7]   mean of |(tran_t[e]-tran_t[s]) - (tran_p[e]-tran_p[s])| / moved(s,e) * w over the frame pairs (s,e) across which
+ *               the ground truth moves at least w = 1..7 m (two-pointer sweep, first start per end); NaN where there is no pair
+ *   count [S,7] number of pairs.
+ * The travelled distance is accumulated sequentially in fp32 like the reference, so the pair sets are the reference's.
+ * T <= 51200 (the running distance lives in shared memory).                                                           */
+int mp_eval_tran_windows(const float* tran_p, const float* tran_t, const int32_t* lengths, int32_t S, int32_t T,
+                         float* err, int32_t* count, mp_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * Whole net = MobilePoserNet.forward / forward_offline           [net.py:101-171]
  * ---------------------------------------------------------------------------------------- */

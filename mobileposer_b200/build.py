@@ -13,7 +13,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, 'csrc')
 LIB_DIR = os.path.join(PKG, 'lib')
 LIB_PATH = os.path.join(LIB_DIR, 'libmobileposer_b200.so')
-SOURCES = ['gemm.cu', 'gemm_tc.cu', 'lstm_rec.cu', 'lstm_rec_tc.cu', 'kinematics.cu', 'physics.cu', 'inputs.cu', 'api.cu']
+SOURCES = ['gemm.cu', 'gemm_tc.cu', 'lstm_rec.cu', 'lstm_rec_tc.cu', 'kinematics.cu', 'physics.cu', 'inputs.cu', 'evaluate.cu', 'api.cu']
 HEADERS = [os.path.join(CSRC, 'mp_common.cuh'),
            os.path.join(os.path.dirname(PKG), 'include', 'mobileposer_b200.h')]
 NVCC_FLAGS = ['-std=c++17', '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3',

@@ -8,6 +8,9 @@ Same entry (`evaluate_pose(model, dataset, ...)`, CLI `--model --dataset`), same
   * the metric rows are computed on the device from SMPL forward kinematics of the 24 joints
     (evaluator.py:292-343: rows 0, 2-9).  The mesh-vertex row (evaluator.py row 1, needs the 6890-vertex SMPL
     template) is NaN unless a `smpl_file` is given -- the evaluator is "next" in SURVEY.md section 8f;
+  * the translation-error windows of `evaluate_tran=True` (evaluate.py:66-92) run on the
+    device too (`tran_window_errors` -> mp_eval_tran_windows), pinned to the reference's own `evaluate_pose` output
+    (tests/golden/tran_windows.npz);
   * `--dataset synthetic_dip` evaluates a synthetic DIP-shaped set (10 subjects x 5 sequences x 3000 frames,
     BASELINE.json config 4) because the real datasets cannot ship.
 """
@@ -80,6 +83,35 @@ def frame_errors_cuda(pose_p, pose_t, tran_p, tran_t):
     return jp, jt, je, lae, gae
 
 
+def tran_window_errors(tran_p, tran_t, lengths=None):
+    """Translation-error windows of `evaluate_pose(..., evaluate_tran=True)` (evaluate.py:66-92) on the device.
+
+    tran_p / tran_t: [T, 3] (one sequence) or [S, T, 3] (padded batch, `lengths` = valid frames per sequence) ->
+    (err [S, 7], count [S, 7]): mean relative drift over the frame pairs across which the ground truth moves at least
+    1..7 m (NaN where a sequence has no such pair) and the number of pairs.  CUDA only (mp_eval_tran_windows)."""
+    from . import _cabi
+    from .modules import _f32c, current_stream_ptr
+    if not tran_p.is_cuda:
+        raise RuntimeError('tran_window_errors runs on the GPU (mp_eval_tran_windows); got a CPU tensor')
+    tp = _f32c(tran_p).view(-1, tran_p.shape[-2], 3)
+    tt = _f32c(tran_t.to(tp.device)).view(-1, tran_p.shape[-2], 3)
+    S, T, dev = tp.shape[0], tp.shape[1], tp.device
+    if tt.shape != tp.shape:
+        raise ValueError(f'tran_p {tuple(tp.shape)} and tran_t {tuple(tt.shape)} differ')
+    ln = None
+    if lengths is not None:
+        ln = torch.as_tensor(lengths, dtype=torch.int32).to(dev).contiguous()
+        if ln.numel() != S:
+            raise ValueError(f'{ln.numel()} lengths for {S} sequences')
+    err = torch.empty(S, 7, device=dev)
+    cnt = torch.empty(S, 7, device=dev, dtype=torch.int32)
+    with torch.cuda.device(dev):
+        _cabi.check(_cabi.lib().mp_eval_tran_windows(tp.data_ptr(), tt.data_ptr(), ln.data_ptr() if ln is not None else None,
+                                                     S, T, err.data_ptr(), cnt.data_ptr(), current_stream_ptr(dev)),
+                    'mp_eval_tran_windows')
+    return err, cnt
+
+
 def full_motion_errors(pose_p, pose_t, tran_p, tran_t, fps=datasets.fps, joint_mask=(2, 5, 16, 20)):
     """[10, 2] mean/std rows of FullMotionEvaluator.__call__ (evaluator.py:292-343); row 1 (mesh) is NaN."""
     f = fps
@@ -150,7 +182,9 @@ def synthetic_dip(n_subjects=10, n_seq=5, frames=3000, combo='lw_rp'):
 
 @torch.no_grad()
 def evaluate_pose(model, dataset, num_past_frame=20, num_future_frame=5, evaluate_tran=False, verbose=True):
-    """evaluate.py:39-107.  Returns the [n_sequences, 8, 2] offline rows in dataset order (on every rank)."""
+    """evaluate.py:39-107.  Returns the [n_sequences, 8, 2] offline rows in dataset order (on every rank); with
+    `evaluate_tran=True` (evaluate.py:66-92, 105-106) a pair (rows, windows [n_sequences, 7]) and prints the reference's
+    `[0, mean drift at 1 m, ..., at 7 m]` list."""
     import torch.distributed as dist
     device = next(model.parameters()).device
     rank = dist.get_rank() if dist.is_initialized() else 0
@@ -162,6 +196,7 @@ def evaluate_pose(model, dataset, num_past_frame=20, num_future_frame=5, evaluat
     model.eval()
     rows = []
     online_rows = []
+    window_rows = []
     for i in mine:
         imu, pose_t, _, tran_t = items[i]
         x = imu.to(device)
@@ -169,6 +204,8 @@ def evaluate_pose(model, dataset, num_past_frame=20, num_future_frame=5, evaluat
         pose_p, _, tran_p, _ = model.forward_offline(x.unsqueeze(0), [x.shape[0]])
         pose_t = r6d_to_rotation_matrix(pose_t.to(device)).view(-1, 24, 3, 3)
         rows.append(evaluator.eval(pose_p, pose_t, tran_p=tran_p, tran_t=tran_t))
+        if evaluate_tran:
+            window_rows.append(tran_window_errors(tran_p, tran_t)[0][0])
         if getenv("ONLINE"):
             outs = [model.forward_online(f) for f in torch.cat((x, x[-1].repeat(num_future_frame, 1)))]
             pose_o = torch.stack([o[0] for o in outs])[num_future_frame:]
@@ -185,6 +222,13 @@ def evaluate_pose(model, dataset, num_past_frame=20, num_future_frame=5, evaluat
         if verbose and rank == 0:
             print('============== online ================')
             PoseEvaluator.print(online.nanmean(dim=0))
+    if evaluate_tran:
+        lw = torch.stack(window_rows) if window_rows else torch.zeros(0, 7, device=device)
+        windows = gather_rows(lw, mine, len(items))
+        if verbose and rank == 0:
+            # evaluate.py:106 -- per window the mean over the sequences that have at least one pair
+            print([0] + [windows[:, k][~torch.isnan(windows[:, k])].mean() for k in range(7)])
+        return table, windows
     return table
 
 
@@ -193,6 +237,7 @@ if __name__ == '__main__':
     parser.add_argument('--model', type=str, default=None, help='state_dict .pth; default: seeded random init')
     parser.add_argument('--dataset', type=str, default='synthetic_dip')
     parser.add_argument('--frames', type=int, default=3000)
+    parser.add_argument('--tran', action='store_true', help='also the translation-error windows (evaluate_tran=True)')
     args = parser.parse_args()
     if args.dataset != 'synthetic_dip':
         raise ValueError(f'Test dataset: {args.dataset} not found.')
@@ -203,4 +248,4 @@ if __name__ == '__main__':
         torch.manual_seed(0)
         net = MobilePoserNet().to(default_device())
     print(f'Starting evaluation: {args.dataset.capitalize()}')
-    evaluate_pose(net, synthetic_dip(frames=args.frames))
+    evaluate_pose(net, synthetic_dip(frames=args.frames), evaluate_tran=args.tran)

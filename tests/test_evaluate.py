@@ -47,3 +47,31 @@ def test_pose_evaluator_rows_and_synthetic_set():
     assert rows.shape == (8, 2)
     ok = [0, 1, 2, 3, 4, 7]
     assert rows[ok, 0].abs().max() < 1e-3          # identical motions -> zero errors (mesh row NaN)
+
+
+def test_tran_window_oracle_matches_reference_evaluate_pose():
+    """oracle/eval_port.py (restatement of evaluate.py:66-92) against what the reference's own evaluate_pose(...,
+    evaluate_tran=True) printed for the same translations (oracle/make_golden_eval.py)."""
+    import numpy as np
+    from oracle.eval_port import frame_pairs, move_distance, tran_window_errors
+    g = load_golden('tran_windows')
+    per_seq = []
+    for i, n in enumerate(g['lengths'].tolist()):
+        err, cnt = tran_window_errors(g['tran_p'][i, :n].numpy(), g['tran_t'][i, :n].numpy())
+        ref = g['per_sequence'][i].numpy()
+        assert np.array_equal(np.isnan(err), np.isnan(ref)), (i, err, ref)
+        assert np.array_equal(cnt > 0, ~np.isnan(ref))
+        ok = ~np.isnan(ref)
+        if ok.any():
+            assert (np.abs(err[ok] - ref[ok]) / np.abs(ref[ok])).max() < 1e-6
+        per_seq.append(err)
+    per_seq = np.stack(per_seq)
+    # the printed list: per window the mean over the sequences that have a pair (evaluate.py:92,106)
+    overall = np.array([np.nanmean(per_seq[:, k]) for k in range(7)], np.float32)
+    assert (np.abs(overall - g['overall'].numpy()) / g['overall'].numpy()).max() < 1e-6
+    # sweep properties: ends strictly increase, every pair spans at least the window, the shorter span does not
+    mv = move_distance(g['tran_t'][0, :g['lengths'][0]].numpy())
+    for w in (1, 4):
+        pairs = frame_pairs(mv, w)
+        assert all(b[1] > a[1] for a, b in zip(pairs, pairs[1:]))
+        assert all(mv[e] - mv[s] >= w and mv[e - 1] - mv[s] < w for s, e in pairs)
