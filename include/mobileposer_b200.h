@@ -190,6 +190,17 @@ int mp_eval_frame_errors(const float* pose_p, const float* pose_t, const float* 
                          int64_t n_frames, float* joint_p, float* joint_t, float* je, float* lae, float* gae,
                          mp_stream_t stream);
 
+/* Mesh row of the evaluator (FullMotionEvaluator.__call__ row 1 [articulate/evaluator.py:319-323] with the linear blend
+ * skinning of ParametricModel.forward_kinematics(calc_mesh=True) [articulate/model.py:233-240], mean shape, no pose
+ * blendshapes, root alignment -- the configuration evaluate.py uses):
+ *   pose_p / pose_t [n,24,3,3] local rotations, rest_vertices [V,3] = v_template - J[0], weights [V,24] skinning weights ->
+ *   err_sum [V], err_sq_sum [V] (float64): per vertex, the sum over the n frames of |v_p - v_t| and of |v_p - v_t|^2
+ *   (root-aligned; translations cancel).  mean = sum(err_sum) / (n V); std over frames per vertex from both sums.
+ * The vertex sets are never materialised (the difference of two skinned meshes is the skinning of the difference of the
+ * joint transforms).  The joint rest positions are the library's SMPL constants.                                       */
+int mp_eval_vertex_errors(const float* pose_p, const float* pose_t, int64_t n_frames, const float* rest_vertices,
+                          const float* weights, int32_t n_vertices, double* err_sum, double* err_sq_sum, mp_stream_t stream);
+
 /* Translation-error windows of evaluate_pose(..., evaluate_tran=True) [evaluate.py:66-92], S sequences
  * per call: tran_p / tran_t [S,T,3] predicted / true root translation (padded to T frames), lengths [S] device ints or NULL ->
  *   err [S,7]   mean of |(tran_t[e]-tran_t[s]) - (tran_p[e]-tran_p[s])| / moved(s,e) * w over the frame pairs (s,e) across which

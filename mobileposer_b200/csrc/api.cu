@@ -348,6 +348,10 @@ int mp_eval_frame_errors(const float* pose_p, const float* pose_t, const float* 
                          float* joint_p, float* joint_t, float* je, float* lae, float* gae, mp_stream_t stream) {
     return launch_eval_frame_errors(pose_p, pose_t, tran_p, tran_t, n_frames, joint_p, joint_t, je, lae, gae, (cudaStream_t)stream);
 }
+int mp_eval_vertex_errors(const float* pose_p, const float* pose_t, int64_t n_frames, const float* rest_vertices, const float* weights,
+                           int32_t n_vertices, double* err_sum, double* err_sq_sum, mp_stream_t stream) {
+    return launch_eval_vertex_errors(pose_p, pose_t, n_frames, rest_vertices, weights, n_vertices, err_sum, err_sq_sum, (cudaStream_t)stream);
+}
 int mp_eval_tran_windows(const float* tran_p, const float* tran_t, const int32_t* lengths, int32_t S, int32_t T, float* err,
                          int32_t* count, mp_stream_t stream) {
     return launch_eval_tran_windows(tran_p, tran_t, lengths, S, T, err, count, (cudaStream_t)stream);

@@ -112,6 +112,8 @@ int physics_prepare();
 int launch_eval_frame_errors(const float* pose_p, const float* pose_t, const float* tran_p, const float* tran_t, int64_t n,
                              float* joint_p, float* joint_t, float* je, float* lae, float* gae, cudaStream_t stream);   // uploads the constant tables of the current device (must not happen inside a graph capture)
 
+int launch_eval_vertex_errors(const float* pose_p, const float* pose_t, int64_t n, const float* v0, const float* weights, int V,
+                              double* vsum, double* vsq, cudaStream_t stream);
 // N3 (evaluate.cu)
 int launch_eval_tran_windows(const float* tran_p, const float* tran_t, const int32_t* lengths, int S, int T, float* err,
                              int32_t* count, cudaStream_t stream);

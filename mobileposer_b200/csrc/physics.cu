@@ -609,6 +609,121 @@ __global__ void __launch_bounds__(256) eval_frame_errors_kernel(const float* __r
     }
 }
 
+
+// ---- N1, mesh row (evaluator.py:319-323 with articulate/model.py:233-240): root-aligned vertex position error -----------
+// The reference skins both motions to [n, V, 3] vertex sets (V = 6890: 165 KB per frame and motion) and subtracts them.  Linear
+// blend skinning is linear in the joint transforms, so the DIFFERENCE of the two meshes is the skinning of the difference
+// of the transforms:  v_p - v_t = sum_j w[v][j] * (A_p[j] - A_t[j]) * [v0; 1],  A[j] = [G_j | P_j - G_j J_j]  (model.py:233).
+// With the default alignment joint (the root, whose position is the translation in both motions) the offset of
+// evaluator.py:322 cancels the translations exactly, so neither a vertex set nor a translation is ever materialised:
+// per frame chunk the CTA runs the forward kinematics of both motions (a warp per frame, lane = joint), leaves the 24
+// difference transforms in shared memory, and every thread skins its two vertices (weights and rest position in registers)
+// against them, accumulating sum and sum of squares of the error per vertex -- all the mean / std rows need.
+constexpr int VE_FC = 32;        // frames per chunk
+constexpr int VE_VPT = 2;        // vertices per thread
+constexpr int VE_THREADS = 256;
+
+__global__ void __launch_bounds__(VE_THREADS)
+eval_vertex_errors_kernel(const float* __restrict__ pose_p, const float* __restrict__ pose_t, long long n,
+                          const float* __restrict__ v0, const float* __restrict__ weights, int V,
+                          double* __restrict__ vsum, double* __restrict__ vsq) {
+    __shared__ __align__(16) float D[VE_FC][NJ][12];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const bool isj = lane < NJ;
+    const int j = isj ? lane : 0;
+    unsigned jump = 0;
+    for (int r = 0, step = 1; r < 4; ++r, step *= 2) {
+        int q = j;
+        for (int sidx = 0; sidx < step && q >= 0; ++sidx) q = c_tab.parent[q];
+        jump |= (unsigned)(q < 0 ? 255 : q) << (8 * r);
+    }
+    const float bone[3] = {c_tab.bone[j][0], c_tab.bone[j][1], c_tab.bone[j][2]};
+    float jz[3];                 // zero-pose joint position (root at the origin): FK of the identity pose
+    {
+        const float I[9] = {1.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 1.f};
+        float Gi[9];
+        warp_fk(I, isj, jump, bone, Gi, jz);
+    }
+
+    float w[VE_VPT][NJ], rest[VE_VPT][3], s1[VE_VPT], s2[VE_VPT];
+#pragma unroll
+    for (int k = 0; k < VE_VPT; ++k) {
+        const int v = blockIdx.x * (VE_THREADS * VE_VPT) + k * VE_THREADS + tid;
+#pragma unroll
+        for (int jj = 0; jj < NJ; ++jj) w[k][jj] = v < V ? __ldg(weights + (size_t)v * NJ + jj) : 0.f;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) rest[k][i] = v < V ? __ldg(v0 + (size_t)v * 3 + i) : 0.f;
+        s1[k] = s2[k] = 0.f;
+    }
+
+    for (long long f0 = (long long)blockIdx.y * VE_FC; f0 < n; f0 += (long long)gridDim.y * VE_FC) {
+        __syncthreads();         // the previous chunk has been consumed
+        for (int ff = warp; ff < VE_FC; ff += VE_THREADS / 32) {
+            const long long f = f0 + ff;
+            if (f >= n) break;
+            float Rp[9], Rt[9], Gp[9], Gt[9], Pp[3], Pt[3];
+#pragma unroll
+            for (int i = 0; i < 9; ++i) {
+                Rp[i] = isj ? __ldg(pose_p + f * 216 + j * 9 + i) : 0.f;
+                Rt[i] = isj ? __ldg(pose_t + f * 216 + j * 9 + i) : 0.f;
+            }
+            warp_fk(Rp, isj, jump, bone, Gp, Pp);
+            warp_fk(Rt, isj, jump, bone, Gt, Pt);
+            if (isj) {
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+                    float tp = Pp[r], tt = Pt[r];
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        tp = fmaf(-Gp[r * 3 + c], jz[c], tp);
+                        tt = fmaf(-Gt[r * 3 + c], jz[c], tt);
+                        D[ff][j][r * 4 + c] = Gp[r * 3 + c] - Gt[r * 3 + c];
+                    }
+                    D[ff][j][r * 4 + 3] = tp - tt;
+                }
+            }
+        }
+        __syncthreads();
+        const int nf = (int)min((long long)VE_FC, n - f0);
+        for (int ff = 0; ff < nf; ++ff) {
+            float a[VE_VPT][12];
+#pragma unroll
+            for (int k = 0; k < VE_VPT; ++k)
+#pragma unroll
+                for (int i = 0; i < 12; ++i) a[k][i] = 0.f;
+#pragma unroll
+            for (int jj = 0; jj < NJ; ++jj) {
+                const float4 d0 = *reinterpret_cast<const float4*>(&D[ff][jj][0]);
+                const float4 d1 = *reinterpret_cast<const float4*>(&D[ff][jj][4]);
+                const float4 d2 = *reinterpret_cast<const float4*>(&D[ff][jj][8]);
+                const float d[12] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w, d2.x, d2.y, d2.z, d2.w};
+#pragma unroll
+                for (int k = 0; k < VE_VPT; ++k)
+#pragma unroll
+                    for (int i = 0; i < 12; ++i) a[k][i] = fmaf(w[k][jj], d[i], a[k][i]);
+            }
+#pragma unroll
+            for (int k = 0; k < VE_VPT; ++k) {
+                float e[3];
+#pragma unroll
+                for (int r = 0; r < 3; ++r)
+                    e[r] = fmaf(a[k][r * 4 + 2], rest[k][2], fmaf(a[k][r * 4 + 1], rest[k][1], fmaf(a[k][r * 4], rest[k][0], a[k][r * 4 + 3])));
+                const float q = fmaf(e[2], e[2], fmaf(e[1], e[1], e[0] * e[0]));
+                s1[k] += sqrtf(q);
+                s2[k] += q;
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < VE_VPT; ++k) {
+        const int v = blockIdx.x * (VE_THREADS * VE_VPT) + k * VE_THREADS + tid;
+        if (v < V) {
+            atomicAdd(vsum + v, (double)s1[k]);
+            atomicAdd(vsq + v, (double)s2[k]);
+        }
+    }
+}
+
 }  // namespace
 
 int launch_eval_frame_errors(const float* pose_p, const float* pose_t, const float* tran_p, const float* tran_t, int64_t n,
@@ -619,6 +734,24 @@ int launch_eval_frame_errors(const float* pose_p, const float* pose_t, const flo
     ProfileScope prof("n1_frame_errors", (double)n * (2 * 864.0 + 24 + 2 * 288 + 3 * 96), stream);
     const int blocks = (int)std::min<int64_t>((n + 7) / 8, 148 * 8);
     eval_frame_errors_kernel<<<blocks, 256, 0, stream>>>(pose_p, pose_t, tran_p, tran_t, n, joint_p, joint_t, je, lae, gae);
+    MP_CUDA_TRY(cudaGetLastError());
+    count_launch();
+    return MP_OK;
+}
+
+int launch_eval_vertex_errors(const float* pose_p, const float* pose_t, int64_t n, const float* v0, const float* weights, int V,
+                              double* vsum, double* vsq, cudaStream_t stream) {
+    MP_REQUIRE(pose_p && pose_t && v0 && weights && vsum && vsq && n > 0 && V > 0, "eval_vertex_errors: bad arguments");
+    MP_TRY(upload_tables());
+    MP_CUDA_TRY(cudaMemsetAsync(vsum, 0, sizeof(double) * V, stream));
+    MP_CUDA_TRY(cudaMemsetAsync(vsq, 0, sizeof(double) * V, stream));
+    // algorithmic bytes: the two motions in (what the reference reads to build 2 x [n, V, 3] vertex sets), 2 x V doubles out
+    ProfileScope prof("n1_vertex_errors", (double)n * 2 * 864.0 + (double)V * (NJ + 3) * 4 + (double)V * 16, stream);
+    const int vtiles = (V + VE_THREADS * VE_VPT - 1) / (VE_THREADS * VE_VPT);
+    const int64_t chunks = (n + VE_FC - 1) / VE_FC;
+    // about 8 CTAs per SM over the whole grid; every CTA walks its frame chunks with a grid stride
+    const int ychunks = (int)std::max<int64_t>(1, std::min<int64_t>(chunks, (148 * 8 + vtiles - 1) / vtiles));
+    eval_vertex_errors_kernel<<<dim3(vtiles, ychunks), VE_THREADS, 0, stream>>>(pose_p, pose_t, n, v0, weights, V, vsum, vsq);
     MP_CUDA_TRY(cudaGetLastError());
     count_launch();
     return MP_OK;

@@ -6,8 +6,11 @@ Same entry (`evaluate_pose(model, dataset, ...)`, CLI `--model --dataset`), same
   * sequences are sharded over the ranks of `torch.distributed` when it is initialised (sharding.py) and the
     per-sequence [8, 2] rows are all-gathered once at the end (SURVEY.md section 8e);
   * the metric rows are computed on the device from SMPL forward kinematics of the 24 joints
-    (evaluator.py:292-343: rows 0, 2-9).  The mesh-vertex row (evaluator.py row 1, needs the 6890-vertex SMPL
-    template) is NaN unless a `smpl_file` is given -- the evaluator is "next" in SURVEY.md section 8f;
+    (evaluator.py:292-343: rows 0, 2-9).  The mesh-vertex row (evaluator.py row 1) needs the 6890-vertex SMPL
+    template, which cannot ship: it is NaN unless `PoseEvaluator(smpl_file=...)` / `--smpl` names the official model
+    file (or a `mesh=(rest_vertices, weights)` pair is given); then it runs on the device too
+    (`vertex_error_row` -> mp_eval_vertex_errors, pinned to the reference's evaluator over a synthetic template,
+    tests/golden/mesh_unit.npz);
   * the translation-error windows of `evaluate_tran=True` (evaluate.py:66-92) run on the
     device too (`tran_window_errors` -> mp_eval_tran_windows), pinned to the reference's own `evaluate_pose` output
     (tests/golden/tran_windows.npz);
@@ -83,6 +86,68 @@ def frame_errors_cuda(pose_p, pose_t, tran_p, tran_t):
     return jp, jt, je, lae, gae
 
 
+class _Opaque:
+    """Stand-in for pickled classes that are not installed (chumpy: only `shapedirs` of the official SMPL file)."""
+
+    def __init__(self, *a, **k):
+        pass
+
+    def __setstate__(self, state):
+        self.state = state
+
+
+def load_smpl_mesh(smpl_file, device=None):
+    """(rest_vertices [V,3] = v_template - J[0], weights [V,24]) of an official SMPL model file, the two arrays
+    ParametricModel.__init__ / get_zero_pose_joint_and_vertex (articulate/model.py:28-39,86-87) feed the skinning with."""
+    import pickle
+
+    import numpy as np
+
+    class Unpickler(pickle.Unpickler):
+        def find_class(self, module, name):
+            if module.split('.')[0] == 'chumpy':
+                return _Opaque
+            return super().find_class(module, name)
+
+    with open(smpl_file, 'rb') as f:
+        data = Unpickler(f, encoding='latin1').load()
+    v = torch.from_numpy(np.asarray(data['v_template'])).float()
+    j = torch.from_numpy(np.asarray(data['J'])).float()
+    w = torch.from_numpy(np.asarray(data['weights'])).float()
+    if w.shape != (v.shape[0], 24) or j.shape != (24, 3):
+        raise ValueError(f'{smpl_file}: not a 24-joint SMPL model (weights {tuple(w.shape)}, J {tuple(j.shape)})')
+    dev = device if device is not None else default_device()
+    return (v - j[:1]).contiguous().to(dev), w.contiguous().to(dev)
+
+
+def vertex_error_row(pose_p, pose_t, mesh):
+    """Row 1 of FullMotionEvaluator.__call__ (evaluator.py:319-323,336): [mean, mean over vertices of the std over
+    frames] of the root-aligned vertex position error, from mp_eval_vertex_errors (per-vertex sum and sum of squares in
+    float64; the skinned vertex sets are never materialised).  mesh = (rest_vertices [V,3], weights [V,24]).  CUDA only."""
+    from . import _cabi
+    from .modules import _f32c, current_stream_ptr
+    if not pose_p.is_cuda:
+        raise RuntimeError('vertex_error_row runs on the GPU (mp_eval_vertex_errors); got a CPU tensor')
+    pose_p, pose_t = _f32c(pose_p).view(-1, 24, 3, 3), _f32c(pose_t).view(-1, 24, 3, 3)
+    n, dev = pose_p.shape[0], pose_p.device
+    rest, w = _f32c(mesh[0].to(dev)), _f32c(mesh[1].to(dev))
+    V = rest.shape[0]
+    if rest.shape != (V, 3) or w.shape != (V, 24) or pose_t.shape != pose_p.shape:
+        raise ValueError(f'vertex_error_row: rest {tuple(rest.shape)}, weights {tuple(w.shape)}, poses {tuple(pose_p.shape)} / {tuple(pose_t.shape)}')
+    vsum = torch.empty(V, device=dev, dtype=torch.float64)
+    vsq = torch.empty(V, device=dev, dtype=torch.float64)
+    with torch.cuda.device(dev):
+        _cabi.check(_cabi.lib().mp_eval_vertex_errors(pose_p.data_ptr(), pose_t.data_ptr(), n, rest.data_ptr(), w.data_ptr(), V,
+                                                      vsum.data_ptr(), vsq.data_ptr(), current_stream_ptr(dev)),
+                    'mp_eval_vertex_errors')
+    mean = vsum.sum() / (n * V)
+    if n > 1:
+        std = ((vsq - vsum * vsum / n).clamp_min(0.0) / (n - 1)).sqrt().mean()
+    else:
+        std = vsum.new_zeros(())
+    return torch.stack((mean, std)).float()
+
+
 def tran_window_errors(tran_p, tran_t, lengths=None):
     """Translation-error windows of `evaluate_pose(..., evaluate_tran=True)` (evaluate.py:66-92) on the device.
 
@@ -112,8 +177,9 @@ def tran_window_errors(tran_p, tran_t, lengths=None):
     return err, cnt
 
 
-def full_motion_errors(pose_p, pose_t, tran_p, tran_t, fps=datasets.fps, joint_mask=(2, 5, 16, 20)):
-    """[10, 2] mean/std rows of FullMotionEvaluator.__call__ (evaluator.py:292-343); row 1 (mesh) is NaN."""
+def full_motion_errors(pose_p, pose_t, tran_p, tran_t, fps=datasets.fps, joint_mask=(2, 5, 16, 20), mesh=None):
+    """[10, 2] mean/std rows of FullMotionEvaluator.__call__ (evaluator.py:292-343); row 1 (mesh) is NaN unless
+    `mesh = (rest_vertices, weights)` is given (CUDA tensors only)."""
     f = fps
     if pose_p.is_cuda:
         # the per-frame part (two forward kinematics, joint / local-angle / global-angle errors) is one kernel
@@ -137,7 +203,8 @@ def full_motion_errors(pose_p, pose_t, tran_p, tran_t, fps=datasets.fps, joint_m
             return nan
         return torch.stack((x.mean(), x.std(dim=0).mean() if x.shape[0] > 1 else x.new_zeros(())))
 
-    return torch.stack([row(je), nan, row(lae), row(gae), row(jkp), row(jkt), row(te), row(je[:, m]), row(lae[:, m]),
+    mesh_row = vertex_error_row(pose_p, pose_t, mesh) if mesh is not None else nan      # row 1
+    return torch.stack([row(je), mesh_row, row(lae), row(gae), row(jkp), row(jkt), row(te), row(je[:, m]), row(lae[:, m]),
                         row(gae[:, m])])
 
 
@@ -145,6 +212,11 @@ class PoseEvaluator:
     """evaluate.py:16-36."""
     names = ['SIP Error (deg)', 'Angular Error (deg)', 'Masked Angular Error (deg)', 'Positional Error (cm)',
              'Masked Positional Error (cm)', 'Mesh Error (cm)', 'Jitter Error (100m/s^3)', 'Distance Error (cm)']
+
+    def __init__(self, smpl_file=None, mesh=None):
+        """`smpl_file`: official SMPL model file (evaluate.py:18 reads paths.smpl_file) or `mesh` = (rest_vertices, weights)
+        for the Mesh Error row; without either that row is NaN."""
+        self.mesh = mesh if mesh is not None else (load_smpl_mesh(smpl_file) if smpl_file else None)
 
     def eval(self, pose_p, pose_t, joint_p=None, tran_p=None, tran_t=None):
         pose_p = pose_p.clone().view(-1, 24, 3, 3)
@@ -154,7 +226,7 @@ class PoseEvaluator:
         eye = torch.eye(3, device=pose_p.device)
         pose_p[:, joint_set.ignored] = eye
         pose_t[:, joint_set.ignored] = eye
-        errs = full_motion_errors(pose_p, pose_t, tran_p, tran_t)
+        errs = full_motion_errors(pose_p, pose_t, tran_p, tran_t, mesh=self.mesh if pose_p.is_cuda else None)
         return torch.stack([errs[9], errs[3], errs[9], errs[0] * 100, errs[7] * 100, errs[1] * 100, errs[4] / 100, errs[6]])
 
     @classmethod
@@ -181,7 +253,8 @@ def synthetic_dip(n_subjects=10, n_seq=5, frames=3000, combo='lw_rp'):
 
 
 @torch.no_grad()
-def evaluate_pose(model, dataset, num_past_frame=20, num_future_frame=5, evaluate_tran=False, verbose=True):
+def evaluate_pose(model, dataset, num_past_frame=20, num_future_frame=5, evaluate_tran=False, verbose=True, smpl_file=None,
+                  mesh=None):
     """evaluate.py:39-107.  Returns the [n_sequences, 8, 2] offline rows in dataset order (on every rank); with
     `evaluate_tran=True` (evaluate.py:66-92, 105-106) a pair (rows, windows [n_sequences, 7]) and prints the reference's
     `[0, mean drift at 1 m, ..., at 7 m]` list."""
@@ -192,7 +265,7 @@ def evaluate_pose(model, dataset, num_past_frame=20, num_future_frame=5, evaluat
     items = list(dataset)
     lengths = [it[0].shape[0] for it in items]
     mine = shard_sequences(lengths, world)[rank]
-    evaluator = PoseEvaluator()
+    evaluator = PoseEvaluator(smpl_file=smpl_file, mesh=mesh)
     model.eval()
     rows = []
     online_rows = []
@@ -237,6 +310,7 @@ if __name__ == '__main__':
     parser.add_argument('--model', type=str, default=None, help='state_dict .pth; default: seeded random init')
     parser.add_argument('--dataset', type=str, default='synthetic_dip')
     parser.add_argument('--frames', type=int, default=3000)
+    parser.add_argument('--smpl', type=str, default=None, help='official SMPL model file: enables the Mesh Error row')
     parser.add_argument('--tran', action='store_true', help='also the translation-error windows (evaluate_tran=True)')
     args = parser.parse_args()
     if args.dataset != 'synthetic_dip':
@@ -248,4 +322,4 @@ if __name__ == '__main__':
         torch.manual_seed(0)
         net = MobilePoserNet().to(default_device())
     print(f'Starting evaluation: {args.dataset.capitalize()}')
-    evaluate_pose(net, synthetic_dip(frames=args.frames), evaluate_tran=args.tran)
+    evaluate_pose(net, synthetic_dip(frames=args.frames), evaluate_tran=args.tran, smpl_file=args.smpl)

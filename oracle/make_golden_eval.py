@@ -1,6 +1,7 @@
-"""TEST INFRASTRUCTURE ONLY -- golden vectors of the reference's TRANSLATION-ERROR WINDOWS.
+"""TEST INFRASTRUCTURE ONLY -- golden vectors of the reference's TRANSLATION-ERROR WINDOWS and of the
+evaluator's MESH ROW (row N1; see mesh_golden below).
 
-    python oracle/make_golden_eval.py        # writes tests/golden/tran_windows.npz
+    python oracle/make_golden_eval.py        # writes tests/golden/tran_windows.npz and tests/golden/mesh_unit.npz
 
 Runs only in the build container (needs /root/reference).  Calls the UNMODIFIED `evaluate_pose(model, dataset,
 evaluate_tran=True)` of mobileposer/evaluate.py:39-107 through the shims of make_golden.py, with a stand-in model
@@ -86,6 +87,51 @@ def main():
     print(overall)
     MG.save('tran_windows', tran_t=tran_t, tran_p=tran_p, lengths=np.array([t.shape[0] for t, _ in cases], np.int32),
             per_sequence=per_seq, overall=overall)
+    mesh_golden()
+
+
+@torch.no_grad()
+def mesh_golden():
+    """Mesh row (evaluator.py row 1): the reference's own FullMotionEvaluator and
+    ParametricModel.forward_kinematics(calc_mesh=True), unmodified, over a SYNTHETIC template -- the SMPL vertices and
+    skinning weights cannot be committed, the skinning code does not care which mesh it skins.  Only `_v_template` and
+    `_skinning_weights` of the loaded model are replaced (700 random vertices around the skeleton, weights with 1-4 and a
+    few with 24 non-zeros); joints, parents and every line of code are the reference's."""
+    cwd = os.getcwd()
+    os.chdir(os.path.join(MG.REF, 'mobileposer'))
+    try:
+        import mobileposer.articulate as art
+        import mobileposer.config as RC
+        ev = art.FullMotionEvaluator(str(RC.paths.smpl_file), joint_mask=torch.tensor([2, 5, 16, 20]), fps=RC.datasets.fps)
+    finally:
+        os.chdir(cwd)
+    g = torch.Generator().manual_seed(4242)
+    V, n = 700, 75
+    J = ev.model._J.clone()
+    near = torch.randint(0, 24, (V,), generator=g)
+    v_template = J[near] + torch.randn(V, 3, generator=g) * 0.06
+    w = torch.zeros(V, 24)
+    for v in range(V):
+        k = 24 if v % 50 == 0 else int(torch.randint(1, 5, (1,), generator=g))
+        idx = torch.randperm(24, generator=g)[:k]
+        idx[0] = near[v]
+        w[v, idx] = torch.rand(k, generator=g) + 0.05
+    w = w / w.sum(dim=1, keepdim=True)
+    ev.model._v_template = v_template
+    ev.model._skinning_weights = w
+
+    def rand_rot(k, scale):
+        a = torch.randn(k, 3, generator=g) * scale
+        return art.math.axis_angle_to_rotation_matrix(a).view(k, 3, 3)
+    pose_t = rand_rot(n * 24, 0.6).view(n, 24, 3, 3)
+    pose_p = torch.matmul(pose_t, rand_rot(n * 24, 0.15).view(n, 24, 3, 3))
+    tran_t = torch.cumsum(torch.randn(n, 3, generator=g) * 0.02, 0)
+    tran_p = tran_t + torch.randn(n, 3, generator=g) * 0.05
+    errs = ev(pose_p, pose_t, tran_p=tran_p, tran_t=tran_t)
+    _, joint, vertex = ev.model.forward_kinematics(pose_p[:3], None, tran_p[:3], calc_mesh=True)
+    print(errs[:2])
+    MG.save('mesh_unit', pose_p=pose_p, pose_t=pose_t, tran_p=tran_p, tran_t=tran_t, rest=v_template - J[:1], weights=w,
+            joints_zero=J - J[:1], errs=errs, vertex3=vertex, joint3=joint)
 
 
 if __name__ == '__main__':

@@ -75,3 +75,48 @@ def test_tran_window_oracle_matches_reference_evaluate_pose():
         pairs = frame_pairs(mv, w)
         assert all(b[1] > a[1] for a, b in zip(pairs, pairs[1:]))
         assert all(mv[e] - mv[s] >= w and mv[e - 1] - mv[s] < w for s, e in pairs)
+
+
+def test_mesh_oracle_matches_reference_skinning_and_evaluator_row():
+    """oracle/eval_port.py (restatement of model.py:208-240 and evaluator.py:319-323) against the reference's own
+    forward_kinematics(calc_mesh=True) / FullMotionEvaluator over the synthetic template of oracle/make_golden_eval.py."""
+    import numpy as np
+    from oracle.eval_port import skinned_vertices, vertex_error_row
+    g = {k: v.numpy() for k, v in load_golden('mesh_unit').items()}
+    joint, vert = skinned_vertices(g['pose_p'][:3], g['tran_p'][:3], g['rest'], g['weights'], g['joints_zero'])
+    assert np.abs(joint - g['joint3']).max() < 1e-6 and np.abs(vert - g['vertex3']).max() < 2e-6
+    row = vertex_error_row(g['pose_p'], g['pose_t'], g['tran_p'], g['tran_t'], g['rest'], g['weights'], g['joints_zero'])
+    assert (np.abs(row - g['errs'][1]) / g['errs'][1]).max() < 1e-5
+    # the template's joints are the SMPL constants the library carries
+    from mobileposer_b200.config import SMPL_J_ZERO
+    assert np.abs(g['joints_zero'] - np.asarray(SMPL_J_ZERO, np.float32)).max() < 1e-7
+
+
+def test_smpl_file_loader_reads_a_model_file_without_chumpy(tmp_path):
+    """load_smpl_mesh: a pickle shaped like the official model file (a chumpy object inside) -> rest vertices and weights."""
+    import pickle
+    import sys
+    import types
+
+    import numpy as np
+    from mobileposer_b200.evaluate import load_smpl_mesh
+    mod = types.ModuleType('chumpy')
+
+    class Ch:                                    # what the official file pickles `shapedirs` as
+        def __init__(self, x=None):
+            self.x = x
+    Ch.__module__, Ch.__qualname__ = 'chumpy', 'Ch'
+    mod.Ch = Ch
+    rng = np.random.default_rng(0)
+    data = {'v_template': rng.normal(size=(50, 3)), 'J': rng.normal(size=(24, 3)), 'weights': rng.random((50, 24)),
+            'shapedirs': Ch(rng.normal(size=(50, 3, 10)))}
+    sys.modules['chumpy'] = mod
+    try:
+        blob = pickle.dumps(data, protocol=2)
+    finally:
+        del sys.modules['chumpy']
+    f = tmp_path / 'model.pkl'
+    f.write_bytes(blob)
+    rest, w = load_smpl_mesh(str(f), device='cpu')
+    assert rest.shape == (50, 3) and w.shape == (50, 24) and rest.dtype == torch.float32
+    assert np.allclose(rest.numpy(), (data['v_template'] - data['J'][:1]).astype(np.float32))

@@ -50,6 +50,62 @@ def test_tran_windows_match_oracle_pair_for_pair(T, step):
         assert (np.abs(e[ok] - o_err[ok]) / np.abs(o_err[ok])).max() < 5e-6
 
 
+def test_mesh_row_matches_reference_evaluator():
+    """mp_eval_vertex_errors behind full_motion_errors(mesh=...) against the reference's FullMotionEvaluator row 1 over
+    the synthetic template (tests/golden/mesh_unit.npz), and the other rows next to it."""
+    from mobileposer_b200.evaluate import full_motion_errors, vertex_error_row
+    g = load_golden('mesh_unit')
+    mesh = (g['rest'].to(DEV), g['weights'].to(DEV))
+    errs = full_motion_errors(g['pose_p'].to(DEV), g['pose_t'].to(DEV), g['tran_p'].to(DEV), g['tran_t'].to(DEV), mesh=mesh).cpu()
+    ref = g['errs']
+    assert ((errs - ref).abs() / ref.abs().clamp_min(1e-6)).max() < 2e-4, (errs, ref)
+    assert ((errs[1] - ref[1]).abs() / ref[1]).max() < 2e-5, (errs[1], ref[1])
+    # identical motions -> exactly zero; a single frame -> std 0 like the other rows of this mirror
+    z = vertex_error_row(g['pose_p'].to(DEV), g['pose_p'].to(DEV), mesh).cpu()
+    assert z.abs().max() == 0.0
+    one = vertex_error_row(g['pose_p'][:1].to(DEV), g['pose_t'][:1].to(DEV), mesh).cpu()
+    assert one[0] > 0 and one[1] == 0
+
+
+@pytest.mark.parametrize('n,V', [(3000, 6890), (33, 513), (1, 1)])
+def test_mesh_row_matches_oracle_at_smpl_size(n, V):
+    """SMPL-sized template (6890 vertices, <= 4 bones per vertex) x a DIP-sized sequence: the fused kernel against the
+    float64 restatement of the reference's skinning on a sample of frames (exact per-frame equality of the formulation)
+    and against its own chunking (frame chunks / vertex tiles change nothing but the summation order)."""
+    from mobileposer_b200.config import SMPL_J_ZERO
+    from mobileposer_b200.evaluate import vertex_error_row
+    from oracle.eval_port import vertex_error_row as oracle_row
+    g = torch.Generator().manual_seed(n + V)
+    jz = torch.tensor(SMPL_J_ZERO)
+    near = torch.randint(0, 24, (V,), generator=g)
+    rest = jz[near] + torch.randn(V, 3, generator=g) * 0.05
+    w = torch.zeros(V, 24)
+    w[torch.arange(V), near] = 1.0
+    extra = torch.randint(0, 24, (V, 3), generator=g)
+    w.scatter_add_(1, extra, torch.rand(V, 3, generator=g) * 0.5)
+    w = w / w.sum(1, keepdim=True)
+
+    def rots(k, scale):
+        a = torch.randn(k, 3, generator=g) * scale
+        th = a.norm(dim=1, keepdim=True).clamp_min(1e-8)
+        u = a / th
+        K = torch.zeros(k, 3, 3)
+        K[:, 0, 1], K[:, 0, 2], K[:, 1, 0], K[:, 1, 2], K[:, 2, 0], K[:, 2, 1] = -u[:, 2], u[:, 1], u[:, 2], -u[:, 0], -u[:, 1], u[:, 0]
+        return torch.eye(3) + torch.sin(th)[:, :, None] * K + (1 - torch.cos(th))[:, :, None] * (K @ K)
+    pose_t = rots(n * 24, 0.5).view(n, 24, 3, 3)
+    pose_p = pose_t @ rots(n * 24, 0.1).view(n, 24, 3, 3)
+    row = vertex_error_row(pose_p.to(DEV), pose_t.to(DEV), (rest, w)).cpu().double().numpy()
+    sub = slice(0, n, max(1, n // 40))                       # the oracle materialises [n, V, 3]: a sample of frames
+    o_sub = oracle_row(pose_p[sub].numpy(), pose_t[sub].numpy(), None, None, rest.numpy(), w.numpy(), jz.numpy())
+    k_sub = vertex_error_row(pose_p[sub].contiguous().to(DEV), pose_t[sub].contiguous().to(DEV), (rest, w)).cpu().double().numpy()
+    assert abs(k_sub[0] - o_sub[0]) / o_sub[0] < 2e-5
+    if pose_p[sub].shape[0] > 1 and V > 1:
+        assert abs(k_sub[1] - o_sub[1]) / max(o_sub[1], 1e-9) < 2e-4
+    assert np.isfinite(row).all() and row[0] > 0
+    if n > 1000:                                             # the full sequence is statistically the same motion as its sample
+        assert abs(row[0] - o_sub[0]) / o_sub[0] < 0.1
+
+
 def test_tran_windows_reject_cpu_tensors_and_oversized_sequences():
     from mobileposer_b200.evaluate import tran_window_errors
     with pytest.raises(RuntimeError):
