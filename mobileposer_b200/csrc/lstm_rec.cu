@@ -401,6 +401,142 @@ __global__ void __launch_bounds__(RecCfg<H, C>::THREADS, 1) lstm_rec_kernel(cons
 }
 
 // ---------------------------------------------------------------------------------------------
+// H = 64, many sequences (the foot-contact head at cfg3 / cfg4): one thread per gate row.
+//
+// The cluster kernel above splits K across the lanes of a warp, which is right for H = 256 (64 k per lane) and wrong for
+// H = 64: 2 k per lane and a 31-shuffle reduction per step -- 1024 threads per CTA busy reducing (measured 2 950 clk per step,
+// 0.45 ms per layer on 128 SMs).  Here a CTA of 256 threads serves 4 sequences; thread t owns gate row (unit t/4, gate t%4)
+// -- the column order of `gin`, so its pre-activation read is coalesced -- with the row's 64 weights in registers, walks
+// h (shared memory, [k][sequence]: one broadcast LDS.128 feeds two packed FFMA2 = 4 sequences) and needs NO reduction.  The 4
+// gates of a unit sit in one lane quad: each lane applies its gate's nonlinearity to its 4 sequences, a two-round butterfly
+// (4 shuffles) transposes gates x sequences so that lane q owns sequence q of the unit, and the cell update, the h store and
+// the y store happen there.  One __syncthreads per step, 2 KB of shared memory, 128 CTAs of 256 threads at B = 256.
+// ---------------------------------------------------------------------------------------------
+struct RowsParams {
+    const float* gin;
+    const float* w0;      // W_hh [4H, H] of direction 0 / 1 (torch layout: row = gate*H + unit)
+    const float* w1;
+    float* y;
+    const float* h0;
+    const float* c0;
+    float* hn;
+    float* cn;
+    const int32_t* lengths;
+    int B, T, dirs;
+};
+
+__global__ void __launch_bounds__(256) lstm_rec_h64_rows_kernel(const RowsParams p) {
+    constexpr int H = 64, NBT = 4;
+    __shared__ __align__(16) float hs[2][H][NBT];      // h_t of the tile's 4 sequences, [parity][k][sequence]
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int unit = tid >> 2, gate = tid & 3, q = gate;   // after the transpose lane `q` of the quad owns sequence q
+    const int dir = blockIdx.y, b_begin = blockIdx.x * NBT;
+    const int nb = min(NBT, p.B - b_begin);
+    const int G4 = p.dirs * 4 * H, Y2 = p.dirs * H;
+    const bool b0 = (lane & 1) != 0, b1 = (lane & 2) != 0;
+
+    // the row's weights, as pairs (w, w) are not needed: FFMA2 broadcasts the scalar operand
+    float w[H];
+    {
+        const float4* src = reinterpret_cast<const float4*>((dir ? p.w1 : p.w0) + (size_t)(gate * H + unit) * H);
+#pragma unroll
+        for (int i = 0; i < H / 4; ++i) {
+            const float4 v = __ldg(src + i);
+            w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w;
+        }
+    }
+    int len[NBT], maxlen = 0;
+#pragma unroll
+    for (int i = 0; i < NBT; ++i) {
+        len[i] = (i < nb) ? (p.lengths ? min(max(p.lengths[b_begin + i], 0), p.T) : p.T) : 0;
+        maxlen = max(maxlen, len[i]);
+    }
+    int len_q = len[0];                                  // this lane's own sequence (the one it owns after the transpose)
+#pragma unroll
+    for (int i = 1; i < NBT; ++i) len_q = (q == i) ? len[i] : len_q;
+    const int bq = b_begin + min(q, nb - 1);
+    // initial state: h of (sequence q, unit) goes to the parity-0 buffer, c stays in a register of lane q
+    hs[0][unit][q] = (p.h0 && q < nb) ? p.h0[((size_t)dir * p.B + bq) * H + unit] : 0.f;
+    hs[1][unit][q] = 0.f;
+    float c_reg = (p.c0 && q < nb) ? p.c0[((size_t)dir * p.B + bq) * H + unit] : 0.f;
+    // gate pre-activations one step ahead: column (unit, gate) = tid of every sequence of the tile
+    float gi_next[NBT];
+#pragma unroll
+    for (int i = 0; i < NBT; ++i) {
+        const int b = b_begin + min(i, nb - 1);
+        gi_next[i] = len[i] > 0 ? __ldg(p.gin + ((size_t)b * p.T + (dir ? len[i] - 1 : 0)) * G4 + dir * 4 * H + tid) : 0.f;
+    }
+    __syncthreads();
+
+    for (int s = 0; s < maxlen; ++s) {
+        const int par = s & 1;
+        float gi[NBT];
+#pragma unroll
+        for (int i = 0; i < NBT; ++i) {
+            gi[i] = gi_next[i];
+            if (s + 1 < len[i]) {
+                const int b = b_begin + i;
+                gi_next[i] = __ldg(p.gin + ((size_t)b * p.T + (dir ? len[i] - 2 - s : s + 1)) * G4 + dir * 4 * H + tid);
+            }
+        }
+        // W_hh row . h for the 4 sequences: two independent packed chains per half of K
+        f32x2 a01 = 0ull, a23 = 0ull, b01 = 0ull, b23 = 0ull;
+#pragma unroll
+        for (int k = 0; k < H; k += 2) {
+            const float4 h0v = *reinterpret_cast<const float4*>(&hs[par][k][0]);
+            const float4 h1v = *reinterpret_cast<const float4*>(&hs[par][k + 1][0]);
+            a01 = ffma2(pack2(h0v.x, h0v.y), w[k], a01);
+            a23 = ffma2(pack2(h0v.z, h0v.w), w[k], a23);
+            b01 = ffma2(pack2(h1v.x, h1v.y), w[k + 1], b01);
+            b23 = ffma2(pack2(h1v.z, h1v.w), w[k + 1], b23);
+        }
+        float v[NBT], t0, t1;
+        unpack2(a01, v[0], v[1]);
+        unpack2(a23, v[2], v[3]);
+        unpack2(b01, t0, t1);
+        v[0] += t0; v[1] += t1;
+        unpack2(b23, t0, t1);
+        v[2] += t0; v[3] += t1;
+        // this lane's gate for the 4 sequences
+#pragma unroll
+        for (int i = 0; i < NBT; ++i) v[i] = sigmoid_or_tanh(v[i] + gi[i], gate == 2);
+        // gates x sequences transpose inside the lane quad (lane = gate -> lane = sequence)
+        const float r0 = __shfl_xor_sync(0xffffffffu, b0 ? v[0] : v[1], 1);
+        const float r1 = __shfl_xor_sync(0xffffffffu, b0 ? v[2] : v[3], 1);
+        const float k0 = b0 ? v[1] : v[0], k1 = b0 ? v[3] : v[2];
+        const float e0 = b0 ? r0 : k0, o0 = b0 ? k0 : r0;      // even / odd gate of the pair, sequence (lane & 1)
+        const float e1 = b0 ? r1 : k1, o1 = b0 ? k1 : r1;      // ... sequence (lane & 1) + 2
+        const float rE = __shfl_xor_sync(0xffffffffu, b1 ? e0 : e1, 2);
+        const float rO = __shfl_xor_sync(0xffffffffu, b1 ? o0 : o1, 2);
+        const float kE = b1 ? e1 : e0, kO = b1 ? o1 : o0;
+        const float iv = b1 ? rE : kE, fv = b1 ? rO : kO, gv = b1 ? kE : rE, ov = b1 ? kO : rO;
+        // cell update of (unit, sequence q)
+        const bool active = s < len_q;
+        const float c_new = fmaf(fv, c_reg, iv * gv);
+        const float h_new = ov * sigmoid_or_tanh(c_new, true);
+        if (active) {
+            c_reg = c_new;
+            const int t = dir ? len_q - 1 - s : s;
+            hs[par ^ 1][unit][q] = h_new;
+            p.y[((size_t)(b_begin + q) * p.T + t) * Y2 + dir * H + unit] = h_new;
+            if (s == len_q - 1) {
+                if (p.hn) p.hn[((size_t)dir * p.B + b_begin + q) * H + unit] = h_new;
+                if (p.cn) p.cn[((size_t)dir * p.B + b_begin + q) * H + unit] = c_new;
+            }
+        }
+        __syncthreads();
+    }
+    // frames >= len of the layer output are zero (pad_packed_sequence, rnn.py:31)
+    for (int i = 0; i < nb; ++i) {
+        const int n = (p.T - len[i]) * H;
+        for (int j = tid; j < n; j += 256) {
+            const int t = len[i] + j / H, u = j % H;
+            p.y[((size_t)(b_begin + i) * p.T + t) * Y2 + dir * H + u] = 0.f;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Debug kernel (MP_REC_IMPL=simple): one CTA per (sequence, direction), W_hh^T streamed from L2
 // every step.  Same arithmetic, no clusters / mbarriers -- used to bisect failures of the kernel
 // above on hardware.  Never selected by default.
@@ -650,7 +786,17 @@ int launch_lstm_recurrence(const RecLayerArgs& a, cudaStream_t stream) {
         return MP_OK;
     }
     if (a.H == 256) return rec_cluster_size(256) == 16 ? launch_for<256, 16>(a, stream) : launch_for<256, 8>(a, stream);
-    if (a.H == 64) return launch_for<64, 1>(a, stream);
+    if (a.H == 64) {
+        // more sequences than the one-CTA-per-sequence latency path has room for: one thread per gate row, 4 sequences per CTA
+        if (a.B * a.dirs > cluster_slots<64, 1, 1>() && a.w_raw[0] && (a.dirs == 1 || a.w_raw[1]) && !env_is("MP_REC_H64", "cluster")) {
+            RowsParams p{a.gin, a.w_raw[0], a.dirs > 1 ? a.w_raw[1] : a.w_raw[0], a.y, a.h0, a.c0, a.hn, a.cn, a.lengths, a.B, a.T, a.dirs};
+            lstm_rec_h64_rows_kernel<<<dim3((a.B + 3) / 4, a.dirs), 256, 0, stream>>>(p);
+            MP_CUDA_TRY(cudaGetLastError());
+            count_launch();
+            return MP_OK;
+        }
+        return launch_for<64, 1>(a, stream);
+    }
     set_error("lstm: hidden size %d not built (64, 256)", a.H);
     return MP_ERR_UNSUPPORTED;
 }

@@ -291,6 +291,36 @@ def test_large_ragged_batch_on_the_64_sequence_tiles(net, oracle, env):
         assert argmax_equal(contact[b, :L], o_contact[b, :L])
 
 
+@pytest.mark.parametrize('B,T', [(203, 40), (300, 7), (152, 300)])
+def test_h64_row_per_thread_recurrence(net, oracle, env, B, T):
+    """The foot-contact head (H = 64) on large batches runs `lstm_rec_h64_rows_kernel` (one thread per gate row, 4 sequences
+    per CTA): ragged lengths incl. a partial last tile, carried (h, c), final states -- against the oracle's nn.LSTM and
+    against the cluster kernel it replaces (MP_REC_H64=cluster)."""
+    g = torch.Generator().manual_seed(B + T)
+    lens = [int(v) for v in torch.randint(1, T + 1, (B,), generator=g)]
+    lens[1] = T
+    x = torch.randn(B, T, 132, generator=g) * 0.5
+    for b, L in enumerate(lens):
+        x[b, L:] = 0
+    h0 = (torch.randn(4, B, 64, generator=g) * 0.3, torch.randn(4, B, 64, generator=g) * 0.3)
+    ref, (rh, rc) = oracle.heads['foot_contact'](x, lens, h0)
+    rnn = net.foot_contact.footcontact
+    out = {}
+    for name, sw in (('rows', None), ('cluster', 'cluster')):
+        env(MP_REC_H64=sw)
+        y, _, (hn, cn) = rnn(x.to(DEV), lens, (h0[0].to(DEV), h0[1].to(DEV)))
+        out[name] = (y.cpu(), hn.cpu(), cn.cpu())
+    y, hn, cn = out['rows']
+    assert y.shape == ref.shape
+    assert max_abs(y, ref) <= VALUE_TOL and max_abs(hn, rh) <= VALUE_TOL and max_abs(cn, rc) <= VALUE_TOL
+    for a, b in zip(out['rows'], out['cluster']):
+        assert max_abs(a, b) <= 2e-6
+    # zero initial state (the way the net calls it) and padded frames: linear2 of a zero row is its bias
+    y0, _, _ = rnn(x.to(DEV), lens)
+    r0, _ = oracle.heads['foot_contact'](x, lens)
+    assert max_abs(y0, r0) <= VALUE_TOL
+
+
 def test_rnn_module_surface(net, oracle):
     """RNN.forward(x, seq_lengths, h) return convention incl. the sequence-first case (rnn.py:15)."""
     from oracle.torch_port import _Head  # noqa: F401
