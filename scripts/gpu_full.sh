@@ -12,6 +12,10 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:lstm_rec_tc -c 1 -o gpurun_out/prof_rec_tc_b256 python scripts/prof_one.py --batch 256 --passes 1 --tile 64 > gpurun_out/prof_a.log 2>&1; echo "ncu rec_tc exit $?"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemm_tf32x3 -s 1 -c 1 -o gpurun_out/prof_gemm_tc python scripts/prof_one.py --batch 256 --passes 1 > gpurun_out/prof_b.log 2>&1; echo "ncu gemm exit $?"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:lstm_rec_kernel -c 1 -o gpurun_out/prof_rec_b1 python scripts/prof_one.py --batch 1 --passes 1 > gpurun_out/prof_c.log 2>&1; echo "ncu rec b1 exit $?"
-MP_REC_IMPL=ffma timeout 900 ncu --set full --clock-control none --import-source on -k regex:lstm_rec_kernel -c 1 -o gpurun_out/prof_rec_b256 python scripts/prof_one.py --batch 256 --passes 1 > gpurun_out/prof_d.log 2>&1; echo "ncu rec ffma exit $?"
+# (the FFMA cluster recurrence at B = 256, MP_REC_IMPL=ffma, is no default path any more: its capture stays in profiles/ from the earlier visits)
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm_bias_act -s 1 -c 1 -o gpurun_out/prof_gemm_ffma2 python scripts/prof_one.py --batch 256 --passes 1 > gpurun_out/prof_f.log 2>&1; echo "ncu gemm ffma2 exit $?"
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:lstm_rec_h64_rows -c 1 -o gpurun_out/prof_rec_h64_rows python scripts/prof_one.py --batch 256 --passes 1 > gpurun_out/prof_g.log 2>&1; echo "ncu h64 rows exit $?"
+timeout 300 python scripts/time_gemm.py > gpurun_out/time_gemm.log 2>&1; cat gpurun_out/time_gemm.log
+timeout 300 python scripts/time_eval.py > gpurun_out/time_eval.log 2>&1; cat gpurun_out/time_eval.log
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:physics_optimize -s 2 -c 1 -o gpurun_out/prof_k8_physics python scripts/time_physics.py --iters 1 > gpurun_out/prof_e.log 2>&1; echo "ncu k8 exit $?"
 timeout 300 python scripts/time_physics.py > gpurun_out/time_physics.log 2>&1; tail -1 gpurun_out/time_physics.log
