@@ -99,6 +99,17 @@ int mp_gemm_bias(const float* A, const float* W, const float* bias, float* C, in
 int mp_imu_assemble(const float* acc, const float* ori, int64_t T, int32_t slots_in, const int32_t* combo_masks_host,
                     int32_t n_combos, float acc_scale, int32_t smooth, float* imu_out, mp_stream_t stream);
 
+/* Live-demo normalisation of n_ticks sensor readings [live_demo.py:210-234] (third part of row N2): per sensor
+ * quaternion (wxyz, unnormalised) -> rotation [articulate/math/angular.py:224-236], calibration into the SMPL frame
+ * (glb_acc = smpl2imu acc - acc_offset, glb_ori = smpl2imu R device2bone; the calibration of live_demo.py:160-177 is
+ * passed as HOST arrays: smpl2imu [3,3], device2bone [5,3,3], acc_offsets [5,3]), slot permutation perm_host[5]
+ * (the reference's [1,4,3,0,2]), acc / acc_scale, device-combo mask -- or, phone_as_watch != 0, slot 0 <- permuted slot 3
+ * and nothing else [live_demo.py:223-226] -- and the cat into imu_out [n_ticks, 60].
+ * quat [n_ticks,5,4], acc_raw [n_ticks,5,3] device pointers.                                                            */
+int mp_imu_live_normalize(const float* quat, const float* acc_raw, int64_t n_ticks, const float* smpl2imu_host,
+                          const float* device2bone_host, const float* acc_offsets_host, const int32_t* perm_host,
+                          int32_t combo_mask, int32_t phone_as_watch, float acc_scale, float* imu_out, mp_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * Kinematic tail.
  * ---------------------------------------------------------------------------------------- */

@@ -66,6 +66,8 @@ SIGNATURES = {
     'mp_tran_offline': (C.c_int, [c_float_p, c_float_p, c_float_p, c_int_p, C.c_int32, C.c_int32, c_float_p, c_stream]),
     'mp_imu_assemble': (C.c_int, [c_float_p, c_float_p, C.c_int64, C.c_int32, C.POINTER(C.c_int32), C.c_int32, C.c_float, C.c_int32,
                                   c_float_p, c_stream]),
+    'mp_imu_live_normalize': (C.c_int, [c_float_p, c_float_p, C.c_int64, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float),
+                                        C.POINTER(C.c_int32), C.c_int32, C.c_int32, C.c_float, c_float_p, c_stream]),
     'mp_physics_optimize': (C.c_int, [c_float_p, c_float_p, c_float_p, c_int_p, c_float_p, C.c_int32, C.c_int32,
                                       C.POINTER(PhysicsParams), c_float_p, c_float_p, c_stream]),
     'mp_physics_optimize_debug': (C.c_int, [c_float_p, c_float_p, c_float_p, c_int_p, c_float_p, C.c_int32, C.c_int32,

@@ -332,6 +332,12 @@ int mp_imu_assemble(const float* acc, const float* ori, int64_t T, int32_t slots
                     float acc_scale, int32_t smooth, float* imu_out, mp_stream_t stream) {
     return launch_imu_assemble(acc, ori, T, slots_in, combo_masks_host, n_combos, acc_scale, smooth, imu_out, (cudaStream_t)stream);
 }
+int mp_imu_live_normalize(const float* quat, const float* acc_raw, int64_t n_ticks, const float* smpl2imu_host, const float* device2bone_host,
+                          const float* acc_offsets_host, const int32_t* perm_host, int32_t combo_mask, int32_t phone_as_watch,
+                          float acc_scale, float* imu_out, mp_stream_t stream) {
+    return launch_imu_live_normalize(quat, acc_raw, n_ticks, smpl2imu_host, device2bone_host, acc_offsets_host, perm_host, combo_mask,
+                                     phone_as_watch, acc_scale, imu_out, (cudaStream_t)stream);
+}
 int mp_physics_optimize(const float* pose, const float* vel, const float* contact, const int32_t* lengths, float* state,
                         int32_t B, int32_t T, const mp_physics_params_t* params, float* pose_out, float* tran_out,
                         mp_stream_t stream) {

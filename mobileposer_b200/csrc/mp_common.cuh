@@ -102,6 +102,10 @@ int launch_online_push(const float* win_in, float* win_out, const float* frame, 
 int launch_imu_assemble(const float* acc, const float* ori, int64_t T, int slots_in, const int32_t* masks_host, int n_combos,
                         float acc_scale, int smooth, float* out, cudaStream_t stream);
 
+int launch_imu_live_normalize(const float* quat, const float* acc_raw, int64_t n, const float* smpl2imu_host,
+                              const float* device2bone_host, const float* acc_offsets_host, const int32_t* perm_host,
+                              int32_t combo_mask, int phone_as_watch, float acc_scale, float* out, cudaStream_t stream);
+
 // K8 (physics.cu)
 int launch_physics_optimize(const float* pose, const float* vel, const float* contact, const int32_t* lengths, float* state,
                             int B, int T, const mp_physics_params_t* prm, float* pose_out, float* tran_out, float* dbg,

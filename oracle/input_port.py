@@ -51,3 +51,34 @@ def assemble_loader(raw_acc, raw_ori, combo, acc_scale=amass.acc_scale):
     acc, ori = _masked(raw_acc, raw_ori, combo, acc_scale)
     acc = smooth_avg(acc)
     return np.concatenate([acc.reshape(len(acc), -1), ori.reshape(len(ori), -1)], axis=1)
+
+
+def quaternion_to_rotation_matrix(q):
+    """articulate/math/angular.py:224-236: (unnormalised) wxyz quaternions -> rotation matrices, float32 like the reference."""
+    q = np.asarray(q, np.float32).reshape(-1, 4)
+    q = q / np.sqrt((q * q).sum(axis=1, keepdims=True, dtype=np.float32))
+    a, b, c, d = q[:, 0], q[:, 1], q[:, 2], q[:, 3]
+    r = np.stack([-2 * c * c - 2 * d * d + 1, 2 * b * c - 2 * a * d, 2 * a * c + 2 * b * d,
+                  2 * b * c + 2 * a * d, -2 * b * b - 2 * d * d + 1, 2 * c * d - 2 * a * b,
+                  2 * b * d - 2 * a * c, 2 * a * b + 2 * c * d, -2 * b * b - 2 * c * c + 1], axis=1)
+    return r.reshape(-1, 3, 3).astype(np.float32)
+
+
+def live_normalize(ori_q, acc_raw, smpl2imu, device2bone, acc_offsets, combo=None, phone_as_watch=False,
+                   perm=(1, 4, 3, 0, 2), acc_scale=amass.acc_scale):
+    """live_demo.py:210-234: sensor quaternions [n,5,4] + accelerations [n,5,3] of one tick -> the [n,60] frame.
+    Calibration (live_demo.py:160-177): smpl2imu [3,3], device2bone [5,3,3], acc_offsets [5,3]."""
+    ori_q, acc_raw = np.asarray(ori_q, np.float32), np.asarray(acc_raw, np.float32)
+    n = ori_q.shape[0]
+    s2i, d2b, off = (np.asarray(x, np.float32) for x in (smpl2imu, device2bone, acc_offsets))
+    ori_raw = quaternion_to_rotation_matrix(ori_q).reshape(n, 5, 3, 3)
+    glb_acc = np.einsum('ab,nsb->nsa', s2i, acc_raw) - off[None]
+    glb_ori = np.einsum('ab,nsbc,scd->nsad', s2i, ori_raw, d2b)
+    _acc = glb_acc[:, list(perm)] / np.float32(acc_scale)
+    _ori = glb_ori[:, list(perm)]
+    acc, ori = np.zeros_like(_acc), np.zeros_like(_ori)
+    if phone_as_watch:
+        acc[:, 0], ori[:, 0] = _acc[:, 3], _ori[:, 3]
+    else:
+        acc[:, combo], ori[:, combo] = _acc[:, combo], _ori[:, combo]
+    return np.concatenate([acc.reshape(n, -1), ori.reshape(n, -1)], axis=1).astype(np.float32)

@@ -1,11 +1,14 @@
 """TEST INFRASTRUCTURE ONLY -- golden vectors of the reference's INPUT ASSEMBLY from the live reference.
 
-    python oracle/make_golden_inputs.py        # writes tests/golden/input_assembly.npz
+    python oracle/make_golden_inputs.py        # writes tests/golden/input_assembly.npz and tests/golden/live_normalize.npz
 
 Runs only in the build container (needs /root/reference).  Calls, unmodified and through the shims of make_golden.py:
   * PoseDataset._process_combo_data   (mobileposer/data.py:69-86)   -- all 12 combos of one raw stream, evaluate mode
   * DataLoader._get_imu               (mobileposer/loader.py:39-49) -- one combo, acc smoothed by smooth_avg
   * smooth_avg                        (mobileposer/utils/model_utils.py:28-37)
+  * live_demo.py:160-177,210-234      -- calibration + per-tick normalisation of the live demo.  Those lines sit inside the
+    script's `__main__` loop (sockets, pygame clock) and cannot be called; live_golden() evaluates the same torch expressions
+    on synthetic sensor readings with the reference's own `quaternion_to_rotation_matrix` and `amass` config.
 """
 from __future__ import annotations
 
@@ -55,5 +58,48 @@ def main():
             smooth3=smooth_avg(raw_acc[:, :5].clone()), acc_scale=np.float32(RC.amass.acc_scale))
 
 
+@torch.no_grad()
+def live_golden():
+    cwd = os.getcwd()
+    os.chdir(os.path.join(MG.REF, 'mobileposer'))
+    try:
+        import mobileposer.config as RC
+        from mobileposer.articulate.math import quaternion_to_rotation_matrix
+    finally:
+        os.chdir(cwd)
+    g = torch.Generator().manual_seed(77)
+    n, n_imus = 9, 5
+    # calibration (live_demo.py:160-177): sensor 0 aligned with the body frame, then a T-pose reading of all sensors
+    oris0 = torch.randn(4, generator=g)
+    smpl2imu = quaternion_to_rotation_matrix(oris0).view(3, 3).t()
+    oris_t, accs_t = torch.randn(n_imus, 4, generator=g), torch.randn(n_imus, 3, generator=g) * 9.8
+    device2bone = smpl2imu.matmul(quaternion_to_rotation_matrix(oris_t)).transpose(1, 2).matmul(torch.eye(3))
+    acc_offsets = smpl2imu.matmul(accs_t.unsqueeze(-1))
+    # per tick (live_demo.py:210-234); the sensor quaternions arrive unnormalised
+    ori_q = torch.randn(n, n_imus, 4, generator=g) * 1.7
+    acc_raw = torch.randn(n, n_imus, 3, generator=g) * 12.0
+    ori_raw = quaternion_to_rotation_matrix(ori_q).view(-1, n_imus, 3, 3)
+    glb_acc = (smpl2imu.matmul(acc_raw.view(-1, n_imus, 3, 1)) - acc_offsets).view(-1, n_imus, 3)
+    glb_ori = smpl2imu.matmul(ori_raw).matmul(device2bone)
+    _acc = glb_acc.view(-1, 5, 3)[:, [1, 4, 3, 0, 2]] / RC.amass.acc_scale
+    _ori = glb_ori.view(-1, 5, 3, 3)[:, [1, 4, 3, 0, 2]]
+    outs = {}
+    for name in ('lw_rp', 'rw_rp_h', 'phone_as_watch'):
+        acc, ori = torch.zeros_like(_acc), torch.zeros_like(_ori)
+        if name == 'phone_as_watch':
+            acc[:, [0]] = _acc[:, [3]]
+            ori[:, [0]] = _ori[:, [3]]
+        else:
+            c = RC.amass.combos[name]
+            acc[:, c] = _acc[:, c]
+            ori[:, c] = _ori[:, c]
+        outs[name] = torch.cat([acc.flatten(1), ori.flatten(1)], dim=1)
+    MG.save('live_normalize', ori_q=ori_q, acc_raw=acc_raw, smpl2imu=smpl2imu, device2bone=device2bone,
+            acc_offsets=acc_offsets.squeeze(-1), perm=np.array([1, 4, 3, 0, 2], np.int32), ori_raw=ori_raw,
+            acc_scale=np.float32(RC.amass.acc_scale), imu_lw_rp=outs['lw_rp'], imu_rw_rp_h=outs['rw_rp_h'],
+            imu_phone_as_watch=outs['phone_as_watch'])
+
+
 if __name__ == '__main__':
     main()
+    live_golden()

@@ -49,3 +49,30 @@ def test_metric_rows_on_the_device_match_the_reference_evaluator():
     assert (jp - jp_ref).abs().max() < 2e-6 and (jt - jt_ref).abs().max() < 2e-6 and (jp - g['joint_a']).abs().max() < 2e-6
     assert (lae - torch.rad2deg(angle_between(g['pose_a'], g['pose_b']))).abs().max() < 2e-3      # degrees
     assert (gae - torch.rad2deg(angle_between(gp, gt))).abs().max() < 2e-3
+
+
+def test_live_normalisation_matches_reference_expressions():
+    """mp_imu_live_normalize (third part of SURVEY.md 8f row N2) against the live demo's expressions evaluated with the
+    reference's own functions (tests/golden/live_normalize.npz), and on a long buffer against the CPU restatement."""
+    import numpy as np
+    from mobileposer_b200.inputs import LiveCalibration, normalize_live
+    from oracle.input_port import live_normalize
+    g = load_golden('live_normalize')
+    cal = LiveCalibration(g['smpl2imu'], g['device2bone'], g['acc_offsets'])
+    q, a = g['ori_q'].to('cuda:0'), g['acc_raw'].to('cuda:0')
+    for name, kw in (('imu_lw_rp', dict(combo='lw_rp')), ('imu_rw_rp_h', dict(combo='rw_rp_h')),
+                     ('imu_phone_as_watch', dict(phone_as_watch=True))):
+        out = normalize_live(q, a, cal, **kw).cpu()
+        assert out.shape == g[name].shape
+        assert torch.equal(out == 0, g[name] == 0)
+        assert (out - g[name]).abs().max() < 2e-6, name
+    gen = torch.Generator().manual_seed(3)
+    qn, an = torch.randn(5000, 5, 4, generator=gen), torch.randn(5000, 5, 3, generator=gen) * 10
+    out = normalize_live(qn.to('cuda:0'), an.to('cuda:0'), cal, combo='lw_rp_h').cpu().numpy()
+    from mobileposer_b200.config import amass
+    ref = live_normalize(qn.numpy(), an.numpy(), g['smpl2imu'].numpy(), g['device2bone'].numpy(), g['acc_offsets'].numpy(),
+                         combo=amass.combos['lw_rp_h'])
+    assert np.abs(out - ref).max() < 5e-6
+    # one tick feeds forward_online directly
+    tick = normalize_live(q[:1], a[:1], cal)
+    assert tick.shape == (1, 60)
