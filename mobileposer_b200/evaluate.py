@@ -254,10 +254,16 @@ def synthetic_dip(n_subjects=10, n_seq=5, frames=3000, combo='lw_rp'):
 
 @torch.no_grad()
 def evaluate_pose(model, dataset, num_past_frame=20, num_future_frame=5, evaluate_tran=False, verbose=True, smpl_file=None,
-                  mesh=None):
+                  mesh=None, batch_size=1):
     """evaluate.py:39-107.  Returns the [n_sequences, 8, 2] offline rows in dataset order (on every rank); with
     `evaluate_tran=True` (evaluate.py:66-92, 105-106) a pair (rows, windows [n_sequences, 7]) and prints the reference's
-    `[0, mean drift at 1 m, ..., at 7 m]` list."""
+    `[0, mean drift at 1 m, ..., at 7 m]` list.
+
+    `batch_size` = 1 is the reference's loop, one `forward_offline(x[None], [T])` per sequence (evaluate.py:56-58), the
+    velocity head's state carried from sequence to sequence exactly as there.  `batch_size` > 1 (extension)
+    runs that many sequences of the rank's shard per `forward_offline` call -- padded to the longest, true lengths passed --
+    on the throughput kernels, with a fresh velocity state per sequence (SURVEY.md 8e option 1): pose, joint and contact rows
+    are the same, the two rows that see the translation (jitter, distance) are those of independent sequences."""
     import torch.distributed as dist
     device = next(model.parameters()).device
     rank = dist.get_rank() if dist.is_initialized() else 0
@@ -270,11 +276,29 @@ def evaluate_pose(model, dataset, num_past_frame=20, num_future_frame=5, evaluat
     rows = []
     online_rows = []
     window_rows = []
-    for i in mine:
+    if batch_size < 1:
+        raise ValueError(f'batch_size must be positive, got {batch_size}')
+    batched = {}                                   # sequence index -> (pose_p [T,24,3,3], tran_p [T,3]) of the current group
+    for pos, i in enumerate(mine):
         imu, pose_t, _, tran_t = items[i]
         x = imu.to(device)
-        model.reset()
-        pose_p, _, tran_p, _ = model.forward_offline(x.unsqueeze(0), [x.shape[0]])
+        if batch_size == 1:
+            model.reset()
+            pose_p, _, tran_p, _ = model.forward_offline(x.unsqueeze(0), [x.shape[0]])
+        else:
+            if i not in batched:                   # first sequence of a group: one forward for the whole group
+                group = mine[pos:pos + batch_size]
+                lens = [lengths[k] for k in group]
+                xb = torch.zeros(len(group), max(lens), imu.shape[1], device=device, dtype=torch.float32)
+                for r, k in enumerate(group):
+                    xb[r, :lens[r]] = items[k][0].to(device)
+                model.reset()
+                pose_b, _, tran_b, _ = model.forward_offline(xb, lens)
+                pose_b = pose_b.view(len(group), max(lens), 24, 3, 3)
+                tran_b = tran_b.view(len(group), max(lens), 3)
+                # the rows of the group are formed before the next forward (the net may reuse its output buffers)
+                batched = {k: (pose_b[r, :lens[r]], tran_b[r, :lens[r]]) for r, k in enumerate(group)}
+            pose_p, tran_p = batched[i]
         pose_t = r6d_to_rotation_matrix(pose_t.to(device)).view(-1, 24, 3, 3)
         rows.append(evaluator.eval(pose_p, pose_t, tran_p=tran_p, tran_t=tran_t))
         if evaluate_tran:
@@ -311,6 +335,7 @@ if __name__ == '__main__':
     parser.add_argument('--dataset', type=str, default='synthetic_dip')
     parser.add_argument('--frames', type=int, default=3000)
     parser.add_argument('--smpl', type=str, default=None, help='official SMPL model file: enables the Mesh Error row')
+    parser.add_argument('--batch', type=int, default=1, help='sequences per forward_offline call (1 = the reference loop)')
     parser.add_argument('--tran', action='store_true', help='also the translation-error windows (evaluate_tran=True)')
     args = parser.parse_args()
     if args.dataset != 'synthetic_dip':
@@ -322,4 +347,4 @@ if __name__ == '__main__':
         torch.manual_seed(0)
         net = MobilePoserNet().to(default_device())
     print(f'Starting evaluation: {args.dataset.capitalize()}')
-    evaluate_pose(net, synthetic_dip(frames=args.frames), evaluate_tran=args.tran, smpl_file=args.smpl)
+    evaluate_pose(net, synthetic_dip(frames=args.frames), evaluate_tran=args.tran, smpl_file=args.smpl, batch_size=args.batch)

@@ -120,3 +120,56 @@ def test_smpl_file_loader_reads_a_model_file_without_chumpy(tmp_path):
     rest, w = load_smpl_mesh(str(f), device='cpu')
     assert rest.shape == (50, 3) and w.shape == (50, 24) and rest.dtype == torch.float32
     assert np.allclose(rest.numpy(), (data['v_template'] - data['J'][:1]).astype(np.float32))
+
+
+class _StandInNet(torch.nn.Module):
+    """What evaluate_pose touches of a model, on the CPU: a pose / translation that depend on the sequence's own frames only
+    (so a padded batch and a loop over single sequences must agree), with MobilePoserNet.forward_offline's return shapes."""
+
+    def __init__(self):
+        super().__init__()
+        self.w = torch.nn.Parameter(torch.zeros(1))
+        self.calls = []
+
+    def reset(self):
+        pass
+
+    @staticmethod
+    def _one(x):
+        a = 0.3 * torch.tanh(x[:, :24])                              # one angle per joint, about z
+        c, s_, z, o = torch.cos(a), torch.sin(a), torch.zeros_like(a), torch.ones_like(a)
+        pose = torch.stack([c, -s_, z, s_, c, z, z, z, o], dim=-1).view(-1, 24, 3, 3)
+        return pose, torch.cumsum(0.01 * x[:, 24:27], dim=0)
+
+    def forward_offline(self, x, lengths):
+        B, T = x.shape[0], x.shape[1]
+        self.calls.append(list(lengths))
+        assert T == max(lengths)
+        pose, tran = torch.zeros(B, T, 24, 3, 3), torch.zeros(B, T, 3)
+        for b, n in enumerate(lengths):
+            pose[b, :n], tran[b, :n] = self._one(x[b, :n])
+            assert (x[b, n:] == 0).all()                              # padding is zero-filled
+        if B == 1:
+            return pose[0], torch.zeros(1, T, 72), tran[0], torch.zeros(T, 2)
+        return pose.view(B * T, 24, 3, 3), torch.zeros(B, T, 72), tran, torch.zeros(B, T, 2)
+
+
+def test_evaluate_pose_batched_groups_equal_the_sequence_loop():
+    """Host logic of evaluate_pose(batch_size=...): grouping in dataset order, padding to the longest, true lengths,
+    per-sequence slices -- against the reference-shaped loop, with a stand-in model on the CPU."""
+    from mobileposer_b200.evaluate import evaluate_pose
+    g = torch.Generator().manual_seed(9)
+    items = []
+    for n in (70, 64, 90, 75, 66, 81, 64):
+        pose_r6d = torch.tensor([1., 0., 0., 0., 1., 0.]).repeat(24) + 0.2 * torch.randn(n, 144, generator=g)
+        items.append((torch.randn(n, 60, generator=g), pose_r6d, torch.zeros(n, 24, 3), torch.cumsum(0.01 * torch.randn(n, 3, generator=g), 0)))
+    loop_net, batch_net = _StandInNet(), _StandInNet()
+    ref = evaluate_pose(loop_net, items, verbose=False)
+    out = evaluate_pose(batch_net, items, verbose=False, batch_size=3)
+    assert loop_net.calls == [[n] for n in (70, 64, 90, 75, 66, 81, 64)]
+    assert batch_net.calls == [[70, 64, 90], [75, 66, 81], [64]]
+    ok = ~torch.isnan(ref)
+    assert torch.equal(torch.isnan(out), torch.isnan(ref))
+    assert torch.allclose(out[ok], ref[ok], rtol=1e-5, atol=1e-7)
+    with pytest.raises(ValueError):
+        evaluate_pose(batch_net, items, verbose=False, batch_size=0)
