@@ -72,3 +72,57 @@ def test_gather_rows_gloo_is_shard_count_invariant(world):
     expect = torch.tensor([[float(i), float(L), i * 0.5] for i, L in enumerate(lengths)])
     for _, out in results:
         assert torch.equal(out, expect)     # identical on every rank, identical to the 1-rank answer
+
+
+# ---- the whole evaluate_pose entry over two ranks (stand-in model on the CPU) ---------------------------------------
+def _eval_items():
+    g = torch.Generator().manual_seed(21)
+    items = []
+    for n in (70, 64, 90, 75, 66):
+        pose_r6d = torch.tensor([1., 0., 0., 0., 1., 0.]).repeat(24) + 0.2 * torch.randn(n, 144, generator=g)
+        items.append((torch.randn(n, 60, generator=g), pose_r6d, torch.zeros(n, 24, 3), torch.cumsum(0.01 * torch.randn(n, 3, generator=g), 0)))
+    return items
+
+
+def _eval_worker(rank, world, port, batch_size, q):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    torch.set_num_threads(1)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        from mobileposer_b200.evaluate import evaluate_pose
+        from test_evaluate import _StandInNet
+        net = _StandInNet()
+        table = evaluate_pose(net, _eval_items(), verbose=False, batch_size=batch_size)
+        q.put((rank, table, net.calls))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('batch_size', [1, 2])
+def test_evaluate_pose_sharded_over_two_ranks_equals_one_rank(batch_size):
+    """evaluate_pose under torch.distributed (gloo, world size 2): every rank evaluates its shard of whole sequences (looped
+    or in batches), the [n, 8, 2] rows are all-gathered once, and every rank ends with the single-process table."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from mobileposer_b200.evaluate import evaluate_pose
+    from test_evaluate import _StandInNet
+    ref = evaluate_pose(_StandInNet(), _eval_items(), verbose=False)
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_eval_worker, args=(r, 2, port, batch_size, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    seen = []
+    for rank, table, calls in results:
+        assert torch.equal(torch.isnan(table), torch.isnan(ref))
+        ok = ~torch.isnan(ref)
+        assert torch.allclose(table[ok], ref[ok], rtol=1e-5, atol=1e-7)
+        seen += [n for c in calls for n in c]
+        assert all(len(c) <= batch_size for c in calls)
+    assert sorted(seen) == sorted([70, 64, 90, 75, 66])       # every sequence evaluated exactly once across the ranks
