@@ -44,6 +44,23 @@ typedef void* mp_stream_t;      /* cudaStream_t                    */
 
 int mp_abi_version(void);
 const char* mp_last_error(void);
+
+/* The constants the kernels bake in (csrc/mp_constants.cuh), for agreement checks against the host-side mirror of the
+ * reference's config (mobileposer/config.py:129-142; models/net.py:47-59; SMPL zero pose of articulate/model.py:77-92).
+ * Host call, needs no device. */
+typedef struct mp_constants {
+    int32_t parent[24];       /* SMPL kinematic tree, -1 = root                         */
+    int32_t reduced[16];      /* joint_set.reduced                                      */
+    int32_t ignored[9];       /* joint_set.ignored                                      */
+    int32_t reduced_slot[24]; /* joint -> index in `reduced` or -1 (what K5 indexes by) */
+    float j_zero[24][3];      /* zero-pose joints J - J[0] (K8, evaluator kernels)      */
+    float feet[6];            /* J[10], J[11]: initial last_lfoot_pos / last_rfoot_pos  */
+    float gravity_velocity;   /* joint_set.gravity_velocity                             */
+    float vel_div;            /* datasets.fps / amass.vel_scale                         */
+    float prob_lo, prob_hi;   /* prob_threshold                                         */
+    double floor_y;           /* min(J[10].y, J[11].y) as float32 widened               */
+} mp_constants_t;
+int mp_constants(mp_constants_t* out);
 /* MP_OK iff the current CUDA device is compute capability 10.x. */
 int mp_device_check(void);
 

@@ -45,11 +45,21 @@ class PhysicsParams(C.Structure):
 
 
 PHYSICS_STATE_FLOATS = 80   # MP_PHYSICS_STATE_FLOATS
+ABI_VERSION = 1             # MP_ABI_VERSION this binding was written against
+
+
+class Constants(C.Structure):
+    """struct mp_constants."""
+    _fields_ = [('parent', C.c_int32 * 24), ('reduced', C.c_int32 * 16), ('ignored', C.c_int32 * 9), ('reduced_slot', C.c_int32 * 24),
+                ('j_zero', (C.c_float * 3) * 24), ('feet', C.c_float * 6), ('gravity_velocity', C.c_float), ('vel_div', C.c_float),
+                ('prob_lo', C.c_float), ('prob_hi', C.c_float), ('floor_y', C.c_double)]
+
 
 # name -> (restype, argtypes); must list every symbol the header declares (tests/test_cabi.py)
 SIGNATURES = {
     'mp_abi_version': (C.c_int, []),
     'mp_last_error': (C.c_char_p, []),
+    'mp_constants': (C.c_int, [C.POINTER(Constants)]),
     'mp_device_check': (C.c_int, []),
     'mp_launch_count': (C.c_int64, []),
     'mp_profile_enable': (C.c_int, [C.c_int32]),
@@ -113,6 +123,9 @@ def lib():
             fn = getattr(handle, name)
             fn.restype = res
             fn.argtypes = args
+        if handle.mp_abi_version() != ABI_VERSION:
+            raise RuntimeError(f'{LIB_PATH} has ABI version {handle.mp_abi_version()}, this package binds version {ABI_VERSION}: '
+                               'rebuild it with `python -m mobileposer_b200.build --force`')
         _lib = handle
     return _lib
 

@@ -2,8 +2,9 @@
 
 Every value here is a *number* the reference defines (mobileposer/config.py and
 the SMPL zero-pose skeleton it loads at mobileposer/models/net.py:47-49); the
-kernels in csrc/ bake the same numbers in (csrc/mp_constants.cuh) and
-tests/test_constants.py checks the two copies agree.
+kernels in csrc/ bake the same numbers in (csrc/mp_constants.cuh, exported by
+the C ABI's mp_constants()) and tests/test_constants.py checks the two copies
+agree bit for bit.
 
 Reference citations (relative to /root/reference):
   model_config  mobileposer/config.py:40-54

@@ -1,6 +1,7 @@
 // C ABI of mobileposer_b200 (include/mobileposer_b200.h): weight packing, one-head forward,
 // whole-net forward on forked streams replayed as a CUDA graph, host-buffer entry point.
 #include "mp_common.cuh"
+#include "mp_constants.cuh"
 
 #include <stdarg.h>
 #include <string.h>
@@ -101,6 +102,25 @@ extern "C" {
 int mp_abi_version(void) { return MP_ABI_VERSION; }
 const char* mp_last_error(void) { return g_err; }
 int64_t mp_launch_count(void) { return g_launches; }
+
+int mp_constants(mp_constants_t* out) {
+    MP_REQUIRE(out, "constants: null");
+    const int parent[24] = MP_SMPL_PARENT_INIT, reduced[16] = MP_REDUCED_INIT, ignored[9] = MP_IGNORED_INIT, slot[24] = MP_REDUCED_SLOT_INIT;
+    const float j0[24][3] = MP_SMPL_J_ZERO_INIT, feet[6] = MP_FEET_INIT;
+    memset(out, 0, sizeof(*out));
+    memcpy(out->parent, parent, sizeof(parent));
+    memcpy(out->reduced, reduced, sizeof(reduced));
+    memcpy(out->ignored, ignored, sizeof(ignored));
+    memcpy(out->reduced_slot, slot, sizeof(slot));
+    memcpy(out->j_zero, j0, sizeof(j0));
+    memcpy(out->feet, feet, sizeof(feet));
+    out->gravity_velocity = kGravityVel;
+    out->vel_div = kVelDiv;
+    out->prob_lo = kProbLo;
+    out->prob_hi = kProbHi;
+    out->floor_y = kFloorY;
+    return MP_OK;
+}
 
 int mp_profile_enable(int32_t on) {
     for (auto& r : g_profile_recs) {

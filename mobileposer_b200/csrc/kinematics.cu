@@ -9,21 +9,23 @@
 // All three are HBM-bound streaming kernels (384 B in / 864 B out per frame for K5); they carry no
 // reuse, so no shared-memory staging beyond the per-warp scan buffers of K6.
 #include "mp_common.cuh"
+#include "mp_constants.cuh"
 
 namespace mp {
 
 namespace {
 
-// joint_set.reduced / ignored (config.py:134-135) and the SMPL tree (smpl/basicmodel_m.pkl kintree_table)
-__constant__ int c_parent[24] = {-1, 0, 0, 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 9, 9, 12, 13, 14, 16, 17, 18, 19, 20, 21};
-__constant__ int c_reduced_slot[24] = {0, 1, 2, 3, 4, 5, 6, -1, -1, 7, -1, -1, 8, 9, 10, 11, 12, 13, 14, 15, -1, -1, -1, -1};
-__constant__ unsigned c_ignored_mask = (1u << 0) | (1u << 7) | (1u << 8) | (1u << 10) | (1u << 11) | (1u << 20) |
-                                       (1u << 21) | (1u << 22) | (1u << 23);
-// zero-pose feet J[10], J[11] - J[0] (net.py:47-48,59)
-__constant__ float c_feet[6] = {0.1282968f, -0.95590985f, 0.074987344f, -0.11935069f, -0.95635235f, 0.07737604f};
-constexpr double kFloorY = -0.9563523530960083;   // float32 min(J[10].y, J[11].y) widened (net.py:49)
-constexpr float kGravityVel = -0.018f;            // joint_set.gravity_velocity (config.py:131)
-constexpr float kVelDiv = 15.0f;                  // datasets.fps / amass.vel_scale (net.py:141)
+// joint_set.reduced / ignored (config.py:134-135), the SMPL tree and the zero-pose feet: mp_constants.cuh
+__constant__ int c_parent[24] = MP_SMPL_PARENT_INIT;
+__constant__ int c_reduced_slot[24] = MP_REDUCED_SLOT_INIT;
+constexpr int kIgnored[9] = MP_IGNORED_INIT;
+constexpr unsigned ignored_mask() {
+    unsigned m = 0;
+    for (int i = 0; i < 9; ++i) m |= 1u << kIgnored[i];
+    return m;
+}
+__constant__ unsigned c_ignored_mask = ignored_mask();
+__constant__ float c_feet[6] = MP_FEET_INIT;
 
 __device__ __forceinline__ float nan_to_zero(float x) { return (x != x) ? 0.f : x; }
 
@@ -91,7 +93,7 @@ __global__ void __launch_bounds__(256) reduced_global_to_full_kernel(const float
 
 __device__ __forceinline__ float prob_to_weight(float p) {
     // (p.clamp(0.5, 0.9) - 0.5) / (0.9 - 0.5)   (net.py:90-91; the divisor is the double 0.9-0.5 cast to fp32)
-    const float lo = 0.5f, hi = 0.9f;
+    const float lo = kProbLo, hi = kProbHi;
     const float c = fminf(fmaxf(p, lo), hi);
     return __fsub_rn(c, lo) / (float)(0.9 - 0.5);
 }

@@ -20,6 +20,7 @@
 // no fill outside the ancestor blocks; the right-hand side rides along as row 48.  No cuBLAS / cuSolver.
 // HBM traffic per frame and skeleton: 864 B pose in + 288 B velocity + 8 B contact, 864 B pose + 12 B tran out.
 #include "mp_common.cuh"
+#include "mp_constants.cuh"
 
 #include <mutex>
 
@@ -49,34 +50,9 @@ struct PhysTables {
 
 __constant__ PhysTables c_tab;
 
-// zero-pose joints J - J[0] as float32 (mobileposer_b200/config.py:SMPL_J_ZERO; tests compare FK against the reference)
-const float kJZero[NJ][3] = {
-    {0.0f, 0.0f, 0.0f},
-    {0.058581352f, -0.08228004f, -0.017664082f},
-    {-0.060309727f, -0.09051329f, -0.013542531f},
-    {0.004439451f, 0.12440355f, -0.03838522f},
-    {0.10203278f, -0.46874952f, -0.009627081f},
-    {-0.103566356f, -0.47420114f, -0.018385574f},
-    {0.008927891f, 0.26235995f, -0.0115648955f},
-    {0.08724245f, -0.8956239f, -0.047055073f},
-    {-0.08451081f, -0.8942467f, -0.052947246f},
-    {0.0066633024f, 0.31839234f, -0.008709848f},
-    {0.1282968f, -0.95590985f, 0.074987344f},
-    {-0.11935069f, -0.95635235f, 0.07737604f},
-    {-0.006726882f, 0.53002787f, -0.042177428f},
-    {0.07836577f, 0.43239203f, -0.02760802f},
-    {-0.076290354f, 0.4308647f, -0.032417234f},
-    {0.0033863292f, 0.61896527f, 0.008232435f},
-    {0.20128717f, 0.47759712f, -0.04665402f},
-    {-0.18951866f, 0.47771794f, -0.040889304f},
-    {0.45661905f, 0.4619481f, -0.06960051f},
-    {-0.44964615f, 0.46334866f, -0.07215803f},
-    {0.7223283f, 0.4746462f, -0.07697524f},
-    {-0.7187546f, 0.47014236f, -0.0781848f},
-    {0.80901885f, 0.46401018f, -0.09256954f},
-    {-0.80750835f, 0.4614908f, -0.088291876f},
-};
-const int kParent[NJ] = {-1, 0, 0, 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 9, 9, 12, 13, 14, 16, 17, 18, 19, 20, 21};
+// zero-pose joints and the tree: mp_constants.cuh (tests/test_constants.py holds them to mobileposer_b200/config.py)
+const float kJZero[NJ][3] = MP_SMPL_J_ZERO_INIT;
+const int kParent[NJ] = MP_SMPL_PARENT_INIT;
 // joint_set.reduced without the root (config.py:134), deepest joints first, one kinematic chain after the other
 const int kOrd[NOPT] = {15, 12, 18, 16, 13, 19, 17, 14, 9, 6, 3, 4, 1, 5, 2};
 

@@ -254,23 +254,29 @@ def synthetic_dip(n_subjects=10, n_seq=5, frames=3000, combo='lw_rp'):
 
 @torch.no_grad()
 def evaluate_pose(model, dataset, num_past_frame=20, num_future_frame=5, evaluate_tran=False, verbose=True, smpl_file=None,
-                  mesh=None, batch_size=1):
+                  mesh=None, batch_size=1, return_online=False):
     """evaluate.py:39-107.  Returns the [n_sequences, 8, 2] offline rows in dataset order (on every rank); with
     `evaluate_tran=True` (evaluate.py:66-92, 105-106) a pair (rows, windows [n_sequences, 7]) and prints the reference's
     `[0, mean drift at 1 m, ..., at 7 m]` list.
+
+    With `ONLINE=1` in the environment (evaluate.py:62-64,97-99) the per-tick path is evaluated too and printed;
+    `return_online=True` appends its [n_sequences, 8, 2] rows to the returned tuple.
 
     `batch_size` = 1 is the reference's loop, one `forward_offline(x[None], [T])` per sequence (evaluate.py:56-58), the
     velocity head's state carried from sequence to sequence exactly as there.  `batch_size` > 1 (extension)
     runs that many sequences of the rank's shard per `forward_offline` call -- padded to the longest, true lengths passed --
     on the throughput kernels, with a fresh velocity state per sequence (SURVEY.md 8e option 1): pose, joint and contact rows
-    are the same, the two rows that see the translation (jitter, distance) are those of independent sequences."""
+    are the same, the two rows that see the translation (jitter, distance) are those of independent sequences.  Under
+    torch.distributed (world size > 1) every sequence starts from a fresh state too, whatever the batch size, so the table is
+    invariant to the number of ranks; the sequence-to-sequence carry is kept only for one process with `batch_size` = 1."""
     import torch.distributed as dist
     device = next(model.parameters()).device
     rank = dist.get_rank() if dist.is_initialized() else 0
     world = dist.get_world_size() if dist.is_initialized() else 1
     items = list(dataset)
     lengths = [it[0].shape[0] for it in items]
-    mine = shard_sequences(lengths, world)[rank]
+    shards = shard_sequences(lengths, world)
+    mine = shards[rank]
     evaluator = PoseEvaluator(smpl_file=smpl_file, mesh=mesh)
     model.eval()
     rows = []
@@ -278,12 +284,26 @@ def evaluate_pose(model, dataset, num_past_frame=20, num_future_frame=5, evaluat
     window_rows = []
     if batch_size < 1:
         raise ValueError(f'batch_size must be positive, got {batch_size}')
+    # The reference's loop carries the velocity head's (and the optimizer's) state from one sequence into the next (SURVEY.md
+    # F5); that chain only exists for ONE process walking the dataset in order.  Sharded or batched runs start every sequence
+    # from a fresh state, so the table does not depend on the world size, the shard order or the batch size.
+    fresh = world > 1 or batch_size > 1
+
+    def fresh_state():
+        if fresh:
+            if getattr(model, 'velocity', None) is not None:
+                model.velocity.rnn_state = None
+            opt = getattr(model, 'dynamics_optimizer', None)
+            if opt is not None:
+                opt.reset_states()
+
     batched = {}                                   # sequence index -> (pose_p [T,24,3,3], tran_p [T,3]) of the current group
     for pos, i in enumerate(mine):
         imu, pose_t, _, tran_t = items[i]
         x = imu.to(device)
         if batch_size == 1:
             model.reset()
+            fresh_state()
             pose_p, _, tran_p, _ = model.forward_offline(x.unsqueeze(0), [x.shape[0]])
         else:
             if i not in batched:                   # first sequence of a group: one forward for the whole group
@@ -293,6 +313,7 @@ def evaluate_pose(model, dataset, num_past_frame=20, num_future_frame=5, evaluat
                 for r, k in enumerate(group):
                     xb[r, :lens[r]] = items[k][0].to(device)
                 model.reset()
+                fresh_state()                      # also covers a trailing group of one, which takes the B == 1 path
                 pose_b, _, tran_b, _ = model.forward_offline(xb, lens)
                 pose_b = pose_b.view(len(group), max(lens), 24, 3, 3)
                 tran_b = tran_b.view(len(group), max(lens), 3)
@@ -304,29 +325,41 @@ def evaluate_pose(model, dataset, num_past_frame=20, num_future_frame=5, evaluat
         if evaluate_tran:
             window_rows.append(tran_window_errors(tran_p, tran_t)[0][0])
         if getenv("ONLINE"):
+            if fresh:
+                # batch_size == 1 and one process: the reset before forward_offline above is the reference's (evaluate.py:56);
+                # otherwise every sequence's ticks start from a reset window / root and a fresh velocity state
+                model.reset()
+                fresh_state()
             outs = [model.forward_online(f) for f in torch.cat((x, x[-1].repeat(num_future_frame, 1)))]
             pose_o = torch.stack([o[0] for o in outs])[num_future_frame:]
             tran_o = torch.stack([o[2] for o in outs])[num_future_frame:]
             online_rows.append(evaluator.eval(pose_o, pose_t, tran_p=tran_o, tran_t=tran_t))
-    local = torch.stack(rows) if rows else torch.zeros(0, 8, 2, device=device)
-    table = gather_rows(local, mine, len(items))
+    # ONE all-gather for everything this call reports: [offline 8x2 | online 8x2 | windows 7] per sequence
+    n_local = len(mine)
+    parts = [torch.stack(rows).reshape(n_local, 16) if rows else torch.zeros(0, 16, device=device)]
+    if getenv("ONLINE"):
+        parts.append(torch.stack(online_rows).reshape(n_local, 16) if online_rows else torch.zeros(0, 16, device=device))
+    if evaluate_tran:
+        parts.append(torch.stack(window_rows).reshape(n_local, 7) if window_rows else torch.zeros(0, 7, device=device))
+    gathered = gather_rows(torch.cat([p.to(device=device, dtype=torch.float32) for p in parts], dim=1), shards, len(items))
+    table = gathered[:, :16].reshape(-1, 8, 2)
+    col = 16
     if verbose and rank == 0:
         print('============== offline ================')
-        PoseEvaluator.print(table.nanmean(dim=0) if table.numel() else table)
+        PoseEvaluator.print(table.mean(dim=0) if table.numel() else table)       # evaluate.py:100 (mean, not nanmean)
     if getenv("ONLINE"):
-        lo = torch.stack(online_rows) if online_rows else torch.zeros(0, 8, 2, device=device)
-        online = gather_rows(lo, mine, len(items))
+        online = gathered[:, col:col + 16].reshape(-1, 8, 2)
+        col += 16
         if verbose and rank == 0:
             print('============== online ================')
-            PoseEvaluator.print(online.nanmean(dim=0))
+            PoseEvaluator.print(online.mean(dim=0))
     if evaluate_tran:
-        lw = torch.stack(window_rows) if window_rows else torch.zeros(0, 7, device=device)
-        windows = gather_rows(lw, mine, len(items))
+        windows = gathered[:, col:col + 7]
         if verbose and rank == 0:
             # evaluate.py:106 -- per window the mean over the sequences that have at least one pair
             print([0] + [windows[:, k][~torch.isnan(windows[:, k])].mean() for k in range(7)])
-        return table, windows
-    return table
+    out = [table] + ([windows] if evaluate_tran else []) + ([online] if (return_online and getenv("ONLINE")) else [])
+    return out[0] if len(out) == 1 else tuple(out)
 
 
 if __name__ == '__main__':

@@ -44,7 +44,7 @@ class PackedHead:
     def __init__(self):
         self.handle = None
         self.key = None
-        self._keep = None
+        self.generation = 0      # bumps on every repack: a freed-and-reallocated handle can come back at the same address
 
     def get(self, rnn: 'RNN') -> int:
         params = rnn.weight_tensors()
@@ -72,6 +72,7 @@ class PackedHead:
         with torch.cuda.device(first.device):
             _cabi.check(lib.mp_rnn_create(C.byref(out), C.byref(w), current_stream_ptr(first.device)), 'mp_rnn_create')
         self.handle, self.key = out.value, key
+        self.generation += 1
         return self.handle
 
     def close(self):
@@ -106,6 +107,10 @@ class RNN(nn.Module):
 
     def packed_handle(self) -> int:
         return self._packed.get(self)
+
+    def packed_key(self):
+        """(handle, generation): what caches built on top of the handle (mp_net graphs) must be keyed on."""
+        return self._packed.get(self), self._packed.generation
 
     @torch.no_grad()
     def forward(self, x, seq_lengths=None, h=None, x2=None):

@@ -103,13 +103,13 @@ class MobilePoserNet(nn.Module):
 
     def _net_handle(self):
         heads = (self.joints.joints, self.pose.pose, self.foot_contact.footcontact, self.velocity.vel)
-        handles = tuple(h.packed_handle() for h in heads)
-        if self._net is None or handles != self._net_key:
+        keys = tuple(h.packed_key() for h in heads)      # (handle, generation): see PackedHead.generation
+        if self._net is None or keys != self._net_key:
             self._close_net()
             out = C.c_void_p()
             with torch.cuda.device(self._device()):
-                _cabi.check(_cabi.lib().mp_net_create(C.byref(out), *handles), 'mp_net_create')
-            self._net, self._net_key = out.value, handles
+                _cabi.check(_cabi.lib().mp_net_create(C.byref(out), *[k[0] for k in keys]), 'mp_net_create')
+            self._net, self._net_key = out.value, keys
             self._slots = {}
             self._net_physics = None
             _cabi.check(_cabi.lib().mp_net_set_rec_tile(self._net, int(self.rec_tile)), 'mp_net_set_rec_tile')
@@ -294,9 +294,10 @@ class MobilePoserNet(nn.Module):
         st = self._online_state(1, data.device)
         pose, joints, root, contact = st.step(data.reshape(1, 60))
         self.imu = st.window[0]
+        pose = self._out(pose[0])             # a fresh tensor per tick like the reference's (the state's buffer is rewritten by the next tick)
         if self.dynamics_optimizer is not None:
-            return pose[0].view(24, 3, 3), joints[0], root[0].clone(), contact[0]      # net.py:216-217
-        return pose[0].view(24, 9), joints[0], root[0].clone(), contact[0]
+            return pose.view(24, 3, 3), joints[0], root[0].clone(), contact[0]      # net.py:216-217
+        return pose.view(24, 9), joints[0], root[0].clone(), contact[0]
 
     @torch.no_grad()
     def forward_online_batch(self, frames):
@@ -304,7 +305,7 @@ class MobilePoserNet(nn.Module):
         _require_cuda(frames, 'input frames')
         st = self._online_state(frames.shape[0], frames.device)
         pose, joints, root, contact = st.step(frames)
-        return pose.view(-1, 24, 9), joints, root.clone(), contact
+        return self._out(pose).view(-1, 24, 9), joints, root.clone(), contact
 
     @property
     def last_root_pos(self):
@@ -392,10 +393,10 @@ class HostOffline:
         self.net, self.B, self.T = net, B, T
         self.dev = device or net._device()
         heads = (net.joints.joints, net.pose.pose, net.foot_contact.footcontact, net.velocity.vel)
-        self._heads_key = tuple(h.packed_handle() for h in heads)
+        self._heads_key = tuple(h.packed_key() for h in heads)
         out = C.c_void_p()
         with torch.cuda.device(self.dev):
-            _cabi.check(lib.mp_net_create(C.byref(out), *self._heads_key), 'mp_net_create')
+            _cabi.check(lib.mp_net_create(C.byref(out), *[k[0] for k in self._heads_key]), 'mp_net_create')
             self.handle = out.value
             _cabi.check(lib.mp_net_set_rec_tile(self.handle, int(rec_tile)), 'mp_net_set_rec_tile')
             self.stream = torch.cuda.Stream(self.dev)
@@ -438,7 +439,7 @@ class HostOffline:
         if tuple(imu_host.shape) != (self.B, self.T, 60):
             raise ValueError(f'expected {(self.B, self.T, 60)}, got {tuple(imu_host.shape)}')
         heads = (self.net.joints.joints, self.net.pose.pose, self.net.foot_contact.footcontact, self.net.velocity.vel)
-        if tuple(h.packed_handle() for h in heads) != self._heads_key:
+        if tuple(h.packed_key() for h in heads) != self._heads_key:
             raise RuntimeError('the parameters of the net changed after this HostOffline was built; build a new one')
         lens_ptr = None
         if input_lengths is not None:
@@ -469,8 +470,10 @@ class HostOffline:
         self._sync_physics()
         # the net's CUDA graph is keyed on its pointers: stage the batch in this slot's own buffer (a device-to-device copy of
         # B*T*240 bytes on the slot's stream) so that every call after the second replays the graph, whatever tensor comes in
+        self.stream.wait_stream(torch.cuda.current_stream(self.dev))     # whoever produced imu_dev on the caller's stream
         with torch.cuda.stream(self.stream):
             self.d_imu.copy_(imu_dev, non_blocking=True)
+        imu_dev.record_stream(self.stream)
         with torch.cuda.device(self.dev):
             _cabi.check(_cabi.lib().mp_net_forward(
                 self.handle, self.d_imu.data_ptr(), self.B, self.T, None, None, None, self.d_hn.data_ptr(), self.d_cn.data_ptr(),

@@ -25,32 +25,35 @@ def shard_sequences(lengths: Sequence[int], world_size: int) -> List[List[int]]:
     return [sorted(s) for s in shards]
 
 
-def gather_rows(local_rows: torch.Tensor, local_ids: Sequence[int], n_total: int, group=None) -> torch.Tensor:
+def gather_rows(local_rows: torch.Tensor, shards, n_total: int, group=None) -> torch.Tensor:
     """All-gather per-sequence rows [n_local, ...] into dataset order [n_total, ...] on every rank.
 
-    One `all_gather_into_tensor` of a padded block plus the ids; rows of sequences nobody owned stay NaN."""
+    `shards` is the whole partition (`shard_sequences(lengths, world)`: every rank computes the same one from the lengths it
+    already has), so neither ids nor counts travel: the exchange is ONE `all_gather_into_tensor` of a fixed
+    [max shard size, ...] block per rank.  A flat list of ids is accepted for a single process.
+    Rows of sequences nobody owned stay NaN."""
     import torch.distributed as dist
     world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    if len(shards) == 0 or not isinstance(shards[0], (list, tuple)):
+        shards = [list(shards)]
+    if len(shards) != world:
+        raise ValueError(f'gather_rows: partition has {len(shards)} shards for a world of {world}')
+    if local_rows.shape[0] != len(shards[rank]):
+        raise ValueError(f'gather_rows: rank {rank} holds {local_rows.shape[0]} rows for a shard of {len(shards[rank])}')
     feat = tuple(local_rows.shape[1:])
-    out = torch.full((n_total,) + feat, float('nan'), dtype=local_rows.dtype, device=local_rows.device)
-    ids = torch.as_tensor(list(local_ids), dtype=torch.int64, device=local_rows.device)
+    dev = local_rows.device
+    out = torch.full((n_total,) + feat, float('nan'), dtype=local_rows.dtype, device=dev)
     if world == 1:
-        out[ids] = local_rows
+        out[torch.as_tensor(shards[0], dtype=torch.int64, device=dev)] = local_rows
         return out
-    n_max = (n_total + world - 1) // world
-    n_max = max(n_max, 1)
-    counts = torch.tensor([len(local_ids)], dtype=torch.int64, device=local_rows.device)
-    all_counts = torch.empty(world, dtype=torch.int64, device=local_rows.device)
-    dist.all_gather_into_tensor(all_counts, counts, group=group)
-    n_max = int(all_counts.max().item())
-    pad_rows = torch.zeros((n_max,) + feat, dtype=local_rows.dtype, device=local_rows.device)
-    pad_rows[:len(local_ids)] = local_rows
-    pad_ids = torch.full((n_max,), -1, dtype=torch.int64, device=local_rows.device)
-    pad_ids[:len(local_ids)] = ids
-    g_rows = torch.empty((world * n_max,) + feat, dtype=local_rows.dtype, device=local_rows.device)
-    g_ids = torch.empty(world * n_max, dtype=torch.int64, device=local_rows.device)
-    dist.all_gather_into_tensor(g_rows, pad_rows, group=group)
-    dist.all_gather_into_tensor(g_ids, pad_ids, group=group)
-    keep = g_ids >= 0
-    out[g_ids[keep]] = g_rows[keep]
+    n_max = max(1, max(len(s) for s in shards))
+    block = torch.zeros((n_max,) + feat, dtype=local_rows.dtype, device=dev)
+    block[:local_rows.shape[0]] = local_rows
+    gathered = torch.empty((world * n_max,) + feat, dtype=local_rows.dtype, device=dev)
+    dist.all_gather_into_tensor(gathered, block, group=group)
+    gathered = gathered.view((world, n_max) + feat)
+    for r, ids in enumerate(shards):
+        if ids:
+            out[torch.as_tensor(ids, dtype=torch.int64, device=dev)] = gathered[r, :len(ids)]
     return out

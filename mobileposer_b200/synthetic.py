@@ -69,3 +69,18 @@ def synthetic_imu_batch(seq_ids, T: int, combo: str = 'lw_rp', base_seed: int = 
 def synthetic_imu(seq_id: int, T: int, combo: str = 'lw_rp', base_seed: int = BASE_SEED) -> torch.Tensor:
     """Return one [T, 60] float32 window."""
     return synthetic_imu_batch([seq_id], T, combo, base_seed)[0]
+
+
+def well_conditioned_state_dict(state_dict: dict) -> dict:
+    """A seeded state_dict whose pose head emits r6d columns near (1,0,0 | 0,1,0), like a trained model does.
+
+    With the default random init the pose head's r6d columns have norm ~0.05 (down to 0.005 for the orthogonal part),
+    so the Gram-Schmidt step of net.py:93-99 amplifies fp32 round-off by up to 200x and the reference's own fp32
+    result sits > 1e-4 rad from a float64 evaluation.  Setting `pose.pose.linear2.bias` to [1,0,0,0,1,0] x 16 and
+    scaling `pose.pose.linear2.weight` by 0.1 keeps every other tensor of the seeded init and makes the r6d -> rotation
+    step well conditioned, so the north star's flat 1e-4 rad can be held on every (frame, joint).  The same dict is
+    loaded into the live reference (oracle/make_golden.py, fixtures `wc_*`) and into the CUDA net."""
+    sd = {k: v.clone() for k, v in state_dict.items()}
+    sd['pose.pose.linear2.bias'] = torch.tensor([1.0, 0, 0, 0, 1.0, 0] * 16, dtype=torch.float32)
+    sd['pose.pose.linear2.weight'] = sd['pose.pose.linear2.weight'] * 0.1
+    return sd

@@ -39,10 +39,10 @@ from mobileposer_b200.config import (HEAD_PREFIX, HEAD_SHAPES, FLOOR_Y, SMPL_J_Z
 class _Head:
     """One RNN head rebuilt from state_dict tensors (rnn.py:13-18)."""
 
-    def __init__(self, sd, prefix, n_in, n_out, hidden, bidir):
+    def __init__(self, sd, prefix, n_in, n_out, hidden, bidir, dtype=torch.float32):
         self.w1, self.b1 = sd[prefix + 'linear1.weight'], sd[prefix + 'linear1.bias']
         self.w2, self.b2 = sd[prefix + 'linear2.weight'], sd[prefix + 'linear2.bias']
-        self.lstm = torch.nn.LSTM(hidden, hidden, num_layers=2, bidirectional=bidir)
+        self.lstm = torch.nn.LSTM(hidden, hidden, num_layers=2, bidirectional=bidir).to(dtype)
         self.lstm.load_state_dict({k[len(prefix) + 4:]: v for k, v in sd.items()
                                    if k.startswith(prefix + 'rnn.')})
         self.lstm.eval()
@@ -58,11 +58,16 @@ class _Head:
 
 
 class OraclePoser:
-    """CPU port of MobilePoserNet's inference surface for a given state_dict."""
+    """CPU port of MobilePoserNet's inference surface for a given state_dict.
 
-    def __init__(self, state_dict):
-        sd = {k: v.detach().to(torch.float32).cpu() for k, v in state_dict.items()}
-        self.heads = {name: _Head(sd, HEAD_PREFIX[name], *HEAD_SHAPES[name]) for name in HEAD_SHAPES}
+    dtype=torch.float64 evaluates the same torch kernels in double precision (inputs must be double too): the arbiter
+    between two fp32 implementations at sizes where the numpy statement (np_port.py) is too slow.  Only `forward` and
+    the heads are meant to be used in that mode."""
+
+    def __init__(self, state_dict, dtype=torch.float32):
+        sd = {k: v.detach().to(dtype).cpu() for k, v in state_dict.items()}
+        self.dtype = dtype
+        self.heads = {name: _Head(sd, HEAD_PREFIX[name], *HEAD_SHAPES[name], dtype=dtype) for name in HEAD_SHAPES}
         self.j = torch.tensor(SMPL_J_ZERO, dtype=torch.float32)
         self.floor_y = FLOOR_Y
         self.vel_state = None           # Velocity.rnn_state (velocity.py:30,45-48)
@@ -145,13 +150,13 @@ def reduced_global_to_full(r6d):
     """net.py:93-99: r6d [*, 96] -> local rotations [N, 24, 3, 3]."""
     glb16 = r6d_to_matrix(r6d).view(-1, joint_set.n_reduced, 3, 3)
     n = glb16.shape[0]
-    glb = torch.eye(3).repeat(n, 24, 1, 1)
+    glb = torch.eye(3, dtype=r6d.dtype).repeat(n, 24, 1, 1)
     glb[:, joint_set.reduced] = glb16
     loc = torch.empty_like(glb)
     loc[:, 0] = glb[:, 0]
     for i in range(1, 24):
         loc[:, i] = glb[:, SMPL_PARENT[i]].transpose(1, 2) @ glb[:, i]
-    loc[:, joint_set.ignored] = torch.eye(3)
+    loc[:, joint_set.ignored] = torch.eye(3, dtype=r6d.dtype)
     loc[:, 0] = glb[:, 0]
     return loc
 

@@ -49,3 +49,33 @@ def seeded_state_dict():
 def oracle(seeded_state_dict):
     from oracle.torch_port import OraclePoser
     return OraclePoser(seeded_state_dict)
+
+
+@pytest.fixture(scope='session')
+def oracle64(seeded_state_dict):
+    """The same torch CPU kernels in float64: the arbiter between the reference's fp32 result and the CUDA path."""
+    from oracle.torch_port import OraclePoser
+    return OraclePoser(seeded_state_dict, dtype=torch.float64)
+
+
+@pytest.fixture(scope='session')
+def wc_state_dict(seeded_state_dict, manifest):
+    """Well-conditioned seeded weights (synthetic.well_conditioned_state_dict), hash-pinned to what the live reference loaded."""
+    import hashlib
+    from mobileposer_b200.synthetic import well_conditioned_state_dict
+    sd = well_conditioned_state_dict(seeded_state_dict)
+    for k, h in manifest['wc_weight_sha256'].items():
+        assert hashlib.sha256(sd[k].contiguous().numpy().tobytes()).hexdigest() == h, k
+    return sd
+
+
+@pytest.fixture(scope='session')
+def wc_oracle(wc_state_dict):
+    from oracle.torch_port import OraclePoser
+    return OraclePoser(wc_state_dict)
+
+
+@pytest.fixture(scope='session')
+def wc_oracle64(wc_state_dict):
+    from oracle.torch_port import OraclePoser
+    return OraclePoser(wc_state_dict, dtype=torch.float64)

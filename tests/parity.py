@@ -78,3 +78,21 @@ def angle_excess(pose, pose_ref, r6d_ref):
     tol = angle_tolerance(r6d_ref)
     err = geodesic(pose.detach().cpu().reshape(-1, 24, 3, 3), pose_ref.detach().cpu().reshape(-1, 24, 3, 3))
     return (err / tol).max().item(), (tol <= ANGLE_TOL).double().mean().item(), err.max().item()
+
+
+def f64_pose(oracle64, imu, lens):
+    """Local rotations [B*T, 24, 3, 3] of the float64 evaluation (joints head -> pose head -> K5, all in double)."""
+    x = imu.double()
+    joints = oracle64.heads['joints'](x, lens)[0]
+    r6d = oracle64.heads['pose'](torch.cat((joints, x), dim=-1), lens)[0]
+    from oracle.torch_port import reduced_global_to_full
+    return reduced_global_to_full(r6d)
+
+
+def angle_report(pose, pose_ref, pose_f64, what=''):
+    """(|cuda - ref|, |ref - f64|, |cuda - f64|) max joint-angle errors in rad; printed so the GPU log carries them."""
+    shape = (-1, 24, 3, 3)
+    p, r, d = (t.detach().cpu().reshape(shape) for t in (pose, pose_ref, pose_f64))
+    e_cr, e_rd, e_cd = geodesic(p, r).max().item(), geodesic(r, d).max().item(), geodesic(p, d).max().item()
+    print(f'[angle] {what}: |cuda-ref| {e_cr:.3e}  |ref-f64| {e_rd:.3e}  |cuda-f64| {e_cd:.3e} rad')
+    return e_cr, e_rd, e_cd

@@ -136,3 +136,119 @@ def test_evaluate_pose_with_translation_windows(capsys):
     _, _, tran_p, _ = net.forward_offline(items[0][0].to(DEV).unsqueeze(0), [200])
     e, _ = tran_window_errors(tran_p, items[0][3])
     assert torch.equal(torch.nan_to_num(e[0], nan=-1.0), torch.nan_to_num(windows[0], nan=-1.0))
+
+
+class _OracleNet(torch.nn.Module):
+    """The CPU oracle behind the surface evaluate_pose drives (reset / forward_offline / forward_online), so the very same
+    evaluate_pose code walks the reference's restatement and the CUDA net."""
+
+    def __init__(self, state_dict):
+        super().__init__()
+        from oracle.torch_port import OraclePoser
+        self.w = torch.nn.Parameter(torch.zeros(1))
+        self.o = o = OraclePoser(state_dict)
+
+        class _Velocity:                     # evaluate_pose clears `model.velocity.rnn_state` in sharded / batched runs
+            rnn_state = property(lambda self: o.vel_state, lambda self, v: setattr(o, 'vel_state', v))
+        self.velocity = _Velocity()
+
+    def reset(self):
+        self.o.reset()
+
+    def forward_offline(self, x, lengths):
+        return self.o.forward_offline(x, lengths)
+
+    def forward_online(self, f):
+        return self.o.forward_online(f)
+
+
+def test_evaluate_pose_online_against_the_oracle(wc_state_dict, monkeypatch):
+    """ONLINE=1 (evaluate.py:62-64,97-99): per-tick poses are kept across ticks and stacked -- every tick must hand out its own
+    tensor (the reference does) -- and the offline + online tables equal the ones the same loop produces over the CPU oracle,
+    including the velocity-state chain from the offline call into the ticks and across sequences."""
+    import mobileposer_b200 as mp
+    from mobileposer_b200.evaluate import evaluate_pose, synthetic_dip
+    monkeypatch.setenv('ONLINE', '1')
+    items = synthetic_dip(n_subjects=1, n_seq=2, frames=48)
+    net = mp.MobilePoserNet()
+    net.load_state_dict(wc_state_dict)
+    net = net.to(DEV).eval()
+    table, online = evaluate_pose(net, items, verbose=False, return_online=True)
+    o_table, o_online = evaluate_pose(_OracleNet(wc_state_dict), items, verbose=False, return_online=True)
+    rows = [0, 1, 2, 3, 4, 7]                      # all but the mesh row (NaN without a template) and jitter (below)
+    for got, want, what in ((table, o_table, 'offline'), (online, o_online, 'online')):
+        got = got.cpu()
+        assert torch.isfinite(got[:, rows]).all(), what
+        assert torch.allclose(got[:, rows], want[:, rows], rtol=2e-3, atol=2e-3), (what, (got[:, rows] - want[:, rows]).abs().max())
+        # jitter = third differences x fps^3: amplifies fp32 round-off of the joint positions by 2.7e4
+        assert torch.allclose(got[:, 6], want[:, 6], rtol=5e-2, atol=1e-3), what
+    # the online rows are not the last tick repeated: poses differ along the sequence
+    ticks = [net.forward_online(f)[0] for f in items[0][0][:6].to(DEV)]
+    assert not torch.equal(ticks[0], ticks[-1]) and ticks[0].data_ptr() != ticks[-1].data_ptr()
+
+
+def test_evaluate_pose_batched_on_the_gpu_equals_the_loop_with_fresh_state(wc_state_dict):
+    """evaluate_pose(batch_size=3) on the device: ragged groups through batched forward_offline (throughput kernels) give the
+    rows of independent sequences -- the loop with the velocity state cleared before every call."""
+    import mobileposer_b200 as mp
+    from mobileposer_b200.evaluate import evaluate_pose, synthetic_dip
+    items = [it for n in (70, 64, 90, 75) for it in synthetic_dip(n_subjects=1, n_seq=1, frames=n)]
+    items = [(imu + 0.001 * k, *rest) for k, (imu, *rest) in enumerate(items)]
+    net = mp.MobilePoserNet()
+    net.load_state_dict(wc_state_dict)
+    net = net.to(DEV).eval()
+    batched = evaluate_pose(net, items, verbose=False, batch_size=3).cpu()
+    rows = []
+    for it in items:
+        net.velocity.rnn_state = None
+        rows.append(evaluate_pose(net, [it], verbose=False)[0].cpu())
+    net.velocity.rnn_state = None
+    loop = torch.stack(rows)
+    keep = [0, 1, 2, 3, 4, 7]
+    assert torch.allclose(batched[:, keep], loop[:, keep], rtol=2e-3, atol=2e-3)
+    assert torch.allclose(batched[:, 6], loop[:, 6], rtol=5e-2, atol=1e-3)
+
+
+@pytest.mark.parametrize('wrapped', [False, True])
+def test_load_model_reads_both_on_disk_formats(tmp_path, wc_state_dict, wrapped):
+    """utils/model_utils.py:6-15: a plain state_dict `.pth` (what combine_weights.py writes) and a Lightning-style checkpoint
+    with the weights under 'state_dict'; the loaded model computes with those weights."""
+    import mobileposer_b200 as mp
+    from mobileposer_b200.model_utils import load_model
+    from mobileposer_b200.synthetic import synthetic_imu
+    path = str(tmp_path / ('ckpt.pth' if wrapped else 'weights.pth'))
+    torch.save({'state_dict': wc_state_dict, 'epoch': 3} if wrapped else wc_state_dict, path)
+    model = load_model(path)
+    assert isinstance(model, mp.MobilePoserNet) and next(model.parameters()).is_cuda
+    for k, v in model.state_dict().items():
+        assert torch.equal(v.cpu(), wc_state_dict[k]), k
+    ref = mp.MobilePoserNet()
+    ref.load_state_dict(wc_state_dict)
+    ref = ref.to(DEV).eval()
+    x = synthetic_imu(5, 40)[None].to(DEV)
+    a, b = model.forward_offline(x, [40]), ref.forward_offline(x, [40])
+    assert all(torch.equal(p, q) for p, q in zip(a, b))
+
+
+def test_weights_changed_in_place_invalidate_the_packed_net(seeded_state_dict, wc_state_dict):
+    """load_state_dict after a forward: the packed heads are rebuilt (a new mp_rnn may land at the freed handle's address),
+    and the mp_net with its captured graphs must be rebuilt with them -- keyed on (handle, generation)."""
+    import mobileposer_b200 as mp
+    from mobileposer_b200.synthetic import synthetic_imu
+    x = synthetic_imu(6, 32)[None].to(DEV)
+    net = mp.MobilePoserNet()
+    net.load_state_dict(seeded_state_dict)
+    net = net.to(DEV).eval()
+    for _ in range(3):                               # eager, capture, replay
+        net.velocity.rnn_state = None
+        before = [t.clone() for t in net.forward_offline(x, [32])]
+    net.load_state_dict(wc_state_dict)
+    for _ in range(3):
+        net.velocity.rnn_state = None
+        after = [t.clone() for t in net.forward_offline(x, [32])]
+    fresh = mp.MobilePoserNet()
+    fresh.load_state_dict(wc_state_dict)
+    fresh = fresh.to(DEV).eval()
+    want = fresh.forward_offline(x, [32])
+    assert not torch.equal(before[0], after[0])
+    assert all(torch.equal(p, q) for p, q in zip(after, want))

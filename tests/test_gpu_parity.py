@@ -10,8 +10,8 @@ import pytest
 import torch
 
 from conftest import load_golden
-from parity import (ANGLE_TOL, R6D_TOL, TRAN_TOL, VALUE_TOL, angle_excess, argmax_equal, max_abs, max_angle,
-                    min_margin)
+from parity import (ANGLE_TOL, R6D_TOL, TRAN_TOL, VALUE_TOL, angle_excess, angle_report, argmax_equal, f64_pose, max_abs,
+                    max_angle, min_margin)
 
 pytestmark = pytest.mark.gpu
 
@@ -57,15 +57,32 @@ def cuda_r6d(net, imu, lens):
     return net.pose.pose(joints, lens, None, x2=imu)[0]
 
 
-def check_pose_tran(pose, tran, contact, g_pose, g_tran, g_contact, what='', r6d_ref=None):
+def check_angles(pose, g_pose, r6d_ref, what='', f64=None):
+    """Random-init weights (K5 ill-conditioned, tests/parity.py): 1e-4 rad wherever the Gram-Schmidt step is well conditioned,
+    scaled by its conditioning elsewhere; the worst error and the share of (frame, joint) pairs held to the flat 1e-4 are
+    printed, and with a float64 evaluation at hand (`f64` = (oracle64, imu, lens)) the worst error must stay within 3x the
+    reference's own distance to it.  The flat gate itself is held with well-conditioned weights in test_gpu_parity_flat.py."""
+    excess, flat_fraction, worst = angle_excess(pose, g_pose, r6d_ref)
+    print(f'[angle] {what}: worst |cuda-ref| {worst:.3e} rad, {100 * flat_fraction:.1f} % of (frame, joint) pairs held to the flat 1e-4, '
+          f'worst error / tolerance {excess:.2f}')
+    assert excess <= 1.0, f'{what}: joint angle error {excess:.2f}x its tolerance (max {worst:.3e} rad)'
+    if f64 is not None:
+        o64, imu, lens = f64
+        p64 = f64_pose(o64, imu, lens).view(len(lens), -1, 24, 3, 3)
+        keep = torch.zeros(p64.shape[:2], dtype=torch.bool)
+        for b, L in enumerate(lens):
+            keep[b, :L] = True
+        sel = lambda t: t.detach().cpu().reshape(p64.shape)[keep]
+        e_cr, e_rd, e_cd = angle_report(sel(pose), sel(g_pose), p64[keep], what)
+        assert e_cr <= max(ANGLE_TOL, 3.0 * e_rd), f'{what}: |cuda-ref| {e_cr:.3e} rad > 3 x |ref-f64| {e_rd:.3e}'
+
+
+def check_pose_tran(pose, tran, contact, g_pose, g_tran, g_contact, what='', r6d_ref=None, f64=None):
     if r6d_ref is None:
         a = max_angle(pose, g_pose)
         assert a <= ANGLE_TOL, f'{what}: max joint angle error {a:.3e} rad'
     else:
-        # 1e-4 rad wherever the Gram-Schmidt step is well conditioned, scaled by its conditioning elsewhere
-        # (tests/parity.py explains why random-init weights need this)
-        excess, flat_fraction, worst = angle_excess(pose, g_pose, r6d_ref)
-        assert excess <= 1.0, f'{what}: joint angle error {excess:.2f}x its tolerance (max {worst:.3e} rad)'
+        check_angles(pose, g_pose, r6d_ref, what, f64)
     if tran is not None:
         t = max_abs(tran, g_tran)
         assert t <= TRAN_TOL, f'{what}: max translation error {t:.3e} m'
@@ -79,7 +96,7 @@ def test_cfg1_joints_head(net):
     assert max_abs(y[0], g['joints']) <= VALUE_TOL
 
 
-def test_cfg2_forward_and_offline(net, oracle):
+def test_cfg2_forward_and_offline(net, oracle, oracle64):
     g = load_golden('cfg2_forward_T300')
     x = g['imu'][None].to(DEV)
     r6d_ref = reference_r6d(oracle, g['imu'][None], [300])
@@ -88,7 +105,7 @@ def test_cfg2_forward_and_offline(net, oracle):
     pose, joints, vel, contact = net.forward(x, [300])
     assert pose.shape == (300, 24, 3, 3) and joints.shape == (1, 300, 72) and vel.shape == (300, 72)
     assert contact.shape == (1, 300, 2)
-    check_pose_tran(pose, None, contact[0], g['pose'], None, g['contact'], 'forward', r6d_ref)
+    check_pose_tran(pose, None, contact[0], g['pose'], None, g['contact'], 'forward', r6d_ref, (oracle64, g['imu'][None], [300]))
     assert max_abs(joints[0], g['joints']) <= VALUE_TOL and max_abs(vel, g['vel']) <= VALUE_TOL
     assert max_abs(contact[0], g['contact']) <= VALUE_TOL
     hn, cn = net.velocity.rnn_state
@@ -101,7 +118,7 @@ def test_cfg2_forward_and_offline(net, oracle):
     check_pose_tran(pose, tran, contact, g['pose'], g['tran'], g['contact'], 'forward_offline', r6d_ref)
 
 
-def test_ragged_batch(net, oracle):
+def test_ragged_batch(net, oracle, oracle64):
     g = load_golden('ragged_forward_B3')
     lens = g['lengths'].tolist()
     r6d_ref = reference_r6d(oracle, g['imu'], lens)
@@ -110,7 +127,7 @@ def test_ragged_batch(net, oracle):
     # padded frames included: the reference leaves linear2.bias there (pad_packed_sequence zero-fills first)
     assert max_abs(joints, g['joints']) <= VALUE_TOL and max_abs(vel, g['vel']) <= VALUE_TOL
     assert max_abs(contact, g['contact']) <= VALUE_TOL
-    assert angle_excess(pose, g['pose'], r6d_ref)[0] <= 1.0
+    check_angles(pose, g['pose'], r6d_ref, 'ragged B3', (oracle64, g['imu'], lens))
     for b, L in enumerate(lens):
         assert argmax_equal(contact[b, :L], g['contact'][b, :L])
     hn, cn = net.velocity.rnn_state
@@ -207,12 +224,13 @@ def test_k7_unit_online_state_machine():
         assert max_abs(pose_out[0].view(24, 9), g['pose'][k]) <= 1e-5, k
 
 
-def test_batch_equals_independent_reference_calls(net, oracle):
+def test_batch_equals_independent_reference_calls(net, oracle, oracle64):
     g = load_golden('batch8_T64')
     r6d_ref = reference_r6d(oracle, g['imu'], [64] * 8)
     pose, joints, tran, contact = net.forward_offline(g['imu'].to(DEV), [64] * 8)
     assert pose.shape == (8 * 64, 24, 3, 3) and tran.shape == (8, 64, 3)
-    check_pose_tran(pose.view(8, 64, 24, 3, 3), tran, contact, g['pose'], g['tran'], g['contact'], 'batch8', r6d_ref)
+    check_pose_tran(pose.view(8, 64, 24, 3, 3), tran, contact, g['pose'], g['tran'], g['contact'], 'batch8', r6d_ref,
+                    (oracle64, g['imu'], [64] * 8))
     assert max_abs(joints, g['joints']) <= VALUE_TOL
 
 
@@ -229,7 +247,7 @@ def test_batch_equals_independent_reference_calls(net, oracle):
     dict(MP_REC_IMPL='tc', MP_REC_NB=11),                # tcgen05 recurrence, one ragged tile
     dict(MP_REC_IMPL='ffma', MP_REC_NB=8),               # FFMA throughput path pinned
 ])
-def test_recurrence_variants_against_oracle(net, oracle, env, variant):
+def test_recurrence_variants_against_oracle(net, oracle, oracle64, env, variant):
     from mobileposer_b200.synthetic import synthetic_imu_batch
     env(**variant)
     lens = [40, 9, 33, 40, 1, 17, 25, 40, 38, 2, 31]
@@ -253,14 +271,14 @@ def test_recurrence_variants_against_oracle(net, oracle, env, variant):
     oracle.vel_state = None
     assert max_abs(joints, o_joints) <= VALUE_TOL and max_abs(vel, o_vel) <= VALUE_TOL
     assert max_abs(contact, o_contact) <= VALUE_TOL
-    assert angle_excess(pose, o_pose, reference_r6d(oracle, x, lens))[0] <= 1.0
+    check_angles(pose, o_pose, reference_r6d(oracle, x, lens), f'variant {variant}', (oracle64, x, lens))
     assert max_abs(state[0], o_state[0]) <= VALUE_TOL and max_abs(state[1], o_state[1]) <= VALUE_TOL
     assert max_abs(vel2, o_vel2) <= VALUE_TOL
     for b, L in enumerate(lens):
         assert argmax_equal(contact[b, :L], o_contact[b, :L])
 
 
-def test_large_ragged_batch_on_the_64_sequence_tiles(net, oracle, env):
+def test_large_ragged_batch_on_the_64_sequence_tiles(net, oracle, oracle64, env):
     """B = 150 >= 128 takes the automatic 64-sequences-per-cluster policy (3 tiles of 50, N = 64): ragged lengths, carried
     velocity state, against the oracle and against the FFMA path."""
     from mobileposer_b200.synthetic import synthetic_imu_batch
@@ -285,7 +303,7 @@ def test_large_ragged_batch_on_the_64_sequence_tiles(net, oracle, env):
         net.set_graph(True)
         net.velocity.rnn_state = None
     assert max_abs(joints, o_joints) <= VALUE_TOL and max_abs(vel, o_vel) <= VALUE_TOL and max_abs(contact, o_contact) <= VALUE_TOL
-    assert angle_excess(pose, o_pose, reference_r6d(oracle, x, lens))[0] <= 1.0
+    check_angles(pose, o_pose, reference_r6d(oracle, x, lens), 'B=150 ragged', (oracle64, x, lens))
     assert max_abs(joints, joints_f) <= 2e-6 and max_abs(vel, vel_f) <= 2e-6 and max_abs(contact, contact_f) <= 2e-6
     for b, L in enumerate(lens):
         assert argmax_equal(contact[b, :L], o_contact[b, :L])
@@ -354,7 +372,7 @@ def test_graph_replay_is_bitwise_identical(net):
 
 
 # ---- BASELINE.json sizes: properties --------------------------------------------------------------------
-def test_cfg3_batch256_is_batch_invariant_and_matches_oracle(net, oracle):
+def test_cfg3_batch256_is_batch_invariant_and_matches_oracle(net, oracle, oracle64):
     from mobileposer_b200.synthetic import synthetic_imu_batch
     ids = list(range(1000, 1256))
     x = synthetic_imu_batch(ids, 300)
@@ -370,18 +388,28 @@ def test_cfg3_batch256_is_batch_invariant_and_matches_oracle(net, oracle):
     for b in (0, 101, 255):
         net.velocity.rnn_state = None
         p1, j1, t1, c1 = net.forward_offline(xd[b:b + 1], [300])
-        assert angle_excess(p1, pose[b], reference_r6d(oracle, x[b:b + 1], [300]))[0] <= 1.0
+        check_angles(p1, pose[b], reference_r6d(oracle, x[b:b + 1], [300]), f'cfg3 seq {b} alone vs in the batch')
         assert max_abs(t1, tran[b]) <= TRAN_TOL
         assert max_abs(j1[0], joints[b]) <= VALUE_TOL and argmax_equal(c1, contact[b])
-    # ... and the oracle agrees on a sample of them
-    for b in (3, 200):
-        oracle.vel_state = None
-        op, oj, ot, oc = oracle.forward_offline(x[b:b + 1], [300])
-        check_pose_tran(pose[b], tran[b], contact[b], op, ot, oc, f'cfg3 seq {b}', reference_r6d(oracle, x[b:b + 1], [300]))
+    # ... and the oracle agrees on ALL 256 of them (one batched CPU forward: packed sequences are independent; K6 per sequence)
+    from oracle.torch_port import offline_translation
+    oracle.vel_state = None
+    op, oj, ov, oc = oracle.forward(x, [300] * 256)
+    oracle.vel_state = None
+    r6d_ref = reference_r6d(oracle, x, [300] * 256)
+    check_angles(pose, op, r6d_ref, 'cfg3 all 256 sequences', (oracle64, x, [300] * 256))
+    assert max_abs(joints, oj) <= VALUE_TOL and max_abs(contact, oc) <= VALUE_TOL
+    assert argmax_equal(contact, oc), f'cfg3: contact argmax differs (min margin {min_margin(oc):.3e})'
+    worst_t = 0.0
+    for b in range(256):
+        ot = offline_translation(oj[b], ov[b], oc[b])
+        worst_t = max(worst_t, max_abs(tran[b], ot))
+    print(f'[tran] cfg3 all 256 sequences: worst |cuda-ref| {worst_t:.3e} m')
+    assert worst_t <= TRAN_TOL
     net.velocity.rnn_state = None
 
 
-def test_cfg4_long_sequence_T3000(net, oracle):
+def test_cfg4_long_sequence_T3000(net, oracle, oracle64):
     from mobileposer_b200.synthetic import synthetic_imu
     x = synthetic_imu(4242, 3000)
     net.velocity.rnn_state = None
@@ -390,7 +418,7 @@ def test_cfg4_long_sequence_T3000(net, oracle):
     op, oj, ot, oc = oracle.forward_offline(x[None], [3000])
     r6d_ref = reference_r6d(oracle, x[None], [3000])
     assert max_abs(cuda_r6d(net, x[None].to(DEV), [3000]), r6d_ref) <= R6D_TOL
-    check_pose_tran(pose, tran, contact, op, ot, oc, 'T=3000', r6d_ref)
+    check_pose_tran(pose, tran, contact, op, ot, oc, 'T=3000', r6d_ref, (oracle64, x[None], [3000]))
     net.velocity.rnn_state = None
 
 

@@ -50,7 +50,7 @@ def _worker(rank, world, port, lengths, q):
         # per-sequence "metric rows": a deterministic function of the sequence id and length only
         rows = torch.stack([torch.tensor([float(i), float(lengths[i]), float(i) * 0.5]) for i in mine]) if mine \
             else torch.zeros(0, 3)
-        out = gather_rows(rows, mine, len(lengths))
+        out = gather_rows(rows, shards, len(lengths))
         q.put((rank, out))
     finally:
         dist.destroy_process_group()
@@ -126,3 +126,64 @@ def test_evaluate_pose_sharded_over_two_ranks_equals_one_rank(batch_size):
         seen += [n for c in calls for n in c]
         assert all(len(c) <= batch_size for c in calls)
     assert sorted(seen) == sorted([70, 64, 90, 75, 66])       # every sequence evaluated exactly once across the ranks
+
+
+# ---- a STATEFUL stand-in: the velocity-state carry must not make the table depend on the sharding ---------------
+def _stateful_net():
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from test_evaluate import _StandInNet
+
+    class _Velocity:
+        rnn_state = None
+
+    class Stateful(_StandInNet):
+        """forward_offline drifts by whatever `velocity.rnn_state` the previous B == 1 call left (like the reference's velocity
+        head), and leaves its own: any result that depends on call order shows up in the Distance / Jitter rows."""
+
+        def __init__(self):
+            super().__init__()
+            self.velocity = _Velocity()
+            self.dynamics_optimizer = None
+
+        def forward_offline(self, x, lengths):
+            out = list(super().forward_offline(x, lengths))
+            if x.shape[0] == 1:
+                carry = self.velocity.rnn_state if self.velocity.rnn_state is not None else 0.0
+                out[2] = out[2] + carry * torch.linspace(0, 1, out[2].shape[0]).view(-1, 1)
+                self.velocity.rnn_state = carry + 0.05 * float(x.abs().mean())
+            return tuple(out)
+    return Stateful()
+
+
+def _stateful_worker(rank, world, port, batch_size, q):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    torch.set_num_threads(1)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        from mobileposer_b200.evaluate import evaluate_pose
+        q.put((rank, evaluate_pose(_stateful_net(), _eval_items(), verbose=False, batch_size=batch_size)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_evaluation_does_not_depend_on_the_carried_state():
+    from mobileposer_b200.evaluate import evaluate_pose
+    chained = evaluate_pose(_stateful_net(), _eval_items(), verbose=False)                 # one process, batch 1: the reference's chain
+    independent = evaluate_pose(_stateful_net(), _eval_items(), verbose=False, batch_size=2)   # fresh state per sequence (5 = 2 + 2 + 1)
+    ok = ~torch.isnan(chained)
+    assert not torch.allclose(chained[ok], independent[ok], rtol=1e-4, atol=1e-6)          # the stand-in's leak is visible
+    for world, batch_size in ((2, 1), (2, 2), (3, 1)):
+        ctx = mp.get_context('spawn')
+        q = ctx.Queue()
+        port = _free_port()
+        procs = [ctx.Process(target=_stateful_worker, args=(r, world, port, batch_size, q)) for r in range(world)]
+        for p in procs:
+            p.start()
+        results = [q.get(timeout=180) for _ in procs]
+        for p in procs:
+            p.join(timeout=60)
+            assert p.exitcode == 0
+        for _, table in results:
+            assert torch.allclose(table[ok], independent[ok], rtol=1e-5, atol=1e-7), (world, batch_size)
