@@ -101,7 +101,9 @@ int mp_rnn_forward(const mp_rnn_t* rnn, const float* xa, int32_t ka, const float
 
 /* The dense contraction under every Linear / LSTM input projection of the path (rnn.py:22,27,32):
  *   C[M,N] = act(A[M,K] * W[N,K]^T + bias[N]).  mode 0 = library's choice, 1 = fp32 FFMA kernel,
- *   2 = tcgen05 3xTF32 tensor-core kernel (needs N % 256 == 0, K % 16 == 0, relu == 0).  Exposed for tests.   */
+ *   2 = tcgen05 3xTF32 tensor-core kernel (needs N % 256 == 0, K % 16 == 0, relu == 0),
+ *   3 = tcgen05 3xFP16 (fp16 hi / scaled-lo split) tensor-core kernel (N % 256 == 0, K % 32 == 0, relu == 0; the operands are
+ *       split into stream-ordered scratch memory first).  Exposed for tests.   */
 int mp_gemm_bias(const float* A, const float* W, const float* bias, float* C, int32_t M, int32_t N, int32_t K,
                  int32_t relu, int32_t mode, mp_stream_t stream);
 

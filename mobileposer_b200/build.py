@@ -13,7 +13,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, 'csrc')
 LIB_DIR = os.path.join(PKG, 'lib')
 LIB_PATH = os.path.join(LIB_DIR, 'libmobileposer_b200.so')
-SOURCES = ['gemm.cu', 'gemm_tc.cu', 'lstm_rec.cu', 'lstm_rec_tc.cu', 'kinematics.cu', 'physics.cu', 'inputs.cu', 'evaluate.cu', 'api.cu']
+SOURCES = ['gemm.cu', 'gemm_tc.cu', 'gemm_f16.cu', 'lstm_rec.cu', 'lstm_rec_tc.cu', 'lstm_rec_f16.cu', 'kinematics.cu', 'physics.cu', 'inputs.cu', 'evaluate.cu', 'api.cu']
 HEADERS = [os.path.join(CSRC, 'mp_common.cuh'), os.path.join(CSRC, 'mp_constants.cuh'),
            os.path.join(os.path.dirname(PKG), 'include', 'mobileposer_b200.h')]
 OBJ_DIR = os.path.join(LIB_DIR, 'obj')
@@ -64,7 +64,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if verbose:
         for _, log in results:
             print(log)
-    cmd = [_nvcc(), '-shared', '-o', LIB_PATH, *[o for o, _ in results]]
+    cmd = [_nvcc(), '-shared', '-gencode', 'arch=compute_100a,code=sm_100a', '-o', LIB_PATH, *[o for o, _ in results]]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError('nvcc link failed:\n' + res.stdout + res.stderr)

@@ -72,6 +72,7 @@ struct mp_rnn {
     float *w1 = nullptr, *b1 = nullptr, *w2 = nullptr, *b2 = nullptr;
     float* wih[2] = {nullptr, nullptr};    // [dirs*4H, In_l]   both directions stacked on N
     float* wih_split[2] = {nullptr, nullptr};   // [2 * dirs*4H, In_l]: TF32 hi rows, then lo rows (tensor-core projection), or null
+    void* wih_f16[2] = {nullptr, nullptr};      // [2 * dirs*4H, In_l] halves: fp16 hi rows, then scaled-lo rows (gemm_f16.cu), or null
     float* bsum[2] = {nullptr, nullptr};   // [dirs*4H]         b_ih + b_hh
     float4* whh_pack[2] = {nullptr, nullptr};
     float* whh_t[2] = {nullptr, nullptr};
@@ -188,10 +189,11 @@ int mp_rnn_create(mp_rnn_t** out, const mp_rnn_weights_t* w, mp_stream_t stream_
     auto take = [&](size_t floats) { size_t o = off; off = align_up(off + floats * sizeof(float)); return o; };
     const size_t o_w1 = take((size_t)H * r->n_in), o_b1 = take(H);
     const size_t o_w2 = take((size_t)r->n_out * dirs * H), o_b2 = take(r->n_out);
-    size_t o_wih[2], o_bs[2], o_pk[2], o_wt[2], o_raw[2], o_split[2];
+    size_t o_wih[2], o_bs[2], o_pk[2], o_wt[2], o_raw[2], o_split[2], o_f16[2];
     for (int l = 0; l < 2; ++l) {
         o_wih[l] = take((size_t)dirs * 4 * H * in_l[l]);
         o_split[l] = take((size_t)2 * dirs * 4 * H * in_l[l]);
+        o_f16[l] = take((size_t)dirs * 4 * H * in_l[l]);          // 2 x n halves = n floats
         o_bs[l] = take((size_t)dirs * 4 * H);
         o_pk[l] = take(whh_pack_float4s(H, dirs) * 4);
         o_wt[l] = take((size_t)dirs * 4 * H * H);
@@ -236,6 +238,10 @@ int mp_rnn_create(mp_rnn_t** out, const mp_rnn_weights_t* w, mp_stream_t stream_
             r->wih_split[l] = (float*)(base + o_split[l]);
             st = launch_split_weights(r->wih[l], (size_t)dirs * 4 * H * in_l[l], r->wih_split[l], stream);
         }
+        if (st == MP_OK && (dirs * 4 * H) % 256 == 0 && in_l[l] % 32 == 0) {
+            r->wih_f16[l] = base + o_f16[l];
+            st = launch_split_f16(r->wih[l], (size_t)dirs * 4 * H * in_l[l], r->wih_f16[l], stream);
+        }
     }
     if (st == MP_OK && cudaStreamSynchronize(stream) != cudaSuccess) {
         set_error("rnn_create: packing failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -256,20 +262,21 @@ void mp_rnn_destroy(mp_rnn_t* r) {
     delete r;
 }
 
-static void rnn_ws_layout(const mp_rnn* r, size_t M, size_t* o_x1, size_t* o_gin, size_t* o_y0, size_t* o_y1, size_t* total) {
+static void rnn_ws_layout(const mp_rnn* r, size_t M, size_t* o_x1, size_t* o_gin, size_t* o_y0, size_t* o_y1, size_t* o_xs, size_t* total) {
     size_t off = 0;
     auto take = [&](size_t floats) { size_t o = off; off = align_up(off + floats * sizeof(float)); return o; };
     *o_x1 = take(M * r->H);
     *o_gin = take(M * r->dirs * 4 * r->H);
     *o_y0 = take(M * r->dirs * r->H);
     *o_y1 = take(M * r->dirs * r->H);
+    *o_xs = take(M * r->dirs * r->H);      // fp16 (hi, lo) planes of the projection's activation operand: 2 x 2 B per element
     *total = off;
 }
 
 size_t mp_rnn_workspace_bytes(const mp_rnn_t* r, int32_t B, int32_t T) {
     if (!r || B <= 0 || T <= 0) return 0;
-    size_t a, b, c, d, total;
-    rnn_ws_layout(r, (size_t)B * T, &a, &b, &c, &d, &total);
+    size_t a, b, c, d, e, total;
+    rnn_ws_layout(r, (size_t)B * T, &a, &b, &c, &d, &e, &total);
     return total;
 }
 
@@ -283,8 +290,8 @@ static int rnn_forward_impl(const mp_rnn_t* r, const float* xa, int32_t ka, cons
     MP_REQUIRE(((uintptr_t)workspace & 255) == 0, "rnn_forward: workspace must be 256-byte aligned");
     const size_t M = (size_t)B * T;
     MP_REQUIRE(M * (size_t)r->dirs * 4 * r->H < (size_t)1 << 40, "rnn_forward: batch too large");
-    size_t o_x1, o_gin, o_y0, o_y1, total;
-    rnn_ws_layout(r, M, &o_x1, &o_gin, &o_y0, &o_y1, &total);
+    size_t o_x1, o_gin, o_y0, o_y1, o_xs, total;
+    rnn_ws_layout(r, M, &o_x1, &o_gin, &o_y0, &o_y1, &o_xs, &total);
     if (workspace_bytes < total) {
         set_error("rnn_forward: workspace %zu < required %zu", workspace_bytes, total);
         return MP_ERR_WORKSPACE;
@@ -300,7 +307,12 @@ static int rnn_forward_impl(const mp_rnn_t* r, const float* xa, int32_t ka, cons
     int in_w = H;
     for (int l = 0; l < 2; ++l) {
         // hoisted input projection of both directions                        rnn.py:27 (W_ih x + b_ih + b_hh)
-        if (r->wih_split[l] && gemm_tc_eligible((int)M, dirs * 4 * H, in_w) && !getenv("MP_GEMM_NOSPLIT"))
+        if (r->wih_f16[l] && gemm_f16_eligible((int)M, dirs * 4 * H, in_w)) {
+            // fp16 hi / scaled-lo planes of the activations (streaming pass), then 3 products at the FP16 tensor rate
+            void* xs = ws + o_xs;
+            MP_TRY(launch_split_f16(layer_in, M * (size_t)in_w, xs, stream));
+            MP_TRY(launch_gemm_f16x3(xs, r->wih_f16[l], r->bsum[l], gin, (int)M, dirs * 4 * H, in_w, stream));
+        } else if (r->wih_split[l] && gemm_tc_eligible((int)M, dirs * 4 * H, in_w) && !getenv("MP_GEMM_NOSPLIT"))
             MP_TRY(launch_gemm_tf32x3_presplit(layer_in, r->wih_split[l], r->bsum[l], gin, (int)M, dirs * 4 * H, in_w, stream));
         else
             MP_TRY(launch_gemm_bias_act(layer_in, in_w, nullptr, 0, r->wih[l], r->bsum[l], gin, (int)M, dirs * 4 * H, 0, stream));
@@ -336,6 +348,20 @@ int mp_gemm_bias(const float* A, const float* W, const float* bias, float* C, in
     if (mode == 2) {
         MP_REQUIRE(!relu, "gemm_bias: the tensor-core path has no activation");
         return launch_gemm_tf32x3(A, W, bias, C, M, N, K, (cudaStream_t)stream);
+    }
+    if (mode == 3) {
+        // test entry of the fp16-split kernel: both operands are split here into stream-ordered scratch
+        MP_REQUIRE(!relu, "gemm_bias: the tensor-core path has no activation");
+        cudaStream_t s = (cudaStream_t)stream;
+        void *as = nullptr, *wsp = nullptr;
+        MP_CUDA_TRY(cudaMallocAsync(&as, (size_t)M * K * 4, s));
+        MP_CUDA_TRY(cudaMallocAsync(&wsp, (size_t)N * K * 4, s));
+        int st = launch_split_f16(A, (size_t)M * K, as, s);
+        if (st == MP_OK) st = launch_split_f16(W, (size_t)N * K, wsp, s);
+        if (st == MP_OK) st = launch_gemm_f16x3(as, wsp, bias, C, M, N, K, s);
+        cudaFreeAsync(as, s);
+        cudaFreeAsync(wsp, s);
+        return st;
     }
     return launch_gemm_bias_act(A, K, nullptr, 0, W, bias, C, M, N, relu, (cudaStream_t)stream);
 }

@@ -508,7 +508,7 @@ bool rec_tc_eligible(const RecLayerArgs& a) {
     const char* v = getenv("MP_REC_IMPL");
     if (v && (strcmp(v, "ffma") == 0 || strcmp(v, "simple") == 0)) return false;
     if (a.H != TH || !a.w_raw[0]) return false;
-    const bool forced = v && strcmp(v, "tc") == 0;
+    const bool forced = v && (strcmp(v, "tc") == 0 || strcmp(v, "tf32") == 0);
     return forced || a.B * a.dirs > 2 * tc_cluster_slots();
 }
 

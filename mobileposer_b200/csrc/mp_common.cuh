@@ -60,6 +60,12 @@ int launch_gemm_tf32x3(const float* A, const float* W, const float* bias, float*
 int launch_gemm_tf32x3_presplit(const float* A, const float* W_split, const float* bias, float* C, int M, int N, int K,
                                 cudaStream_t stream);
 int launch_split_weights(const float* W, size_t n, float* W_split, cudaStream_t stream);
+// second generation (gemm_f16.cu): fp16 hi / scaled-lo operands, 3 products at the FP16 tensor rate.  Operands arrive split:
+// A_split = [2][M, K] halves (hi plane, lo plane), W_split = [2N, K] halves (hi rows, lo rows); launch_split_f16 makes either
+// from an fp32 array of n elements (out = n hi halves, then n lo halves)
+bool gemm_f16_eligible(int M, int N, int K);
+int launch_gemm_f16x3(const void* A_split, const void* W_split, const float* bias, float* C, int M, int N, int K, cudaStream_t stream);
+int launch_split_f16(const float* x, size_t n, void* out_hi_lo, cudaStream_t stream);
 int launch_gemm_ffma(const float* A1, int K1, const float* A2, int K2, const float* W, const float* bias, float* C,
                      int M, int N, int relu, cudaStream_t stream);
 
@@ -81,6 +87,9 @@ int launch_lstm_recurrence(const RecLayerArgs& a, cudaStream_t stream);
 // tcgen05 3xTF32 variant for H = 256 and large batches (lstm_rec_tc.cu)
 bool rec_tc_eligible(const RecLayerArgs& a);
 int launch_lstm_recurrence_tc(const RecLayerArgs& a, cudaStream_t stream);
+// second generation: fp16 hi / scaled-lo operands (lstm_rec_f16.cu); supersedes the TF32 kernel (MP_REC_IMPL=tf32 pins the old one)
+bool rec_f16_eligible(const RecLayerArgs& a);
+int launch_lstm_recurrence_f16(const RecLayerArgs& a, cudaStream_t stream);
 // number of float4 in the packed recurrent weights of one layer
 size_t whh_pack_float4s(int H, int dirs);
 // pack W_hh[dirs][4H,H] (device, torch layout) into the register-resident layout + transpose

@@ -17,7 +17,7 @@ lens = [T] * B
 os.environ['MP_REC_IMPL'] = 'ffma'
 ref = net.joints(x, lens).clone()
 torch.cuda.synchronize()
-os.environ['MP_REC_IMPL'] = 'tc'
+os.environ['MP_REC_IMPL'] = sys.argv[3] if len(sys.argv) > 3 else 'tc'      # tc / f16 = the fp16-split kernel, tf32 = the first-generation one
 out = net.joints(x, lens)
 torch.cuda.synchronize()
-print('B', B, 'T', T, 'max |tc - ffma|', (out - ref).abs().max().item(), 'ref max', ref.abs().max().item())
+print('B', B, 'T', T, os.environ['MP_REC_IMPL'], 'max |tc - ffma|', (out - ref).abs().max().item(), 'ref max', ref.abs().max().item())

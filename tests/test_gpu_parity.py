@@ -67,14 +67,23 @@ def check_angles(pose, g_pose, r6d_ref, what='', f64=None):
           f'worst error / tolerance {excess:.2f}')
     assert excess <= 1.0, f'{what}: joint angle error {excess:.2f}x its tolerance (max {worst:.3e} rad)'
     if f64 is not None:
+        # with a float64 evaluation at hand: |cuda - ref| against the reference's own distance to exact arithmetic.  The MAXIMA sit
+        # on single ill-conditioned (frame, joint) pairs (amplification up to 200x) and are printed; the assertion compares the
+        # errors in conditioning-normalised units (error / K5 sensitivity = the r6d-level deviation): within 3x the reference's.
+        from parity import geodesic, k5_sensitivity
         o64, imu, lens = f64
         p64 = f64_pose(o64, imu, lens).view(len(lens), -1, 24, 3, 3)
         keep = torch.zeros(p64.shape[:2], dtype=torch.bool)
         for b, L in enumerate(lens):
             keep[b, :L] = True
         sel = lambda t: t.detach().cpu().reshape(p64.shape)[keep]
-        e_cr, e_rd, e_cd = angle_report(sel(pose), sel(g_pose), p64[keep], what)
-        assert e_cr <= max(ANGLE_TOL, 3.0 * e_rd), f'{what}: |cuda-ref| {e_cr:.3e} rad > 3 x |ref-f64| {e_rd:.3e}'
+        pc, pr, pd = sel(pose), sel(g_pose), p64[keep]
+        e_cr, e_rd, e_cd = angle_report(pc, pr, pd, what)
+        sens = k5_sensitivity(r6d_ref).view(len(lens), -1, 24)[keep].clamp_min(1.0)
+        n_cr, n_rd = (geodesic(pc, pr) / sens).max().item(), (geodesic(pr, pd) / sens).max().item()
+        print(f'[angle] {what}: conditioning-normalised worst |cuda-ref| {n_cr:.3e}  |ref-f64| {n_rd:.3e}  (ratio {n_cr / max(n_rd, 1e-12):.2f}; '
+              f'raw maxima ratio {e_cr / max(e_rd, 1e-12):.2f})')
+        assert n_cr <= 3.0 * n_rd + 2e-7, f'{what}: normalised |cuda-ref| {n_cr:.3e} > 3 x |ref-f64| {n_rd:.3e} + 2e-7'
 
 
 def check_pose_tran(pose, tran, contact, g_pose, g_tran, g_contact, what='', r6d_ref=None, f64=None):
@@ -243,8 +252,10 @@ def test_batch_equals_independent_reference_calls(net, oracle, oracle64):
     dict(MP_REC_NB=12),                                  # odd number of sequence groups (unroll remainder)
     dict(MP_REC_NB=8),
     dict(MP_REC_NB=3),                                   # latency path, several sequences per cluster
-    dict(MP_REC_IMPL='tc'),                              # tcgen05 recurrence, several small tiles (N = 16)
-    dict(MP_REC_IMPL='tc', MP_REC_NB=11),                # tcgen05 recurrence, one ragged tile
+    dict(MP_REC_IMPL='tc'),                              # tcgen05 fp16-split recurrence, several small tiles (N = 16)
+    dict(MP_REC_IMPL='tc', MP_REC_NB=11),                # tcgen05 fp16-split recurrence, one ragged tile
+    dict(MP_REC_IMPL='tf32'),                            # first-generation tcgen05 recurrence (3xTF32), small tiles
+    dict(MP_REC_IMPL='tf32', MP_REC_NB=11, MP_GEMM='tf32'),   # ... one ragged tile, with the 3xTF32 projection
     dict(MP_REC_IMPL='ffma', MP_REC_NB=8),               # FFMA throughput path pinned
 ])
 def test_recurrence_variants_against_oracle(net, oracle, oracle64, env, variant):
@@ -526,7 +537,7 @@ def test_float64_arbitration(net, oracle, seeded_state_dict):
     assert e_gpu <= 3.0 * e_ref + 5e-8, (e_ref, e_gpu)
 
 
-@pytest.mark.parametrize('M,N,K', [(128, 256, 16), (300, 256, 64), (4096, 2048, 256), (5000, 1024, 512), (2500, 512, 128),
+@pytest.mark.parametrize('M,N,K', [(128, 256, 16), (300, 256, 64), (4096, 2048, 256), (5000, 1024, 512), (2500, 512, 128), (77, 256, 32),
                                    (3000, 72, 512), (2100, 96, 512), (700, 72, 256), (4100, 200, 64), (130, 16, 32)])
 def test_tensor_core_gemm_matches_fp32(M, N, K):
     """tcgen05 3xTF32 input projection (gemm_tc.cu) against the FFMA kernel and a float64 product."""
@@ -538,7 +549,8 @@ def test_tensor_core_gemm_matches_fp32(M, N, K):
     bias = torch.randn(N, generator=g).to(DEV)
     stream = torch.cuda.current_stream().cuda_stream
     out = {}
-    for mode in (1, 2):
+    f16_ok = N % 256 == 0 and K % 32 == 0
+    for mode in (1, 2) + ((3,) if f16_ok else ()):
         C = torch.full((M, N), float('nan'), device=DEV)
         _cabi.check(lib.mp_gemm_bias(A.data_ptr(), W.data_ptr(), bias.data_ptr(), C.data_ptr(), M, N, K, 0, mode, stream))
         out[mode] = C
@@ -551,6 +563,11 @@ def test_tensor_core_gemm_matches_fp32(M, N, K):
     assert torch.isfinite(out[2]).all()
     assert e_ffma < 4e-7, e_ffma               # a few ulp (2^-24 = 6e-8) of the accumulated magnitude
     assert e_tc < 1e-6, (e_tc, e_ffma)         # a single TF32 pass would be ~5e-4 on this scale
+    if f16_ok:
+        e_h = ((out[3].double() - ref).abs() / scale).max().item()
+        print(f'gemm M={M} N={N} K={K}: max scaled |err| f16x3 {e_h:.2e}')
+        assert torch.isfinite(out[3]).all()
+        assert e_h < 1e-6, (e_h, e_ffma)       # fp16 hi + scaled lo carries the same 22 bits as the TF32 pair
 
 
 @pytest.mark.parametrize('M,N,K,relu', [(19000, 72, 512, 0), (19001, 96, 256, 0), (20000, 64, 132, 1), (19003, 256, 60, 1),
@@ -588,3 +605,25 @@ def test_evaluate_pose_entry(net):
     keep = [0, 1, 2, 3, 4, 6, 7]                    # all but the mesh row
     assert torch.isfinite(table[:, keep]).all()
     net.velocity.rnn_state = None
+
+
+def test_fp16_split_gemm_keeps_small_and_large_magnitudes():
+    """The fp16 hi / scaled-lo split (gemm_f16.cu) over the magnitudes the path can see: activations down to 1e-7 (fp16
+    subnormal range, both halves) and up to 1e3, weights from 1e-5 to 4 -- every output within fp32-grade backward error."""
+    from mobileposer_b200 import _cabi
+    lib = _cabi.lib()
+    g = torch.Generator().manual_seed(3)
+    M, N, K = 1000, 256, 256
+    A = torch.randn(M, K, generator=g) * torch.logspace(-7, 3, M).view(M, 1)
+    W = torch.randn(N, K, generator=g) * torch.logspace(-5, 0.6, N).view(N, 1)
+    bias = torch.zeros(N)
+    A, W, bias = A.to(DEV), W.to(DEV), bias.to(DEV)
+    C = torch.full((M, N), float('nan'), device=DEV)
+    _cabi.check(lib.mp_gemm_bias(A.data_ptr(), W.data_ptr(), bias.data_ptr(), C.data_ptr(), M, N, K, 0, 3, torch.cuda.current_stream().cuda_stream))
+    ref = A.double() @ W.double().t()
+    # operands below the fp16 normal range (|x| < 6e-5) keep an ABSOLUTE accuracy instead of a relative one: after hi + lo the
+    # residual is <= 2^-35 per element, and the dropped lo x lo term is at most 2^-25 x 2^-25 per product where both are that small
+    a_abs, w_abs = A.double().abs(), W.double().abs()
+    bound = 1e-6 * (a_abs @ w_abs.t()) + (2.0 ** -35) * (w_abs.sum(1).view(1, N) + a_abs.sum(1).view(M, 1)) + K * 2.0 ** -50
+    err = ((C.double() - ref).abs() / bound).max().item()
+    assert torch.isfinite(C).all() and err < 1.0, err
