@@ -263,7 +263,7 @@ void mp_rnn_destroy(mp_rnn_t* r) {
 }
 
 static void rnn_ws_layout(const mp_rnn* r, size_t M, size_t* o_x1, size_t* o_gin, size_t* o_y0, size_t* o_y1, size_t* o_xs, size_t* total) {
-    size_t off = 0;
+    size_t off = 256;      // first 256 bytes: tile-scheduler words of the persistent projection launches (cleared per forward)
     auto take = [&](size_t floats) { size_t o = off; off = align_up(off + floats * sizeof(float)); return o; };
     *o_x1 = take(M * r->H);
     *o_gin = take(M * r->dirs * 4 * r->H);
@@ -301,17 +301,28 @@ static int rnn_forward_impl(const mp_rnn_t* r, const float* xa, int32_t ka, cons
     float* gin = (float*)(ws + o_gin);
     float* ybuf[2] = {(float*)(ws + o_y0), (float*)(ws + o_y1)};
     const int H = r->H, dirs = r->dirs;
+    // which projections run on the fp16-split tensor-core kernel: their activation operand is wanted as (hi, lo) planes of halves,
+    // which the producing kernel writes directly where it can (linear1's epilogue, the fp16-split recurrence) -- same bytes as fp32
+    const bool proj16[2] = {r->wih_f16[0] && gemm_f16_eligible((int)M, dirs * 4 * H, H),
+                            r->wih_f16[1] && gemm_f16_eligible((int)M, dirs * 4 * H, dirs * H)};
+    const bool fuse_split = !getenv("MP_NO_FUSED_SPLIT");
+    unsigned int* sched = reinterpret_cast<unsigned int*>(ws);
+    if (proj16[0] || proj16[1]) MP_CUDA_TRY(cudaMemsetAsync(sched, 0, 256, stream));
+    const bool x1_split = proj16[0] && fuse_split;
     // linear1 + ReLU (dropout is the identity in eval)                         rnn.py:22
-    MP_TRY(launch_gemm_bias_act(xa, ka, xb, kb, r->w1, r->b1, x1, (int)M, H, 1, stream));
+    MP_TRY(launch_gemm_ffma(xa, ka, xb, kb, r->w1, r->b1, x1, (int)M, H, x1_split ? 3 : 1, stream));
     const float* layer_in = x1;
+    bool layer_in_split = x1_split;
     int in_w = H;
     for (int l = 0; l < 2; ++l) {
         // hoisted input projection of both directions                        rnn.py:27 (W_ih x + b_ih + b_hh)
-        if (r->wih_f16[l] && gemm_f16_eligible((int)M, dirs * 4 * H, in_w)) {
-            // fp16 hi / scaled-lo planes of the activations (streaming pass), then 3 products at the FP16 tensor rate
-            void* xs = ws + o_xs;
-            MP_TRY(launch_split_f16(layer_in, M * (size_t)in_w, xs, stream));
-            MP_TRY(launch_gemm_f16x3(xs, r->wih_f16[l], r->bsum[l], gin, (int)M, dirs * 4 * H, in_w, stream));
+        if (proj16[l]) {
+            const void* xs = layer_in;
+            if (!layer_in_split) {             // the producer could not write the planes itself: one streaming split pass
+                MP_TRY(launch_split_f16(layer_in, M * (size_t)in_w, ws + o_xs, stream));
+                xs = ws + o_xs;
+            }
+            MP_TRY(launch_gemm_f16x3(xs, r->wih_f16[l], r->bsum[l], gin, (int)M, dirs * 4 * H, in_w, sched + 2 * l, stream));
         } else if (r->wih_split[l] && gemm_tc_eligible((int)M, dirs * 4 * H, in_w) && !getenv("MP_GEMM_NOSPLIT"))
             MP_TRY(launch_gemm_tf32x3_presplit(layer_in, r->wih_split[l], r->bsum[l], gin, (int)M, dirs * 4 * H, in_w, stream));
         else
@@ -324,8 +335,11 @@ static int rnn_forward_impl(const mp_rnn_t* r, const float* xa, int32_t ka, cons
         a.hn = hn ? hn + so : nullptr; a.cn = cn ? cn + so : nullptr;
         a.lengths = lengths; a.B = B; a.T = T; a.H = H; a.dirs = dirs;
         a.tile_hint = tile_hint;
+        // layer 0 feeds layer 1's projection only: written as (hi, lo) planes when both ends are the fp16-split kernels
+        a.y_split = (l == 0 && proj16[1] && fuse_split && rec_f16_eligible(a)) ? 1 : 0;
         MP_TRY(launch_lstm_recurrence(a, stream));
         layer_in = ybuf[l];
+        layer_in_split = a.y_split != 0;
         in_w = dirs * H;
     }
     // linear2                                                                 rnn.py:32
@@ -353,14 +367,17 @@ int mp_gemm_bias(const float* A, const float* W, const float* bias, float* C, in
         // test entry of the fp16-split kernel: both operands are split here into stream-ordered scratch
         MP_REQUIRE(!relu, "gemm_bias: the tensor-core path has no activation");
         cudaStream_t s = (cudaStream_t)stream;
-        void *as = nullptr, *wsp = nullptr;
+        void *as = nullptr, *wsp = nullptr, *sched = nullptr;
         MP_CUDA_TRY(cudaMallocAsync(&as, (size_t)M * K * 4, s));
         MP_CUDA_TRY(cudaMallocAsync(&wsp, (size_t)N * K * 4, s));
+        MP_CUDA_TRY(cudaMallocAsync(&sched, 256, s));
+        MP_CUDA_TRY(cudaMemsetAsync(sched, 0, 256, s));
         int st = launch_split_f16(A, (size_t)M * K, as, s);
         if (st == MP_OK) st = launch_split_f16(W, (size_t)N * K, wsp, s);
-        if (st == MP_OK) st = launch_gemm_f16x3(as, wsp, bias, C, M, N, K, s);
+        if (st == MP_OK) st = launch_gemm_f16x3(as, wsp, bias, C, M, N, K, (unsigned int*)sched, s);
         cudaFreeAsync(as, s);
         cudaFreeAsync(wsp, s);
+        cudaFreeAsync(sched, s);
         return st;
     }
     return launch_gemm_bias_act(A, K, nullptr, 0, W, bias, C, M, N, relu, (cudaStream_t)stream);

@@ -10,6 +10,8 @@
 // FFMA, double-buffered smem with a register prefetch of the next k-slab, one barrier per slab.
 #include "mp_common.cuh"
 
+#include <cuda_fp16.h>
+
 #include <algorithm>
 #include <cstdlib>
 
@@ -192,10 +194,24 @@ gemm_bias_act_kernel(const float* __restrict__ A1, int K1, const float* __restri
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     float x = acc[gi * 4 + i][gj * 4 + j] + ((n + j < N) ? __ldg(bias + n + j) : 0.f);
-                    v[j] = relu ? fmaxf(x, 0.f) : x;
+                    v[j] = (relu & 1) ? fmaxf(x, 0.f) : x;
                 }
                 float* dst = C + (size_t)m * N + n;
-                if (vec) {
+                if (relu & 2) {
+                    // output for the fp16-split tensor-core projection (gemm_f16.cu): C holds two [M, N] planes of halves, hi = fp16(x)
+                    // and lo = fp16((x - hi) * 2^11) -- the same bytes as the fp32 array, no separate split pass (N % 4 == 0)
+                    __half* hi = reinterpret_cast<__half*>(C) + (size_t)m * N + n;
+                    __half* lo = hi + (size_t)M * N;
+                    const __half2 h0 = __floats2half2_rn(v[0], v[1]), h1 = __floats2half2_rn(v[2], v[3]);
+                    const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+                    const __half2 l0 = __floats2half2_rn((v[0] - f0.x) * 2048.0f, (v[1] - f0.y) * 2048.0f);
+                    const __half2 l1 = __floats2half2_rn((v[2] - f1.x) * 2048.0f, (v[3] - f1.y) * 2048.0f);
+                    uint2 ph, pl;
+                    ph.x = *reinterpret_cast<const uint32_t*>(&h0); ph.y = *reinterpret_cast<const uint32_t*>(&h1);
+                    pl.x = *reinterpret_cast<const uint32_t*>(&l0); pl.y = *reinterpret_cast<const uint32_t*>(&l1);
+                    *reinterpret_cast<uint2*>(hi) = ph;
+                    *reinterpret_cast<uint2*>(lo) = pl;
+                } else if (vec) {
                     *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
                 } else {
 #pragma unroll
@@ -260,7 +276,7 @@ gemm_rowdot_kernel(const float* __restrict__ A, int K, const float* __restrict__
 #pragma unroll
                     for (int r = 0; r < RPW; ++r) v = (lane == r) ? acc[r][n] : v;
                     v += __ldg(bias + n);
-                    C[(size_t)(m0 + lane) * N + n] = relu ? fmaxf(v, 0.f) : v;
+                    C[(size_t)(m0 + lane) * N + n] = (relu & 1) ? fmaxf(v, 0.f) : v;
                 }
             }
         }
@@ -282,6 +298,7 @@ int launch_gemm_ffma(const float* A1, int K1, const float* A2, int K2, const flo
     MP_REQUIRE(A1 && W && bias && C, "gemm: null pointer");
     MP_REQUIRE(K1 > 0 && (K1 & 3) == 0 && K2 >= 0 && (K2 & 3) == 0, "gemm: K1=%d K2=%d must be multiples of 4", K1, K2);
     MP_REQUIRE(K2 == 0 || A2, "gemm: second operand missing");
+    MP_REQUIRE(!(relu & 2) || ((N & 3) == 0 && N > ROWDOT_NMAX), "gemm: the fp16-split output needs N %% 4 == 0 (N=%d)", N);
     MP_REQUIRE(((uintptr_t)A1 & 15) == 0 && ((uintptr_t)A2 & 15) == 0 && ((uintptr_t)W & 15) == 0 &&
                    ((uintptr_t)C & 15) == 0, "gemm: pointers must be 16-byte aligned");
     ProfileScope prof(N >= 512 ? "gemm_input_proj" : "gemm_linear",

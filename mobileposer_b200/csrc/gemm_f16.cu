@@ -15,10 +15,11 @@
 //
 // Both operands arrive ALREADY split (A: [2][M, K] halves from the producing kernel's epilogue or launch_split_f16; W: [2N, K]
 // halves made once at pack time), so there are no splitter warps: the kernel is the plain TMA -> tcgen05 pipeline.
-//   warp 0      TMA producer: cp.async.bulk.tensor (64B swizzle), 4 boxes per stage (A_hi, A_lo, W_hi, W_lo), K = 32 per stage
+//   warp 0      TMA producer: cp.async.bulk.tensor (64B swizzle), 4 boxes per stage (A_hi, A_lo, W_hi, W_lo), K = 32 per stage;
+//               the ring runs on across the CTA's tiles (persistent kernel)
 //   warp 1      TMEM allocation + single-thread tcgen05.mma.kind::f16 issue: 3 products x 2 K-steps (UMMA 128x256x16) per stage;
-//               tcgen05.commit releases the stage; a final commit hands the accumulators to the epilogue
-//   warps 2-5   epilogue: tcgen05.ld both accumulators, main + corr * 2^-11 + bias, fp32 rows to global
+//               tcgen05.commit releases the stage; a final commit per tile hands the accumulators to the epilogue
+//   warps 2-5   epilogue: tcgen05.ld both accumulators, main + corr * 2^-11 + bias, 32 x 32 boxes through shared memory, TMA store
 // Shared-memory traffic per stage (what bounds gemm_tc.cu): 48 KB landed + 72 KB operand fetch against 768 clk of MMA.
 #include "mp_common.cuh"
 
@@ -37,7 +38,7 @@ constexpr int HB_THREADS = 192;
 constexpr uint32_t HA_TILE = HB_M * HB_K * 2;   // 8 KiB
 constexpr uint32_t HW_TILE = HB_N * HB_K * 2;   // 16 KiB
 constexpr uint32_t H_STAGE = 2 * HA_TILE + 2 * HW_TILE;
-constexpr uint32_t H_SMEM = HB_STAGES * H_STAGE + 1024 /*align*/ + 256 /*barriers*/;
+constexpr uint32_t H_SMEM = HB_STAGES * H_STAGE + 4 * 4096 /*epilogue boxes*/ + 1024 /*align*/ + 256 /*barriers*/;
 constexpr uint32_t H_TMEM_COLS = 512;   // [0,256) main, [256,512) correction
 constexpr float kLoScale = 2048.0f, kLoInv = 1.0f / 2048.0f;
 
@@ -79,22 +80,41 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         : "memory");
 }
 
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(map)),
+                 "r"(src), "r"(c0), "r"(c1)
+                 : "memory");
+}
+
+// Persistent with a DYNAMIC tile queue: gridDim.x CTAs draw 128 x 256 output tiles from a global counter (column tile fastest, so
+// the CTAs running at the same time share A rows in L2).  Dynamic because this kernel rarely has the GPU to itself: the cluster
+// recurrences of other heads / batches hold SMs for a millisecond at a time, a CTA that gets its SM late must simply find less work
+// left, not a statically assigned share.  The producer warp draws the tile ids and hands them to the MMA and epilogue warps through
+// a two-entry shared-memory queue.  The TMA producer's stage ring runs on across tile boundaries, so the first K stages of the next tile land
+// while the epilogue drains the accumulators; the epilogue stores through shared memory (32 x 32 fp32 boxes, 128B swizzle) with TMA
+// so every store is whole 128-byte rows (thread-per-row fp32 stores cost one L1 wavefront per 16 bytes: 8 k clk per tile, more than
+// the K = 256 main loop itself -- ncu on the first version: tensor pipe 29 % active).
 __global__ void __launch_bounds__(HB_THREADS, 1)
 gemm_f16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
-                  const __grid_constant__ CUtensorMap map_w, const float* __restrict__ bias, float* __restrict__ C, int M, int N,
-                  int K) {
+                  const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_c,
+                  const float* __restrict__ bias, int M, int N, int K, unsigned int* __restrict__ sched) {
     extern __shared__ unsigned char smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t bars = base + HB_STAGES * H_STAGE;
+    const uint32_t s_out = base + HB_STAGES * H_STAGE;                 // 4 epilogue warps x one 32 x 32 fp32 box (4 KiB)
+    const uint32_t bars = s_out + 4 * 4096;
     auto bar_full = [&](int s) { return bars + 8u * s; };
     auto bar_free = [&](int s) { return bars + 8u * (HB_STAGES + s); };
-    const uint32_t bar_accum = bars + 8u * (2 * HB_STAGES);
-    const uint32_t tmem_slot = bars + 8u * (2 * HB_STAGES + 1);
+    const uint32_t bar_accum = bars + 8u * (2 * HB_STAGES);            // MMAs of a tile committed
+    const uint32_t bar_drained = bars + 8u * (2 * HB_STAGES + 1);      // epilogue has read the accumulators
+    auto bar_tile_full = [&](int q) { return bars + 8u * (2 * HB_STAGES + 2 + q); };      // tile id q published
+    auto bar_tile_free = [&](int q) { return bars + 8u * (2 * HB_STAGES + 4 + q); };      // ... and read by the MMA thread + 4 epilogue warps
+    const uint32_t tmem_slot = bars + 8u * (2 * HB_STAGES + 6);
     unsigned char* gen = smem_raw + (base - smem_u32(smem_raw));
+    volatile int* tile_q = reinterpret_cast<volatile int*>(gen + (tmem_slot + 8 - base));
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int n0 = blockIdx.x * HB_N, m0 = blockIdx.y * HB_M;
     const int KB = K / HB_K;
+    const int tiles_n = N / HB_N, tiles = tiles_n * ((M + HB_M - 1) / HB_M);
 
     if (tid == 0) {
         for (int s = 0; s < HB_STAGES; ++s) {
@@ -102,6 +122,11 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
             mbar_init(bar_free(s), 1);
         }
         mbar_init(bar_accum, 1);
+        mbar_init(bar_drained, 4);
+        for (int q = 0; q < 2; ++q) {
+            mbar_init(bar_tile_full(q), 1);
+            mbar_init(bar_tile_free(q), 5);
+        }
         mbar_fence_init_cluster();
     }
     if (warp == 1) {
@@ -115,68 +140,111 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
 
     if (warp == 0) {
         if (lane == 0) {
-            for (int kb = 0; kb < KB; ++kb) {
-                const int s = kb % HB_STAGES;
-                if (kb >= HB_STAGES) mbar_wait(bar_free(s), ((kb / HB_STAGES) - 1) & 1);
-                mbar_arrive_expect_tx(bar_full(s), H_STAGE);
-                const uint32_t st = base + s * H_STAGE;
-                tma_load_2d(st, &map_a_hi, kb * HB_K, m0, bar_full(s));
-                tma_load_2d(st + HA_TILE, &map_a_lo, kb * HB_K, m0, bar_full(s));
-                tma_load_2d(st + 2 * HA_TILE, &map_w, kb * HB_K, n0, bar_full(s));
-                tma_load_2d(st + 2 * HA_TILE + HW_TILE, &map_w, kb * HB_K, N + n0, bar_full(s));
+            int it = 0;
+            for (int j = 0;; ++j) {
+                const int q = j & 1;
+                if (j >= 2) mbar_wait(bar_tile_free(q), ((j >> 1) - 1) & 1);
+                const int t = (int)atomicAdd(sched, 1u);
+                tile_q[q] = t < tiles ? t : -1;
+                asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(bar_tile_full(q)) : "memory");
+                if (t >= tiles) break;
+                const int n0 = (t % tiles_n) * HB_N, m0 = (t / tiles_n) * HB_M;
+                for (int kb = 0; kb < KB; ++kb, ++it) {
+                    const int s = it % HB_STAGES;
+                    if (it >= HB_STAGES) mbar_wait(bar_free(s), ((it / HB_STAGES) - 1) & 1);
+                    mbar_arrive_expect_tx(bar_full(s), H_STAGE);
+                    const uint32_t st = base + s * H_STAGE;
+                    tma_load_2d(st, &map_a_hi, kb * HB_K, m0, bar_full(s));
+                    tma_load_2d(st + HA_TILE, &map_a_lo, kb * HB_K, m0, bar_full(s));
+                    tma_load_2d(st + 2 * HA_TILE, &map_w, kb * HB_K, n0, bar_full(s));
+                    tma_load_2d(st + 2 * HA_TILE + HW_TILE, &map_w, kb * HB_K, N + n0, bar_full(s));
+                }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
             // instruction descriptor: D = f32, A = B = f16, both K-major, N = 256, M = 128
             const uint32_t idesc = (1u << 4) | ((uint32_t)(HB_N >> 3) << 17) | ((uint32_t)(HB_M >> 4) << 24);
-            for (int kb = 0; kb < KB; ++kb) {
-                const int s = kb % HB_STAGES;
-                mbar_wait(bar_full(s), (kb / HB_STAGES) & 1);
-                tc_fence_after();
-                const uint32_t a_hi = base + s * H_STAGE, a_lo = a_hi + HA_TILE;
-                const uint32_t w_hi = a_hi + 2 * HA_TILE, w_lo = w_hi + HW_TILE;
-#pragma unroll
-                for (int p = 0; p < 3; ++p) {
-                    const uint32_t a = (p == 0) ? a_lo : a_hi;
-                    const uint32_t w = (p == 1) ? w_lo : w_hi;
-                    const uint32_t d = (p == 2) ? tmem : tmem + HB_N;
-#pragma unroll
-                    for (int k2 = 0; k2 < HB_K / 16; ++k2)
-                        umma_f16(d, umma_desc_sw64(a + k2 * 32), umma_desc_sw64(w + k2 * 32), idesc,
-                                 (kb | (p == 1 ? 1 : 0) | k2) != 0 ? 1u : 0u);
+            int it = 0;
+            for (int j = 0;; ++j) {
+                mbar_wait(bar_tile_full(j & 1), (j >> 1) & 1);
+                const int t = tile_q[j & 1];
+                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_tile_free(j & 1)) : "memory");
+                if (t < 0) break;
+                if (j > 0) {                               // the epilogue must have drained the previous tile's accumulators
+                    mbar_wait(bar_drained, (j - 1) & 1);
+                    tc_fence_after();
                 }
-                tc_commit(bar_free(s));
+                for (int kb = 0; kb < KB; ++kb, ++it) {
+                    const int s = it % HB_STAGES;
+                    mbar_wait(bar_full(s), (it / HB_STAGES) & 1);
+                    tc_fence_after();
+                    const uint32_t a_hi = base + s * H_STAGE, a_lo = a_hi + HA_TILE;
+                    const uint32_t w_hi = a_hi + 2 * HA_TILE, w_lo = w_hi + HW_TILE;
+#pragma unroll
+                    for (int p = 0; p < 3; ++p) {
+                        const uint32_t a = (p == 0) ? a_lo : a_hi;
+                        const uint32_t w = (p == 1) ? w_lo : w_hi;
+                        const uint32_t d = (p == 2) ? tmem : tmem + HB_N;
+#pragma unroll
+                        for (int k2 = 0; k2 < HB_K / 16; ++k2)
+                            umma_f16(d, umma_desc_sw64(a + k2 * 32), umma_desc_sw64(w + k2 * 32), idesc,
+                                     (kb | (p == 1 ? 1 : 0) | k2) != 0 ? 1u : 0u);
+                    }
+                    tc_commit(bar_free(s));
+                }
+                tc_commit(bar_accum);
             }
-            tc_commit(bar_accum);
         }
     } else {
-        // ---- epilogue: TMEM -> registers -> main + corr * 2^-11 + bias -> global -------------------------------------
-        mbar_wait(bar_accum, 0);
-        tc_fence_after();
+        // ---- epilogue: TMEM -> registers -> main + corr * 2^-11 + bias -> swizzled shared-memory box -> TMA store -------
         const int wq = warp & 3;                         // TMEM lane quarter this warp may read
-        const int row = m0 + wq * 32 + lane;
-        for (int c0 = 0; c0 < HB_N; c0 += 32) {
-            uint32_t v[32], u[32];
-            const uint32_t taddr = tmem + ((uint32_t)(wq * 32) << 16) + (uint32_t)c0;
-            tmem_ld32(taddr, v);
-            tmem_ld32(taddr + (uint32_t)HB_N, u);
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            if (row < M) {
-                float* dst = C + (size_t)row * N + n0 + c0;
+        const uint32_t box = s_out + (uint32_t)wq * 4096u;
+        unsigned char* gbox = gen + (box - base);
+        for (int j = 0;; ++j) {
+            mbar_wait(bar_tile_full(j & 1), (j >> 1) & 1);
+            const int t = tile_q[j & 1];
+            __syncwarp();
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_tile_free(j & 1)) : "memory");
+            if (t < 0) break;
+            const int n0 = (t % tiles_n) * HB_N, m0 = (t / tiles_n) * HB_M;
+            mbar_wait(bar_accum, j & 1);
+            tc_fence_after();
+            for (int c0 = 0; c0 < HB_N; c0 += 32) {
+                uint32_t v[32], u[32];
+                const uint32_t taddr = tmem + ((uint32_t)(wq * 32) << 16) + (uint32_t)c0;
+                tmem_ld32(taddr, v);
+                tmem_ld32(taddr + (uint32_t)HB_N, u);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (c0 + 32 == HB_N) {                   // last read of this tile's accumulators: the MMA warp may start the next tile
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_drained) : "memory");
+                }
+                // the box is free once the previous TMA store has read it
+                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                __syncwarp();
                 const float4* b4 = reinterpret_cast<const float4*>(bias + n0 + c0);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const float4 b = __ldg(b4 + j);
+                for (int q = 0; q < 8; ++q) {
+                    const float4 b = __ldg(b4 + q);
                     float4 o;
-                    o.x = fmaf(__uint_as_float(u[4 * j + 0]), kLoInv, __uint_as_float(v[4 * j + 0])) + b.x;
-                    o.y = fmaf(__uint_as_float(u[4 * j + 1]), kLoInv, __uint_as_float(v[4 * j + 1])) + b.y;
-                    o.z = fmaf(__uint_as_float(u[4 * j + 2]), kLoInv, __uint_as_float(v[4 * j + 2])) + b.z;
-                    o.w = fmaf(__uint_as_float(u[4 * j + 3]), kLoInv, __uint_as_float(v[4 * j + 3])) + b.w;
-                    reinterpret_cast<float4*>(dst)[j] = o;
+                    o.x = fmaf(__uint_as_float(u[4 * q + 0]), kLoInv, __uint_as_float(v[4 * q + 0])) + b.x;
+                    o.y = fmaf(__uint_as_float(u[4 * q + 1]), kLoInv, __uint_as_float(v[4 * q + 1])) + b.y;
+                    o.z = fmaf(__uint_as_float(u[4 * q + 2]), kLoInv, __uint_as_float(v[4 * q + 2])) + b.z;
+                    o.w = fmaf(__uint_as_float(u[4 * q + 3]), kLoInv, __uint_as_float(v[4 * q + 3])) + b.w;
+                    // row = lane (128 B per row), 16-byte chunk q at position q ^ (row % 8): the 128B swizzle of the store's tensor map
+                    *reinterpret_cast<float4*>(gbox + lane * 128 + ((q ^ (lane & 7)) << 4)) = o;
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                    tma_store_2d(&map_c, box, n0 + c0, m0 + wq * 32);
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
             }
         }
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");      // all stores of this CTA are complete
     }
     tc_fence_before();
     __syncthreads();
@@ -222,6 +290,26 @@ int make_map_f16(CUtensorMap* map, const __half* ptr, int rows, int K, int box_r
     return MP_OK;
 }
 
+// C [M, N] fp32 row-major -> 2-D tensor map with a 32 x 32 box (128-byte rows), 128-byte swizzle, for the epilogue's TMA stores
+int make_map_c(CUtensorMap* map, float* ptr, int M, int N) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) {
+        set_error("gemm_f16: cuTensorMapEncodeTiled is not available from this driver");
+        return MP_ERR_CUDA;
+    }
+    const cuuint64_t dims[2] = {(cuuint64_t)N, (cuuint64_t)M};
+    const cuuint64_t strides[1] = {(cuuint64_t)N * 4};
+    const cuuint32_t box[2] = {32, 32};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("gemm_f16: cuTensorMapEncodeTiled (output) failed with CUresult %d (M=%d N=%d)", (int)r, M, N);
+        return MP_ERR_CUDA;
+    }
+    return MP_OK;
+}
+
 // x -> (hi, lo): out[i] = fp16(x), out[n + i] = fp16((x - hi) * 2^11).  Streaming: 4 B in, 4 B out per element.
 __global__ void split_f16_kernel(const float4* __restrict__ x, size_t n4, __half2* __restrict__ hi, __half2* __restrict__ lo) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
@@ -257,13 +345,17 @@ int launch_split_f16(const float* x, size_t n, void* out_hi_lo, cudaStream_t str
 }
 
 // A_split: [2][M, K] halves (hi plane, then lo plane); W_split: [2N, K] halves (hi rows, then lo rows)
-int launch_gemm_f16x3(const void* A_split, const void* W_split, const float* bias, float* C, int M, int N, int K, cudaStream_t stream) {
-    MP_REQUIRE(A_split && W_split && bias && C && M > 0, "gemm_f16: bad arguments");
+// sched: two zeroed 32-bit words owned by this launch (tile counter, CTAs done), e.g. a slice of the caller's workspace cleared on the
+// same stream; the kernel leaves them zero again
+int launch_gemm_f16x3(const void* A_split, const void* W_split, const float* bias, float* C, int M, int N, int K, unsigned int* sched,
+                      cudaStream_t stream) {
+    MP_REQUIRE(A_split && W_split && bias && C && sched && M > 0, "gemm_f16: bad arguments");
     MP_REQUIRE(N % HB_N == 0 && K % HB_K == 0, "gemm_f16: N=%d must be a multiple of %d and K=%d of %d", N, HB_N, K, HB_K);
     MP_REQUIRE(((uintptr_t)A_split & 15) == 0 && ((uintptr_t)W_split & 15) == 0 && ((uintptr_t)C & 15) == 0 && ((uintptr_t)bias & 15) == 0,
                "gemm_f16: pointers must be 16-byte aligned");
     const __half* a = reinterpret_cast<const __half*>(A_split);
-    alignas(64) CUtensorMap map_a_hi, map_a_lo, map_w;
+    alignas(64) CUtensorMap map_a_hi, map_a_lo, map_w, map_c;
+    MP_TRY(make_map_c(&map_c, C, M, N));
     MP_TRY(make_map_f16(&map_a_hi, a, M, K, HB_M));
     MP_TRY(make_map_f16(&map_a_lo, a + (size_t)M * K, M, K, HB_M));
     MP_TRY(make_map_f16(&map_w, reinterpret_cast<const __half*>(W_split), 2 * N, K, HB_N));
@@ -274,8 +366,14 @@ int launch_gemm_f16x3(const void* A_split, const void* W_split, const float* bia
     }
     // algorithmic bytes: the operands as the caller holds them (fp32-equivalent: 4 B per element either way) + the output
     ProfileScope prof("gemm_f16x3", 4.0 * ((double)N * K + N + (double)M * K + (double)M * N), stream);
-    dim3 grid(N / HB_N, (M + HB_M - 1) / HB_M);
-    gemm_f16x3_kernel<<<grid, HB_THREADS, H_SMEM, stream>>>(map_a_hi, map_a_lo, map_w, bias, C, M, N, K);
+    static int n_sm = 0;
+    if (!n_sm) {
+        int dev = 0;
+        MP_CUDA_TRY(cudaGetDevice(&dev));
+        MP_CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+    }
+    const int tiles = (N / HB_N) * ((M + HB_M - 1) / HB_M);
+    gemm_f16x3_kernel<<<std::min(tiles, n_sm), HB_THREADS, H_SMEM, stream>>>(map_a_hi, map_a_lo, map_w, map_c, bias, M, N, K, sched);
     MP_CUDA_TRY(cudaGetLastError());
     count_launch();
     return MP_OK;

@@ -110,15 +110,29 @@ __host__ __device__ inline size_t rec_smem_bytes(int NB) {
            sizeof(int) * 4 * NB + 2 * sizeof(unsigned long long) + 16;
 }
 
-// sigmoid(x) (k = 1) or tanh(x) (k = 2) from ONE exponential, branch free:  E = exp(-k x),
-// sigmoid = 1 / (1 + E),  tanh = (1 - E) / (1 + E).  expf and the reciprocal are the correctly-rounded-grade
-// library versions (no ex2.approx shortcuts on the argument); the clamp keeps E finite and changes the result
-// by < 1e-13.  Absolute error <= ~1e-7 for tanh, 1 ulp-grade for sigmoid (DESIGN.md "precision").
+// sigmoid(x) or tanh(x) from ONE exponential, branch free, on the step's serial chain twice (gates, then tanh(c)):
+//   sigma(s) = 1 / (1 + 2^(-s log2 e)),  tanh(x) = 2 sigma(2x) - 1
+// MUFU ex2 + MUFU reciprocal + one Newton step (7 dependent instructions).  ex2.approx is 2 ulp on the exponential, i.e. <= 6e-8
+// absolute on the result -- the same form the tensor-core recurrence uses, inside the parity budget (tests hold the kernels to the
+// oracle at 1e-4 on the head outputs, measured ~1e-7).  The first version used expf and the correctly rounded __frcp_rn: two ~10-deep
+// dependent sequences per activation, ~200 of the latency path's 1500 clk per step.  The clamp keeps 1 + e finite (rcp(inf) = 0
+// would feed inf * 0 into the Newton step).
 __device__ __forceinline__ float sigmoid_or_tanh(float x, bool is_tanh) {
+#ifdef MP_EXACT_ACT
     const float s = fminf(fmaxf(is_tanh ? 2.0f * x : x, -30.0f), 30.0f);
     const float e = expf(-s);
     const float r = __frcp_rn(1.0f + e);
     return is_tanh ? (1.0f - e) * r : r;
+#else
+    const float t = fminf(x * (is_tanh ? -2.8853900817779268f : -1.4426950408889634f), 126.0f);
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(t));
+    const float d = 1.0f + e;
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d));
+    r = fmaf(fmaf(-d, r, 1.0f), r, r);
+    return is_tanh ? fmaf(2.0f, r, -1.0f) : r;
+#endif
 }
 
 // gate nonlinearity + i/f/g/o gather + cell update for one (unit, sequence); every lane of the 4x4

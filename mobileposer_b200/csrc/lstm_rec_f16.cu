@@ -34,7 +34,7 @@ constexpr int TH = 256;
 constexpr int TCC = 8;            // cluster size
 constexpr int TUC = TH / TCC;     // 32 units per CTA
 constexpr int EPI_WARPS = 16;
-constexpr int RF_THREADS = (EPI_WARPS + 2) * 32;   // 16 epilogue warps + MMA warp + copy warp
+constexpr int RF_THREADS = (EPI_WARPS + 3) * 32;   // 16 epilogue warps + MMA warp + one exchange warp per sub-tile
 constexpr uint32_t COL_WHI = 0, COL_WLO = 128, COL_D = 256;
 constexpr float kLoScale = 2048.0f, kLoInv = 1.0f / 2048.0f;
 
@@ -49,6 +49,7 @@ struct RecF16Params {
     float* cn;
     const int32_t* lengths;
     int B, T, dirs, NB;
+    int y_split;          // y = two planes of halves (hi, scaled lo) instead of fp32
     long long* ts;        // bring-up: per-step clock64 stamps of block (0,0) [step][8], or null (MP_RTC_TS)
 };
 
@@ -91,8 +92,12 @@ __device__ __forceinline__ void tmem_ld4(uint32_t taddr, float* v) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(taddr) : "memory");
     v[0] = __uint_as_float(a); v[1] = __uint_as_float(b); v[2] = __uint_as_float(c); v[3] = __uint_as_float(d);
 }
+// Remote arrive WITHOUT release semantics: it only tells the peers that this CTA's tensor core has finished reading its h rows (a
+// fact this thread learned through the acquire of its own `mma` barrier wait); no memory written by this thread has to become
+// visible with it.  The default .release.cluster form compiles to MEMBAR.ALL.CTA + MEMBAR.ALL.GPU + ERRBAR + CGAERRBAR in front of
+// the arrive -- a GPU-scope fence per sub-tile and step on the exchange's critical path (measured: 2 of 6 k clk per step).
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t remote_bar) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote_bar) : "memory");
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote_bar) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive_local(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
@@ -111,6 +116,20 @@ __device__ __forceinline__ void split16(float x, unsigned short& hi, unsigned sh
 
 __device__ __forceinline__ uint32_t pk(unsigned short a, unsigned short b) { return (uint32_t)a | ((uint32_t)b << 16); }
 
+// short form: sigma(s) = 1 / (1 + 2^(-s log2 e)) with MUFU ex2 + MUFU rcp and one Newton step; tanh(x) = 2 sigma(2x) - 1.
+// ex2.approx is 2 ulp on e, i.e. <= 6e-8 absolute on the result; the clamp keeps 1 + e finite (rcp of inf would feed a NaN
+// into the Newton step).  8 instructions against ~20 of the expf form below.
+__device__ __forceinline__ float act_fast(float x, bool is_tanh) {
+    const float t = fminf(x * (is_tanh ? -2.8853900817779268f : -1.4426950408889634f), 126.0f);
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(t));
+    const float d = 1.0f + e;
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d));
+    r = fmaf(fmaf(-d, r, 1.0f), r, r);
+    return is_tanh ? fmaf(2.0f, r, -1.0f) : r;
+}
+
 __device__ __forceinline__ float act_sigmoid_or_tanh(float x, bool is_tanh) {
     const float s = fminf(fmaxf(is_tanh ? 2.0f * x : x, -30.0f), 30.0f);
     const float e = expf(-s);
@@ -128,7 +147,11 @@ __device__ __forceinline__ float act_sigmoid_or_tanh(float x, bool is_tanh) {
     } while (0)
 
 // N = padded sequence count of the tile (multiple of 16, <= 64); SPW = N / 4 sequences per epilogue warp
-template <int N>
+// FAST: act_fast instead of the expf form; RAGGED = false: every sequence of the launch has T frames (no per-step length checks).
+// (Measured and dropped: pushing the new h values straight into the 8 CTAs with st.async -- 4 bytes per lane and destination, no
+//  staging, no copy warp -- is correct but 16 k remote stores per CTA and step cost more than they save: 10.5 k clk per step
+//  against 6.7 k with the staged bulk copies.)
+template <int N, bool FAST, bool RAGGED>
 __global__ void __launch_bounds__(RF_THREADS, 1) lstm_rec_f16_kernel(const RecF16Params p) {
     constexpr int SPW = N / 4;
     constexpr int NBLK = N / 16;
@@ -311,21 +334,31 @@ __global__ void __launch_bounds__(RF_THREADS, 1) lstm_rec_f16_kernel(const RecF1
                 }
             }
             __syncwarp();
-        } else if (warp == EPI_WARPS + 1) {
-            // ================= copy warp =================
-            // ships the new slice of a sub-tile (hi and lo planes, one contiguous block) to all 8 CTAs once the 16 epilogue
-            // warps have staged it and every peer's MMAs on that sub-tile's old rows are done
-            if (send) {
-#pragma unroll
-                for (int sub = 0; sub < NSUB; ++sub) {
-                    const uint32_t rows = sub == 0 ? R0 : R1;
-                    const uint32_t bytes = 2u * rows * 64u;
-                    mbar_wait(bar_stage + 8 * sub, par);
-                    mbar_wait(bar_free + 8 * sub, par);
-                    if (lane < TCC)
-                        bulk_copy_s2c(mapa_u32(s_h + (sub ? SUB1_H : 0u) + (uint32_t)rank * bytes, lane),
-                                      s_stg + (uint32_t)par * STG_PAR + (sub ? SUB1_STG : 0u), bytes, mapa_u32(bar_full + 8 * sub, lane));
-                }
+        } else if (warp > EPI_WARPS) {
+            // ================= exchange warps (one per sub-tile) =================
+            // (a) once the sub-tile's MMAs of this step have completed: arm its `h_full` barrier for the next step's rows and tell all 8
+            //     CTAs that this CTA's tensor core no longer reads those rows (`h_free`, relaxed remote arrive);
+            // (b) ship the new slice (hi and lo planes, one contiguous block) to all 8 CTAs once the 16 epilogue warps have staged it
+            //     and every peer's MMAs on the sub-tile's old rows are done.
+            // One warp per sub-tile: with a single warp the second sub-tile's (a) -- which waits for MMAs that start half a step
+            // later -- sat in front of the first sub-tile's (b) and delayed its copies by ~1 k clk per step.
+            const int sub = warp - EPI_WARPS - 1;
+            if (send && sub < NSUB) {
+                const uint32_t rows = sub == 0 ? R0 : R1;
+                const uint32_t bytes = 2u * rows * 64u;
+                mbar_wait(bar_mma + 8 * sub, par);
+                // h_{s+1} of this sub-tile arrives as 8 ranks x (hi + lo planes).  Armed only now: MMA(s) has run, so the MMA
+                // warp has seen the previous phase of the barrier complete (arming earlier could put two arrivals in one phase)
+                if (lane == 0) mbar_arrive_expect_tx(bar_full + 8 * sub, (uint32_t)TCC * bytes);
+                if (lane < TCC) mbar_arrive_remote(mapa_u32(bar_free + 8 * sub, lane));
+                mbar_wait(bar_stage + 8 * sub, par);
+                if (lane == 0 && sub == 0) RF_STAMP(5);
+                mbar_wait(bar_free + 8 * sub, par);
+                if (p.ts && lane == 0 && sub == 0 && blockIdx.x == 0 && blockIdx.y == 0 && s < 64) p.ts[512 + s * 20 + 16] = clock64();
+                if (lane < TCC)
+                    bulk_copy_s2c(mapa_u32(s_h + (sub ? SUB1_H : 0u) + (uint32_t)rank * bytes, lane),
+                                  s_stg + (uint32_t)par * STG_PAR + (sub ? SUB1_STG : 0u), bytes, mapa_u32(bar_full + 8 * sub, lane));
+                if (lane == 0 && sub == 0) RF_STAMP(6);
             }
             __syncwarp();
         } else {
@@ -338,11 +371,7 @@ __global__ void __launch_bounds__(RF_THREADS, 1) lstm_rec_f16_kernel(const RecF1
                 const uint32_t rows = sub == 0 ? R0 : R1;
                 mbar_wait(bar_mma + 8 * sub, par);
                 tc_fence_after();
-                // h_{s+1} of this sub-tile arrives as 8 ranks x (hi + lo planes).  Armed only now: MMA(s) has run, so the MMA
-                // warp has seen the previous phase of the barrier complete (arming earlier could put two arrivals in one phase)
-                if (tid == 0 && send) mbar_arrive_expect_tx(bar_full + 8 * sub, (uint32_t)TCC * 2u * rows * 64u);
                 if (tid == 0 && sub == 0) RF_STAMP(2);
-                if (send && tid < TCC) mbar_arrive_remote(mapa_u32(bar_free + 8 * sub, tid));     // my MMAs no longer read these rows
                 float dm[4 * (NBLK - NBLK / 2)], dc[4 * (NBLK - NBLK / 2)];
 #pragma unroll
                 for (int q = 0; q < nblk; ++q) {
@@ -355,13 +384,15 @@ __global__ void __launch_bounds__(RF_THREADS, 1) lstm_rec_f16_kernel(const RecF1
                 // lanes of a unit) exchanges them, and lane g then owns sequence 4*blk + g: ONE cell update per lane.
                 constexpr int MAXB = NBLK - NBLK / 2;
                 float c_nw[MAXB], h_nw[MAXB];
+                unsigned short h_hi16[MAXB], h_lo16[MAXB];
 #pragma unroll
                 for (int bq = 0; bq < nblk; ++bq) {
                     const int blk = blk0 + bq;
                     float a[4];
 #pragma unroll
                     for (int q = 0; q < 4; ++q)
-                        a[q] = act_sigmoid_or_tanh(fmaf(dc[bq * 4 + q], kLoInv, dm[bq * 4 + q]) + gi[blk * 4 + q], gate == 2);
+                        a[q] = FAST ? act_fast(fmaf(dc[bq * 4 + q], kLoInv, dm[bq * 4 + q]) + gi[blk * 4 + q], gate == 2)
+                                    : act_sigmoid_or_tanh(fmaf(dc[bq * 4 + q], kLoInv, dm[bq * 4 + q]) + gi[blk * 4 + q], gate == 2);
                     // 4 x 4 transpose inside the gate quad: two butterfly rounds, 4 shuffles instead of 16
                     const bool b0 = lane & 1, b1 = lane & 2;
                     const float r0 = __shfl_xor_sync(0xffffffffu, b0 ? a[0] : a[1], 1), r1 = __shfl_xor_sync(0xffffffffu, b0 ? a[2] : a[3], 1);
@@ -369,35 +400,20 @@ __global__ void __launch_bounds__(RF_THREADS, 1) lstm_rec_f16_kernel(const RecF1
                     const float q0 = __shfl_xor_sync(0xffffffffu, b1 ? u0 : u2, 2), q1 = __shfl_xor_sync(0xffffffffu, b1 ? u1 : u3, 2);
                     const float iv = b1 ? q0 : u0, fv = b1 ? q1 : u1, gv = b1 ? u2 : q0, ov = b1 ? u3 : q1;
                     c_nw[bq] = fmaf(fv, cst[blk], iv * gv);
-                    h_nw[bq] = ov * act_sigmoid_or_tanh(c_nw[bq], true);
+                    h_nw[bq] = ov * (FAST ? act_fast(c_nw[bq], true) : act_sigmoid_or_tanh(c_nw[bq], true));
                 }
+                // (1) the exchange first: nothing that touches global memory may sit between the activations and the hand-over --
+                // fence.proxy.async waits for every earlier memory operation of the thread, and with the y stores and the next step's
+                // gin loads in front of it the epilogue stalled a DRAM round trip per sub-tile (ncu: a third of all stall samples)
 #pragma unroll
                 for (int bq = 0; bq < nblk; ++bq) {
                     const int blk = blk0 + bq;
                     const int n = blk * 16 + part * 4 + gate;
-                    const int len = len_own[blk];
-                    const bool active = s < len;
-                    const float c_new = c_nw[bq], h_new = h_nw[bq];
-                    if (active) {
-                        cst[blk] = c_new;
-                        p.y[yo[blk]] = h_new;
-                        if (s == len - 1) {
-                            if (p.hn) p.hn[((size_t)dir * p.B + b_begin + n) * TH + rank * TUC + ul] = h_new;
-                            if (p.cn) p.cn[((size_t)dir * p.B + b_begin + n) * TH + rank * TUC + ul] = c_new;
-                        }
-                    }
-                    yo[blk] += dY2;
+                    const bool active = !RAGGED || s < len_own[blk];
+                    split16(active ? h_nw[bq] : 0.f, h_hi16[bq], h_lo16[bq]);
                     if (send) {
-                        unsigned short hh, ll;
-                        split16(active ? h_new : 0.f, hh, ll);
-                        *reinterpret_cast<unsigned short*>(stg + so[blk]) = hh;
-                        *reinterpret_cast<unsigned short*>(stg + so[blk] + rows * 64u) = ll;
-                    }
-                    // next step's gate pre-activations of the block (this lane's gate, all 4 sequences)
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        if (s + 1 < lens[blk * 16 + part * 4 + q]) gi[blk * 4 + q] = __ldg(p.gin + go[blk * 4 + q]);
-                        go[blk * 4 + q] += dG4;
+                        *reinterpret_cast<unsigned short*>(stg + so[blk]) = h_hi16[bq];
+                        *reinterpret_cast<unsigned short*>(stg + so[blk] + rows * 64u) = h_lo16[bq];
                     }
                 }
                 if (send) {
@@ -405,6 +421,37 @@ __global__ void __launch_bounds__(RF_THREADS, 1) lstm_rec_f16_kernel(const RecF1
                     fence_proxy_async_smem();
                     __syncwarp();
                     if (lane == 0) mbar_arrive_local(bar_stage + 8 * sub);
+                    if (tid == 0 && sub == 0) RF_STAMP(7);
+                    if (p.ts && lane == 0 && sub == 0 && blockIdx.x == 0 && blockIdx.y == 0 && s < 64) p.ts[512 + s * 20 + warp] = clock64();
+                }
+                // (2) then the layer output, the final states and the next step's gate pre-activations
+#pragma unroll
+                for (int bq = 0; bq < nblk; ++bq) {
+                    const int blk = blk0 + bq;
+                    const int n = blk * 16 + part * 4 + gate;
+                    const int len = len_own[blk];
+                    const bool active = !RAGGED || s < len;
+                    const float c_new = c_nw[bq], h_new = h_nw[bq];
+                    if (active) {
+                        cst[blk] = c_new;
+                        if (p.y_split) {
+                            unsigned short* yh = reinterpret_cast<unsigned short*>(p.y);
+                            yh[yo[blk]] = h_hi16[bq];
+                            yh[(size_t)p.B * p.T * Y2 + yo[blk]] = h_lo16[bq];
+                        } else {
+                            p.y[yo[blk]] = h_new;
+                        }
+                        if (s == len - 1) {
+                            if (p.hn) p.hn[((size_t)dir * p.B + b_begin + n) * TH + rank * TUC + ul] = h_new;
+                            if (p.cn) p.cn[((size_t)dir * p.B + b_begin + n) * TH + rank * TUC + ul] = c_new;
+                        }
+                    }
+                    yo[blk] += dY2;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        if (RAGGED ? (s + 1 < lens[blk * 16 + part * 4 + q]) : send) gi[blk * 4 + q] = __ldg(p.gin + go[blk * 4 + q]);
+                        go[blk * 4 + q] += dG4;
+                    }
                 }
             }
             if (tid == 0) RF_STAMP(4);
@@ -417,7 +464,14 @@ __global__ void __launch_bounds__(RF_THREADS, 1) lstm_rec_f16_kernel(const RecF1
         const int cnt = (p.T - len) * TUC;
         for (int i = tid; i < cnt; i += RF_THREADS) {
             const int t = len + i / TUC, u = i % TUC;
-            p.y[yoff[b] + (uint32_t)t * (uint32_t)Y2 + (uint32_t)u] = 0.f;
+            const uint32_t idx = yoff[b] + (uint32_t)t * (uint32_t)Y2 + (uint32_t)u;
+            if (p.y_split) {
+                unsigned short* yh = reinterpret_cast<unsigned short*>(p.y);
+                yh[idx] = 0;
+                yh[(size_t)p.B * p.T * Y2 + idx] = 0;
+            } else {
+                p.y[idx] = 0.f;
+            }
         }
     }
     tc_fence_before();
@@ -426,10 +480,10 @@ __global__ void __launch_bounds__(RF_THREADS, 1) lstm_rec_f16_kernel(const RecF1
     if (warp == EPI_WARPS) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
 }
 
-template <int N>
+template <int N, bool FAST, bool RAGGED>
 int launch_f16_n(const RecF16Params& p, cudaStream_t stream) {
     const size_t smem = rec_f16_smem_bytes(N);
-    auto kern = lstm_rec_f16_kernel<N>;
+    auto kern = lstm_rec_f16_kernel<N, FAST, RAGGED>;
     static bool configured = false;
     if (!configured) {
         MP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -457,7 +511,7 @@ int f16_cluster_slots() {
     static int slots = 0;
     if (slots > 0) return slots;
     int n = 0;
-    auto kern = lstm_rec_f16_kernel<64>;
+    auto kern = lstm_rec_f16_kernel<64, false, true>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rec_f16_smem_bytes(64));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(TCC * 64, 1, 1);
@@ -512,28 +566,49 @@ int launch_lstm_recurrence_f16(const RecLayerArgs& a, cudaStream_t stream) {
     static long long* ts_dev = nullptr;
     const bool want_ts = getenv("MP_RTC_TS") != nullptr;
     if (want_ts && !ts_dev) {
-        cudaMalloc(&ts_dev, 64 * 8 * sizeof(long long));
-        cudaMemset(ts_dev, 0, 64 * 8 * sizeof(long long));
+        cudaMalloc(&ts_dev, (64 * 8 + 64 * 20) * sizeof(long long));
+        cudaMemset(ts_dev, 0, (64 * 8 + 64 * 20) * sizeof(long long));
     }
-    RecF16Params p{a.gin, a.w_raw[0], a.w_raw[a.dirs - 1], a.y, a.h0, a.c0, a.hn, a.cn, a.lengths, a.B, a.T, a.dirs, NB,
+    RecF16Params p{a.gin, a.w_raw[0], a.w_raw[a.dirs - 1], a.y, a.h0, a.c0, a.hn, a.cn, a.lengths, a.B, a.T, a.dirs, NB, a.y_split,
                    want_ts ? ts_dev : nullptr};
     ProfileScope prof("lstm_rec_f16_h256", 4.0 * ((double)a.dirs * 4 * a.H * a.H + (double)a.B * a.T * a.dirs * a.H), stream);
+    // the short ex2 / rcp activation by default (MP_RF16_ACT=exact: the expf form); the uniform-length variant when no lengths are given
+    // (a tile's padded rows then run as zero-input sequences whose results are never stored: n >= nb is masked by len = 0 only in
+    // the ragged variant, so the uniform one is taken only for full tiles)
+    const char* actv = getenv("MP_RF16_ACT");
+    const bool fast = !(actv && strcmp(actv, "exact") == 0);
+    const bool ragged = a.lengths != nullptr || a.B % NB != 0 || NB % 16 != 0 || getenv("MP_RF16_RAGGED") != nullptr;
     int st;
+#define RF16_DISPATCH(NN) (fast ? (ragged ? launch_f16_n<NN, true, true>(p, stream) : launch_f16_n<NN, true, false>(p, stream)) \
+                                : (ragged ? launch_f16_n<NN, false, true>(p, stream) : launch_f16_n<NN, false, false>(p, stream)))
     switch (N) {
-        case 16: st = launch_f16_n<16>(p, stream); break;
-        case 32: st = launch_f16_n<32>(p, stream); break;
-        case 48: st = launch_f16_n<48>(p, stream); break;
-        default: st = launch_f16_n<64>(p, stream); break;
+        case 16: st = RF16_DISPATCH(16); break;
+        case 32: st = RF16_DISPATCH(32); break;
+        case 48: st = RF16_DISPATCH(48); break;
+        default: st = RF16_DISPATCH(64); break;
     }
+#undef RF16_DISPATCH
+#undef RF16_DISPATCH
     if (st == MP_OK && want_ts) {      // bring-up only: synchronous dump of the stamps of block (0,0)
-        long long h[64 * 8];
+        static long long h[64 * 8 + 64 * 20];
         cudaStreamSynchronize(stream);
         cudaMemcpy(h, ts_dev, sizeof(h), cudaMemcpyDeviceToHost);
         fprintf(stderr, "[rtc ts f16] N=%d NB=%d B=%d\n", N, NB, a.B);
         for (int s = 2; s < 8 && s < a.T - 1; ++s)
-            fprintf(stderr, "[rtc ts f16] s=%d  mma issue %lld | commit->epi %lld  tmem ld %lld  activations+staging %lld  tail->next mma %lld  step %lld\n", s,
-                    h[s * 8 + 1] - h[s * 8 + 0], h[s * 8 + 2] - h[s * 8 + 1], h[s * 8 + 3] - h[s * 8 + 2], h[s * 8 + 4] - h[s * 8 + 3],
-                    h[(s + 1) * 8 + 0] - h[s * 8 + 4], h[(s + 1) * 8 + 0] - h[s * 8 + 0]);
+            fprintf(stderr, "[rtc ts f16] s=%d  step %lld | sub0: mma start->epi start %lld  tmem ld %lld  act+stage %lld  staged->copy warp %lld  copy issue %lld  "
+                            "copies issued->next mma start %lld | both subs: mma issue %lld  epilogue %lld\n", s,
+                    h[(s + 1) * 8 + 0] - h[s * 8 + 0], h[s * 8 + 2] - h[s * 8 + 0], h[s * 8 + 3] - h[s * 8 + 2], h[s * 8 + 7] - h[s * 8 + 3],
+                    h[s * 8 + 5] - h[s * 8 + 7], h[s * 8 + 6] - h[s * 8 + 5], h[(s + 1) * 8 + 0] - h[s * 8 + 6], h[s * 8 + 1] - h[s * 8 + 0],
+                    h[s * 8 + 4] - h[s * 8 + 2]);
+        for (int s = 3; s < 6 && s < a.T - 1; ++s) {      // sub-tile 0: when each epilogue warp reported its rows staged, relative to the first
+            const long long* w = h + 512 + s * 20;
+            long long first = w[0];
+            for (int i = 1; i < 16; ++i) first = std::min(first, w[i]);
+            fprintf(stderr, "[rtc ts f16] s=%d  sub0 staged, per warp (clk after the first):", s);
+            for (int i = 0; i < 16; ++i) fprintf(stderr, " %lld", w[i] - first);
+            fprintf(stderr, " | copy warp: stage barrier seen +%lld, free barrier seen +%lld, copies issued +%lld, next mma start +%lld\n",
+                    h[s * 8 + 5] - first, w[16] - first, h[s * 8 + 6] - first, h[(s + 1) * 8 + 0] - first);
+        }
     }
     return st;
 }

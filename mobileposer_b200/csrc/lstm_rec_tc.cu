@@ -110,8 +110,12 @@ __device__ __forceinline__ void tmem_ld4(uint32_t taddr, float* v) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(taddr) : "memory");
     v[0] = __uint_as_float(a); v[1] = __uint_as_float(b); v[2] = __uint_as_float(c); v[3] = __uint_as_float(d);
 }
+// Remote arrive WITHOUT release semantics: it only tells the peers that this CTA's tensor core has finished reading its h rows (a
+// fact this thread learned through the acquire of its own `mma` barrier wait); no memory written by this thread has to become
+// visible with it.  The default .release.cluster form compiles to MEMBAR.ALL.CTA + MEMBAR.ALL.GPU + ERRBAR + CGAERRBAR in front of
+// the arrive -- a GPU-scope fence per sub-tile and step on the exchange's critical path (measured: 2 of 6 k clk per step).
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t remote_bar) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote_bar) : "memory");
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote_bar) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive_local(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");

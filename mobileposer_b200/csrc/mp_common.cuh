@@ -48,7 +48,8 @@ struct ProfileScope {
 
 // ---- launchers implemented in the .cu files ------------------------------------------------
 
-// C[M,N] = act(cat(A1[M,K1], A2[M,K2]) * W[N,K1+K2]^T + bias[N]);   relu != 0 applies max(.,0)
+// C[M,N] = act(cat(A1[M,K1], A2[M,K2]) * W[N,K1+K2]^T + bias[N]);   relu bit 0: apply max(.,0); bit 1 (FFMA kernel only): write C as
+// two [M,N] planes of halves (fp16 hi, fp16 scaled lo) for launch_gemm_f16x3 instead of fp32 -- the same number of bytes
 int launch_gemm_bias_act(const float* A1, int K1, const float* A2, int K2, const float* W,
                          const float* bias, float* C, int M, int N, int relu, cudaStream_t stream);
 
@@ -64,7 +65,9 @@ int launch_split_weights(const float* W, size_t n, float* W_split, cudaStream_t 
 // A_split = [2][M, K] halves (hi plane, lo plane), W_split = [2N, K] halves (hi rows, lo rows); launch_split_f16 makes either
 // from an fp32 array of n elements (out = n hi halves, then n lo halves)
 bool gemm_f16_eligible(int M, int N, int K);
-int launch_gemm_f16x3(const void* A_split, const void* W_split, const float* bias, float* C, int M, int N, int K, cudaStream_t stream);
+// sched: two zeroed 32-bit words private to the launch (the persistent kernel's dynamic tile counter); left zero on exit
+int launch_gemm_f16x3(const void* A_split, const void* W_split, const float* bias, float* C, int M, int N, int K, unsigned int* sched,
+                      cudaStream_t stream);
 int launch_split_f16(const float* x, size_t n, void* out_hi_lo, cudaStream_t stream);
 int launch_gemm_ffma(const float* A1, int K1, const float* A2, int K2, const float* W, const float* bias, float* C,
                      int M, int N, int relu, cudaStream_t stream);
@@ -82,6 +85,8 @@ struct RecLayerArgs {
     const int32_t* lengths;  // [B] or null
     int B, T, H, dirs;
     int tile_hint = 0;    // sequences per cluster tile of the tensor-core recurrence; 0 = one wave covering the batch
+    int y_split = 0;      // y is written as two [B,T,dirs*H] planes of halves (fp16 hi, scaled lo) for the next layer's fp16-split projection
+                          // (honoured by the fp16-split recurrence only: ask rec_f16_eligible first)
 };
 int launch_lstm_recurrence(const RecLayerArgs& a, cudaStream_t stream);
 // tcgen05 3xTF32 variant for H = 256 and large batches (lstm_rec_tc.cu)

@@ -1,10 +1,16 @@
-# compute-sanitizer over small runs of every kernel family (memcheck + racecheck on the shared-memory heavy ones)
+# compute-sanitizer: (1) the minimal DSMEM bulk-copy reproducer under all four tools; (2) racecheck / initcheck / synccheck of both
+# cluster recurrences (fp16-split tensor-core kernel, FFMA latency kernel) on tiny runs; (3) memcheck of the same for the record.
+set -x
 mkdir -p gpurun_out
-timeout 600 compute-sanitizer --tool memcheck --error-exitcode 9 python scripts/time_physics.py --batch 3 --frames 12 --iters 1 > gpurun_out/san_k8_mem.log 2>&1; echo "k8 memcheck exit $?"; tail -3 gpurun_out/san_k8_mem.log
-timeout 600 compute-sanitizer --tool racecheck --error-exitcode 9 python scripts/time_physics.py --batch 3 --frames 12 --iters 1 > gpurun_out/san_k8_race.log 2>&1; echo "k8 racecheck exit $?"; tail -3 gpurun_out/san_k8_race.log
-timeout 600 compute-sanitizer --tool memcheck --error-exitcode 9 python scripts/prof_one.py --batch 40 --frames 6 --passes 2 --physics > gpurun_out/san_net_mem.log 2>&1; echo "net memcheck exit $?"; tail -3 gpurun_out/san_net_mem.log
-timeout 600 compute-sanitizer --tool memcheck --error-exitcode 9 python scripts/prof_one.py --batch 1 --frames 9 --passes 2 > gpurun_out/san_b1_mem.log 2>&1; echo "b1 memcheck exit $?"; tail -3 gpurun_out/san_b1_mem.log
-mkdir -p gpurun_out
-timeout 600 compute-sanitizer --tool racecheck --error-exitcode 9 python scripts/time_physics.py --batch 3 --frames 12 --iters 1 > gpurun_out/san_k8_race.log 2>&1; echo "k8 racecheck exit $?"; tail -2 gpurun_out/san_k8_race.log
-MP_REC_IMPL=ffma timeout 600 compute-sanitizer --tool memcheck --error-exitcode 9 python scripts/prof_one.py --batch 40 --frames 6 --passes 2 > gpurun_out/san_net_ffma_mem.log 2>&1; echo "net ffma memcheck exit $?"; grep "^========= [A-Z]" gpurun_out/san_net_ffma_mem.log | sort | uniq -c | sort -rn | head -5
-timeout 300 python -m pytest tests/test_gpu_physics.py -x -q 2>&1 | tail -2
+cd scripts/sanitizer && nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -o dsmem_bulk_repro dsmem_bulk_repro.cu && cd ../..
+./scripts/sanitizer/dsmem_bulk_repro
+for tool in memcheck racecheck initcheck synccheck; do
+  timeout 300 compute-sanitizer --tool $tool ./scripts/sanitizer/dsmem_bulk_repro > gpurun_out/san_repro_$tool.log 2>&1; echo "repro $tool exit $?"
+  grep -E "^========= [A-Z]|ERROR SUMMARY|RACECHECK SUMMARY|dsmem bulk" gpurun_out/san_repro_$tool.log | sort | uniq -c | sort -rn | head -6
+done
+for tool in racecheck initcheck synccheck memcheck; do
+  MP_REC_IMPL=f16 timeout 600 compute-sanitizer --tool $tool python scripts/rtc_debug.py 20 5 f16 > gpurun_out/san_rec_f16_$tool.log 2>&1; echo "rec f16 $tool exit $?"
+  grep -E "^========= [A-Z]|ERROR SUMMARY|RACECHECK SUMMARY|max \|tc" gpurun_out/san_rec_f16_$tool.log | sort | uniq -c | sort -rn | head -6
+  timeout 600 compute-sanitizer --tool $tool python scripts/prof_one.py --batch 1 --frames 6 --passes 1 > gpurun_out/san_rec_b1_$tool.log 2>&1; echo "rec b1 $tool exit $?"
+  grep -E "^========= [A-Z]|ERROR SUMMARY|RACECHECK SUMMARY" gpurun_out/san_rec_b1_$tool.log | sort | uniq -c | sort -rn | head -6
+done
