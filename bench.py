@@ -503,7 +503,7 @@ def measure_cfg4(net, dev, dist, rank, world, steps, warmup, min_seconds):
     import hashlib
     from mobileposer_b200.evaluate import evaluate_pose, synthetic_dip
     from mobileposer_b200.sharding import shard_sequences
-    items = synthetic_dip()
+    items = [(imu.pin_memory(), pose, joint, tran) for imu, pose, joint, tran in synthetic_dip()]    # the dataset lives in pinned host memory
     n = len(items)
     lengths = [it[0].shape[0] for it in items]
     shards = shard_sequences(lengths, world)

@@ -103,7 +103,9 @@ int mp_rnn_forward(const mp_rnn_t* rnn, const float* xa, int32_t ka, const float
  *   C[M,N] = act(A[M,K] * W[N,K]^T + bias[N]).  mode 0 = library's choice, 1 = fp32 FFMA kernel,
  *   2 = tcgen05 3xTF32 tensor-core kernel (needs N % 256 == 0, K % 16 == 0, relu == 0),
  *   3 = tcgen05 3xFP16 (fp16 hi / scaled-lo split) tensor-core kernel (N % 256 == 0, K % 32 == 0, relu == 0; the operands are
- *       split into stream-ordered scratch memory first).  Exposed for tests.   */
+ *       split into stream-ordered scratch memory first),
+ *   4 = the same kernel for a narrow output (N <= 256, N % 4 == 0: linear2), W and bias zero-padded to one 256-row tile.
+ *   Exposed for tests.   */
 int mp_gemm_bias(const float* A, const float* W, const float* bias, float* C, int32_t M, int32_t N, int32_t K,
                  int32_t relu, int32_t mode, mp_stream_t stream);
 
@@ -230,6 +232,13 @@ int mp_eval_frame_errors(const float* pose_p, const float* pose_t, const float* 
  * joint transforms).  The joint rest positions are the library's SMPL constants.                                       */
 int mp_eval_vertex_errors(const float* pose_p, const float* pose_t, int64_t n_frames, const float* rest_vertices,
                           const float* weights, int32_t n_vertices, double* err_sum, double* err_sq_sum, mp_stream_t stream);
+
+/* The [10, 2] (mean, std) rows of FullMotionEvaluator.__call__ [articulate/evaluator.py:326-343] from the per-frame outputs of
+ * mp_eval_frame_errors: rows 0, 2-9 (joint position / local angle / global angle errors, jitter of both motions, one-second root
+ * translation error in cm, the first three again on the joints of `joint_mask_bits` (bit j = joint j)); row 1 (mesh) is NaN.
+ * Every row is x.mean() and x.std(dim=0).mean() of a [frames, joints] array (unbiased std over frames), from per-column sums in double. */
+int mp_eval_motion_rows(const float* joint_p, const float* joint_t, const float* je, const float* lae, const float* gae,
+                        int64_t n_frames, int32_t fps, uint32_t joint_mask_bits, float* rows, mp_stream_t stream);
 
 /* Translation-error windows of evaluate_pose(..., evaluate_tran=True) [evaluate.py:66-92], S sequences
  * per call: tran_p / tran_t [S,T,3] predicted / true root translation (padded to T frames), lengths [S] device ints or NULL ->

@@ -73,6 +73,8 @@ struct mp_rnn {
     float* wih[2] = {nullptr, nullptr};    // [dirs*4H, In_l]   both directions stacked on N
     float* wih_split[2] = {nullptr, nullptr};   // [2 * dirs*4H, In_l]: TF32 hi rows, then lo rows (tensor-core projection), or null
     void* wih_f16[2] = {nullptr, nullptr};      // [2 * dirs*4H, In_l] halves: fp16 hi rows, then scaled-lo rows (gemm_f16.cu), or null
+    void* w2_f16 = nullptr;                     // linear2 for the same kernel: [2 * 256, dirs*H] halves, rows >= n_out zero; or null
+    float* b2_pad = nullptr;                    // [256] linear2 bias, zero padded
     float* bsum[2] = {nullptr, nullptr};   // [dirs*4H]         b_ih + b_hh
     float4* whh_pack[2] = {nullptr, nullptr};
     float* whh_t[2] = {nullptr, nullptr};
@@ -189,6 +191,9 @@ int mp_rnn_create(mp_rnn_t** out, const mp_rnn_weights_t* w, mp_stream_t stream_
     auto take = [&](size_t floats) { size_t o = off; off = align_up(off + floats * sizeof(float)); return o; };
     const size_t o_w1 = take((size_t)H * r->n_in), o_b1 = take(H);
     const size_t o_w2 = take((size_t)r->n_out * dirs * H), o_b2 = take(r->n_out);
+    const bool lin2_tc = r->n_out >= 16 && r->n_out <= 256 && (r->n_out & 3) == 0 && (dirs * H) % 32 == 0;
+    const size_t o_w2pad = take(lin2_tc ? (size_t)256 * dirs * H : 0), o_w2f16 = take(lin2_tc ? (size_t)256 * dirs * H : 0),
+                 o_b2pad = take(lin2_tc ? 256 : 0);
     size_t o_wih[2], o_bs[2], o_pk[2], o_wt[2], o_raw[2], o_split[2], o_f16[2];
     for (int l = 0; l < 2; ++l) {
         o_wih[l] = take((size_t)dirs * 4 * H * in_l[l]);
@@ -219,6 +224,22 @@ int mp_rnn_create(mp_rnn_t** out, const mp_rnn_weights_t* w, mp_stream_t stream_
     copy(r->b1, w->linear1_b, H);
     copy(r->w2, w->linear2_w, (size_t)r->n_out * dirs * H);
     copy(r->b2, w->linear2_b, r->n_out);
+    if (lin2_tc && st == MP_OK) {
+        // linear2 on the fp16-split tensor-core kernel: the weight padded with zero rows to one 256-row tile, then split
+        float* w2pad = (float*)(base + o_w2pad);
+        r->b2_pad = (float*)(base + o_b2pad);
+        if (cudaMemsetAsync(w2pad, 0, (size_t)256 * dirs * H * sizeof(float), stream) != cudaSuccess ||
+            cudaMemsetAsync(r->b2_pad, 0, 256 * sizeof(float), stream) != cudaSuccess) {
+            set_error("rnn_create: memset failed: %s", cudaGetErrorString(cudaGetLastError()));
+            st = MP_ERR_CUDA;
+        }
+        copy(w2pad, w->linear2_w, (size_t)r->n_out * dirs * H);
+        copy(r->b2_pad, w->linear2_b, r->n_out);
+        if (st == MP_OK) {
+            r->w2_f16 = base + o_w2f16;
+            st = launch_split_f16(w2pad, (size_t)256 * dirs * H, r->w2_f16, stream);
+        }
+    }
     for (int l = 0; l < 2 && st == MP_OK; ++l) {
         r->wih[l] = (float*)(base + o_wih[l]);
         r->bsum[l] = (float*)(base + o_bs[l]);
@@ -306,8 +327,9 @@ static int rnn_forward_impl(const mp_rnn_t* r, const float* xa, int32_t ka, cons
     const bool proj16[2] = {r->wih_f16[0] && gemm_f16_eligible((int)M, dirs * 4 * H, H),
                             r->wih_f16[1] && gemm_f16_eligible((int)M, dirs * 4 * H, dirs * H)};
     const bool fuse_split = !getenv("MP_NO_FUSED_SPLIT");
+    const bool lin2_16 = r->w2_f16 && gemm_f16_eligible((int)M, 256, dirs * H) && !getenv("MP_LINEAR2_FFMA");
     unsigned int* sched = reinterpret_cast<unsigned int*>(ws);
-    if (proj16[0] || proj16[1]) MP_CUDA_TRY(cudaMemsetAsync(sched, 0, 256, stream));
+    if (proj16[0] || proj16[1] || lin2_16) MP_CUDA_TRY(cudaMemsetAsync(sched, 0, 256, stream));
     const bool x1_split = proj16[0] && fuse_split;
     // linear1 + ReLU (dropout is the identity in eval)                         rnn.py:22
     MP_TRY(launch_gemm_ffma(xa, ka, xb, kb, r->w1, r->b1, x1, (int)M, H, x1_split ? 3 : 1, stream));
@@ -322,7 +344,7 @@ static int rnn_forward_impl(const mp_rnn_t* r, const float* xa, int32_t ka, cons
                 MP_TRY(launch_split_f16(layer_in, M * (size_t)in_w, ws + o_xs, stream));
                 xs = ws + o_xs;
             }
-            MP_TRY(launch_gemm_f16x3(xs, r->wih_f16[l], r->bsum[l], gin, (int)M, dirs * 4 * H, in_w, sched + 2 * l, stream));
+            MP_TRY(launch_gemm_f16x3(xs, r->wih_f16[l], r->bsum[l], gin, (int)M, dirs * 4 * H, in_w, dirs * 4 * H, sched + 2 * l, stream));
         } else if (r->wih_split[l] && gemm_tc_eligible((int)M, dirs * 4 * H, in_w) && !getenv("MP_GEMM_NOSPLIT"))
             MP_TRY(launch_gemm_tf32x3_presplit(layer_in, r->wih_split[l], r->bsum[l], gin, (int)M, dirs * 4 * H, in_w, stream));
         else
@@ -336,14 +358,24 @@ static int rnn_forward_impl(const mp_rnn_t* r, const float* xa, int32_t ka, cons
         a.lengths = lengths; a.B = B; a.T = T; a.H = H; a.dirs = dirs;
         a.tile_hint = tile_hint;
         // layer 0 feeds layer 1's projection only: written as (hi, lo) planes when both ends are the fp16-split kernels
-        a.y_split = (l == 0 && proj16[1] && fuse_split && rec_f16_eligible(a)) ? 1 : 0;
+        // (layer 1 feeds linear2 only: the same when that runs on the tensor cores)
+        a.y_split = (((l == 0 && proj16[1]) || (l == 1 && lin2_16)) && fuse_split && rec_f16_eligible(a)) ? 1 : 0;
         MP_TRY(launch_lstm_recurrence(a, stream));
         layer_in = ybuf[l];
         layer_in_split = a.y_split != 0;
         in_w = dirs * H;
     }
     // linear2                                                                 rnn.py:32
-    MP_TRY(launch_gemm_bias_act(layer_in, in_w, nullptr, 0, r->w2, r->b2, y, (int)M, r->n_out, 0, stream));
+    if (lin2_16) {
+        const void* xs = layer_in;
+        if (!layer_in_split) {
+            MP_TRY(launch_split_f16(layer_in, M * (size_t)in_w, ws + o_xs, stream));
+            xs = ws + o_xs;
+        }
+        MP_TRY(launch_gemm_f16x3(xs, r->w2_f16, r->b2_pad, y, (int)M, 256, in_w, r->n_out, sched + 4, stream));
+    } else {
+        MP_TRY(launch_gemm_bias_act(layer_in, in_w, nullptr, 0, r->w2, r->b2, y, (int)M, r->n_out, 0, stream));
+    }
     return MP_OK;
 }
 
@@ -374,10 +406,32 @@ int mp_gemm_bias(const float* A, const float* W, const float* bias, float* C, in
         MP_CUDA_TRY(cudaMemsetAsync(sched, 0, 256, s));
         int st = launch_split_f16(A, (size_t)M * K, as, s);
         if (st == MP_OK) st = launch_split_f16(W, (size_t)N * K, wsp, s);
-        if (st == MP_OK) st = launch_gemm_f16x3(as, wsp, bias, C, M, N, K, (unsigned int*)sched, s);
+        if (st == MP_OK) st = launch_gemm_f16x3(as, wsp, bias, C, M, N, K, N, (unsigned int*)sched, s);
         cudaFreeAsync(as, s);
         cudaFreeAsync(wsp, s);
         cudaFreeAsync(sched, s);
+        return st;
+    }
+    if (mode == 4) {
+        // test entry of the same kernel for narrow outputs (linear2): W and the bias are zero-padded to one 256-row tile first
+        MP_REQUIRE(!relu && N <= 256 && (N & 3) == 0 && K % 32 == 0, "gemm_bias mode 4: N <= 256, N %% 4 == 0, K %% 32 == 0, no activation");
+        cudaStream_t s = (cudaStream_t)stream;
+        void *as = nullptr, *wsp = nullptr, *sched = nullptr;
+        float *wpad = nullptr, *bpad = nullptr;
+        MP_CUDA_TRY(cudaMallocAsync(&as, (size_t)M * K * 4, s));
+        MP_CUDA_TRY(cudaMallocAsync(&wsp, (size_t)256 * K * 4, s));
+        MP_CUDA_TRY(cudaMallocAsync((void**)&wpad, (size_t)256 * K * 4, s));
+        MP_CUDA_TRY(cudaMallocAsync((void**)&bpad, 256 * 4, s));
+        MP_CUDA_TRY(cudaMallocAsync(&sched, 256, s));
+        MP_CUDA_TRY(cudaMemsetAsync(sched, 0, 256, s));
+        MP_CUDA_TRY(cudaMemsetAsync(wpad, 0, (size_t)256 * K * 4, s));
+        MP_CUDA_TRY(cudaMemsetAsync(bpad, 0, 256 * 4, s));
+        MP_CUDA_TRY(cudaMemcpyAsync(wpad, W, (size_t)N * K * 4, cudaMemcpyDeviceToDevice, s));
+        MP_CUDA_TRY(cudaMemcpyAsync(bpad, bias, (size_t)N * 4, cudaMemcpyDeviceToDevice, s));
+        int st = launch_split_f16(A, (size_t)M * K, as, s);
+        if (st == MP_OK) st = launch_split_f16(wpad, (size_t)256 * K, wsp, s);
+        if (st == MP_OK) st = launch_gemm_f16x3(as, wsp, bpad, C, M, 256, K, N, (unsigned int*)sched, s);
+        cudaFreeAsync(as, s); cudaFreeAsync(wsp, s); cudaFreeAsync(wpad, s); cudaFreeAsync(bpad, s); cudaFreeAsync(sched, s);
         return st;
     }
     return launch_gemm_bias_act(A, K, nullptr, 0, W, bias, C, M, N, relu, (cudaStream_t)stream);
@@ -420,6 +474,10 @@ int mp_eval_frame_errors(const float* pose_p, const float* pose_t, const float* 
 int mp_eval_vertex_errors(const float* pose_p, const float* pose_t, int64_t n_frames, const float* rest_vertices, const float* weights,
                            int32_t n_vertices, double* err_sum, double* err_sq_sum, mp_stream_t stream) {
     return launch_eval_vertex_errors(pose_p, pose_t, n_frames, rest_vertices, weights, n_vertices, err_sum, err_sq_sum, (cudaStream_t)stream);
+}
+int mp_eval_motion_rows(const float* joint_p, const float* joint_t, const float* je, const float* lae, const float* gae, int64_t n_frames,
+                        int32_t fps, uint32_t joint_mask_bits, float* rows, mp_stream_t stream) {
+    return launch_eval_motion_rows(joint_p, joint_t, je, lae, gae, n_frames, fps, joint_mask_bits, rows, (cudaStream_t)stream);
 }
 int mp_eval_tran_windows(const float* tran_p, const float* tran_t, const int32_t* lengths, int32_t S, int32_t T, float* err,
                          int32_t* count, mp_stream_t stream) {

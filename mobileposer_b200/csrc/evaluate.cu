@@ -77,7 +77,105 @@ eval_tran_windows_kernel(const float* __restrict__ tran_p, const float* __restri
     }
 }
 
+// ---- the [10, 2] mean / std rows of FullMotionEvaluator.__call__ (articulate/evaluator.py:326-343) from the per-frame errors ------
+// One CTA per sequence.  Every row is `x.mean()` and `x.std(dim=0).mean()` of a [frames, columns] array: per column the sum and the
+// sum of squares over the frames are all that is needed, accumulated in double (lane = joint column, warps stride over frames).
+//   0 joint position error [n,24]   2 local angle error   3 global angle error   4 / 5 jitter of the predicted / true joints
+//   ((p[t+3] - 3 p[t+2] + 3 p[t+1] - p[t]) f^3, norm)   6 root translation error over one second, cm   7-9 rows 0, 2, 3 on the masked joints
+// Row 1 (mesh) is left NaN: mp_eval_vertex_errors fills it when a template is given.  Replaces ~40 small torch launches per sequence.
+constexpr int ER_THREADS = 256, ER_WARPS = ER_THREADS / 32, ER_ACC = 12;
+
+__global__ void __launch_bounds__(ER_THREADS)
+eval_motion_rows_kernel(const float* __restrict__ jp, const float* __restrict__ jt, const float* __restrict__ je, const float* __restrict__ lae,
+                        const float* __restrict__ gae, int n, int fps, unsigned mask_bits, float* __restrict__ rows) {
+    __shared__ double red[ER_WARPS][32][ER_ACC];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    double acc[ER_ACC];
+#pragma unroll
+    for (int i = 0; i < ER_ACC; ++i) acc[i] = 0.0;
+    const float f3 = (float)fps * (float)fps * (float)fps;
+    for (int t = warp; t < n; t += ER_WARPS) {
+        if (lane < 24) {
+            const float a = je[(size_t)t * 24 + lane], b = lae[(size_t)t * 24 + lane], c = gae[(size_t)t * 24 + lane];
+            acc[0] += a; acc[1] += (double)a * a;
+            acc[2] += b; acc[3] += (double)b * b;
+            acc[4] += c; acc[5] += (double)c * c;
+            if (t + 3 < n) {
+#pragma unroll
+                for (int w = 0; w < 2; ++w) {
+                    const float* q = (w ? jt : jp) + ((size_t)t * 24 + lane) * 3;
+                    float v[3];
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        // ((p3 - 3 p2) + 3 p1) - p0, then * f^3: the order of the torch expression
+                        const float d = __fsub_rn(__fadd_rn(__fsub_rn(q[216 + k], __fmul_rn(3.f, q[144 + k])), __fmul_rn(3.f, q[72 + k])), q[k]);
+                        v[k] = __fmul_rn(d, f3);
+                    }
+                    const float jn = norm3_rn(v[0], v[1], v[2]);
+                    acc[6 + 2 * w] += jn; acc[7 + 2 * w] += (double)jn * jn;
+                }
+            }
+        } else if (lane == 24 && t + fps < n) {
+            float v[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+                v[k] = __fsub_rn(__fsub_rn(jp[(size_t)(t + fps) * 72 + k], jp[(size_t)t * 72 + k]),
+                                 __fsub_rn(jt[(size_t)(t + fps) * 72 + k], jt[(size_t)t * 72 + k]));
+            const float e = __fmul_rn(norm3_rn(v[0], v[1], v[2]), 100.f);
+            acc[10] += e; acc[11] += (double)e * e;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < ER_ACC; ++i) red[warp][lane][i] = acc[i];
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+        for (int i = 0; i < ER_ACC; ++i) {
+            double v = 0.0;
+            for (int w = 0; w < ER_WARPS; ++w) v += red[w][lane][i];
+            red[0][lane][i] = v;
+        }
+    }
+    __syncthreads();
+    if (tid < 10) {
+        // row -> (accumulator pair, frames, column set)
+        const int r = tid;
+        const float nan = __int_as_float(0x7fc00000);
+        float mean = nan, sd = nan;
+        if (r != 1) {
+            const int a = (r == 0 || r == 7) ? 0 : (r == 2 || r == 8) ? 2 : (r == 3 || r == 9) ? 4 : (r == 4) ? 6 : (r == 5) ? 8 : 10;
+            const long long cnt = (r == 4 || r == 5) ? (long long)n - 3 : (r == 6) ? (long long)n - fps : (long long)n;
+            const unsigned cols = (r == 6) ? (1u << 24) : (r >= 7) ? mask_bits : 0x00FFFFFFu;
+            if (cnt > 0 && cols) {
+                double sum = 0.0, sds = 0.0;
+                int nc = 0;
+                for (int c = 0; c < 25; ++c)
+                    if ((cols >> c) & 1u) {
+                        const double s1 = red[0][c][a], s2 = red[0][c][a + 1];
+                        sum += s1;
+                        if (cnt > 1) sds += sqrt(fmax((s2 - s1 * s1 / (double)cnt) / (double)(cnt - 1), 0.0));
+                        ++nc;
+                    }
+                mean = (float)(sum / ((double)cnt * nc));
+                sd = (float)(sds / nc);
+            }
+        }
+        rows[2 * r] = mean;
+        rows[2 * r + 1] = sd;
+    }
+}
+
 }  // namespace
+
+int launch_eval_motion_rows(const float* jp, const float* jt, const float* je, const float* lae, const float* gae, int64_t n, int fps,
+                            unsigned mask_bits, float* rows, cudaStream_t stream) {
+    MP_REQUIRE(jp && jt && je && lae && gae && rows && n > 0 && n < (int64_t)1 << 30 && fps > 0, "eval_motion_rows: bad arguments");
+    MP_REQUIRE((mask_bits & ~0x00FFFFFFu) == 0, "eval_motion_rows: the joint mask has 24 bits");
+    eval_motion_rows_kernel<<<1, ER_THREADS, 0, stream>>>(jp, jt, je, lae, gae, (int)n, fps, mask_bits, rows);
+    MP_CUDA_TRY(cudaGetLastError());
+    count_launch();
+    return MP_OK;
+}
 
 int launch_eval_tran_windows(const float* tran_p, const float* tran_t, const int32_t* lengths, int S, int T, float* err,
                              int32_t* count, cudaStream_t stream) {

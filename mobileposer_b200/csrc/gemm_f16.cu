@@ -97,7 +97,7 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t sr
 __global__ void __launch_bounds__(HB_THREADS, 1)
 gemm_f16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                   const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_c,
-                  const float* __restrict__ bias, int M, int N, int K, unsigned int* __restrict__ sched) {
+                  const float* __restrict__ bias, int M, int N, int K, int N_out, unsigned int* __restrict__ sched) {
     extern __shared__ unsigned char smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t s_out = base + HB_STAGES * H_STAGE;                 // 4 epilogue warps x one 32 x 32 fp32 box (4 KiB)
@@ -210,13 +210,16 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
             const int n0 = (t % tiles_n) * HB_N, m0 = (t / tiles_n) * HB_M;
             mbar_wait(bar_accum, j & 1);
             tc_fence_after();
-            for (int c0 = 0; c0 < HB_N; c0 += 32) {
+            // narrow outputs (linear2: N_out = 72 / 96 columns of a zero-padded 256-row weight tile): only the boxes that hold real
+            // columns are read and stored; the store's tensor map clips the last one
+            const int c_end = min(HB_N, ((N_out - n0 + 31) >> 5) << 5);
+            for (int c0 = 0; c0 < c_end; c0 += 32) {
                 uint32_t v[32], u[32];
                 const uint32_t taddr = tmem + ((uint32_t)(wq * 32) << 16) + (uint32_t)c0;
                 tmem_ld32(taddr, v);
                 tmem_ld32(taddr + (uint32_t)HB_N, u);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (c0 + 32 == HB_N) {                   // last read of this tile's accumulators: the MMA warp may start the next tile
+                if (c0 + 32 == c_end) {                  // last read of this tile's accumulators: the MMA warp may start the next tile
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_drained) : "memory");
@@ -346,16 +349,18 @@ int launch_split_f16(const float* x, size_t n, void* out_hi_lo, cudaStream_t str
 
 // A_split: [2][M, K] halves (hi plane, then lo plane); W_split: [2N, K] halves (hi rows, then lo rows)
 // sched: two zeroed 32-bit words owned by this launch (tile counter, CTAs done), e.g. a slice of the caller's workspace cleared on the
-// same stream; the kernel leaves them zero again
-int launch_gemm_f16x3(const void* A_split, const void* W_split, const float* bias, float* C, int M, int N, int K, unsigned int* sched,
-                      cudaStream_t stream) {
+// same stream; the kernel leaves them zero again.  N_out <= N: C is [M, N_out] and only its columns are stored (W_split and bias are
+// padded to N rows / entries with zeros); N_out % 4 == 0.
+int launch_gemm_f16x3(const void* A_split, const void* W_split, const float* bias, float* C, int M, int N, int K, int N_out,
+                      unsigned int* sched, cudaStream_t stream) {
     MP_REQUIRE(A_split && W_split && bias && C && sched && M > 0, "gemm_f16: bad arguments");
+    MP_REQUIRE(N_out > 0 && N_out <= N && (N_out & 3) == 0, "gemm_f16: N_out=%d must be a positive multiple of 4, at most N=%d", N_out, N);
     MP_REQUIRE(N % HB_N == 0 && K % HB_K == 0, "gemm_f16: N=%d must be a multiple of %d and K=%d of %d", N, HB_N, K, HB_K);
     MP_REQUIRE(((uintptr_t)A_split & 15) == 0 && ((uintptr_t)W_split & 15) == 0 && ((uintptr_t)C & 15) == 0 && ((uintptr_t)bias & 15) == 0,
                "gemm_f16: pointers must be 16-byte aligned");
     const __half* a = reinterpret_cast<const __half*>(A_split);
     alignas(64) CUtensorMap map_a_hi, map_a_lo, map_w, map_c;
-    MP_TRY(make_map_c(&map_c, C, M, N));
+    MP_TRY(make_map_c(&map_c, C, M, N_out));
     MP_TRY(make_map_f16(&map_a_hi, a, M, K, HB_M));
     MP_TRY(make_map_f16(&map_a_lo, a + (size_t)M * K, M, K, HB_M));
     MP_TRY(make_map_f16(&map_w, reinterpret_cast<const __half*>(W_split), 2 * N, K, HB_N));
@@ -365,7 +370,7 @@ int launch_gemm_f16x3(const void* A_split, const void* W_split, const float* bia
         configured = true;
     }
     // algorithmic bytes: the operands as the caller holds them (fp32-equivalent: 4 B per element either way) + the output
-    ProfileScope prof("gemm_f16x3", 4.0 * ((double)N * K + N + (double)M * K + (double)M * N), stream);
+    ProfileScope prof(N_out < N ? "gemm_f16x3_linear2" : "gemm_f16x3", 4.0 * ((double)N_out * K + N_out + (double)M * K + (double)M * N_out), stream);
     static int n_sm = 0;
     if (!n_sm) {
         int dev = 0;
@@ -373,7 +378,7 @@ int launch_gemm_f16x3(const void* A_split, const void* W_split, const float* bia
         MP_CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
     }
     const int tiles = (N / HB_N) * ((M + HB_M - 1) / HB_M);
-    gemm_f16x3_kernel<<<std::min(tiles, n_sm), HB_THREADS, H_SMEM, stream>>>(map_a_hi, map_a_lo, map_w, map_c, bias, M, N, K, sched);
+    gemm_f16x3_kernel<<<std::min(tiles, n_sm), HB_THREADS, H_SMEM, stream>>>(map_a_hi, map_a_lo, map_w, map_c, bias, M, N, K, N_out, sched);
     MP_CUDA_TRY(cudaGetLastError());
     count_launch();
     return MP_OK;

@@ -66,8 +66,9 @@ int launch_split_weights(const float* W, size_t n, float* W_split, cudaStream_t 
 // from an fp32 array of n elements (out = n hi halves, then n lo halves)
 bool gemm_f16_eligible(int M, int N, int K);
 // sched: two zeroed 32-bit words private to the launch (the persistent kernel's dynamic tile counter); left zero on exit
-int launch_gemm_f16x3(const void* A_split, const void* W_split, const float* bias, float* C, int M, int N, int K, unsigned int* sched,
-                      cudaStream_t stream);
+// N_out <= N: C is [M, N_out]; W_split / bias are zero-padded to N rows / entries (narrow outputs: linear2)
+int launch_gemm_f16x3(const void* A_split, const void* W_split, const float* bias, float* C, int M, int N, int K, int N_out,
+                      unsigned int* sched, cudaStream_t stream);
 int launch_split_f16(const float* x, size_t n, void* out_hi_lo, cudaStream_t stream);
 int launch_gemm_ffma(const float* A1, int K1, const float* A2, int K2, const float* W, const float* bias, float* C,
                      int M, int N, int relu, cudaStream_t stream);
@@ -132,6 +133,9 @@ int launch_eval_frame_errors(const float* pose_p, const float* pose_t, const flo
 
 int launch_eval_vertex_errors(const float* pose_p, const float* pose_t, int64_t n, const float* v0, const float* weights, int V,
                               double* vsum, double* vsq, cudaStream_t stream);
+// N1 rows (evaluate.cu): the [10, 2] mean / std table of FullMotionEvaluator from the per-frame errors; row 1 (mesh) left NaN
+int launch_eval_motion_rows(const float* jp, const float* jt, const float* je, const float* lae, const float* gae, int64_t n, int fps,
+                            unsigned mask_bits, float* rows, cudaStream_t stream);
 // N3 (evaluate.cu)
 int launch_eval_tran_windows(const float* tran_p, const float* tran_t, const int32_t* lengths, int S, int T, float* err,
                              int32_t* count, cudaStream_t stream);

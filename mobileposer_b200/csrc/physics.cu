@@ -20,6 +20,8 @@
 // no fill outside the ancestor blocks; the right-hand side rides along as row 48.  No cuBLAS / cuSolver.
 // HBM traffic per frame and skeleton: 864 B pose in + 288 B velocity + 8 B contact, 864 B pose + 12 B tran out.
 #include "mp_common.cuh"
+
+#include <cstdlib>
 #include "mp_constants.cuh"
 
 #include <mutex>
@@ -172,22 +174,43 @@ __device__ __forceinline__ float phys_prob_to_weight(float logit) {
     return (fminf(fmaxf(p, 0.5f), 0.9f) - 0.5f) / 0.4f;       // net.py:90-91
 }
 
-__global__ void __launch_bounds__(32) physics_optimize_kernel(const PhysParams p) {
-    __shared__ float sG[NJ * 9];
-    __shared__ float sP[NJ * 3];
-    __shared__ float sC[NJ];
-    __shared__ float sS[NJ * 3];
-    __shared__ float sS1[NJ * 3];
-    __shared__ float sS2[NJ * 6];
-    __shared__ float sT1[NJ * 3];
-    __shared__ __align__(16) float sH[NROW * LDH];
-    __shared__ float sX[NX];
-    __shared__ uint32_t sItem[MAX_PAIRS];     // rotation-rotation blocks: joint a | joint d << 5 | slot a << 10 | slot d << 14
-    __shared__ int sOrd[NOPT];
-    __shared__ unsigned char sRow[NBLK * 32];
+// Per-skeleton scratch (one warp each).  A CTA packs `blockDim.x / 32` skeletons: with one warp per CTA the batch's 256 tiny CTAs spread
+// over every SM of the chip for the kernel's 3 ms, and their registers / shared memory kept the cluster recurrences and the
+// persistent projection CTAs of the other batches in the pipeline off those SMs (1 ms per cfg3 step); packed, the optimizer
+// occupies a few SMs and leaves the rest whole.
+struct PhysScratch {
+    float G[NJ * 9];
+    float P[NJ * 3];
+    float C[NJ];
+    float S[NJ * 3];
+    float S1[NJ * 3];
+    float S2[NJ * 6];
+    float T1[NJ * 3];
+    float X[NX];
+    uint32_t Item[MAX_PAIRS];     // rotation-rotation blocks: joint a | joint d << 5 | slot a << 10 | slot d << 14
+    int Ord[NOPT + 1];
+    unsigned char Row[NBLK * 32];
+    float H[NROW * LDH] __attribute__((aligned(16)));
+};
 
-    const int lane = threadIdx.x;
-    const int b = blockIdx.x;
+__global__ void __launch_bounds__(512) physics_optimize_kernel(const PhysParams p) {
+    extern __shared__ __align__(16) unsigned char phys_smem[];
+    PhysScratch& scr = reinterpret_cast<PhysScratch*>(phys_smem)[threadIdx.x >> 5];
+    float* const sG = scr.G;
+    float* const sP = scr.P;
+    float* const sC = scr.C;
+    float* const sS = scr.S;
+    float* const sS1 = scr.S1;
+    float* const sS2 = scr.S2;
+    float* const sT1 = scr.T1;
+    float* const sH = scr.H;
+    float* const sX = scr.X;
+    uint32_t* const sItem = scr.Item;
+    int* const sOrd = scr.Ord;
+    unsigned char* const sRow = scr.Row;
+
+    const int lane = threadIdx.x & 31;
+    const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (b >= p.B) return;
     const bool isj = lane < NJ;
     const int j = isj ? lane : 0;
@@ -745,7 +768,17 @@ int launch_physics_optimize(const float* pose, const float* vel, const float* co
                  prm->w_vel, prm->w_contact, prm->damping, prm->damping_abs, prm->floor_y};
     // algorithmic bytes: pose in + out, velocity, contact, translation
     ProfileScope prof("k8_physics", (double)B * T * (864.0 * 2 + 288 + 8 + 12), stream);
-    physics_optimize_kernel<<<B, 32, 0, stream>>>(p);
+    // skeletons (warps) per CTA: MP_K8_WARPS, default 4 (measured on the pipelined cfg3 step, 256 skeletons: 1 warp per CTA 6.63 ms per
+    // step, 4: 6.12, 8: 6.23, 12: 6.07 -- while the kernel alone slows from 3.48 to 3.50 / 3.90 / 4.35 ms as the warps share schedulers)
+    static int wpc = 0;
+    if (!wpc) {
+        const char* v = getenv("MP_K8_WARPS");
+        wpc = v ? atoi(v) : 4;
+        wpc = std::min(12, std::max(1, wpc));
+        MP_CUDA_TRY(cudaFuncSetAttribute(physics_optimize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(12 * sizeof(PhysScratch))));
+    }
+    const int w = std::min(wpc, B);
+    physics_optimize_kernel<<<(B + w - 1) / w, 32 * w, (size_t)w * sizeof(PhysScratch), stream>>>(p);
     MP_CUDA_TRY(cudaGetLastError());
     count_launch();
     return MP_OK;

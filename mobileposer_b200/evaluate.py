@@ -182,8 +182,22 @@ def full_motion_errors(pose_p, pose_t, tran_p, tran_t, fps=datasets.fps, joint_m
     `mesh = (rest_vertices, weights)` is given (CUDA tensors only)."""
     f = fps
     if pose_p.is_cuda:
-        # the per-frame part (two forward kinematics, joint / local-angle / global-angle errors) is one kernel
+        # the per-frame part (two forward kinematics, joint / local-angle / global-angle errors) is one kernel, the reduction of
+        # its outputs to the ten (mean, std) rows a second one (mp_eval_motion_rows)
+        from . import _cabi
+        from .modules import current_stream_ptr
         jp, jt, je, lae, gae = frame_errors_cuda(pose_p, pose_t, tran_p, tran_t)
+        rows = torch.empty(10, 2, device=pose_p.device, dtype=torch.float32)
+        bits = 0
+        for j in joint_mask:
+            bits |= 1 << int(j)
+        with torch.cuda.device(pose_p.device):
+            _cabi.check(_cabi.lib().mp_eval_motion_rows(jp.data_ptr(), jt.data_ptr(), je.data_ptr(), lae.data_ptr(), gae.data_ptr(),
+                                                        jp.shape[0], int(f), bits, rows.data_ptr(), current_stream_ptr(pose_p.device)),
+                        'mp_eval_motion_rows')
+        if mesh is not None:
+            rows[1] = vertex_error_row(pose_p, pose_t, mesh)
+        return rows
     else:
         # CPU tensors: the torch statement of the same rows (what tests/test_evaluate.py pins to the reference's evaluator)
         gp, jp = forward_kinematics(pose_p, tran_p)

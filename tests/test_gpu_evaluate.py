@@ -252,3 +252,21 @@ def test_weights_changed_in_place_invalidate_the_packed_net(seeded_state_dict, w
     want = fresh.forward_offline(x, [32])
     assert not torch.equal(before[0], after[0])
     assert all(torch.equal(p, q) for p, q in zip(after, want))
+
+
+@pytest.mark.parametrize('n', [1, 2, 3, 4, 30, 31, 90])
+def test_motion_rows_kernel_equals_the_torch_statement(n):
+    """mp_eval_motion_rows (one launch for the ten (mean, std) rows) against the torch statement of the same rows on the CPU
+    (itself pinned to the reference's evaluator in tests/test_evaluate.py), including the empty cases: fewer than 4 frames (no
+    jitter), no more than fps frames (no one-second translation error), a single frame (std = 0)."""
+    from mobileposer_b200.evaluate import full_motion_errors, r6d_to_rotation_matrix
+    g = torch.Generator().manual_seed(100 + n)
+    eye6 = torch.tensor([1., 0., 0., 0., 1., 0.]).repeat(24)
+    pose_p = r6d_to_rotation_matrix(eye6 + 0.3 * torch.randn(n, 144, generator=g)).view(n, 24, 3, 3)
+    pose_t = r6d_to_rotation_matrix(eye6 + 0.3 * torch.randn(n, 144, generator=g)).view(n, 24, 3, 3)
+    tran_p, tran_t = torch.randn(n, 3, generator=g) * 0.1, torch.randn(n, 3, generator=g) * 0.1
+    want = full_motion_errors(pose_p, pose_t, tran_p, tran_t)
+    got = full_motion_errors(pose_p.to(DEV), pose_t.to(DEV), tran_p.to(DEV), tran_t.to(DEV)).cpu()
+    assert torch.equal(torch.isnan(got), torch.isnan(want)), (got, want)
+    ok = ~torch.isnan(want)
+    assert ((got[ok] - want[ok]).abs() / want[ok].abs().clamp_min(1e-3)).max() < 2e-4

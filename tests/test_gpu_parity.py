@@ -563,6 +563,13 @@ def test_tensor_core_gemm_matches_fp32(M, N, K):
     assert torch.isfinite(out[2]).all()
     assert e_ffma < 4e-7, e_ffma               # a few ulp (2^-24 = 6e-8) of the accumulated magnitude
     assert e_tc < 1e-6, (e_tc, e_ffma)         # a single TF32 pass would be ~5e-4 on this scale
+    if N <= 256 and N % 4 == 0 and K % 32 == 0:       # narrow output through the zero-padded tile (linear2's route), one guard row
+        Cn = torch.full((M + 1, N), float('nan'), device=DEV)
+        _cabi.check(lib.mp_gemm_bias(A.data_ptr(), W.data_ptr(), bias.data_ptr(), Cn.data_ptr(), M, N, K, 0, 4, stream))
+        e_n = ((Cn[:M].double() - ref).abs() / scale).max().item()
+        print(f'gemm M={M} N={N} K={K}: max scaled |err| f16x3 narrow {e_n:.2e}')
+        assert torch.isfinite(Cn[:M]).all() and torch.isnan(Cn[M]).all()
+        assert e_n < 1e-6, e_n
     if f16_ok:
         e_h = ((out[3].double() - ref).abs() / scale).max().item()
         print(f'gemm M={M} N={N} K={K}: max scaled |err| f16x3 {e_h:.2e}')
