@@ -443,8 +443,10 @@ def measure_cfg3(net, mp, xs, xs_host, B, T, D, args, dist, world, physics):
     # e2e: host buffers through the C ABI, copies inside the timed region; depth-D pipeline over batches (HostOffline objects with
     # their own net handle, stream, staging and pinned outputs): batch i+1 is submitted before batch i is awaited
     hosts = [mp.HostOffline(net, B, T) for _ in range(D)]
+    slots = {'hosts': hosts}
 
     def body(n_steps, off, pipelined):
+        hosts = slots['hosts']
         if not pipelined:
             for i in range(n_steps):
                 hosts[0].run(xs_host[(off + i) % n_sets], None)
@@ -491,7 +493,16 @@ def measure_cfg3(net, mp, xs, xs_host, B, T, D, args, dist, world, physics):
                   'how': f'depth-{D} pipeline over batches through mp_net_enqueue_offline_host (HostOffline.submit / wait): pinned host imu '
                          'in, pose/joints/tran/contact out to pinned host memory, every step',
                   'one_batch_at_a_time': {'value': frames_per_step * sync_n / sync_s, 'unit': 'frames/s', 'ms_per_step': sync_s / sync_n * 1e3}}
+    # the same with the compact pose transfer ([B*T,16,6]: 384 instead of 864 B per frame; model_utils.local6d_to_pose rebuilds the
+    # matrices on the consumer's side): what a host link shared by 8 GPUs can carry
     del hosts
+    slots['hosts'] = None                  # frees the full-transfer slots (3.3 GB of workspace each) before the compact ones exist
+    slots['hosts'] = [mp.HostOffline(net, B, T, compact=True) for _ in range(D)]
+    c_s, c_n = e2e_time(True, min(args.min_seconds, 1.5))
+    out['e2e_compact'] = {'value': frames_per_step * c_n / c_s, 'unit': 'frames/s', 'h2d_bytes_per_step': B * T * 60 * 4,
+                          'd2h_bytes_per_step': B * T * (96 + 72 + 3 + 2) * 4, 'ms_per_step': c_s / c_n * 1e3, 'steps_timed': c_n,
+                          'how': 'as e2e, pose transferred as the first two columns of the 16 non-ignored joints (HostOffline(compact=True))'}
+    slots['hosts'] = None
     return out
 
 
@@ -728,7 +739,7 @@ def run_ours(args):
                       'parallelism': f'{world} x (one process per GPU, sequences sharded, no data-path collective); '
                                      f'{D} batches in flight per GPU (pipeline over steps)',
                       'rank_core_binding': cores},
-            'e2e': head['e2e'], 'gpu_launches': launches * head['steps_timed'], 'gpu_launches_per_step': launches,
+            'e2e': head['e2e'], 'e2e_compact': head['e2e_compact'], 'gpu_launches': launches * head['steps_timed'], 'gpu_launches_per_step': launches,
             'roofline': roofline, 'whole_path_algorithmic_GBps': whole, 'whole_path_hbm_frac': whole / peak,
             'kernels': kernels, 'one_batch_at_a_time': sequential, 'pinned_path': pinned, 'cpu_baseline': cpu, 'batch1': batch1,
             'streaming': streaming, 'cfg4': cfg4, 'clocks': clocks.summary(),

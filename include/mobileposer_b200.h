@@ -99,6 +99,36 @@ int mp_rnn_forward(const mp_rnn_t* rnn, const float* xa, int32_t ka, const float
                    const float* h0, const float* c0, float* hn, float* cn, float* y,
                    void* workspace, size_t workspace_bytes, mp_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Training step of one head -- first slice of the training path:
+ * forward with saved activations and the full backward pass of RNN.forward [models/rnn.py:20-33], plus the Joints loss
+ * [models/joints.py:54-75].  Weights are read in torch's layouts straight from the module's parameters (`mp_rnn_weights_t`, no
+ * packing: they change every step); gradients are written (not accumulated) in the same layouts.  `mask` = NULL is eval mode
+ * (dropout off), otherwise the [B, T, H] tensor that multiplies relu(linear1(x)) (nn.Dropout's keep / (1 - p) pattern).
+ * The workspace carries the saved activations from mp_rnn_train_forward to mp_rnn_train_backward.
+ * Plain fp32 kernels (correctness first: pinned to the reference's own shared_step + backward); not the inference kernels.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct mp_rnn_grads {
+    float* linear1_w; /* [H, n_input]        */
+    float* linear1_b; /* [H]                 */
+    float* linear2_w; /* [n_output, dirs*H]  */
+    float* linear2_b; /* [n_output]          */
+    float* w_ih[2][2]; /* [layer][dir] [4H, In] */
+    float* w_hh[2][2]; /* [4H, H]               */
+    float* b_ih[2][2]; /* [4H]                  */
+    float* b_hh[2][2]; /* [4H] (equal to b_ih's gradient) */
+} mp_rnn_grads_t;
+size_t mp_rnn_train_workspace_bytes(const mp_rnn_weights_t* w, int32_t B, int32_t T);
+int mp_rnn_train_forward(const mp_rnn_weights_t* w, const float* x, int32_t B, int32_t T, const int32_t* lengths,
+                         const float* mask, float* y, void* workspace, size_t workspace_bytes, mp_stream_t stream);
+int mp_rnn_train_backward(const mp_rnn_weights_t* w, const float* x, int32_t B, int32_t T, const int32_t* lengths,
+                          const float* mask, const float* dy, const mp_rnn_grads_t* grads, void* workspace,
+                          size_t workspace_bytes, mp_stream_t stream);
+/* Joints.shared_step's loss on a padded prediction [B, T, D]: mean squared error to `target` + t_weight x the batch mean of the
+ * summed L1 norm of the second differences along T [joints.py:66-75]; writes the scalar (double, device) and d loss / d pred. */
+int mp_joints_loss(const float* pred, const float* target, int32_t B, int32_t T, int32_t D, float t_weight, double* loss,
+                   float* dpred, mp_stream_t stream);
+
 /* The dense contraction under every Linear / LSTM input projection of the path (rnn.py:22,27,32):
  *   C[M,N] = act(A[M,K] * W[N,K]^T + bias[N]).  mode 0 = library's choice, 1 = fp32 FFMA kernel,
  *   2 = tcgen05 3xTF32 tensor-core kernel (needs N % 256 == 0, K % 16 == 0, relu == 0),
@@ -284,6 +314,15 @@ int mp_net_forward(mp_net_t* net, const float* imu, int32_t B, int32_t T, const 
  * pose/joints/tran/contact, then a stream synchronise.  `dev_io` is device staging of at least
  * mp_net_host_staging_bytes(B,T).  Used for the end-to-end number of bench.py.               */
 size_t mp_net_host_staging_bytes(int32_t B, int32_t T);
+/* The same enqueue with a COMPACT pose transfer: pose6d_host [B*T,16,6] = the first two columns of the 16 non-ignored joints' local
+ * rotations (384 B per frame instead of 864 B; the ignored joints are the identity, the third column is the cross product of the two:
+ * `model_utils.local6d_to_pose` rebuilds [B*T,24,3,3] up to the matrices' own orthonormality).  For consumers behind a host link that the full pose saturates
+ * (8 GPUs x 90 MB per step through one host).  mp_pose_full_to_local6d is the conversion alone (device pointers). */
+int mp_net_enqueue_offline_host_compact(mp_net_t* net, const float* imu_host, int32_t B, int32_t T, const int32_t* lengths_host,
+                                        float* pose6d_host, float* joints_host, float* tran_host, float* contact_host,
+                                        void* dev_io, void* workspace, size_t workspace_bytes, mp_stream_t stream);
+int mp_pose_full_to_local6d(const float* pose, int64_t n_frames, float* pose6d, mp_stream_t stream);
+
 /* The same without the final synchronise: everything (H2D, forward, D2H) is enqueued on `stream` and the call
  * returns; the host buffers are valid once the stream has drained.  Two nets (mp_net_create on the same heads), each
  * with its own staging / workspace / stream, give a depth-2 software pipeline over batches: the copies of one batch

@@ -29,6 +29,12 @@ class RnnWeights(C.Structure):
     ]
 
 
+class RnnGrads(C.Structure):
+    """struct mp_rnn_grads."""
+    _fields_ = [('linear1_w', C.c_void_p), ('linear1_b', C.c_void_p), ('linear2_w', C.c_void_p), ('linear2_b', C.c_void_p),
+                ('w_ih', (C.c_void_p * 2) * 2), ('w_hh', (C.c_void_p * 2) * 2), ('b_ih', (C.c_void_p * 2) * 2), ('b_hh', (C.c_void_p * 2) * 2)]
+
+
 class ProfileEntry(C.Structure):
     """struct mp_profile_entry."""
     _fields_ = [('name', C.c_char * 32), ('launches', C.c_int64), ('total_ms', C.c_double),
@@ -70,6 +76,12 @@ SIGNATURES = {
     'mp_rnn_forward': (C.c_int, [C.c_void_p, c_float_p, C.c_int32, c_float_p, C.c_int32, C.c_int32, C.c_int32,
                                  c_int_p, c_float_p, c_float_p, c_float_p, c_float_p, c_float_p,
                                  C.c_void_p, C.c_size_t, c_stream]),
+    'mp_rnn_train_workspace_bytes': (C.c_size_t, [C.POINTER(RnnWeights), C.c_int32, C.c_int32]),
+    'mp_rnn_train_forward': (C.c_int, [C.POINTER(RnnWeights), c_float_p, C.c_int32, C.c_int32, c_int_p, c_float_p, c_float_p, C.c_void_p,
+                                       C.c_size_t, c_stream]),
+    'mp_rnn_train_backward': (C.c_int, [C.POINTER(RnnWeights), c_float_p, C.c_int32, C.c_int32, c_int_p, c_float_p, c_float_p,
+                                        C.POINTER(RnnGrads), C.c_void_p, C.c_size_t, c_stream]),
+    'mp_joints_loss': (C.c_int, [c_float_p, c_float_p, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_void_p, c_float_p, c_stream]),
     'mp_gemm_bias': (C.c_int, [c_float_p, c_float_p, c_float_p, c_float_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                C.c_int32, c_stream]),
     'mp_pose_reduced_global_to_full': (C.c_int, [c_float_p, C.c_int64, c_float_p, c_stream]),
@@ -105,6 +117,10 @@ SIGNATURES = {
     'mp_net_enqueue_offline_host': (C.c_int, [C.c_void_p, c_float_p, C.c_int32, C.c_int32, c_int_p, c_float_p,
                                               c_float_p, c_float_p, c_float_p, C.c_void_p, C.c_void_p, C.c_size_t,
                                               c_stream]),
+    'mp_net_enqueue_offline_host_compact': (C.c_int, [C.c_void_p, c_float_p, C.c_int32, C.c_int32, c_int_p, c_float_p,
+                                                      c_float_p, c_float_p, c_float_p, C.c_void_p, C.c_void_p, C.c_size_t,
+                                                      c_stream]),
+    'mp_pose_full_to_local6d': (C.c_int, [c_float_p, C.c_int64, c_float_p, c_stream]),
     'mp_net_forward_offline_host': (C.c_int, [C.c_void_p, c_float_p, C.c_int32, C.c_int32, c_int_p, c_float_p,
                                               c_float_p, c_float_p, c_float_p, C.c_void_p, C.c_void_p, C.c_size_t,
                                               c_stream]),

@@ -387,6 +387,23 @@ int mp_rnn_forward(const mp_rnn_t* r, const float* xa, int32_t ka, const float* 
                             (cudaStream_t)stream);
 }
 
+size_t mp_rnn_train_workspace_bytes(const mp_rnn_weights_t* w, int32_t B, int32_t T) { return rnn_train_workspace_bytes(w, B, T); }
+int mp_rnn_train_forward(const mp_rnn_weights_t* w, const float* x, int32_t B, int32_t T, const int32_t* lengths, const float* mask,
+                         float* y, void* workspace, size_t workspace_bytes, mp_stream_t stream) {
+    g_launches = 0;
+    MP_TRY(mp_device_check());
+    return rnn_train_forward(w, x, B, T, lengths, mask, y, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+int mp_rnn_train_backward(const mp_rnn_weights_t* w, const float* x, int32_t B, int32_t T, const int32_t* lengths, const float* mask,
+                          const float* dy, const mp_rnn_grads_t* grads, void* workspace, size_t workspace_bytes, mp_stream_t stream) {
+    g_launches = 0;
+    return rnn_train_backward(w, x, B, T, lengths, mask, dy, grads, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+int mp_joints_loss(const float* pred, const float* target, int32_t B, int32_t T, int32_t D, float t_weight, double* loss, float* dpred,
+                   mp_stream_t stream) {
+    return joints_loss(pred, target, B, T, D, t_weight, loss, dpred, (cudaStream_t)stream);
+}
+
 int mp_gemm_bias(const float* A, const float* W, const float* bias, float* C, int32_t M, int32_t N, int32_t K,
                  int32_t relu, int32_t mode, mp_stream_t stream) {
     g_launches = 0;
@@ -697,11 +714,11 @@ int mp_net_forward(mp_net_t* n, const float* imu, int32_t B, int32_t T, const in
     return MP_OK;
 }
 
-// staging layout: imu | lengths | pose | joints | tran | contact | vel
-static void host_staging_layout(size_t B, size_t T, size_t off[7], size_t* total) {
+// staging layout: imu | lengths | pose | joints | tran | contact | vel | pose as local 6D (compact transfers)
+static void host_staging_layout(size_t B, size_t T, size_t off[8], size_t* total) {
     size_t o = 0;
-    const size_t sz[7] = {B * T * 60 * 4, B * 4, B * T * 216 * 4, B * T * 72 * 4, B * T * 3 * 4, B * T * 2 * 4, B * T * 72 * 4};
-    for (int i = 0; i < 7; ++i) {
+    const size_t sz[8] = {B * T * 60 * 4, B * 4, B * T * 216 * 4, B * T * 72 * 4, B * T * 3 * 4, B * T * 2 * 4, B * T * 72 * 4, B * T * 96 * 4};
+    for (int i = 0; i < 8; ++i) {
         off[i] = o;
         o = align_up(o + sz[i]);
     }
@@ -710,35 +727,58 @@ static void host_staging_layout(size_t B, size_t T, size_t off[7], size_t* total
 
 size_t mp_net_host_staging_bytes(int32_t B, int32_t T) {
     if (B <= 0 || T <= 0) return 0;
-    size_t off[7], total;
+    size_t off[8], total;
     host_staging_layout(B, T, off, &total);
     return total;
 }
 
-int mp_net_enqueue_offline_host(mp_net_t* n, const float* imu_host, int32_t B, int32_t T, const int32_t* lengths_host,
-                                float* pose_host, float* joints_host, float* tran_host, float* contact_host, void* dev_io,
-                                void* workspace, size_t workspace_bytes, mp_stream_t stream_) {
+static int enqueue_offline_host_impl(mp_net_t* n, const float* imu_host, int32_t B, int32_t T, const int32_t* lengths_host,
+                                     float* pose_host, float* joints_host, float* tran_host, float* contact_host, void* dev_io,
+                                     void* workspace, size_t workspace_bytes, mp_stream_t stream_, bool compact) {
     cudaStream_t stream = (cudaStream_t)stream_;
     MP_REQUIRE(n && imu_host && dev_io && pose_host && joints_host && tran_host && contact_host, "forward_offline_host: null argument");
     MP_REQUIRE(B > 0 && T > 0, "forward_offline_host: empty batch");
     MP_REQUIRE(((uintptr_t)dev_io & 255) == 0, "forward_offline_host: staging must be 256-byte aligned");
-    size_t off[7], total;
+    size_t off[8], total;
     host_staging_layout(B, T, off, &total);
     char* d = (char*)dev_io;
     float* d_imu = (float*)(d + off[0]);
     int32_t* d_len = (int32_t*)(d + off[1]);
     float *d_pose = (float*)(d + off[2]), *d_joints = (float*)(d + off[3]), *d_tran = (float*)(d + off[4]),
-          *d_contact = (float*)(d + off[5]), *d_vel = (float*)(d + off[6]);
+          *d_contact = (float*)(d + off[5]), *d_vel = (float*)(d + off[6]), *d_pose6 = (float*)(d + off[7]);
     const size_t F = (size_t)B * T;
     MP_CUDA_TRY(cudaMemcpyAsync(d_imu, imu_host, F * 60 * 4, cudaMemcpyHostToDevice, stream));
     if (lengths_host) MP_CUDA_TRY(cudaMemcpyAsync(d_len, lengths_host, (size_t)B * 4, cudaMemcpyHostToDevice, stream));
     MP_TRY(mp_net_forward(n, d_imu, B, T, lengths_host ? d_len : nullptr, nullptr, nullptr, nullptr, nullptr, d_pose,
                           d_joints, d_vel, d_contact, d_tran, workspace, workspace_bytes, stream));
-    MP_CUDA_TRY(cudaMemcpyAsync(pose_host, d_pose, F * 216 * 4, cudaMemcpyDeviceToHost, stream));
+    if (compact) {
+        MP_TRY(launch_pose_local6d(d_pose, (int64_t)F, d_pose6, stream));
+        MP_CUDA_TRY(cudaMemcpyAsync(pose_host, d_pose6, F * 96 * 4, cudaMemcpyDeviceToHost, stream));
+    } else {
+        MP_CUDA_TRY(cudaMemcpyAsync(pose_host, d_pose, F * 216 * 4, cudaMemcpyDeviceToHost, stream));
+    }
     MP_CUDA_TRY(cudaMemcpyAsync(joints_host, d_joints, F * 72 * 4, cudaMemcpyDeviceToHost, stream));
     MP_CUDA_TRY(cudaMemcpyAsync(tran_host, d_tran, F * 3 * 4, cudaMemcpyDeviceToHost, stream));
     MP_CUDA_TRY(cudaMemcpyAsync(contact_host, d_contact, F * 2 * 4, cudaMemcpyDeviceToHost, stream));
     return MP_OK;
+}
+
+int mp_net_enqueue_offline_host(mp_net_t* n, const float* imu_host, int32_t B, int32_t T, const int32_t* lengths_host,
+                                float* pose_host, float* joints_host, float* tran_host, float* contact_host, void* dev_io,
+                                void* workspace, size_t workspace_bytes, mp_stream_t stream_) {
+    return enqueue_offline_host_impl(n, imu_host, B, T, lengths_host, pose_host, joints_host, tran_host, contact_host, dev_io, workspace,
+                                     workspace_bytes, stream_, false);
+}
+
+int mp_net_enqueue_offline_host_compact(mp_net_t* n, const float* imu_host, int32_t B, int32_t T, const int32_t* lengths_host,
+                                        float* pose6d_host, float* joints_host, float* tran_host, float* contact_host, void* dev_io,
+                                        void* workspace, size_t workspace_bytes, mp_stream_t stream_) {
+    return enqueue_offline_host_impl(n, imu_host, B, T, lengths_host, pose6d_host, joints_host, tran_host, contact_host, dev_io, workspace,
+                                     workspace_bytes, stream_, true);
+}
+
+int mp_pose_full_to_local6d(const float* pose, int64_t n_frames, float* pose6d, mp_stream_t stream) {
+    return launch_pose_local6d(pose, n_frames, pose6d, (cudaStream_t)stream);
 }
 
 int mp_net_forward_offline_host(mp_net_t* n, const float* imu_host, int32_t B, int32_t T, const int32_t* lengths_host,

@@ -272,6 +272,37 @@ int launch_reduced_global_to_full(const float* r6d, int64_t n, float* pose, cuda
     return MP_OK;
 }
 
+// Compact form of the full local pose for transfers: the first two COLUMNS of the 16 non-ignored ("reduced") joints' local
+// rotations, [n, 16, 6] = 384 B per frame instead of 864 B.  The ignored joints are the identity by construction (net.py:98) and a
+// rotation's third column is the cross product of the first two, so the consumer rebuilds the [24, 3, 3] matrices up to their
+// own orthonormality (model_utils.local6d_to_pose).  One thread per (frame, reduced joint).
+__global__ void pose_local6d_kernel(const float* __restrict__ pose, long long n, float* __restrict__ out) {
+    constexpr int kReduced[16] = MP_REDUCED_INIT;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * 16) return;
+    const long long f = i >> 4;
+    const int slot = (int)(i & 15);
+    int joint = 0;
+#pragma unroll
+    for (int k = 0; k < 16; ++k)
+        if (k == slot) joint = kReduced[k];
+    const float* R = pose + (f * 24 + joint) * 9;          // row major: R[r][c] = R[3 r + c]
+    float* o = out + i * 6;
+    o[0] = R[0]; o[1] = R[3]; o[2] = R[6];                  // column 0
+    o[3] = R[1]; o[4] = R[4]; o[5] = R[7];                  // column 1
+}
+
+int launch_pose_local6d(const float* pose, int64_t n, float* out, cudaStream_t stream) {
+    if (n <= 0) return MP_OK;
+    MP_REQUIRE(pose && out, "pose_local6d: null pointer");
+    ProfileScope prof("pose_local6d", 4.0 * (216 + 96) * (double)n, stream);
+    const long long threads = (long long)n * 16;
+    pose_local6d_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(pose, n, out);
+    MP_CUDA_TRY(cudaGetLastError());
+    count_launch();
+    return MP_OK;
+}
+
 int launch_tran_offline(const float* joints, const float* vel, const float* contact, const int32_t* lengths,
                         int B, int T, float* tran, cudaStream_t stream) {
     if (B <= 0 || T <= 0) return MP_OK;

@@ -104,6 +104,8 @@ int launch_pack_whh(const float* const* w_hh_dirs, int H, int dirs, float4* wpac
 int rec_cluster_size(int H);
 
 int launch_reduced_global_to_full(const float* r6d, int64_t n, float* pose, cudaStream_t stream);
+// full local pose [n,24,3,3] -> the first two columns of the 16 non-ignored joints [n,16,6] (compact transfer form)
+int launch_pose_local6d(const float* pose, int64_t n, float* out, cudaStream_t stream);
 int launch_tran_offline(const float* joints, const float* vel, const float* contact,
                         const int32_t* lengths, int B, int T, float* tran, cudaStream_t stream);
 int launch_online_update(mp_online_state_t* st, const float* pose, const float* joints,
@@ -139,6 +141,14 @@ int launch_eval_motion_rows(const float* jp, const float* jt, const float* je, c
 // N3 (evaluate.cu)
 int launch_eval_tran_windows(const float* tran_p, const float* tran_t, const int32_t* lengths, int S, int T, float* err,
                              int32_t* count, cudaStream_t stream);
+
+// N4 first slice (train.cu): forward with saved activations + backward of one RNN head in torch layouts, and the Joints loss
+size_t rnn_train_workspace_bytes(const mp_rnn_weights_t* w, int B, int T);
+int rnn_train_forward(const mp_rnn_weights_t* w, const float* x, int B, int T, const int32_t* lengths, const float* mask, float* y,
+                      void* workspace, size_t workspace_bytes, cudaStream_t stream);
+int rnn_train_backward(const mp_rnn_weights_t* w, const float* x, int B, int T, const int32_t* lengths, const float* mask, const float* dy,
+                       const mp_rnn_grads_t* grads, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+int joints_loss(const float* pred, const float* target, int B, int T, int D, float t_weight, double* loss, float* dpred, cudaStream_t stream);
 
 // ---- PTX helpers (clusters, mbarrier, distributed shared memory) ---------------------------
 #ifdef __CUDACC__

@@ -31,3 +31,16 @@ def reduced_pose_to_full(reduced_pose: torch.Tensor) -> torch.Tensor:
     full = torch.eye(3, device=reduced_pose.device).repeat(B, S, 24, 1, 1)
     full[:, :, joint_set.reduced] = reduced_pose.view(B, S, joint_set.n_reduced, 3, 3)
     return full.view(B, S, -1)
+
+
+def local6d_to_pose(pose6d: torch.Tensor) -> torch.Tensor:
+    """[..., 16, 6] compact local pose (the first two columns of the 16 non-ignored joints' local rotations, what
+    `HostOffline(compact=True)` / mp_net_enqueue_offline_host_compact transfer) -> [..., 24, 3, 3] full local pose: third column =
+    cross product, ignored joints = identity (net.py:98).  Pure layout + one cross product on the consumer's side; works on any device."""
+    lead = pose6d.shape[:-2]
+    v = pose6d.reshape(-1, joint_set.n_reduced, 6)
+    c0, c1 = v[..., :3], v[..., 3:]
+    r = torch.stack((c0, c1, torch.linalg.cross(c0, c1, dim=-1)), dim=-1)          # columns
+    full = torch.eye(3, dtype=pose6d.dtype, device=pose6d.device).repeat(v.shape[0], 24, 1, 1)
+    full[:, joint_set.reduced] = r
+    return full.view(*lead, 24, 3, 3)

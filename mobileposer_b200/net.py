@@ -387,8 +387,10 @@ class HostOffline:
 
     `run()` = submit + wait (one batch at a time, what evaluate.py's loop does)."""
 
-    def __init__(self, net: MobilePoserNet, B: int, T: int, device=None, rec_tile: int = 0):
-        """rec_tile: mp_net_set_rec_tile policy of this slot's net handle (0 = auto)."""
+    def __init__(self, net: MobilePoserNet, B: int, T: int, device=None, rec_tile: int = 0, compact: bool = False):
+        """rec_tile: mp_net_set_rec_tile policy of this slot's net handle (0 = auto).
+        compact: transfer the pose as [B*T, 16, 6] (first two columns of the 16 non-ignored joints' local rotations, 384 B per
+        frame instead of 864 B) -- `self.pose` is then that array and `model_utils.local6d_to_pose` rebuilds [B*T, 24, 3, 3]."""
         lib = _cabi.lib()
         self.net, self.B, self.T = net, B, T
         self.dev = device or net._device()
@@ -404,7 +406,8 @@ class HostOffline:
             self.ws_bytes = lib.mp_net_workspace_bytes(self.handle, B, T)
             self.ws = torch.empty(self.ws_bytes, device=self.dev, dtype=torch.uint8)
         self._physics = None
-        self.pose = torch.empty(B * T, 24, 3, 3).pin_memory()
+        self.compact = bool(compact)
+        self.pose = (torch.empty(B * T, 16, 6) if compact else torch.empty(B * T, 24, 3, 3)).pin_memory()
         self.joints = torch.empty(B, T, 72).pin_memory()
         self.tran = torch.empty(B, T, 3).pin_memory()
         self.contact = torch.empty(B, T, 2).pin_memory()
@@ -447,8 +450,9 @@ class HostOffline:
             self.lengths.copy_(torch.tensor(lens, dtype=torch.int32))
             lens_ptr = self.lengths.data_ptr()
         self._sync_physics()
+        entry = _cabi.lib().mp_net_enqueue_offline_host_compact if self.compact else _cabi.lib().mp_net_enqueue_offline_host
         with torch.cuda.device(self.dev):
-            _cabi.check(_cabi.lib().mp_net_enqueue_offline_host(
+            _cabi.check(entry(
                 self.handle, imu_host.data_ptr(), self.B, self.T, lens_ptr, self.pose.data_ptr(),
                 self.joints.data_ptr(), self.tran.data_ptr(), self.contact.data_ptr(), self.staging.data_ptr(),
                 self.ws.data_ptr(), self.ws_bytes, self.stream.cuda_stream), 'mp_net_enqueue_offline_host')

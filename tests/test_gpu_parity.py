@@ -468,6 +468,36 @@ def test_host_buffer_entry_matches_device_entry(net):
         assert torch.equal(tran_h[b, :L], tran[b, :L].cpu())
 
 
+def test_compact_pose_transfer_rebuilds_the_full_pose(net, wc_state_dict):
+    """HostOffline(compact=True): the pose travels as [B*T, 16, 6] (two columns of the 16 non-ignored joints) and
+    model_utils.local6d_to_pose gives back the [B*T, 24, 3, 3] the full transfer delivers -- with and without the physics hook.
+    The third column is rebuilt as a cross product, so the two agree to the ORTHONORMALITY of the matrices: ~1e-7 with
+    well-conditioned weights, ~2e-5 with the random init (K5's Gram-Schmidt on r6d columns of norm 0.05; the reference's own
+    matrices are orthonormal to the same 1e-5) -- in both cases far inside the 1e-4 rad gate."""
+    import mobileposer_b200 as mp
+    from mobileposer_b200.model_utils import local6d_to_pose
+    from mobileposer_b200.synthetic import synthetic_imu_batch
+    x = synthetic_imu_batch([71, 72, 73], 40).pin_memory()
+    wc = mp.MobilePoserNet()
+    wc.load_state_dict(wc_state_dict)
+    wc = wc.to(DEV).eval()
+    for model, tol in ((wc, 1e-6), (net, 5e-5)):
+        try:
+            for physics in (False, True):
+                model.enable_physics(physics)
+                full = [t.clone() for t in mp.HostOffline(model, 3, 40).run(x)]
+                comp = [t.clone() for t in mp.HostOffline(model, 3, 40, compact=True).run(x)]
+                assert comp[0].shape == (120, 16, 6)
+                rebuilt = local6d_to_pose(comp[0])
+                assert rebuilt.shape == full[0].shape
+                assert torch.equal(rebuilt[..., :2], full[0][..., :2])          # the transferred columns and the identities: bit for bit
+                assert max_abs(rebuilt, full[0]) <= tol
+                assert max_angle(rebuilt, full[0]) <= ANGLE_TOL
+                assert all(torch.equal(a, b) for a, b in zip(comp[1:], full[1:]))
+        finally:
+            model.enable_physics(False)
+
+
 def test_pipelined_host_batches_equal_one_at_a_time(net):
     """Two HostOffline objects as a depth-2 pipeline (bench.py's e2e): results are bit-identical to submit + wait per batch,
     with and without the physics hook inside the graph."""

@@ -1,0 +1,67 @@
+"""GPU suite, SURVEY.md 8f row N4 (first slice): the Joints head's training step on the device -- forward with saved activations,
+the loss of joints.py:54-75 and the full backward pass -- against
+  (1) the fixture the LIVE reference produced (its own `Joints.shared_step` + `loss.backward()`, eval mode and with a fixed dropout
+      mask: tests/golden/train_joints_step.npz, oracle/make_golden_train.py),
+  (2) the oracle (oracle/train_port.py: the same torch modules under autograd) on a larger ragged batch, every gradient tensor."""
+import pytest
+import torch
+
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+DEV = 'cuda:0'
+
+
+def _module(seeded_state_dict):
+    import mobileposer_b200 as mp
+    m = mp.Joints()
+    m.load_state_dict({k[len('joints.'):]: v for k, v in seeded_state_dict.items() if k.startswith('joints.')})
+    return m.to(DEV)
+
+
+def _rel(a, b):
+    return ((a.double().cpu() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-12)).item()
+
+
+@pytest.mark.parametrize('tag', ['eval', 'mask'])
+def test_joints_training_step_against_the_live_reference(tag):
+    import mobileposer_b200 as mp
+    from mobileposer_b200.training import joints_shared_step
+    g = load_golden('train_joints_step')
+    torch.manual_seed(0)                 # the fixture's module: torch.manual_seed(0); Joints() -- the same constructor order here
+    mod = mp.Joints().to(DEV)
+    mask = g['mask'].to(DEV) if tag == 'mask' else None
+    loss, grads, _ = joints_shared_step(mod, g['imu'].to(DEV), g['lengths'].tolist(), g['target'].to(DEV), mask)
+    assert abs(loss.item() - g[f'{tag}_loss'].item()) <= 1e-6 * abs(g[f'{tag}_loss'].item()) + 1e-9
+    worst = 0.0
+    for name, gr in grads.items():
+        short = name[len('joints.'):]
+        ref = g[f'{tag}_grad.{short}']
+        got = gr.cpu() if gr.numel() <= 40000 else gr[::7, ::5].cpu()
+        worst = max(worst, _rel(got, ref))
+        assert _rel(got, ref) < 2e-4, (name, _rel(got, ref))
+        assert abs(gr.norm().item() - g[f'{tag}_norm.{short}'].item()) <= 2e-4 * g[f'{tag}_norm.{short}'].item(), name
+    print(f'[train] {tag}: loss {loss.item():.6f}, worst relative gradient error over 20 tensors {worst:.2e}')
+
+
+def test_joints_training_step_against_the_oracle_on_a_ragged_batch(seeded_state_dict):
+    from mobileposer_b200.synthetic import synthetic_imu_batch
+    from mobileposer_b200.training import dropout_mask, joints_shared_step
+    from oracle.train_port import joints_shared_step as oracle_step
+    B, T = 19, 37                                   # three CTAs of 8 sequences, the last one partial
+    gen = torch.Generator().manual_seed(5)
+    lens = [int(v) for v in torch.randint(1, T + 1, (B,), generator=gen)]
+    lens[4] = T
+    imu = synthetic_imu_batch(list(range(400, 400 + B)), T)
+    for b, L in enumerate(lens):
+        imu[b, L:] = 0
+    target = torch.randn(B, T, 72, generator=gen) * 0.3
+    mask = dropout_mask((B, T, 256), generator=gen)
+    sd = {k: v for k, v in seeded_state_dict.items() if k.startswith('joints.')}
+    o_loss, o_grads, o_pred = oracle_step(sd, imu, lens, target, mask, prefix='joints.joints.')
+    loss, grads, pred = joints_shared_step(_module(seeded_state_dict), imu.to(DEV), lens, target.to(DEV), mask.to(DEV))
+    assert (pred.cpu() - o_pred).abs().max() < 1e-5
+    assert abs(loss.item() - o_loss.item()) <= 1e-6 * abs(o_loss.item())
+    for k, ref in o_grads.items():
+        assert _rel(grads['joints.' + k], ref) < 2e-4, (k, _rel(grads['joints.' + k], ref))
