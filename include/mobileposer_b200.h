@@ -128,6 +128,17 @@ int mp_rnn_train_backward(const mp_rnn_weights_t* w, const float* x, int32_t B, 
  * summed L1 norm of the second differences along T [joints.py:66-75]; writes the scalar (double, device) and d loss / d pred. */
 int mp_joints_loss(const float* pred, const float* target, int32_t B, int32_t T, int32_t D, float t_weight, double* loss,
                    float* dpred, mp_stream_t stream);
+/* Poser.shared_step's loss [poser.py:65-98] on a padded r6d prediction [B, T, 96]: MSE to pose_t [B, T, 96] + t_weight x jerk L1
+ * [poser.py:100-103] + the joint-position MSE through _reduced_global_to_full and the zero-pose forward kinematics
+ * [poser.py:93-96] against joints_t [B, T, 72]; writes the scalar and d loss / d pred (Gram-Schmidt and tree adjoints included). */
+int mp_poser_loss(const float* pred, const float* pose_t, const float* joints_t, int32_t B, int32_t T, float t_weight,
+                  double* loss, float* dpred, mp_stream_t stream);
+/* FootContact.shared_step's loss [footcontact.py:31,63]: nn.BCEWithLogitsLoss over the padded [B, T, 2] logits. */
+int mp_footcontact_loss(const float* pred, const float* target, int32_t B, int32_t T, double* loss, float* dpred,
+                        mp_stream_t stream);
+/* Velocity.shared_step's loss [velocity.py:72-86]: sum over n in {1, 3, 9} of the MSE of the T // n windows of n frames. */
+int mp_velocity_loss(const float* pred, const float* target, int32_t B, int32_t T, int32_t D, double* loss, float* dpred,
+                     mp_stream_t stream);
 
 /* The dense contraction under every Linear / LSTM input projection of the path (rnn.py:22,27,32):
  *   C[M,N] = act(A[M,K] * W[N,K]^T + bias[N]).  mode 0 = library's choice, 1 = fp32 FFMA kernel,

@@ -82,6 +82,9 @@ SIGNATURES = {
     'mp_rnn_train_backward': (C.c_int, [C.POINTER(RnnWeights), c_float_p, C.c_int32, C.c_int32, c_int_p, c_float_p, c_float_p,
                                         C.POINTER(RnnGrads), C.c_void_p, C.c_size_t, c_stream]),
     'mp_joints_loss': (C.c_int, [c_float_p, c_float_p, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_void_p, c_float_p, c_stream]),
+    'mp_poser_loss': (C.c_int, [c_float_p, c_float_p, c_float_p, C.c_int32, C.c_int32, C.c_float, C.c_void_p, c_float_p, c_stream]),
+    'mp_footcontact_loss': (C.c_int, [c_float_p, c_float_p, C.c_int32, C.c_int32, C.c_void_p, c_float_p, c_stream]),
+    'mp_velocity_loss': (C.c_int, [c_float_p, c_float_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, c_float_p, c_stream]),
     'mp_gemm_bias': (C.c_int, [c_float_p, c_float_p, c_float_p, c_float_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                C.c_int32, c_stream]),
     'mp_pose_reduced_global_to_full': (C.c_int, [c_float_p, C.c_int64, c_float_p, c_stream]),

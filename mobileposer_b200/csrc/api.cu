@@ -404,6 +404,17 @@ int mp_joints_loss(const float* pred, const float* target, int32_t B, int32_t T,
     return joints_loss(pred, target, B, T, D, t_weight, loss, dpred, (cudaStream_t)stream);
 }
 
+int mp_poser_loss(const float* pred, const float* pose_t, const float* joints_t, int32_t B, int32_t T, float t_weight, double* loss,
+                  float* dpred, mp_stream_t stream) {
+    return poser_loss(pred, pose_t, joints_t, B, T, t_weight, loss, dpred, (cudaStream_t)stream);
+}
+int mp_footcontact_loss(const float* pred, const float* target, int32_t B, int32_t T, double* loss, float* dpred, mp_stream_t stream) {
+    return footcontact_loss(pred, target, B, T, loss, dpred, (cudaStream_t)stream);
+}
+int mp_velocity_loss(const float* pred, const float* target, int32_t B, int32_t T, int32_t D, double* loss, float* dpred, mp_stream_t stream) {
+    return velocity_loss(pred, target, B, T, D, loss, dpred, (cudaStream_t)stream);
+}
+
 int mp_gemm_bias(const float* A, const float* W, const float* bias, float* C, int32_t M, int32_t N, int32_t K,
                  int32_t relu, int32_t mode, mp_stream_t stream) {
     g_launches = 0;

@@ -148,6 +148,10 @@ int rnn_train_forward(const mp_rnn_weights_t* w, const float* x, int B, int T, c
                       void* workspace, size_t workspace_bytes, cudaStream_t stream);
 int rnn_train_backward(const mp_rnn_weights_t* w, const float* x, int B, int T, const int32_t* lengths, const float* mask, const float* dy,
                        const mp_rnn_grads_t* grads, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+int poser_loss(const float* pred, const float* pose_t, const float* joints_t, int B, int T, float t_weight, double* loss, float* dpred,
+               cudaStream_t stream);
+int footcontact_loss(const float* pred, const float* target, int B, int T, double* loss, float* dpred, cudaStream_t stream);
+int velocity_loss(const float* pred, const float* target, int B, int T, int D, double* loss, float* dpred, cudaStream_t stream);
 int joints_loss(const float* pred, const float* target, int B, int T, int D, float t_weight, double* loss, float* dpred, cudaStream_t stream);
 
 // ---- PTX helpers (clusters, mbarrier, distributed shared memory) ---------------------------

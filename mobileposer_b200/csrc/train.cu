@@ -7,6 +7,7 @@
 // weight-gradient contractions are an atomics-based split-M kernel.  Everything is in torch's layouts (gate rows i, f, g, o), so the
 // results compare with autograd tensor by tensor.
 #include "mp_common.cuh"
+#include "mp_constants.cuh"
 
 #include <algorithm>
 
@@ -35,6 +36,17 @@ __global__ void transpose_kernel(const float* __restrict__ in, float* __restrict
 
 __global__ void mul_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ o, size_t n) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) o[i] = a[i] * b[i];
+}
+
+// out[m, n] = sum_k a[m, k] * w[k, n]   for a handful of k (the foot-contact head's two logits): one thread per output element
+__global__ void gemm_small_k_kernel(const float* __restrict__ a, const float* __restrict__ w, float* __restrict__ out, size_t M, int K, int N) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < M * N; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t m = i / N;
+        const int n = (int)(i % N);
+        float acc = 0.f;
+        for (int k = 0; k < K; ++k) acc = fmaf(a[m * K + k], __ldg(w + (size_t)k * N + n), acc);
+        out[i] = acc;
+    }
 }
 
 // dz = g * mask * (relu_out > 0)
@@ -243,6 +255,19 @@ __global__ void colsum_kernel(const float* __restrict__ A, int lda, float* __res
     atomicAdd(out + n, acc);
 }
 
+// block + grid reduction of a per-thread double into *out
+__device__ __forceinline__ void reduce_add_double(double local, double* out) {
+    __shared__ double red[32];
+    for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = local;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        double v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.0;
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (threadIdx.x == 0) atomicAdd(out, v);
+    }
+}
+
 // joints.py:54-75 on a padded prediction [B, T, D]:  loss = mean((p - y)^2) + tw * mean_b sum_t |p[t+2] + p[t] - 2 p[t+1]|_1 ;
 // dpred = 2 (p - y) / (B T D) + tw / B * (sign(acc[t-2]) + sign(acc[t]) - 2 sign(acc[t-1]))   (terms that exist)
 __global__ void joints_loss_kernel(const float* __restrict__ pred, const float* __restrict__ target, int B, int T, int D, float tw,
@@ -266,16 +291,165 @@ __global__ void joints_loss_kernel(const float* __restrict__ pred, const float* 
         if (t >= 1 && t + 1 < T) s -= 2.f * sgn(acc_at(t - 1));   // ... the `-2 p[t+1]` term of acc[t-1]
         dpred[i] = g + tw / (float)B * s;
     }
-    // block reduction of the loss contribution
-    __shared__ double red[32];
-    for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = local;
-    __syncthreads();
-    if (threadIdx.x < 32) {
-        double v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.0;
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if (threadIdx.x == 0) atomicAdd(loss, v);
+    reduce_add_double(local, loss);
+}
+
+// footcontact.py:31,63: nn.BCEWithLogitsLoss() over every element of the padded [B, T, 2] logits:
+//   loss = mean(max(p, 0) - p y + log(1 + exp(-|p|))),  dpred = (sigmoid(p) - y) / n
+__global__ void bce_logits_loss_kernel(const float* __restrict__ pred, const float* __restrict__ target, size_t n, double* __restrict__ loss,
+                                       float* __restrict__ dpred) {
+    double local = 0.0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float p = pred[i], y = target[i];
+        local += (double)(fmaxf(p, 0.f) - p * y + log1pf(expf(-fabsf(p)))) / (double)n;
+        dpred[i] = (1.0f / (1.0f + expf(-p)) - y) / (float)n;
     }
+    reduce_add_double(local, loss);
+}
+
+// velocity.py:72-86: sum over n in {1, 3, 9} of the MSE losses of the T // n windows of n frames; a window's MSE is a mean over
+// B * n * D elements, so frame t carries the weight c_t = sum_n [t < n (T // n)] / (B n D):  loss = sum c_t e^2,  dpred = 2 c_t e
+__global__ void velocity_loss_kernel(const float* __restrict__ pred, const float* __restrict__ target, int B, int T, int D,
+                                     double* __restrict__ loss, float* __restrict__ dpred) {
+    const size_t n = (size_t)B * T * D;
+    double local = 0.0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int t = (int)((i / D) % T);
+        float c = 0.f;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const int w = k == 0 ? 1 : (k == 1 ? 3 : 9);
+            if (t < w * (T / w)) c += 1.0f / ((float)B * (float)w * (float)D);
+        }
+        const float e = pred[i] - target[i];
+        local += (double)c * e * e;
+        dpred[i] = 2.f * c * e;
+    }
+    reduce_add_double(local, loss);
+}
+
+// poser.py:65-98 on a padded prediction p [B, T, 96] (r6d of the 16 reduced joints, global rotations):
+//   loss = mean((p - pose_t)^2) + tw * mean_b sum_t |p[t+3] - 3 p[t+2] + 3 p[t+1] - p[t]|_1
+//          + mean((FK(reduced_global_to_full(p)) - joints_t)^2)          (use_pos_loss: poser.py:93-96)
+// One thread per frame.  The position term: every reduced joint's global rotation is the Gram-Schmidt of its 6 numbers
+// (angular.py:167-182), the other joints inherit their parent's (their local rotation is the identity, poser.py:55), joint positions
+// follow the zero-pose bones down the tree (model.py:208-232); backward = subtree sums of d loss / d position, outer products with the
+// bones into d loss / d rotation, then the Gram-Schmidt's adjoint.  (Composing local = parent^T child and recomposing it in the forward
+// kinematics cancels identically because Gram-Schmidt always returns orthonormal matrices, so the derivative is that of the
+// telescoped form.)
+__global__ void poser_loss_kernel(const float* __restrict__ pred, const float* __restrict__ pose_t, const float* __restrict__ joints_t, int B,
+                                  int T, float tw, double* __restrict__ loss, float* __restrict__ dpred) {
+    constexpr int kParent[24] = MP_SMPL_PARENT_INIT, kSlot[24] = MP_REDUCED_SLOT_INIT;
+    constexpr float kJ[24][3] = MP_SMPL_J_ZERO_INIT;
+    const long long n_frames = (long long)B * T;
+    double local = 0.0;
+    auto sgn = [](float v) { return v > 0.f ? 1.f : (v < 0.f ? -1.f : 0.f); };
+    for (long long f = (long long)blockIdx.x * blockDim.x + threadIdx.x; f < n_frames; f += (long long)gridDim.x * blockDim.x) {
+        const int t = (int)(f % T);
+        const float* p = pred + f * 96;
+        float g[96];
+        // (1) + (2): element-wise terms
+        const float inv_n = 1.0f / ((float)n_frames * 96.f);
+        for (int k = 0; k < 96; ++k) {
+            const float e = p[k] - pose_t[f * 96 + k];
+            local += (double)e * e * inv_n;
+            float gk = 2.f * e * inv_n;
+            auto jerk_at = [&](int t0) {
+                const float* q = p + (long long)(t0 - t) * 96 + k;
+                return q[3 * 96] - 3.f * q[2 * 96] + 3.f * q[96] - q[0];
+            };
+            float sj = 0.f;
+            if (t + 3 < T) {
+                const float j = jerk_at(t);
+                sj -= sgn(j);
+                local += (double)tw * fabsf(j) / (double)B;
+            }
+            if (t >= 1 && t + 2 < T) sj += 3.f * sgn(jerk_at(t - 1));
+            if (t >= 2 && t + 1 < T) sj -= 3.f * sgn(jerk_at(t - 2));
+            if (t >= 3) sj += sgn(jerk_at(t - 3));
+            g[k] = gk + tw / (float)B * sj;
+        }
+        // (3) position term
+        float G[24][9], a_n[16], u_n[16], c0b[16];
+        for (int j = 0; j < 24; ++j) {
+            const int sl = kSlot[j];
+            if (sl < 0) {
+                for (int i = 0; i < 9; ++i) G[j][i] = G[kParent[j]][i];
+                continue;
+            }
+            const float ax = p[sl * 6], ay = p[sl * 6 + 1], az = p[sl * 6 + 2], bx = p[sl * 6 + 3], by = p[sl * 6 + 4], bz = p[sl * 6 + 5];
+            const float na = sqrtf(ax * ax + ay * ay + az * az);
+            const float c0x = ax / na, c0y = ay / na, c0z = az / na;
+            const float d = c0x * bx + c0y * by + c0z * bz;
+            const float ux = bx - d * c0x, uy = by - d * c0y, uz = bz - d * c0z;
+            const float nu = sqrtf(ux * ux + uy * uy + uz * uz);
+            const float c1x = ux / nu, c1y = uy / nu, c1z = uz / nu;
+            const float c2x = c0y * c1z - c0z * c1y, c2y = c0z * c1x - c0x * c1z, c2z = c0x * c1y - c0y * c1x;
+            // columns c0, c1, c2; row major R[r][c]
+            G[j][0] = c0x; G[j][1] = c1x; G[j][2] = c2x;
+            G[j][3] = c0y; G[j][4] = c1y; G[j][5] = c2y;
+            G[j][6] = c0z; G[j][7] = c1z; G[j][8] = c2z;
+            a_n[sl] = na; u_n[sl] = nu; c0b[sl] = d;
+        }
+        float P[24][3], S[24][3];
+        P[0][0] = P[0][1] = P[0][2] = 0.f;
+        const float inv_p = 1.0f / ((float)n_frames * 72.f);
+        for (int j = 1; j < 24; ++j) {
+            const int pa = kParent[j];
+            const float b0 = kJ[j][0] - kJ[pa][0], b1 = kJ[j][1] - kJ[pa][1], b2 = kJ[j][2] - kJ[pa][2];
+            for (int r = 0; r < 3; ++r) P[j][r] = P[pa][r] + G[pa][3 * r] * b0 + G[pa][3 * r + 1] * b1 + G[pa][3 * r + 2] * b2;
+        }
+        for (int j = 0; j < 24; ++j)
+            for (int r = 0; r < 3; ++r) {
+                const float e = P[j][r] - joints_t[f * 72 + j * 3 + r];
+                local += (double)e * e * inv_p;
+                S[j][r] = 2.f * e * inv_p;
+            }
+        for (int j = 23; j >= 1; --j)
+            for (int r = 0; r < 3; ++r) S[kParent[j]][r] += S[j][r];          // subtree sums of d loss / d position
+        float dG[24][9];
+        for (int j = 0; j < 24; ++j)
+            for (int i = 0; i < 9; ++i) dG[j][i] = 0.f;
+        for (int j = 1; j < 24; ++j) {
+            const int pa = kParent[j];
+            const float b[3] = {kJ[j][0] - kJ[pa][0], kJ[j][1] - kJ[pa][1], kJ[j][2] - kJ[pa][2]};
+            for (int r = 0; r < 3; ++r)
+                for (int c = 0; c < 3; ++c) dG[pa][3 * r + c] += S[j][r] * b[c];
+        }
+        for (int j = 23; j >= 1; --j)                                          // a non-reduced joint's rotation IS its parent's
+            if (kSlot[j] < 0)
+                for (int i = 0; i < 9; ++i) dG[kParent[j]][i] += dG[j][i];
+        for (int j = 0; j < 24; ++j) {
+            const int sl = kSlot[j];
+            if (sl < 0) continue;
+            const float c0[3] = {G[j][0], G[j][3], G[j][6]}, c1[3] = {G[j][1], G[j][4], G[j][7]};
+            float d0[3] = {dG[j][0], dG[j][3], dG[j][6]}, d1[3] = {dG[j][1], dG[j][4], dG[j][7]};
+            const float d2[3] = {dG[j][2], dG[j][5], dG[j][8]};
+            // c2 = c0 x c1:  d0 += c1 x d2,  d1 += d2 x c0
+            d0[0] += c1[1] * d2[2] - c1[2] * d2[1]; d0[1] += c1[2] * d2[0] - c1[0] * d2[2]; d0[2] += c1[0] * d2[1] - c1[1] * d2[0];
+            d1[0] += d2[1] * c0[2] - d2[2] * c0[1]; d1[1] += d2[2] * c0[0] - d2[0] * c0[2]; d1[2] += d2[0] * c0[1] - d2[1] * c0[0];
+            // c1 = u / |u|
+            const float c1d1 = c1[0] * d1[0] + c1[1] * d1[1] + c1[2] * d1[2];
+            float du[3];
+            for (int r = 0; r < 3; ++r) du[r] = (d1[r] - c1[r] * c1d1) / u_n[sl];
+            // u = b - (c0 . b) c0
+            const float c0du = c0[0] * du[0] + c0[1] * du[1] + c0[2] * du[2];
+            const float bvec[3] = {p[sl * 6 + 3], p[sl * 6 + 4], p[sl * 6 + 5]};
+            float db[3];
+            for (int r = 0; r < 3; ++r) {
+                db[r] = du[r] - c0[r] * c0du;
+                d0[r] += -c0b[sl] * du[r] - c0du * bvec[r];
+            }
+            // c0 = a / |a|
+            const float c0d0 = c0[0] * d0[0] + c0[1] * d0[1] + c0[2] * d0[2];
+            for (int r = 0; r < 3; ++r) {
+                g[sl * 6 + r] += (d0[r] - c0[r] * c0d0) / a_n[sl];
+                g[sl * 6 + 3 + r] += db[r];
+            }
+        }
+        for (int k = 0; k < 96; ++k) dpred[f * 96 + k] = g[k];
+    }
+    reduce_add_double(local, loss);
 }
 
 inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
@@ -306,7 +480,7 @@ TrainLayout train_layout(const mp_rnn_weights_t* w, size_t M) {
 int check_train_args(const mp_rnn_weights_t* w, const float* x, int B, int T, void* ws, size_t ws_bytes) {
     MP_REQUIRE(w && x && ws, "rnn_train: null argument");
     MP_REQUIRE(w->n_layers == 2 && (w->n_hidden == 256 || w->n_hidden == 64), "rnn_train: 2 layers, hidden 64 or 256");
-    MP_REQUIRE((w->n_input & 3) == 0 && (w->n_output & 3) == 0, "rnn_train: n_input and n_output must be multiples of 4");
+    MP_REQUIRE((w->n_input & 3) == 0 && w->n_output > 0, "rnn_train: n_input must be a multiple of 4");
     MP_REQUIRE(B > 0 && T > 0, "rnn_train: empty batch");
     MP_REQUIRE(((uintptr_t)ws & 255) == 0, "rnn_train: workspace must be 256-byte aligned");
     const size_t need = train_layout(w, (size_t)B * T).total;
@@ -407,8 +581,13 @@ int rnn_train_backward(const mp_rnn_weights_t* w, const float* x, int B, int T, 
     // linear2: dW2 = dy^T y1, db2 = colsum(dy), dY1 = dy W2
     MP_TRY(gemm_tn(dy, NO, F(L.y[1]), D * H, g->linear2_w, D * H, M, NO, D * H, s));
     MP_TRY(colsum(dy, NO, g->linear2_b, M, NO, s));
-    MP_TRY(transpose(w->linear2_w, F(L.w2T), NO, D * H, s));                      // [DH, NO]
-    MP_TRY(launch_gemm_ffma(dy, NO, nullptr, 0, F(L.w2T), F(L.zeros), F(L.dY), M, D * H, 0, s));
+    if ((NO & 3) == 0) {
+        MP_TRY(transpose(w->linear2_w, F(L.w2T), NO, D * H, s));                  // [DH, NO]
+        MP_TRY(launch_gemm_ffma(dy, NO, nullptr, 0, F(L.w2T), F(L.zeros), F(L.dY), M, D * H, 0, s));
+    } else {                                                                      // a handful of outputs (foot-contact logits)
+        gemm_small_k_kernel<<<296, 256, 0, s>>>(dy, w->linear2_w, F(L.dY), (size_t)M, NO, D * H);
+        MP_CUDA_TRY(cudaGetLastError());
+    }
     for (int l = 1; l >= 0; --l) {
         const int in_w = l == 0 ? H : D * H;
         const float* lin = l == 0 ? x1in : F(L.y[0]);
@@ -452,6 +631,37 @@ int joints_loss(const float* pred, const float* target, int B, int T, int D, flo
     MP_CUDA_TRY(cudaMemsetAsync(loss, 0, sizeof(double), s));
     const size_t n = (size_t)B * T * D;
     joints_loss_kernel<<<(unsigned)std::min<size_t>((n + 255) / 256, 148 * 8), 256, 0, s>>>(pred, target, B, T, D, t_weight, loss, dpred);
+    MP_CUDA_TRY(cudaGetLastError());
+    count_launch();
+    return MP_OK;
+}
+
+int poser_loss(const float* pred, const float* pose_t, const float* joints_t, int B, int T, float t_weight, double* loss, float* dpred,
+               cudaStream_t s) {
+    MP_REQUIRE(pred && pose_t && joints_t && loss && dpred && B > 0 && T > 0, "poser_loss: bad arguments");
+    MP_CUDA_TRY(cudaMemsetAsync(loss, 0, sizeof(double), s));
+    const long long n = (long long)B * T;
+    poser_loss_kernel<<<(unsigned)std::min<long long>((n + 63) / 64, 148 * 16), 64, 0, s>>>(pred, pose_t, joints_t, B, T, t_weight, loss, dpred);
+    MP_CUDA_TRY(cudaGetLastError());
+    count_launch();
+    return MP_OK;
+}
+
+int footcontact_loss(const float* pred, const float* target, int B, int T, double* loss, float* dpred, cudaStream_t s) {
+    MP_REQUIRE(pred && target && loss && dpred && B > 0 && T > 0, "footcontact_loss: bad arguments");
+    MP_CUDA_TRY(cudaMemsetAsync(loss, 0, sizeof(double), s));
+    const size_t n = (size_t)B * T * 2;
+    bce_logits_loss_kernel<<<(unsigned)std::min<size_t>((n + 255) / 256, 148 * 8), 256, 0, s>>>(pred, target, n, loss, dpred);
+    MP_CUDA_TRY(cudaGetLastError());
+    count_launch();
+    return MP_OK;
+}
+
+int velocity_loss(const float* pred, const float* target, int B, int T, int D, double* loss, float* dpred, cudaStream_t s) {
+    MP_REQUIRE(pred && target && loss && dpred && B > 0 && T > 0 && D > 0, "velocity_loss: bad arguments");
+    MP_CUDA_TRY(cudaMemsetAsync(loss, 0, sizeof(double), s));
+    const size_t n = (size_t)B * T * D;
+    velocity_loss_kernel<<<(unsigned)std::min<size_t>((n + 255) / 256, 148 * 8), 256, 0, s>>>(pred, target, B, T, D, loss, dpred);
     MP_CUDA_TRY(cudaGetLastError());
     count_launch();
     return MP_OK;

@@ -1,6 +1,10 @@
-"""Training step of the Joints head -- the first slice of the reference's training path on the device.
+"""Training steps of the Joints, FootContact and Velocity heads -- the first slice of the reference's training path on the device
+(SURVEY.md 8f row N4).
 
     joints_shared_step(module, imu, lengths, target, mask=None) -> (loss, grads, pred)
+    footcontact_shared_step / velocity_shared_step: the same for footcontact.py:43-65 (BCE with logits) and velocity.py:50-86
+    (windowed MSE); poser_shared_step: poser.py:65-98 (MSE + jerk L1 + the joint-position loss through _reduced_global_to_full and
+    the zero-pose forward kinematics, with the Gram-Schmidt and tree adjoints in the loss kernel).
 
 is `Joints.shared_step` (mobileposer/models/joints.py:54-75: MSE to the target joints + 1e-5 x temporal L1 of the second
 differences) followed by `loss.backward()`: the forward of `RNN.forward` (models/rnn.py:20-33) with saved activations, the loss and
@@ -100,3 +104,61 @@ def joints_shared_step(module, imu, lengths, target, mask=None):
 
     pred, grads = rnn_forward_backward(module.joints, imu, lengths, dloss, mask)
     return box['loss'], {'joints.' + k: v for k, v in grads.items()}, pred
+
+
+def _step_with_loss(rnn, prefix, x, lengths, target, mask, loss_call):
+    lib = _cabi.lib()
+    box = {}
+
+    def dloss(pred):
+        B, T, D = pred.shape
+        tgt = _f32c(target.to(pred.device)).view(B, T, D)
+        loss = torch.zeros((), device=pred.device, dtype=torch.float64)
+        dpred = torch.empty_like(pred)
+        loss_call(lib, pred, tgt, B, T, D, loss, dpred, current_stream_ptr(pred.device))
+        box['loss'] = loss
+        return dpred
+
+    pred, grads = rnn_forward_backward(rnn, x, lengths, dloss, mask)
+    return box['loss'], {prefix + k: v for k, v in grads.items()}, pred
+
+
+@torch.no_grad()
+def footcontact_shared_step(module, contact_input, lengths, foot_contacts, mask=None):
+    """FootContact.shared_step + backward (footcontact.py:43-65).  contact_input [B,T,132] = cat(noisy target joints, imu) as the
+    reference forms it (footcontact.py:57-61; the noise is the caller's, like the dropout mask); foot_contacts [B,T,2] in {0, 1}."""
+    def call(lib, pred, tgt, B, T, D, loss, dpred, stream):
+        _cabi.check(lib.mp_footcontact_loss(pred.data_ptr(), tgt.data_ptr(), B, T, loss.data_ptr(), dpred.data_ptr(), stream), 'mp_footcontact_loss')
+    return _step_with_loss(module.footcontact, 'footcontact.', contact_input, lengths, foot_contacts, mask, call)
+
+
+@torch.no_grad()
+def velocity_shared_step(module, vel_input, lengths, target_vel, mask=None):
+    """Velocity.shared_step + backward (velocity.py:50-86).  vel_input [B,T,132] = cat(noisy target joints, imu); target_vel [B,T,72]."""
+    def call(lib, pred, tgt, B, T, D, loss, dpred, stream):
+        _cabi.check(lib.mp_velocity_loss(pred.data_ptr(), tgt.data_ptr(), B, T, D, loss.data_ptr(), dpred.data_ptr(), stream), 'mp_velocity_loss')
+    return _step_with_loss(module.vel, 'vel.', vel_input, lengths, target_vel, mask, call)
+
+
+@torch.no_grad()
+def poser_shared_step(module, pose_input, lengths, target_pose_r6d, target_joints, mask=None):
+    """Poser.shared_step + backward (poser.py:65-98).  pose_input [B,T,132] = cat(noisy target joints, imu) (poser.py:81-85; the noise
+    is the caller's); target_pose_r6d [B,T,144] the 24 joints' global r6d (the 16 reduced ones are selected here like poser.py:88);
+    target_joints [B,T,72]."""
+    from .config import joint_set
+    lib = _cabi.lib()
+    box = {}
+
+    def dloss(pred):
+        B, T, D = pred.shape
+        pose_t = _f32c(target_pose_r6d.to(pred.device).view(B, T, 24, 6)[:, :, joint_set.reduced].reshape(B, T, 96))
+        joints_t = _f32c(target_joints.to(pred.device)).view(B, T, 72)
+        loss = torch.zeros((), device=pred.device, dtype=torch.float64)
+        dpred = torch.empty_like(pred)
+        _cabi.check(lib.mp_poser_loss(pred.data_ptr(), pose_t.data_ptr(), joints_t.data_ptr(), B, T, T_WEIGHT, loss.data_ptr(),
+                                      dpred.data_ptr(), current_stream_ptr(pred.device)), 'mp_poser_loss')
+        box['loss'] = loss
+        return dpred
+
+    pred, grads = rnn_forward_backward(module.pose, pose_input, lengths, dloss, mask)
+    return box['loss'], {'pose.' + k: v for k, v in grads.items()}, pred

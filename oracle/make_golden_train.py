@@ -77,7 +77,83 @@ def main():
             ref = out[f'{tag}_grad.{k}']
             got = gr if gr.numel() <= 40000 else gr[::7, ::5]
             assert (got - ref).abs().max() <= 1e-6 * max(1.0, ref.abs().max().item()), (tag, k)
-    print('oracle/train_port.py agrees with the live reference')
+    print('oracle/train_port.py agrees with the live reference (joints)')
+
+    # ---- FootContact (footcontact.py:43-65, BCE with logits) and Velocity (velocity.py:50-86, windowed MSE), eval mode; the noise the
+    # reference draws inside shared_step (torch.randn right after torch.manual_seed) is reproduced and the noisy input saved --------------
+    from oracle.train_port import head_shared_step
+    os.chdir(os.path.join(REF, 'mobileposer'))
+    try:
+        from mobileposer.models import FootContact, Velocity
+        torch.manual_seed(0)
+        foot = FootContact()
+        torch.manual_seed(0)
+        velm = Velocity()
+    finally:
+        os.chdir(cwd)
+    joints_gt = torch.randn(B, T, 24, 3, generator=g) * 0.3
+    contacts = (torch.rand(B, T, 2, generator=g) > 0.5).float()
+    vels = torch.randn(B, T, 24, 3, generator=g) * 0.5
+    out2 = {'imu': imu, 'lengths': np.asarray(lens), 'foot_contacts': contacts, 'vels': vels}
+    for name, mod, std, outputs, kind, prefix in (('foot', foot, 0.04, {'joints': joints_gt.clone(), 'foot_contacts': contacts}, 'footcontact', 'footcontact.'),
+                                                  ('vel', velm, 0.025, {'joints': joints_gt.clone(), 'vels': vels}, 'velocity', 'vel.')):
+        mod.eval()
+        mod.zero_grad()
+        torch.manual_seed(77)
+        noise = torch.randn(B, T, 72) * std
+        torch.manual_seed(77)                       # shared_step draws the same tensor
+        loss = mod.shared_step(((imu, lens), (outputs, None)))
+        loss.backward()
+        x_cat = torch.cat((joints_gt.view(B, T, 72) + noise, imu), dim=-1)
+        out2[f'{name}_input'] = x_cat
+        out2[f'{name}_loss'] = loss.detach()
+        sdm = {k: v.detach().clone() for k, v in mod.state_dict().items() if k.startswith(prefix)}
+        target = contacts if name == 'foot' else vels.view(B, T, 72)
+        p_loss, p_grads, _ = head_shared_step(sdm, x_cat, lens, target, kind, prefix=prefix)
+        assert abs(p_loss.item() - loss.item()) < 1e-6 * max(1.0, abs(loss.item())), (name, p_loss, loss)
+        for pname, prm in mod.named_parameters():
+            if not pname.startswith(prefix):
+                continue
+            gname = pname[len(prefix):]
+            gr = prm.grad.detach()
+            assert (p_grads[gname] - gr).abs().max() <= 1e-6 * max(1.0, gr.abs().max().item()), (name, gname)
+            out2[f'{name}_norm.{gname}'] = gr.norm()
+            out2[f'{name}_grad.{gname}'] = gr if gr.numel() <= 40000 else gr[::7, ::5].contiguous()
+    # ---- Poser (poser.py:65-98): MSE + jerk L1 + joint-position loss through _reduced_global_to_full and the body model's FK --------
+    os.chdir(os.path.join(REF, 'mobileposer'))
+    try:
+        from mobileposer.models import Poser
+        torch.manual_seed(0)
+        poser = Poser()
+    finally:
+        os.chdir(cwd)
+    eye6 = torch.tensor([1., 0., 0., 0., 1., 0.]).repeat(24)
+    poses = eye6 + 0.3 * torch.randn(B, T, 144, generator=g)                 # target pose: 24 joints x r6d
+    poser.eval()
+    poser.zero_grad()
+    torch.manual_seed(78)
+    noise = torch.randn(B, T, 72) * 0.04
+    torch.manual_seed(78)
+    loss = poser.shared_step(((imu, lens), ({'poses': poses, 'joints': joints_gt.clone()}, None)))
+    loss.backward()
+    x_cat = torch.cat((joints_gt.view(B, T, 72) + noise, imu), dim=-1)
+    import mobileposer.config as RC
+    pose_t96 = poses.view(B, T, 24, 6)[:, :, RC.joint_set.reduced].reshape(B, T, 96)
+    out2.update(pose_input=x_cat, poses=poses, joints_gt=joints_gt.view(B, T, 72), pose_loss=loss.detach())
+    sdm = {k: v.detach().clone() for k, v in poser.state_dict().items() if k.startswith('pose.')}
+    p_loss, p_grads, _ = head_shared_step(sdm, x_cat, lens, torch.cat((pose_t96, joints_gt.view(B, T, 72)), dim=-1), 'poser', prefix='pose.')
+    assert abs(p_loss.item() - loss.item()) < 1e-6 * max(1.0, abs(loss.item())), (p_loss, loss)
+    for pname, prm in poser.named_parameters():
+        if not pname.startswith('pose.'):
+            continue
+        gname = pname[len('pose.'):]
+        gr = prm.grad.detach()
+        assert (p_grads[gname] - gr).abs().max() <= 2e-6 * max(1.0, gr.abs().max().item()), ('pose', gname, (p_grads[gname] - gr).abs().max())
+        out2[f'pose_norm.{gname}'] = gr.norm()
+        out2[f'pose_grad.{gname}'] = gr if gr.numel() <= 40000 else gr[::7, ::5].contiguous()
+    print('oracle/train_port.py agrees with the live reference (poser)')
+    np.savez_compressed(os.path.join(OUT, 'train_heads_step.npz'), **{k: (v.numpy() if torch.is_tensor(v) else v) for k, v in out2.items()})
+    print('wrote train_heads_step.npz; oracle/train_port.py agrees with the live reference (footcontact, velocity)')
 
 
 if __name__ == '__main__':

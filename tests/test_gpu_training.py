@@ -65,3 +65,51 @@ def test_joints_training_step_against_the_oracle_on_a_ragged_batch(seeded_state_
     assert abs(loss.item() - o_loss.item()) <= 1e-6 * abs(o_loss.item())
     for k, ref in o_grads.items():
         assert _rel(grads['joints.' + k], ref) < 2e-4, (k, _rel(grads['joints.' + k], ref))
+
+
+@pytest.mark.parametrize('name', ['foot', 'vel'])
+def test_footcontact_and_velocity_training_steps_against_the_live_reference(name):
+    """FootContact.shared_step (BCE with logits, H = 64 bidirectional) and Velocity.shared_step (windowed MSE, H = 256
+    unidirectional) + backward: loss and every gradient tensor against the live reference's (tests/golden/train_heads_step.npz;
+    the reference's in-step noise is reproduced in the fixture's input)."""
+    import mobileposer_b200 as mp
+    from mobileposer_b200.training import footcontact_shared_step, velocity_shared_step
+    g = load_golden('train_heads_step')
+    torch.manual_seed(0)
+    if name == 'foot':
+        mod, step, target, prefix = mp.FootContact().to(DEV), footcontact_shared_step, g['foot_contacts'], 'footcontact.'
+    else:
+        mod, step, target, prefix = mp.Velocity().to(DEV), velocity_shared_step, g['vels'].view(3, 20, 72), 'vel.'
+    loss, grads, _ = step(mod, g[f'{name}_input'].to(DEV), g['lengths'].tolist(), target.to(DEV))
+    assert abs(loss.item() - g[f'{name}_loss'].item()) <= 2e-6 * abs(g[f'{name}_loss'].item()) + 1e-9
+    worst = 0.0
+    for pname, gr in grads.items():
+        short = pname[len(prefix):]
+        ref = g[f'{name}_grad.{short}']
+        got = gr.cpu() if gr.numel() <= 40000 else gr[::7, ::5].cpu()
+        worst = max(worst, _rel(got, ref))
+        assert _rel(got, ref) < 2e-4, (pname, _rel(got, ref))
+        assert abs(gr.norm().item() - g[f'{name}_norm.{short}'].item()) <= 2e-4 * g[f'{name}_norm.{short}'].item(), pname
+    print(f'[train] {name}: loss {loss.item():.6f}, worst relative gradient error over {len(grads)} tensors {worst:.2e}')
+
+
+def test_poser_training_step_against_the_live_reference():
+    """Poser.shared_step (poser.py:65-98: MSE + jerk L1 + joint-position loss through _reduced_global_to_full and the zero-pose
+    forward kinematics) + backward: the loss kernel carries the Gram-Schmidt and kinematic-tree adjoints; loss and every gradient
+    tensor against the live reference's autograd."""
+    import mobileposer_b200 as mp
+    from mobileposer_b200.training import poser_shared_step
+    g = load_golden('train_heads_step')
+    torch.manual_seed(0)
+    mod = mp.Poser().to(DEV)
+    loss, grads, _ = poser_shared_step(mod, g['pose_input'].to(DEV), g['lengths'].tolist(), g['poses'].to(DEV), g['joints_gt'].to(DEV))
+    assert abs(loss.item() - g['pose_loss'].item()) <= 2e-6 * abs(g['pose_loss'].item())
+    worst = 0.0
+    for pname, gr in grads.items():
+        short = pname[len('pose.'):]
+        ref = g[f'pose_grad.{short}']
+        got = gr.cpu() if gr.numel() <= 40000 else gr[::7, ::5].cpu()
+        worst = max(worst, _rel(got, ref))
+        assert _rel(got, ref) < 2e-4, (pname, _rel(got, ref))
+        assert abs(gr.norm().item() - g[f'pose_norm.{short}'].item()) <= 2e-4 * g[f'pose_norm.{short}'].item(), pname
+    print(f'[train] pose: loss {loss.item():.6f}, worst relative gradient error over {len(grads)} tensors {worst:.2e}')
