@@ -75,6 +75,9 @@ struct mp_rnn {
     void* wih_f16[2] = {nullptr, nullptr};      // [2 * dirs*4H, In_l] halves: fp16 hi rows, then scaled-lo rows (gemm_f16.cu), or null
     void* w2_f16 = nullptr;                     // linear2 for the same kernel: [2 * 256, dirs*H] halves, rows >= n_out zero; or null
     float* b2_pad = nullptr;                    // [256] linear2 bias, zero padded
+    void* w1_f16 = nullptr;                     // linear1 for the same kernel: [2 * 256, k1p] halves (rows >= H and columns >= n_in zero); or null
+    float* b1_pad = nullptr;                    // [256] linear1 bias, zero padded
+    int k1p = 0;                                // n_in rounded up to the kernel's K step (32)
     float* bsum[2] = {nullptr, nullptr};   // [dirs*4H]         b_ih + b_hh
     float4* whh_pack[2] = {nullptr, nullptr};
     float* whh_t[2] = {nullptr, nullptr};
@@ -194,6 +197,11 @@ int mp_rnn_create(mp_rnn_t** out, const mp_rnn_weights_t* w, mp_stream_t stream_
     const bool lin2_tc = r->n_out >= 16 && r->n_out <= 256 && (r->n_out & 3) == 0 && (dirs * H) % 32 == 0;
     const size_t o_w2pad = take(lin2_tc ? (size_t)256 * dirs * H : 0), o_w2f16 = take(lin2_tc ? (size_t)256 * dirs * H : 0),
                  o_b2pad = take(lin2_tc ? 256 : 0);
+    // linear1 on the same kernel: [H, n_in] padded to one 256-row tile and to a multiple of the K step
+    r->k1p = (r->n_in + 31) / 32 * 32;
+    const bool lin1_tc = (H & 7) == 0 && H <= 256;
+    const size_t o_w1pad = take(lin1_tc ? (size_t)256 * r->k1p : 0), o_w1f16 = take(lin1_tc ? (size_t)256 * r->k1p : 0),
+                 o_b1pad = take(lin1_tc ? 256 : 0);
     size_t o_wih[2], o_bs[2], o_pk[2], o_wt[2], o_raw[2], o_split[2], o_f16[2];
     for (int l = 0; l < 2; ++l) {
         o_wih[l] = take((size_t)dirs * 4 * H * in_l[l]);
@@ -238,6 +246,22 @@ int mp_rnn_create(mp_rnn_t** out, const mp_rnn_weights_t* w, mp_stream_t stream_
         if (st == MP_OK) {
             r->w2_f16 = base + o_w2f16;
             st = launch_split_f16(w2pad, (size_t)256 * dirs * H, r->w2_f16, stream);
+        }
+    }
+    if (lin1_tc && st == MP_OK) {
+        float* w1pad = (float*)(base + o_w1pad);
+        r->b1_pad = (float*)(base + o_b1pad);
+        if (cudaMemsetAsync(w1pad, 0, (size_t)256 * r->k1p * sizeof(float), stream) != cudaSuccess ||
+            cudaMemsetAsync(r->b1_pad, 0, 256 * sizeof(float), stream) != cudaSuccess ||
+            cudaMemcpy2DAsync(w1pad, (size_t)r->k1p * sizeof(float), w->linear1_w, (size_t)r->n_in * sizeof(float),
+                              (size_t)r->n_in * sizeof(float), H, cudaMemcpyDeviceToDevice, stream) != cudaSuccess) {
+            set_error("rnn_create: linear1 padding failed: %s", cudaGetErrorString(cudaGetLastError()));
+            st = MP_ERR_CUDA;
+        }
+        copy(r->b1_pad, w->linear1_b, H);
+        if (st == MP_OK) {
+            r->w1_f16 = base + o_w1f16;
+            st = launch_split_f16(w1pad, (size_t)256 * r->k1p, r->w1_f16, stream);
         }
     }
     for (int l = 0; l < 2 && st == MP_OK; ++l) {
@@ -290,7 +314,9 @@ static void rnn_ws_layout(const mp_rnn* r, size_t M, size_t* o_x1, size_t* o_gin
     *o_gin = take(M * r->dirs * 4 * r->H);
     *o_y0 = take(M * r->dirs * r->H);
     *o_y1 = take(M * r->dirs * r->H);
-    *o_xs = take(M * r->dirs * r->H);      // fp16 (hi, lo) planes of the projection's activation operand: 2 x 2 B per element
+    // fp16 (hi, lo) planes of a tensor-core launch's activation operand (2 x 2 B per element): linear1's packed input, or the split of
+    // a layer input whose producer could not write the planes itself
+    *o_xs = take(M * (size_t)std::max(r->dirs * r->H, r->k1p));
     *total = off;
 }
 
@@ -332,7 +358,16 @@ static int rnn_forward_impl(const mp_rnn_t* r, const float* xa, int32_t ka, cons
     if (proj16[0] || proj16[1] || lin2_16) MP_CUDA_TRY(cudaMemsetAsync(sched, 0, 256, stream));
     const bool x1_split = proj16[0] && fuse_split;
     // linear1 + ReLU (dropout is the identity in eval)                         rnn.py:22
-    MP_TRY(launch_gemm_ffma(xa, ka, xb, kb, r->w1, r->b1, x1, (int)M, H, x1_split ? 3 : 1, stream));
+    const bool lin1_16 = x1_split && r->w1_f16 && gemm_f16_eligible((int)M, 256, r->k1p) && (ka & 3) == 0 && (kb & 3) == 0 &&
+                         !getenv("MP_LINEAR1_FFMA");
+    if (lin1_16) {
+        // tensor-core linear1: the two-source operand is packed into padded (hi, lo) planes, the epilogue applies bias + ReLU and
+        // writes the planes the layer-0 projection reads
+        MP_TRY(launch_pack_cat_f16(xa, ka, xb, kb, M, r->k1p, ws + o_xs, stream));
+        MP_TRY(launch_gemm_f16x3_act(ws + o_xs, r->w1_f16, r->b1_pad, x1, (int)M, 256, r->k1p, H, 3, sched + 6, stream));
+    } else {
+        MP_TRY(launch_gemm_ffma(xa, ka, xb, kb, r->w1, r->b1, x1, (int)M, H, x1_split ? 3 : 1, stream));
+    }
     const float* layer_in = x1;
     bool layer_in_split = x1_split;
     int in_w = H;
@@ -432,12 +467,29 @@ int mp_gemm_bias(const float* A, const float* W, const float* bias, float* C, in
         MP_CUDA_TRY(cudaMallocAsync(&wsp, (size_t)N * K * 4, s));
         MP_CUDA_TRY(cudaMallocAsync(&sched, 256, s));
         MP_CUDA_TRY(cudaMemsetAsync(sched, 0, 256, s));
-        int st = launch_split_f16(A, (size_t)M * K, as, s);
-        if (st == MP_OK) st = launch_split_f16(W, (size_t)N * K, wsp, s);
-        if (st == MP_OK) st = launch_gemm_f16x3(as, wsp, bias, C, M, N, K, N, (unsigned int*)sched, s);
+        const bool il = getenv("MP_GEMM_IL") != nullptr;      // experiment: interleaved (hi, lo) operand layout, 128-byte TMA rows
+        int st = il ? launch_split_f16_il(A, (size_t)M * K, as, s) : launch_split_f16(A, (size_t)M * K, as, s);
+        if (st == MP_OK) st = il ? launch_split_f16_il(W, (size_t)N * K, wsp, s) : launch_split_f16(W, (size_t)N * K, wsp, s);
+        if (getenv("MP_GEMM_DBG")) {       // clock stamps of CTA 0's issuing thread land in the last 48 bytes of C's first row... no: own buffer
+            static unsigned long long* dbg_buf = nullptr;
+            if (!dbg_buf) MP_CUDA_TRY(cudaMallocManaged((void**)&dbg_buf, 64));
+            g_gemm_dbg = dbg_buf;
+        } else {
+            g_gemm_dbg = nullptr;
+        }
+        const char* pv = getenv("MP_GEMM_PAIR_TEST");       // test entry: 1 = CTA-pair kernel, 0 = single-CTA kernel, unset = default
+        const int pf = pv ? (atoi(pv) ? 16 : 32) : 0;
+        if (st == MP_OK) st = launch_gemm_f16x3_act(as, wsp, bias, C, M, N, K, N, (il ? 4 : 0) | pf, (unsigned int*)sched, s);
         cudaFreeAsync(as, s);
         cudaFreeAsync(wsp, s);
         cudaFreeAsync(sched, s);
+        if (g_gemm_dbg) {
+            cudaStreamSynchronize(s);
+            fprintf(stderr, "[gemm dbg] M=%d N=%d K=%d flags=%d: CTA0 issuer %llu clk = %llu ns (%.3f GHz), %llu tiles; waiting for operands %llu clk, "
+                    "for the epilogue %llu clk, for the tile queue %llu clk\n", M, N, K, (il ? 4 : 0) | pf, g_gemm_dbg[0], g_gemm_dbg[3],
+                    (double)g_gemm_dbg[0] / (double)g_gemm_dbg[3], g_gemm_dbg[4], g_gemm_dbg[1], g_gemm_dbg[2], g_gemm_dbg[5]);
+            g_gemm_dbg = nullptr;
+        }
         return st;
     }
     if (mode == 4) {

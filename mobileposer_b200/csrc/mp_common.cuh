@@ -70,6 +70,16 @@ bool gemm_f16_eligible(int M, int N, int K);
 int launch_gemm_f16x3(const void* A_split, const void* W_split, const float* bias, float* C, int M, int N, int K, int N_out,
                       unsigned int* sched, cudaStream_t stream);
 int launch_split_f16(const float* x, size_t n, void* out_hi_lo, cudaStream_t stream);
+// the same kernel with an activation epilogue: flags bit 0 = ReLU, bit 1 = C written as two [M, N_out] planes of halves (hi, scaled lo),
+// bit 2 = operands in the interleaved layout (launch_split_f16_il), bit 4 / bit 5 = force the CTA-pair / single-CTA kernel (default: pair
+// unless MP_GEMM_PAIR=0)
+int launch_gemm_f16x3_act(const void* A_split, const void* W_split, const float* bias, void* C, int M, int N, int K, int N_out,
+                          int flags, unsigned int* sched, cudaStream_t stream);
+// interleaved operand layout [rows, K/32, {hi[32], lo[32]}] (flags bit 2 of launch_gemm_f16x3_act: 128-byte TMA rows)
+int launch_split_f16_il(const float* x, size_t n, void* out, cudaStream_t stream);
+extern unsigned long long* g_gemm_dbg;
+// cat(A1[M,K1], A2[M,K2]), zero-padded to Kp columns, as (hi, lo) planes [2][M, Kp] of halves (linear1's operand)
+int launch_pack_cat_f16(const float* A1, int K1, const float* A2, int K2, size_t M, int Kp, void* out_hi_lo, cudaStream_t stream);
 int launch_gemm_ffma(const float* A1, int K1, const float* A2, int K2, const float* W, const float* bias, float* C,
                      int M, int N, int relu, cudaStream_t stream);
 
