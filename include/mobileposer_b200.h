@@ -140,6 +140,17 @@ int mp_footcontact_loss(const float* pred, const float* target, int32_t B, int32
 int mp_velocity_loss(const float* pred, const float* target, int32_t B, int32_t T, int32_t D, double* loss, float* dpred,
                      mp_stream_t stream);
 
+/* The optimizer step Lightning runs after shared_step's backward [overfit.py:41-50: Trainer(gradient_clip_val=1);
+ * joints.py:113-114 (and the other heads): torch.optim.AdamW(self.parameters(), lr=1e-3)] over FLAT fp32 buffers holding all of a
+ * head's parameters / gradients / moments.  mp_grad_sq_norm ADDS the sum of squares of `grads` to *sq_norm (double, device; zero it
+ * first) -- torch.nn.utils.clip_grad_norm_'s total norm, squared.  mp_adamw_step is one fused pass: g' = g * grad_scale (e.g. 1 / world
+ * size after a gradient all-reduce) * min(1, max_norm / (sqrt(*sq_norm) * grad_scale + 1e-6)) when sq_norm is given, then torch's
+ * AdamW update (decoupled weight decay, bias corrections of step `step` >= 1, amsgrad off). */
+int mp_grad_sq_norm(const float* grads, size_t n, double* sq_norm, mp_stream_t stream);
+int mp_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, size_t n, float lr, float beta1, float beta2,
+                  float eps, float weight_decay, int32_t step, const double* sq_norm, float max_norm, float grad_scale,
+                  mp_stream_t stream);
+
 /* The dense contraction under every Linear / LSTM input projection of the path (rnn.py:22,27,32):
  *   C[M,N] = act(A[M,K] * W[N,K]^T + bias[N]).  mode 0 = library's choice, 1 = fp32 FFMA kernel,
  *   2 = tcgen05 3xTF32 tensor-core kernel (needs N % 256 == 0, K % 16 == 0, relu == 0),

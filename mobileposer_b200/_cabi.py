@@ -85,6 +85,9 @@ SIGNATURES = {
     'mp_poser_loss': (C.c_int, [c_float_p, c_float_p, c_float_p, C.c_int32, C.c_int32, C.c_float, C.c_void_p, c_float_p, c_stream]),
     'mp_footcontact_loss': (C.c_int, [c_float_p, c_float_p, C.c_int32, C.c_int32, C.c_void_p, c_float_p, c_stream]),
     'mp_velocity_loss': (C.c_int, [c_float_p, c_float_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, c_float_p, c_stream]),
+    'mp_grad_sq_norm': (C.c_int, [c_float_p, C.c_size_t, C.c_void_p, c_stream]),
+    'mp_adamw_step': (C.c_int, [c_float_p, c_float_p, c_float_p, c_float_p, C.c_size_t, C.c_float, C.c_float, C.c_float, C.c_float,
+                                C.c_float, C.c_int32, C.c_void_p, C.c_float, C.c_float, c_stream]),
     'mp_gemm_bias': (C.c_int, [c_float_p, c_float_p, c_float_p, c_float_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                C.c_int32, c_stream]),
     'mp_pose_reduced_global_to_full': (C.c_int, [c_float_p, C.c_int64, c_float_p, c_stream]),

@@ -450,6 +450,17 @@ int mp_velocity_loss(const float* pred, const float* target, int32_t B, int32_t 
     return velocity_loss(pred, target, B, T, D, loss, dpred, (cudaStream_t)stream);
 }
 
+int mp_grad_sq_norm(const float* grads, size_t n, double* sq_norm, mp_stream_t stream) {
+    return grad_sq_norm(grads, n, sq_norm, (cudaStream_t)stream);
+}
+int mp_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, size_t n, float lr, float beta1, float beta2,
+                  float eps, float weight_decay, int32_t step, const double* sq_norm, float max_norm, float grad_scale, mp_stream_t stream) {
+    g_launches = 0;
+    MP_TRY(mp_device_check());
+    return adamw_step(params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, step, sq_norm, max_norm, grad_scale,
+                      (cudaStream_t)stream);
+}
+
 int mp_gemm_bias(const float* A, const float* W, const float* bias, float* C, int32_t M, int32_t N, int32_t K,
                  int32_t relu, int32_t mode, mp_stream_t stream) {
     g_launches = 0;

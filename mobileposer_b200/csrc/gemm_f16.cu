@@ -699,9 +699,10 @@ int launch_gemm_f16x3_act(const void* A_split, const void* W_split, const float*
         MP_TRY(make_map_c(&map_c, C, M, N_out));
         map_c_lo = map_c;
     }
-    // the CTA-pair kernel is correct but not faster (the TMEM read-out gap and the pair hand-shake cost more than the operand stream saves:
-    // profiles/r02_gemm_f16_variants.txt) -- opt-in
-    static const bool pair_default = getenv("MP_GEMM_PAIR") && atoi(getenv("MP_GEMM_PAIR")) != 0;
+    // the CTA-pair kernel wins 10-12 % where the K loop is long enough to amortise the pair hand-shake (K >= 256: 0.372 vs 0.421 ms at
+    // N = 2048, K = 512; slower at K = 64): profiles/r02_gemm_f16_variants.txt.  MP_GEMM_PAIR=0 / 1 forces either.
+    static const int pair_env = getenv("MP_GEMM_PAIR") ? (atoi(getenv("MP_GEMM_PAIR")) != 0 ? 1 : 0) : -1;
+    const bool pair_default = pair_env >= 0 ? pair_env == 1 : (K >= 256 && M >= 4 * HB_M);
     const bool pair = (flags & 16) || (pair_default && !(flags & 32));
     const int w_box = pair ? HB_N / 2 : HB_N;
     if (flags & 4) {

@@ -162,6 +162,9 @@ int poser_loss(const float* pred, const float* pose_t, const float* joints_t, in
                cudaStream_t stream);
 int footcontact_loss(const float* pred, const float* target, int B, int T, double* loss, float* dpred, cudaStream_t stream);
 int velocity_loss(const float* pred, const float* target, int B, int T, int D, double* loss, float* dpred, cudaStream_t stream);
+int grad_sq_norm(const float* g, size_t n, double* out, cudaStream_t stream);
+int adamw_step(float* p, const float* g, float* m, float* v, size_t n, float lr, float beta1, float beta2, float eps, float weight_decay,
+               int step, const double* sq_norm, float max_norm, float grad_scale, cudaStream_t stream);
 int joints_loss(const float* pred, const float* target, int B, int T, int D, float t_weight, double* loss, float* dpred, cudaStream_t stream);
 
 // ---- PTX helpers (clusters, mbarrier, distributed shared memory) ---------------------------

@@ -626,6 +626,88 @@ int rnn_train_backward(const mp_rnn_weights_t* w, const float* x, int B, int T, 
     return MP_OK;
 }
 
+// ---- optimizer: what Lightning runs between shared_step's backward and the next step (overfit.py:41-50: gradient_clip_val = 1;
+// joints.py:113-114: torch.optim.AdamW(lr = 1e-3) with torch's defaults) ----------------------------------------------------------
+// sum of squares of a flat gradient buffer, accumulated into a double (torch.nn.utils.clip_grad_norm_'s total norm, squared)
+__global__ void __launch_bounds__(256) grad_sq_norm_kernel(const float* __restrict__ g, size_t n, double* __restrict__ out) {
+    double acc = 0.0;
+    const size_t n4 = n >> 2;
+    const float4* g4 = reinterpret_cast<const float4*>(g);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+        const float4 v = __ldg(g4 + i);
+        acc += (double)v.x * v.x + (double)v.y * v.y + (double)v.z * v.z + (double)v.w * v.w;
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+        const float v = g[(n4 << 2) + threadIdx.x];
+        acc += (double)v * v;
+    }
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    __shared__ double part[8];
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w) t += part[w];
+        atomicAdd(out, t);
+    }
+}
+
+// One fused pass over the flat parameter buffer: gradient scaling (mean over ranks x clip coefficient), decoupled weight decay, both
+// moment updates and the parameter step, in torch.optim.AdamW's operation order (single-tensor path, amsgrad off):
+//   p *= 1 - lr wd;  m += (g - m)(1 - b1);  v = v b2 + (1 - b2) g g;  p -= (lr / bc1) m / (sqrt(v) / sqrt(bc2) + eps)
+// 20 B read + 12 B written per parameter: HBM-bound streaming (float4, grid-stride).
+__global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                                    float* __restrict__ v, size_t n, float lr, float b1, float b2, float eps, float wd,
+                                                    float bc1, float sqrt_bc2, const double* __restrict__ sq_norm, float max_norm,
+                                                    float grad_scale) {
+    float gs = grad_scale;
+    if (sq_norm) {            // clip_grad_norm_: coefficient max_norm / (total_norm + 1e-6), clamped to 1
+        const float total = (float)sqrt(*sq_norm) * grad_scale;
+        gs *= fminf(max_norm / (total + 1e-6f), 1.0f);
+    }
+    const float decay = 1.0f - lr * wd, step = lr / bc1;
+    auto upd = [&](float& pp, float gg, float& mm, float& vv) {
+        gg *= gs;
+        pp *= decay;
+        mm = mm + (gg - mm) * (1.0f - b1);
+        vv = vv * b2 + (1.0f - b2) * gg * gg;
+        pp = pp - step * (mm / (sqrtf(vv) / sqrt_bc2 + eps));
+    };
+    const size_t n4 = n >> 2;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+        float4 pp = reinterpret_cast<float4*>(p)[i], mm = reinterpret_cast<float4*>(m)[i], vv = reinterpret_cast<float4*>(v)[i];
+        const float4 gg = __ldg(reinterpret_cast<const float4*>(g) + i);
+        upd(pp.x, gg.x, mm.x, vv.x); upd(pp.y, gg.y, mm.y, vv.y); upd(pp.z, gg.z, mm.z, vv.z); upd(pp.w, gg.w, mm.w, vv.w);
+        reinterpret_cast<float4*>(p)[i] = pp; reinterpret_cast<float4*>(m)[i] = mm; reinterpret_cast<float4*>(v)[i] = vv;
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+        const size_t i = (n4 << 2) + threadIdx.x;
+        upd(p[i], g[i], m[i], v[i]);
+    }
+}
+
+int grad_sq_norm(const float* g, size_t n, double* out, cudaStream_t s) {
+    MP_REQUIRE(g && out && n > 0 && ((uintptr_t)g & 15) == 0, "grad_sq_norm: bad arguments (the buffer must be 16-byte aligned)");
+    grad_sq_norm_kernel<<<(unsigned)std::min<size_t>((n / 4 + 255) / 256 + 1, 148 * 8), 256, 0, s>>>(g, n, out);
+    MP_CUDA_TRY(cudaGetLastError());
+    count_launch();
+    return MP_OK;
+}
+
+int adamw_step(float* p, const float* g, float* m, float* v, size_t n, float lr, float beta1, float beta2, float eps, float weight_decay,
+               int step, const double* sq_norm, float max_norm, float grad_scale, cudaStream_t s) {
+    MP_REQUIRE(p && g && m && v && n > 0 && step >= 1, "adamw_step: bad arguments");
+    MP_REQUIRE((((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) == 0, "adamw_step: the buffers must be 16-byte aligned");
+    const double bc1 = 1.0 - pow((double)beta1, step), bc2 = 1.0 - pow((double)beta2, step);
+    ProfileScope prof("adamw", 32.0 * (double)n, s);
+    adamw_kernel<<<(unsigned)std::min<size_t>((n / 4 + 255) / 256 + 1, 148 * 8), 256, 0, s>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay,
+                                                                                             (float)bc1, (float)sqrt(bc2), sq_norm, max_norm,
+                                                                                             grad_scale);
+    MP_CUDA_TRY(cudaGetLastError());
+    count_launch();
+    return MP_OK;
+}
+
 int joints_loss(const float* pred, const float* target, int B, int T, int D, float t_weight, double* loss, float* dpred, cudaStream_t s) {
     MP_REQUIRE(pred && target && loss && dpred && B > 0 && T > 0 && D > 0, "joints_loss: bad arguments");
     MP_CUDA_TRY(cudaMemsetAsync(loss, 0, sizeof(double), s));

@@ -44,15 +44,16 @@ def main():
     keep = (torch.rand(B, T, 256, generator=g) >= 0.4).float() / 0.6         # nn.Dropout(p=0.4) in training mode: keep / (1 - p)
     out = {'imu': imu, 'lengths': np.asarray(lens), 'target': target, 'mask': keep}
     sd = {k: v.detach().clone() for k, v in mod.state_dict().items() if k.startswith('joints.')}
+    class FixedMask(torch.nn.Module):        # stands in for nn.Dropout(p=0.4): the same keep / (1 - p) scaling, a fixed pattern
+        def forward(self, x, m=keep):
+            return x * m
+
     for tag, mask in (('eval', None), ('mask', keep)):
         mod.zero_grad()
         if mask is None:
             mod.eval()
         else:
             mod.train()
-            class FixedMask(torch.nn.Module):        # stands in for nn.Dropout(p=0.4): the same keep / (1 - p) scaling, a fixed pattern
-                def forward(self, x, m=mask):
-                    return x * m
             mod.joints.dropout = FixedMask()
         batch = ((imu, lens), ({'joints': target}, None))
         loss = mod.shared_step(batch)
@@ -78,6 +79,46 @@ def main():
             got = gr if gr.numel() <= 40000 else gr[::7, ::5]
             assert (got - ref).abs().max() <= 1e-6 * max(1.0, ref.abs().max().item()), (tag, k)
     print('oracle/train_port.py agrees with the live reference (joints)')
+
+    # ---- the optimisation loop: Lightning is not installed here, so its Trainer(overfit_batches=1, gradient_clip_val=c) loop is spelled
+    # out around the LIVE module's own shared_step and configure_optimizers (AdamW, lr 1e-3): zero_grad, shared_step, backward,
+    # clip_grad_norm_, step -- 6 steps on the fixed batch above, dropout as the fixed mask, c = 1 (overfit.py:46) and c = 0.005 (so that
+    # the clip is active) ------------------------------------------------------------------------------------------------------------
+    from oracle.train_port import overfit_loop
+    out3 = {'imu': imu, 'lengths': np.asarray(lens), 'target': target, 'mask': keep}
+    for tag, clip in (('clip1', 1.0), ('clip005', 0.005)):
+        os.chdir(os.path.join(REF, 'mobileposer'))
+        try:
+            torch.manual_seed(0)
+            mod = Joints()
+        finally:
+            os.chdir(cwd)
+        mod.train()
+        mod.joints.dropout = FixedMask()
+        sd0 = {k: v.detach().clone() for k, v in mod.state_dict().items() if k.startswith('joints.')}
+        opt = mod.configure_optimizers()
+        losses, norms = [], []
+        for _ in range(6):
+            opt.zero_grad()
+            loss = mod.shared_step(((imu, lens), ({'joints': target}, None)))
+            loss.backward()
+            norms.append(torch.nn.utils.clip_grad_norm_(mod.parameters(), clip))
+            opt.step()
+            losses.append(loss.detach())
+        out3[f'{tag}_losses'] = torch.stack(losses)
+        out3[f'{tag}_grad_norms'] = torch.stack(norms)
+        for name, prm in mod.named_parameters():
+            gname = name[len('joints.'):]
+            val = prm.detach()
+            out3[f'{tag}_pnorm.{gname}'] = val.norm()
+            out3[f'{tag}_param.{gname}'] = val if val.numel() <= 40000 else val[::7, ::5].contiguous()
+        p_losses, p_final = overfit_loop(sd0, imu, lens, target, keep, 6, gradient_clip_val=clip)
+        assert (p_losses - out3[f'{tag}_losses']).abs().max() <= 1e-6 * out3[f'{tag}_losses'].abs().max(), (tag, p_losses, out3[f'{tag}_losses'])
+        for k, v in p_final.items():
+            assert abs(v.norm().item() - out3[f'{tag}_pnorm.{k}'].item()) <= 1e-5 * out3[f'{tag}_pnorm.{k}'].item(), (tag, k)
+        print(tag, 'losses', [round(float(v), 6) for v in losses], 'grad norms', [round(float(v), 4) for v in norms])
+    np.savez_compressed(os.path.join(OUT, 'train_overfit_joints.npz'), **{k: (v.numpy() if torch.is_tensor(v) else v) for k, v in out3.items()})
+    print('wrote train_overfit_joints.npz; oracle/train_port.py overfit_loop agrees with the live reference')
 
     # ---- FootContact (footcontact.py:43-65, BCE with logits) and Velocity (velocity.py:50-86, windowed MSE), eval mode; the noise the
     # reference draws inside shared_step (torch.randn right after torch.manual_seed) is reproduced and the noisy input saved --------------

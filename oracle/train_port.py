@@ -91,3 +91,23 @@ def _shared_step(state_dict, imu, lengths, target, mask, prefix, loss_fn):
     loss = loss_fn(pred, target.view(target.shape[0], target.shape[1], -1))
     loss.backward()
     return loss.detach(), {k: v.grad for k, v in sd.items()}, pred.detach()
+
+
+def overfit_loop(state_dict, imu, lengths, target, mask, steps, prefix='joints.', kind='joints', lr=1e-3, gradient_clip_val=1.0):
+    """The loop Lightning's Trainer(overfit_batches=1, gradient_clip_val=1) runs around training_step (overfit.py:41-56) with the
+    optimizer of configure_optimizers (joints.py:113-114: torch.optim.AdamW(lr=1e-3)): zero_grad, shared_step, backward,
+    clip_grad_norm_, step -- on ONE fixed batch.  -> (losses [steps], final {name: tensor})."""
+    sd = {k[len(prefix):]: v.detach().clone().float() for k, v in state_dict.items() if k.startswith(prefix)}
+    params = {k: torch.nn.Parameter(v) for k, v in sd.items()}
+    opt = torch.optim.AdamW(list(params.values()), lr=lr)
+    losses = []
+    for _ in range(steps):
+        opt.zero_grad()
+        loss, grads, _ = head_shared_step({k: v.detach() for k, v in params.items()}, imu, lengths, target, kind, mask)
+        for k, p in params.items():
+            p.grad = grads[k]
+        if gradient_clip_val is not None:
+            torch.nn.utils.clip_grad_norm_(list(params.values()), gradient_clip_val)
+        opt.step()
+        losses.append(loss)
+    return torch.stack(losses), {k: v.detach() for k, v in params.items()}

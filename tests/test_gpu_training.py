@@ -113,3 +113,68 @@ def test_poser_training_step_against_the_live_reference():
         assert _rel(got, ref) < 2e-4, (pname, _rel(got, ref))
         assert abs(gr.norm().item() - g[f'pose_norm.{short}'].item()) <= 2e-4 * g[f'pose_norm.{short}'].item(), pname
     print(f'[train] pose: loss {loss.item():.6f}, worst relative gradient error over {len(grads)} tensors {worst:.2e}')
+
+
+@pytest.mark.parametrize('tag,clip', [('clip1', 1.0), ('clip005', 0.005)])
+def test_overfit_loop_against_the_live_reference(tag, clip):
+    """HeadTrainer = the loop Lightning runs for overfit.py:41-56 (zero_grad, shared_step, backward, clip_grad_norm_, the AdamW of
+    joints.py:113-114): 6 steps on one fixed batch with a fixed dropout mask; the loss of every step, the gradient norms and the
+    final parameters against the live reference's module + torch.optim.AdamW (tests/golden/train_overfit_joints.npz)."""
+    import mobileposer_b200 as mp
+    from mobileposer_b200.training import HeadTrainer
+    g = load_golden('train_overfit_joints')
+    torch.manual_seed(0)
+    mod = mp.Joints().to(DEV)
+    tr = HeadTrainer(mod, gradient_clip_val=clip)
+    imu, lens, target, mask = g['imu'].to(DEV), g['lengths'].tolist(), g['target'].to(DEV), g['mask'].to(DEV)
+    losses, norms = [], []
+    for _ in range(6):
+        losses.append(tr.training_step(imu, lens, target, mask=mask).item())
+        norms.append(tr.grad_norm())
+    ref_l, ref_n = g[f'{tag}_losses'].double(), g[f'{tag}_grad_norms'].double()
+    worst_l = max(abs(a - b.item()) / abs(b.item()) for a, b in zip(losses, ref_l))
+    worst_n = max(abs(a - b.item()) / abs(b.item()) for a, b in zip(norms, ref_n))
+    assert worst_l < 2e-5, (losses, ref_l)
+    assert worst_n < 2e-3, (norms, ref_n)
+    worst_p = 0.0
+    for name, p in mod.joints.named_parameters():
+        ref = g[f'{tag}_param.{name}']
+        got = p.detach().cpu() if p.numel() <= 40000 else p.detach()[::7, ::5].cpu()
+        worst_p = max(worst_p, (got - ref).abs().max().item())
+        assert (got - ref).abs().max().item() < 2e-5, (name, (got - ref).abs().max().item())      # six steps of lr = 1e-3 move a weight by <= 6e-3
+        assert abs(p.norm().item() - g[f'{tag}_pnorm.{name}'].item()) <= 1e-5 * g[f'{tag}_pnorm.{name}'].item(), name
+    # the trained values are what the inference path sees (the parameters are views of the flat buffer; versions were bumped)
+    y, _, _ = mod.joints(imu, lens)
+    assert torch.isfinite(y).all()
+    print(f'[train] overfit loop {tag}: losses {[round(v, 6) for v in losses]}, worst relative loss error {worst_l:.1e}, '
+          f'gradient-norm error {worst_n:.1e}, worst final-parameter error {worst_p:.1e}')
+
+
+def test_adamw_kernel_against_torch_on_a_ragged_buffer():
+    """mp_adamw_step / mp_grad_sq_norm on a flat buffer whose length is not a multiple of 4, 3 steps, against torch.optim.AdamW +
+    clip_grad_norm_ on the same numbers."""
+    import ctypes as C
+    from mobileposer_b200 import _cabi
+    lib = _cabi.lib()
+    n = 4099
+    gen = torch.Generator().manual_seed(3)
+    p0 = torch.randn(n, generator=gen)
+    ref = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.AdamW([ref], lr=1e-3)
+    p = torch.zeros(n + 1, device=DEV)[:n]
+    p.copy_(p0)
+    m, v = torch.zeros(n, device=DEV), torch.zeros(n, device=DEV)
+    sq = torch.zeros((), device=DEV, dtype=torch.float64)
+    s = torch.cuda.current_stream().cuda_stream
+    for step in range(1, 4):
+        gr = torch.randn(n, generator=gen) * (3.0 if step == 2 else 0.01)
+        ref.grad = gr.clone()
+        torch.nn.utils.clip_grad_norm_([ref], 1.0)
+        opt.step()
+        gd = gr.to(DEV)
+        sq.zero_()
+        _cabi.check(lib.mp_grad_sq_norm(gd.data_ptr(), n, sq.data_ptr(), s))
+        assert abs(sq.sqrt().item() - gr.double().norm().item()) < 1e-9 * gr.double().norm().item() + 1e-12
+        _cabi.check(lib.mp_adamw_step(p.data_ptr(), gd.data_ptr(), m.data_ptr(), v.data_ptr(), n, 1e-3, 0.9, 0.999, 1e-8, 1e-2, step,
+                                      sq.data_ptr(), 1.0, 1.0, s))
+        assert (p.cpu() - ref.detach()).abs().max().item() < 2e-6, step

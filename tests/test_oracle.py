@@ -196,3 +196,21 @@ def test_wc_weights_make_k5_well_conditioned(wc_oracle, wc_oracle64, oracle, ora
             assert (angle_tolerance(r6d) <= ANGLE_TOL).all()       # the relaxed gate of parity.py collapses to the flat one
         else:
             assert e > 5e-6, e
+
+
+def test_training_loop_port_matches_the_live_reference_fixture():
+    """oracle/train_port.py:overfit_loop (shared_step + clip_grad_norm_ + AdamW on one fixed batch) against the losses and final
+    parameters the live reference's module + configure_optimizers produced (tests/golden/train_overfit_joints.npz)."""
+    import torch
+    from conftest import load_golden
+    from oracle.train_port import overfit_loop
+    g = load_golden('train_overfit_joints')
+    torch.manual_seed(0)
+    import mobileposer_b200 as mp
+    sd = {'joints.' + k: v for k, v in mp.Joints().joints.state_dict().items()}       # the seeded default init = the fixture's module
+    torch.set_num_threads(1)
+    for tag, clip in (('clip1', 1.0), ('clip005', 0.005)):
+        losses, final = overfit_loop(sd, g['imu'], g['lengths'].tolist(), g['target'], g['mask'], 6, gradient_clip_val=clip)
+        assert (losses - g[f'{tag}_losses']).abs().max() <= 2e-6 * g[f'{tag}_losses'].abs().max()
+        for k, v in final.items():
+            assert abs(v.norm().item() - g[f'{tag}_pnorm.{k}'].item()) <= 1e-5 * g[f'{tag}_pnorm.{k}'].item(), (tag, k)

@@ -187,3 +187,40 @@ def test_sharded_evaluation_does_not_depend_on_the_carried_state():
             assert p.exitcode == 0
         for _, table in results:
             assert torch.allclose(table[ok], independent[ok], rtol=1e-5, atol=1e-7), (world, batch_size)
+
+
+def _grad_worker(rank, world, port, q):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        from mobileposer_b200.training import average_gradients
+        flat = torch.arange(10, dtype=torch.float32) * (rank + 1)       # this rank's gradient shard contribution
+        scale = average_gradients(flat)
+        q.put((rank, flat * scale))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('world', [2, 3])
+def test_average_gradients_gloo(world):
+    """The data-parallel exchange of a training step (training.average_gradients): one all-reduce of the flat gradient buffer; the
+    returned factor turns the sum into the mean, identical on every rank."""
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_grad_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    outs = dict(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+    want = torch.arange(10, dtype=torch.float32) * (sum(range(1, world + 1)) / world)
+    for r in range(world):
+        assert torch.allclose(outs[r], want)
+
+
+def test_average_gradients_without_a_process_group_is_the_identity():
+    from mobileposer_b200.training import average_gradients
+    flat = torch.ones(5)
+    assert average_gradients(flat) == 1.0 and torch.equal(flat, torch.ones(5))
