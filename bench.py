@@ -422,12 +422,20 @@ def bind_rank_to_cores(local, world):
         return None
 
 
+def pipeline_tile(B, D):
+    """Recurrence tile policy of the pipelined slots: with several batches in flight SM-time counts, not one batch's latency -- 128
+    sequences per cluster (the four-sub-tile kernel, half the CTAs per layer launch for 1.2 x the time) where the batch holds whole
+    tiles; one batch at a time keeps the automatic 64."""
+    return 128 if D > 1 and B % 128 == 0 and os.environ.get('MP_BENCH_TILE', '') != '64' else 0
+
+
 def measure_cfg3(net, mp, xs, xs_host, B, T, D, args, dist, world, physics):
     """Pipelined device-resident `value` and host-buffer `e2e` of one cfg3 configuration (K8 on or off)."""
     n_sets = len(xs)
     net.enable_physics(physics)
     frames_per_step = B * T * world
-    pipes = [mp.HostOffline(net, B, T) for _ in range(D)]
+    tile = pipeline_tile(B, D)
+    pipes = [mp.HostOffline(net, B, T, rec_tile=tile) for _ in range(D)]
 
     def pipe_step(i):
         pipes[i % D].submit_device(xs[i % n_sets])
@@ -442,7 +450,7 @@ def measure_cfg3(net, mp, xs, xs_host, B, T, D, args, dist, world, physics):
 
     # e2e: host buffers through the C ABI, copies inside the timed region; depth-D pipeline over batches (HostOffline objects with
     # their own net handle, stream, staging and pinned outputs): batch i+1 is submitted before batch i is awaited
-    hosts = [mp.HostOffline(net, B, T) for _ in range(D)]
+    hosts = [mp.HostOffline(net, B, T, rec_tile=tile) for _ in range(D)]
     slots = {'hosts': hosts}
 
     def body(n_steps, off, pipelined):
@@ -497,7 +505,7 @@ def measure_cfg3(net, mp, xs, xs_host, B, T, D, args, dist, world, physics):
     # matrices on the consumer's side): what a host link shared by 8 GPUs can carry
     del hosts
     slots['hosts'] = None                  # frees the full-transfer slots (3.3 GB of workspace each) before the compact ones exist
-    slots['hosts'] = [mp.HostOffline(net, B, T, compact=True) for _ in range(D)]
+    slots['hosts'] = [mp.HostOffline(net, B, T, rec_tile=tile, compact=True) for _ in range(D)]
     c_s, c_n = e2e_time(True, min(args.min_seconds, 1.5))
     out['e2e_compact'] = {'value': frames_per_step * c_n / c_s, 'unit': 'frames/s', 'h2d_bytes_per_step': B * T * 60 * 4,
                           'd2h_bytes_per_step': B * T * (96 + 72 + 3 + 2) * 4, 'ms_per_step': c_s / c_n * 1e3, 'steps_timed': c_n,
@@ -653,7 +661,7 @@ def run_ours(args):
     # (through one pipeline slot, i.e. with the tile policy of the headline number; one batch at a time so that a kernel's
     #  duration is its own and not its wait for SMs held by another batch)
     lib = _cabi.lib()
-    prof_pipe = mp.HostOffline(net, B, T)
+    prof_pipe = mp.HostOffline(net, B, T, rec_tile=pipeline_tile(B, D))
     prof_pipe.submit_device(xs[0])
     prof_pipe.wait()
     _cabi.check(lib.mp_profile_enable(1))
@@ -738,6 +746,7 @@ def run_ours(args):
                             f'({net_workspace_mb(net, B, T):.0f} MB) exceed the 126 MB L2',
                       'parallelism': f'{world} x (one process per GPU, sequences sharded, no data-path collective); '
                                      f'{D} batches in flight per GPU (pipeline over steps)',
+                      'recurrence_tile': pipeline_tile(B, D) or 'auto (64 sequences per cluster)',
                       'rank_core_binding': cores},
             'e2e': head['e2e'], 'e2e_compact': head['e2e_compact'], 'gpu_launches': launches * head['steps_timed'], 'gpu_launches_per_step': launches,
             'roofline': roofline, 'whole_path_algorithmic_GBps': whole, 'whole_path_hbm_frac': whole / peak,

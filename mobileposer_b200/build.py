@@ -13,7 +13,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, 'csrc')
 LIB_DIR = os.path.join(PKG, 'lib')
 LIB_PATH = os.path.join(LIB_DIR, 'libmobileposer_b200.so')
-SOURCES = ['gemm.cu', 'gemm_tc.cu', 'gemm_f16.cu', 'lstm_rec.cu', 'lstm_rec_tc.cu', 'lstm_rec_f16.cu', 'kinematics.cu', 'physics.cu', 'inputs.cu', 'evaluate.cu', 'train.cu', 'api.cu']
+SOURCES = ['gemm.cu', 'gemm_tc.cu', 'gemm_f16.cu', 'lstm_rec.cu', 'lstm_rec_tc.cu', 'lstm_rec_f16.cu', 'lstm_rec_f16w.cu', 'kinematics.cu', 'physics.cu', 'inputs.cu', 'evaluate.cu', 'train.cu', 'api.cu']
 HEADERS = [os.path.join(CSRC, 'mp_common.cuh'), os.path.join(CSRC, 'mp_constants.cuh'),
            os.path.join(os.path.dirname(PKG), 'include', 'mobileposer_b200.h')]
 OBJ_DIR = os.path.join(LIB_DIR, 'obj')

@@ -646,7 +646,8 @@ int mp_net_set_physics(mp_net_t* n, const mp_physics_params_t* params) {
 }
 
 int mp_net_set_rec_tile(mp_net_t* n, int32_t sequences_per_tile) {
-    MP_REQUIRE(n && sequences_per_tile >= -1 && sequences_per_tile <= 64, "net_set_rec_tile: -1 (one wave), 0 (auto), 1 .. 64");
+    MP_REQUIRE(n && sequences_per_tile >= -1 && (sequences_per_tile <= 64 || sequences_per_tile == 128),
+               "net_set_rec_tile: -1 (one wave), 0 (auto), 1 .. 64, or 128 (the four-sub-tile kernel where the batch holds whole tiles)");
     n->rec_tile = sequences_per_tile;
     return MP_OK;
 }

@@ -779,6 +779,7 @@ int launch_lstm_recurrence(const RecLayerArgs& a, cudaStream_t stream) {
     MP_REQUIRE(a.gin && a.wpack && a.y && a.B > 0 && a.T > 0 && (a.dirs == 1 || a.dirs == 2), "lstm: bad arguments");
     MP_REQUIRE((double)a.B * a.T * a.dirs * 4 * a.H < 4.0e9, "lstm: B*T = %lld frames exceeds the 32-bit gate buffer indexing of one launch",
                (long long)a.B * a.T);
+    if (!env_is("MP_REC_IMPL", "simple") && rec_f16_eligible(a) && rec_f16w_eligible(a)) return launch_lstm_recurrence_f16w(a, stream);
     if (!env_is("MP_REC_IMPL", "simple") && rec_f16_eligible(a)) return launch_lstm_recurrence_f16(a, stream);
     if (!env_is("MP_REC_IMPL", "simple") && rec_tc_eligible(a)) return launch_lstm_recurrence_tc(a, stream);
     // algorithmic bytes of the recurrence: W_hh once + the layer's h output; the gate

@@ -106,6 +106,9 @@ int launch_lstm_recurrence_tc(const RecLayerArgs& a, cudaStream_t stream);
 // second generation: fp16 hi / scaled-lo operands (lstm_rec_f16.cu); supersedes the TF32 kernel (MP_REC_IMPL=tf32 pins the old one)
 bool rec_f16_eligible(const RecLayerArgs& a);
 int launch_lstm_recurrence_f16(const RecLayerArgs& a, cudaStream_t stream);
+// the same kernel with 128 sequences per cluster as four sub-tiles (lstm_rec_f16w.cu): whole tiles of equal length, tile_hint == 128
+bool rec_f16w_eligible(const RecLayerArgs& a);
+int launch_lstm_recurrence_f16w(const RecLayerArgs& a, cudaStream_t stream);
 // number of float4 in the packed recurrent weights of one layer
 size_t whh_pack_float4s(int H, int dirs);
 // pack W_hh[dirs][4H,H] (device, torch layout) into the register-resident layout + transpose

@@ -1,0 +1,12 @@
+set -x
+mkdir -p gpurun_out
+timeout 120 python scripts/rec_wide_ab.py 2>&1 | tail -6
+timeout 1200 python -m pytest tests/test_gpu_parity.py tests/test_gpu_parity_flat.py -q -x -rP > gpurun_out/pytest_r.log 2>&1; echo "pytest exit $?"; grep -E "passed|failed|^FAILED|^ERROR|^E  |^\[flat\]" gpurun_out/pytest_r.log | cut -c1-300 | tail -16
+timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-cfg4 --min-seconds 1.5 > gpurun_out/bench_r.json 2> gpurun_out/bench_r.err; echo "bench exit $?"; tail -2 gpurun_out/bench_r.err
+python - <<'PY'
+import json
+d=json.load(open('gpurun_out/bench_r.json'))
+print(d['value'], d['ms_per_step'], 'pinned', d['pinned_path']['value'], d['pinned_path']['ms_per_step'], 'e2e', d['e2e']['value'], 'one at a time', d['one_batch_at_a_time']['ms_per_step'])
+print('  ', {k:(round(v['ms_per_step'],3)) for k,v in d['kernels'].items()})
+print(d['batch1'], d['streaming'])
+PY

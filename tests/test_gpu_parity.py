@@ -664,3 +664,52 @@ def test_fp16_split_gemm_keeps_small_and_large_magnitudes():
     bound = 1e-6 * (a_abs @ w_abs.t()) + (2.0 ** -35) * (w_abs.sum(1).view(1, N) + a_abs.sum(1).view(M, 1)) + K * 2.0 ** -50
     err = ((C.double() - ref).abs() / bound).max().item()
     assert torch.isfinite(C).all() and err < 1.0, err
+
+
+def test_wide_recurrence_is_bit_identical_to_the_64_sequence_kernel(seeded_state_dict):
+    """lstm_rec_f16w.cu (128 sequences per cluster as four sub-tiles, the pipelined slots' tile policy) against lstm_rec_f16.cu: every
+    sequence is one MMA column and the epilogue arithmetic is the same, so outputs and final states are equal bit for bit --
+    bidirectional (joints) and unidirectional (velocity) heads, one and three tiles, with and without initial states."""
+    import mobileposer_b200 as mp
+    from mobileposer_b200.synthetic import synthetic_imu_batch
+    net = mp.MobilePoserNet()
+    net.load_state_dict(seeded_state_dict)
+    net = net.eval().to(DEV)
+    saved = os.environ.get('MP_REC_WIDE')
+    try:
+        for B, T in ((128, 9), (384, 33)):
+            x = synthetic_imu_batch(list(range(300, 300 + B)), T).to(DEV)
+            xv = torch.cat((torch.randn(B, T, 72, device=DEV) * 0.3, x), -1)
+            h0 = (torch.randn(2, B, 256, device=DEV) * 0.2, torch.randn(2, B, 256, device=DEV) * 0.2)
+            outs = {}
+            for wide in ('0', '1'):
+                os.environ['MP_REC_WIDE'] = wide
+                yj, _, (hj, cj) = net.joints.joints(x, [T] * B)
+                yv, _, (hv, cv) = net.velocity.vel(xv, [T] * B, h=h0)
+                torch.cuda.synchronize()
+                outs[wide] = [t.clone() for t in (yj, hj, cj, yv, hv, cv)]
+            for a, b in zip(outs['0'], outs['1']):
+                assert torch.equal(a, b), (B, T, (a - b).abs().max().item())
+    finally:
+        if saved is None:
+            os.environ.pop('MP_REC_WIDE', None)
+        else:
+            os.environ['MP_REC_WIDE'] = saved
+
+
+def test_pipelined_slots_with_the_wide_tile_match_forward_offline(seeded_state_dict):
+    """HostOffline(rec_tile=128) -- what bench.py's pipelined cfg3 slots use -- returns what MobilePoserNet.forward_offline returns."""
+    import mobileposer_b200 as mp
+    from mobileposer_b200.synthetic import synthetic_imu_batch
+    net = mp.MobilePoserNet()
+    net.load_state_dict(seeded_state_dict)
+    net = net.eval().to(DEV)
+    B, T = 256, 48
+    x = synthetic_imu_batch(list(range(500, 500 + B)), T)
+    pose, joints, tran, contact = net.forward_offline(x.to(DEV), [T] * B)
+    slot = mp.HostOffline(net, B, T, rec_tile=128)
+    for _ in range(3):                      # eager, capture, replay
+        slot.submit(x.contiguous())
+        slot.wait()
+    assert torch.equal(slot.joints.view(B, T, 72), joints.cpu().view(B, T, 72))
+    assert torch.equal(slot.pose.view(-1), pose.cpu().view(-1)) and torch.equal(slot.tran.view(-1), tran.cpu().view(-1))
