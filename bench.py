@@ -677,7 +677,9 @@ def run_ours(args):
     roofline = None
     if dom:
         gbs = dom['algorithmic_bytes'] / (dom['total_ms'] / 1e3) / 1e9
-        roofline = {'bound': 'hbm', 'kernel': {'lstm_rec_f16_h256': 'lstm_rec_f16_kernel<N> (tcgen05 3xFP16 split, W_hh hi+lo in TMEM)',
+        roofline = {'bound': 'hbm', 'kernel': {'lstm_rec_f16_h256': ('lstm_rec_f16w_kernel (tcgen05 3xFP16 split, W_hh hi+lo in TMEM, 128 sequences per 8-CTA cluster)'
+                                                                     if pipeline_tile(B, D) == 128 else
+                                                                     'lstm_rec_f16_kernel<N> (tcgen05 3xFP16 split, W_hh hi+lo in TMEM)'),
                                                'lstm_rec_tc_h256': 'lstm_rec_tc_kernel<N> (tcgen05 3xTF32, W_hh in TMEM)',
                                                'lstm_rec_h256': 'lstm_rec_kernel<256,8,*> (FFMA2, W_hh in registers)'}.get(dom_name, dom_name),
                     'achieved': gbs, 'peak': peak, 'unit': 'GB/s', 'frac': gbs / peak, 'traffic': load_traffic(dom_name),
@@ -686,6 +688,15 @@ def run_ours(args):
                     'launches_per_step': dom['launches'] / args.steps,
                     'note': 'the recurrence is serial in T: bound by the per-step MMA + activation + DSMEM-exchange chain, not by '
                             'HBM (DESIGN.md 4.1); the HBM fraction is the contract figure of the brief'}
+        # the launches of this kernel overlap in the pipelined step (6 batches in flight, each launch holds 32 or 16 of the 148 SMs with
+        # the 128-sequence tile): what the kernel type moves per unit of wall time is the per-launch figure x the launches in flight
+        per_step_ms = dom['total_ms'] / args.steps
+        roofline['concurrency'] = {
+            'launches_in_flight_avg': per_step_ms / head['ms_per_step'],
+            'aggregate_GBps': dom['algorithmic_bytes'] / args.steps / (head['ms_per_step'] / 1e3) / 1e9,
+            'aggregate_frac': dom['algorithmic_bytes'] / args.steps / (head['ms_per_step'] / 1e3) / 1e9 / peak,
+            'ctas_per_bidirectional_launch': (2 * 8 * (B // 128)) if pipeline_tile(B, D) == 128 else None,
+            'note': 'avg_launch_ms is measured one batch at a time through a pipeline slot (same tile policy as the timed region)'}
         if dom_name in ('lstm_rec_tc_h256', 'lstm_rec_f16_h256'):
             f16 = dom_name == 'lstm_rec_f16_h256'
             tf = tensor_peak_tflops() * (2.0 if f16 else 1.0)

@@ -16,6 +16,7 @@
 // 64-wide kernel (2 registers per column) are recomputed from two running bases -- uniform lengths make them affine in the sequence index.
 #include "mp_common.cuh"
 
+#include <cuda.h>
 #include <cuda_fp16.h>
 
 #include <cstdlib>
@@ -54,6 +55,8 @@ struct RecF16WParams {
     int B, T, dirs;
     int y_split;          // y = two planes of halves (hi, scaled lo) instead of fp32
     long long* ts;        // bring-up (MP_RECW_TS): clock64 stamps of block (0,0), [step][16], or null
+    int skip;             // bring-up (MP_RECW_SKIP, WRONG RESULTS): bit 0 no y stores, bit 1 no gin prefetch, bit 2 no activations
+    int y_tma;            // y_split only: the layer output leaves through TMA stores of the staged slices (map_y_hi / map_y_lo)
 };
 
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -128,8 +131,16 @@ __device__ __forceinline__ float act_exact(float x, bool is_tanh) {
         if (p.ts && blockIdx.x == 0 && blockIdx.y == 0 && s < 64) p.ts[s * 16 + (slot)] = clock64();           \
     } while (0)
 
+// one staged plane (32 sequences x this rank's 32 units, 64-byte rows, 64B swizzle) -> y plane [B, T, dirs * H] at (unit0, t, sequence0)
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(reinterpret_cast<uint64_t>(map)),
+                 "r"(src), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+
 template <bool FAST>
-__global__ void __launch_bounds__(WF_THREADS, 1) lstm_rec_f16w_kernel(const RecF16WParams p) {
+__global__ void __launch_bounds__(WF_THREADS, 1) lstm_rec_f16w_kernel(const RecF16WParams p, const __grid_constant__ CUtensorMap map_y_hi,
+                                                                       const __grid_constant__ CUtensorMap map_y_lo) {
     extern __shared__ unsigned char smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     unsigned char* gen = smem_raw + (base - smem_u32(smem_raw));
@@ -272,15 +283,28 @@ __global__ void __launch_bounds__(WF_THREADS, 1) lstm_rec_f16w_kernel(const RecF
             __syncwarp();
         } else if (warp > EPI_WARPS) {
             // ================= exchange warps: ship the staged slices (sub-tiles 0, 2 / 1, 3) to all 8 CTAs =================
-            if (send) {
+            // ... and, when the layer output is wanted as (hi, lo) planes, to global memory: the staged slice IS the output block of
+            // this rank for the sub-tile (32 sequences x 32 units, both planes), so two TMA stores replace 4 scattered 2-byte stores per
+            // thread, sub-tile and step (those cost 22 % of the kernel: MP_RECW_SKIP ablation, profiles/r02_rec_wide_ab.txt)
 #pragma unroll
-                for (int k = 0; k < 2; ++k) {
-                    const int sub = (warp - EPI_WARPS - 1) + 2 * k;
-                    mbar_wait(bar_stage + 8 * sub, par);       // the 16 epilogue warps have staged the slice (hi + lo planes, contiguous)
+            for (int k = 0; k < 2; ++k) {
+                if (!send && !p.y_tma) break;                  // last step without TMA output: nothing was staged
+                const int sub = (warp - EPI_WARPS - 1) + 2 * k;
+                const uint32_t src = s_stg + (uint32_t)par * STG_PAR + (uint32_t)sub * KBLOCK;
+                mbar_wait(bar_stage + 8 * sub, par);           // the 16 epilogue warps have staged the slice (hi + lo planes, contiguous)
+                if (p.y_tma && lane == 0) {
+                    // the stores of this sub-tile two steps ago (same staging parity) have been read out long since; keep it a guarantee
+                    asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                    const int t = dir ? T - 1 - s : s;
+                    tma_store_3d(&map_y_hi, src, dir * TH + rank * TUC, t, b_begin + sub * WR);
+                    tma_store_3d(&map_y_lo, src + PLANE, dir * TH + rank * TUC, t, b_begin + sub * WR);
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+                if (send) {
                     mbar_wait(bar_free + 8 * sub, par);        // every CTA's MMAs of this step on the sub-tile's old rows are done
                     if (lane < TCC)
-                        bulk_copy_s2c(mapa_u32(s_h + (uint32_t)sub * SUBH + (uint32_t)rank * KBLOCK, lane),
-                                      s_stg + (uint32_t)par * STG_PAR + (uint32_t)sub * KBLOCK, KBLOCK, mapa_u32(bar_full + 8 * sub, lane));
+                        bulk_copy_s2c(mapa_u32(s_h + (uint32_t)sub * SUBH + (uint32_t)rank * KBLOCK, lane), src, KBLOCK,
+                                      mapa_u32(bar_full + 8 * sub, lane));
                     if (lane == 0) WF_STAMP(12 + sub);
                 }
             }
@@ -320,7 +344,7 @@ __global__ void __launch_bounds__(WF_THREADS, 1) lstm_rec_f16w_kernel(const RecF
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         const float pre = fmaf(dc[q * 4 + j], kLoInv, dm[q * 4 + j]) + gi[blk * 4 + j];
-                        a[j] = FAST ? act_fast(pre, gate == 2) : act_exact(pre, gate == 2);
+                        a[j] = (p.skip & 4) ? pre : FAST ? act_fast(pre, gate == 2) : act_exact(pre, gate == 2);
                     }
                     // 4 x 4 transpose inside the gate quad: lane `gate` ends up with i, f, g, o of sequence 16 blk + 4 part + gate
                     const bool b0 = lane & 1, b1 = lane & 2;
@@ -332,13 +356,13 @@ __global__ void __launch_bounds__(WF_THREADS, 1) lstm_rec_f16w_kernel(const RecF
                     h_nw[q] = ov * (FAST ? act_fast(c_nw[q], true) : act_exact(c_nw[q], true));
                     cst[blk] = c_nw[q];
                     split16(h_nw[q], h_hi16[q], h_lo16[q]);
-                    if (send) {
+                    if (send || p.y_tma) {
                         const uint32_t so = (uint32_t)sub * KBLOCK + sw64_off(q * 16 + part * 4 + gate, ul);
                         *reinterpret_cast<unsigned short*>(stg + so) = h_hi16[q];
                         *reinterpret_cast<unsigned short*>(stg + so + PLANE) = h_lo16[q];
                     }
                 }
-                if (send) {
+                if (send || p.y_tma) {
                     // the exchange first, global traffic after (fence.proxy.async waits for every earlier memory operation of the thread)
                     fence_proxy_async_smem();
                     __syncwarp();
@@ -349,7 +373,8 @@ __global__ void __launch_bounds__(WF_THREADS, 1) lstm_rec_f16w_kernel(const RecF
                 for (int q = 0; q < 2; ++q) {
                     const int blk = 2 * sub + q;
                     const size_t yo = (size_t)(blk * 16) * TY2;
-                    if (p.y_split) {
+                    if ((p.skip & 1) || p.y_tma) {
+                    } else if (p.y_split) {
                         yh[yo] = h_hi16[q];
                         yl[yo] = h_lo16[q];
                     } else {
@@ -359,7 +384,7 @@ __global__ void __launch_bounds__(WF_THREADS, 1) lstm_rec_f16w_kernel(const RecF
                         const int n = blk * 16 + part * 4 + gate;
                         if (p.hn) p.hn[((size_t)dir * p.B + b_begin + n) * TH + rank * TUC + ul] = h_nw[q];
                         if (p.cn) p.cn[((size_t)dir * p.B + b_begin + n) * TH + rank * TUC + ul] = c_nw[q];
-                    } else {
+                    } else if (!(p.skip & 2)) {
 #pragma unroll
                         for (int j = 0; j < 4; ++j) gi[blk * 4 + j] = __ldg(gp + (size_t)(blk * 16 + j) * TG4);
                     }
@@ -370,10 +395,42 @@ __global__ void __launch_bounds__(WF_THREADS, 1) lstm_rec_f16w_kernel(const RecF
         }
     }
 
+    if (warp > EPI_WARPS && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");      // this thread's y stores are complete
     tc_fence_before();
     __syncthreads();
     cluster_sync_all();
     if (warp == EPI_WARPS) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// one plane of the split layer output, [B, T, Y2] halves, as a 3-D tensor map with a (32 units, 1 frame, 32 sequences) box whose
+// shared-memory image is the staged slice (64-byte rows, 64B swizzle)
+int make_map_y(CUtensorMap* map, void* ptr, int B, int T, int Y2) {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* q = nullptr;
+        cudaDriverEntryPointQueryResult r;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &q, cudaEnableDefault, &r) == cudaSuccess && r == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(q);
+    }
+    if (!fn) {
+        set_error("lstm_f16w: cuTensorMapEncodeTiled is not available from this driver");
+        return MP_ERR_CUDA;
+    }
+    const cuuint64_t dims[3] = {(cuuint64_t)Y2, (cuuint64_t)T, (cuuint64_t)B};
+    const cuuint64_t strides[2] = {(cuuint64_t)Y2 * 2, (cuuint64_t)T * Y2 * 2};
+    const cuuint32_t box[3] = {(cuuint32_t)TUC, 1, (cuuint32_t)WR};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("lstm_f16w: cuTensorMapEncodeTiled (layer output) failed with CUresult %d (B=%d T=%d Y2=%d)", (int)r, B, T, Y2);
+        return MP_ERR_CUDA;
+    }
+    return MP_OK;
 }
 
 }  // namespace
@@ -396,7 +453,17 @@ int launch_lstm_recurrence_f16w(const RecLayerArgs& a, cudaStream_t stream) {
         cudaMalloc(&ts_dev, 64 * 16 * sizeof(long long));
         cudaMemset(ts_dev, 0, 64 * 16 * sizeof(long long));
     }
-    RecF16WParams p{a.gin, a.w_raw[0], a.w_raw[a.dirs - 1], a.y, a.h0, a.c0, a.hn, a.cn, a.B, a.T, a.dirs, a.y_split, want_ts ? ts_dev : nullptr};
+    RecF16WParams p{a.gin, a.w_raw[0], a.w_raw[a.dirs - 1], a.y, a.h0, a.c0, a.hn, a.cn, a.B, a.T, a.dirs, a.y_split, want_ts ? ts_dev : nullptr,
+                    getenv("MP_RECW_SKIP") ? atoi(getenv("MP_RECW_SKIP")) : 0, 0};
+    alignas(64) CUtensorMap map_hi, map_lo;
+    memset(&map_hi, 0, sizeof(map_hi));
+    memset(&map_lo, 0, sizeof(map_lo));
+    if (a.y_split && !getenv("MP_RECW_NO_TMA_Y")) {
+        const int Y2 = a.dirs * a.H;
+        MP_TRY(make_map_y(&map_hi, a.y, a.B, a.T, Y2));
+        MP_TRY(make_map_y(&map_lo, reinterpret_cast<unsigned short*>(a.y) + (size_t)a.B * a.T * Y2, a.B, a.T, Y2));
+        p.y_tma = 1;
+    }
     ProfileScope prof("lstm_rec_f16_h256", 4.0 * ((double)a.dirs * 4 * a.H * a.H + (double)a.B * a.T * a.dirs * a.H), stream);
     const char* actv = getenv("MP_RF16_ACT");
     const bool fast = !(actv && strcmp(actv, "exact") == 0);
@@ -418,8 +485,8 @@ int launch_lstm_recurrence_f16w(const RecLayerArgs& a, cudaStream_t stream) {
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    if (fast) MP_CUDA_TRY(cudaLaunchKernelEx(&cfg, lstm_rec_f16w_kernel<true>, p));
-    else MP_CUDA_TRY(cudaLaunchKernelEx(&cfg, lstm_rec_f16w_kernel<false>, p));
+    if (fast) MP_CUDA_TRY(cudaLaunchKernelEx(&cfg, lstm_rec_f16w_kernel<true>, p, map_hi, map_lo));
+    else MP_CUDA_TRY(cudaLaunchKernelEx(&cfg, lstm_rec_f16w_kernel<false>, p, map_hi, map_lo));
     count_launch();
     if (want_ts) {      // bring-up only: synchronous dump of the stamps of block (0,0)
         static long long h[64 * 16];

@@ -9,3 +9,5 @@ timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --mas
 if [ "${2:-}" = "ref" ]; then
 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 bench.py --impl reference --gpus $N --steps 3 --warmup 1 > gpurun_out/bench_ref_n$N.json 2> gpurun_out/bench_ref_n$N.err; echo "ref n=$N exit $?"; cat gpurun_out/bench_ref_n$N.json | cut -c1-300
 fi
+# data-parallel training steps (HeadTrainer + NCCL all-reduce of the flat gradient buffer) == single-process steps on the whole batch
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29514 scripts/gpu_train_ddp.py > gpurun_out/train_ddp_n$N.log 2>&1; echo "train ddp n=$N exit $?"; grep "\[ddp\]" gpurun_out/train_ddp_n$N.log
