@@ -120,10 +120,11 @@ __device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t adesc, u
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {     // release at cluster scope, any CTA of the cluster
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
 }
-// ... without release semantics: the arriving thread only reports that it has finished READING (tensor memory behind tcgen05.wait::ld +
-// tcgen05.fence, a tile id); the .release.cluster form puts MEMBAR.ALL.GPU in front of the arrive (see lstm_rec_f16.cu)
-__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_bar) {
-    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+// ... with the default semantics (.release at CTA scope, what CUTLASS's umma_arrive_2x1SM_sm0 uses for the same hand-shake): orders
+// this thread's earlier reads (the tile id, the accumulators behind tcgen05.wait::ld + tcgen05.fence) before the arrive without the
+// MEMBAR.ALL.GPU the .release.cluster form puts in front of it (see lstm_rec_f16.cu)
+__device__ __forceinline__ void mbar_arrive_cluster_cta(uint32_t cluster_bar) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
 }
 __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {       // acquire at cluster scope (remote arrivals)
     asm volatile(
@@ -235,7 +236,7 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
                 } else {
                     mbar_wait_cluster(bar_tile_full(q), (j >> 1) & 1);
                     t = tile_q[q];
-                    mbar_arrive_cluster_relaxed(mapa_u32(bar_tile_free(q), 0));
+                    mbar_arrive_cluster_cta(mapa_u32(bar_tile_free(q), 0));
                 }
                 if (t < 0) break;
                 const int n0 = (t % tiles_n) * HB_N, m0 = (t / tiles_n) * TILE_M + (int)rank * HB_M;
@@ -356,7 +357,7 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
             const int t = tile_q[j & 1];
             __syncwarp();
             if (lane == 0) {
-                if (PAIR) mbar_arrive_cluster_relaxed(lead_tile_free[j & 1]);
+                if (PAIR) mbar_arrive_cluster_cta(lead_tile_free[j & 1]);
                 else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_tile_free(j & 1)) : "memory");
             }
             if (t < 0) break;
@@ -387,7 +388,7 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {
-                if (PAIR) mbar_arrive_cluster_relaxed(lead_drained);
+                if (PAIR) mbar_arrive_cluster_cta(lead_drained);
                 else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_drained) : "memory");
             }
             // (2) bias / activation / store, chunk by chunk through the warp's box
