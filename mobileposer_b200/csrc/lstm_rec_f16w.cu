@@ -9,7 +9,8 @@
 // costs and a cluster serves twice the sequences: half the CTAs per layer launch (32 instead of 64 for a bidirectional cfg3 layer) for
 // about 1.2 x the time.  Same numerics, operands, exchange protocol and thread coordinates as lstm_rec_f16.cu (read its header first):
 //   TMEM     W_hi columns [0, 128), W_lo [128, 256) (fp16 pairs), main accumulators [256, 384), correction [384, 512): all 512 columns
-//   smem     h: [sub-tile][K-block = source rank][hi | lo][32 rows x 64 B] (128 KB); staging [parity][sub-tile][hi | lo][32 x 64 B] (32 KB)
+//   smem     h: [sub-tile][K-block = source rank][hi | lo][32 rows x 64 B] (128 KB); staging [parity][sub-tile][hi | lo][32 x 64 B] (32 KB);
+//            gate pre-activations of the next step [sub-tile][32 sequences][128 floats] (64 KB), landed by TMA
 //   warps    0-15 epilogue (TMEM lane quarter = warp % 4, column part = warp / 4), 16 MMA issuer, 17 / 18 exchange (sub-tiles 0, 2 / 1, 3)
 // Differences: (a) the per-sub-tile housekeeping after the MMAs (arm `h_full`, tell the peers the rows are free) is done by epilogue
 // warp 0 at the moment it has seen the MMAs complete anyway, the exchange warps only ship; (b) the per-sequence running offsets of the
@@ -40,7 +41,8 @@ constexpr uint32_t KBLOCK = 2u * PLANE;              // hi + lo: what one rank s
 constexpr uint32_t SUBH = TCC * KBLOCK;              // h of one sub-tile: 32 KB
 constexpr uint32_t HBYTES = WSUB * SUBH;             // 128 KB
 constexpr uint32_t STG_PAR = WSUB * KBLOCK;          // 16 KB per parity
-constexpr uint32_t WF_SMEM = 1024 + HBYTES + 2 * STG_PAR + 256;
+constexpr uint32_t GIN_SUB = WR * 128u * 4u;           // gate pre-activations of one sub-tile and step: 32 sequences x 128 floats (16 KB)
+constexpr uint32_t WF_SMEM = 1024 + HBYTES + 2 * STG_PAR + WSUB * GIN_SUB + 256;
 constexpr float kLoScale = 2048.0f, kLoInv = 1.0f / 2048.0f;
 
 struct RecF16WParams {
@@ -138,9 +140,20 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t sr
                  : "memory");
 }
 
-template <bool FAST>
+// this CTA's 128 gate columns of 32 sequences at one frame of gin [B, T, dirs * 4H] -> shared memory, bytes counted on `bar`
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
+        : "memory");
+}
+
+// GTMA: the next step's gate pre-activations arrive by TMA in shared memory (one 16 KB box per sub-tile and step, issued by the
+// exchange warp once the 16 epilogue warps have consumed the previous one) instead of 8 LDG + address arithmetic per thread and sub-tile
+template <bool FAST, bool GTMA>
 __global__ void __launch_bounds__(WF_THREADS, 1) lstm_rec_f16w_kernel(const RecF16WParams p, const __grid_constant__ CUtensorMap map_y_hi,
-                                                                       const __grid_constant__ CUtensorMap map_y_lo) {
+                                                                       const __grid_constant__ CUtensorMap map_y_lo,
+                                                                       const __grid_constant__ CUtensorMap map_gin) {
     extern __shared__ unsigned char smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     unsigned char* gen = smem_raw + (base - smem_u32(smem_raw));
@@ -148,8 +161,10 @@ __global__ void __launch_bounds__(WF_THREADS, 1) lstm_rec_f16w_kernel(const RecF
     unsigned char* g_h = gen;
     unsigned char* g_stg = gen + HBYTES;
     // per sub-tile: bar_full (h rows arrived), bar_mma (MMAs committed), bar_free (all peers' MMAs done), bar_stage (slice staged)
-    const uint32_t bar_full = s_stg + 2 * STG_PAR, bar_mma = bar_full + 8 * WSUB, bar_free = bar_mma + 8 * WSUB,
-                   bar_stage = bar_free + 8 * WSUB, tmem_slot = bar_stage + 8 * WSUB;
+    const uint32_t s_gin = s_stg + 2 * STG_PAR;
+    const unsigned char* g_gin = gen + HBYTES + 2 * STG_PAR;
+    const uint32_t bar_full = s_gin + WSUB * GIN_SUB, bar_mma = bar_full + 8 * WSUB, bar_free = bar_mma + 8 * WSUB,
+                   bar_stage = bar_free + 8 * WSUB, bar_gin = bar_stage + 8 * WSUB, tmem_slot = bar_gin + 8 * WSUB;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int rank = (int)cluster_ctarank();
@@ -164,6 +179,7 @@ __global__ void __launch_bounds__(WF_THREADS, 1) lstm_rec_f16w_kernel(const RecF
             mbar_init(bar_mma + 8 * b, 1);
             mbar_init(bar_free + 8 * b, TCC);
             mbar_init(bar_stage + 8 * b, EPI_WARPS);
+            mbar_init(bar_gin + 8 * b, 1);
         }
         mbar_fence_init_cluster();
     }
@@ -244,8 +260,18 @@ __global__ void __launch_bounds__(WF_THREADS, 1) lstm_rec_f16w_kernel(const RecF
     uint32_t y_run = ((uint32_t)(b_begin + part * 4 + gate) * (uint32_t)T + (uint32_t)(dir ? T - 1 : 0)) * (uint32_t)Y2 +
                      (uint32_t)(dir * TH + rank * TUC + ul);
     // gate pre-activations of step 0 (gin columns are (unit, gate)-ordered: a warp reads 128 contiguous bytes)
-    float gi[WN / 4];
-    if (warp < EPI_WARPS) {
+    float gi[GTMA ? 1 : WN / 4];
+    if (GTMA) {
+        if (warp > EPI_WARPS && lane == 0) {
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const int sub = (warp - EPI_WARPS - 1) + 2 * k;
+                mbar_arrive_expect_tx(bar_gin + 8 * sub, GIN_SUB);
+                tma_load_3d(s_gin + (uint32_t)sub * GIN_SUB, &map_gin, dir * 4 * TH + rank * TUC * 4, dir ? T - 1 : 0, b_begin + sub * WR,
+                            bar_gin + 8 * sub);
+            }
+        }
+    } else if (warp < EPI_WARPS) {
         const float* gp = p.gin + g_run;
 #pragma unroll
         for (int j = 0; j < WN / 4; ++j) gi[j] = __ldg(gp + (size_t)((j >> 2) * 16 + (j & 3)) * TG4);
@@ -300,6 +326,11 @@ __global__ void __launch_bounds__(WF_THREADS, 1) lstm_rec_f16w_kernel(const RecF
                     tma_store_3d(&map_y_lo, src + PLANE, dir * TH + rank * TUC, t, b_begin + sub * WR);
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
+                if (GTMA && send && lane == 0) {               // the epilogue warps have consumed this step's gate pre-activations
+                    mbar_arrive_expect_tx(bar_gin + 8 * sub, GIN_SUB);
+                    tma_load_3d(s_gin + (uint32_t)sub * GIN_SUB, &map_gin, dir * 4 * TH + rank * TUC * 4, dir ? T - 2 - s : s + 1,
+                                b_begin + sub * WR, bar_gin + 8 * sub);
+                }
                 if (send) {
                     mbar_wait(bar_free + 8 * sub, par);        // every CTA's MMAs of this step on the sub-tile's old rows are done
                     if (lane < TCC)
@@ -328,11 +359,20 @@ __global__ void __launch_bounds__(WF_THREADS, 1) lstm_rec_f16w_kernel(const RecF
                     if (lane == 0) mbar_arrive_expect_tx(bar_full + 8 * sub, (uint32_t)TCC * KBLOCK);
                     if (lane < TCC) mbar_arrive_remote_relaxed(mapa_u32(bar_free + 8 * sub, lane));
                 }
-                float dm[8], dc[8];
+                float dm[8], dc[8], g8[8];
 #pragma unroll
                 for (int q = 0; q < 2; ++q) {
                     tmem_ld4(d_main + lane_base + (2 * sub + q) * 16 + part * 4, dm + 4 * q);
                     tmem_ld4(d_corr + lane_base + (2 * sub + q) * 16 + part * 4, dc + 4 * q);
+                }
+                if (GTMA) {
+                    mbar_wait(bar_gin + 8 * sub, par);         // this step's box has landed (row = sequence, 128 floats: lane = column)
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        g8[i] = *reinterpret_cast<const float*>(g_gin + (size_t)sub * GIN_SUB + (size_t)((i >> 2) * 16 + part * 4 + (i & 3)) * 512 + m * 4);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) g8[i] = gi[(2 * sub + (i >> 2)) * 4 + (i & 3)];
                 }
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                 float c_nw[2], h_nw[2];
@@ -343,7 +383,7 @@ __global__ void __launch_bounds__(WF_THREADS, 1) lstm_rec_f16w_kernel(const RecF
                     float a[4];
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        const float pre = fmaf(dc[q * 4 + j], kLoInv, dm[q * 4 + j]) + gi[blk * 4 + j];
+                        const float pre = fmaf(dc[q * 4 + j], kLoInv, dm[q * 4 + j]) + g8[q * 4 + j];
                         a[j] = (p.skip & 4) ? pre : FAST ? act_fast(pre, gate == 2) : act_exact(pre, gate == 2);
                     }
                     // 4 x 4 transpose inside the gate quad: lane `gate` ends up with i, f, g, o of sequence 16 blk + 4 part + gate
@@ -384,7 +424,7 @@ __global__ void __launch_bounds__(WF_THREADS, 1) lstm_rec_f16w_kernel(const RecF
                         const int n = blk * 16 + part * 4 + gate;
                         if (p.hn) p.hn[((size_t)dir * p.B + b_begin + n) * TH + rank * TUC + ul] = h_nw[q];
                         if (p.cn) p.cn[((size_t)dir * p.B + b_begin + n) * TH + rank * TUC + ul] = c_nw[q];
-                    } else if (!(p.skip & 2)) {
+                    } else if (!GTMA && !(p.skip & 2)) {
 #pragma unroll
                         for (int j = 0; j < 4; ++j) gi[blk * 4 + j] = __ldg(gp + (size_t)(blk * 16 + j) * TG4);
                     }
@@ -408,7 +448,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 
 // one plane of the split layer output, [B, T, Y2] halves, as a 3-D tensor map with a (32 units, 1 frame, 32 sequences) box whose
 // shared-memory image is the staged slice (64-byte rows, 64B swizzle)
-int make_map_y(CUtensorMap* map, void* ptr, int B, int T, int Y2) {
+EncodeTiledFn encode_tiled() {
     static EncodeTiledFn fn = nullptr;
     if (!fn) {
         void* q = nullptr;
@@ -416,6 +456,11 @@ int make_map_y(CUtensorMap* map, void* ptr, int B, int T, int Y2) {
         if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &q, cudaEnableDefault, &r) == cudaSuccess && r == cudaDriverEntryPointSuccess)
             fn = reinterpret_cast<EncodeTiledFn>(q);
     }
+    return fn;
+}
+
+int make_map_y(CUtensorMap* map, void* ptr, int B, int T, int Y2) {
+    EncodeTiledFn fn = encode_tiled();
     if (!fn) {
         set_error("lstm_f16w: cuTensorMapEncodeTiled is not available from this driver");
         return MP_ERR_CUDA;
@@ -428,6 +473,27 @@ int make_map_y(CUtensorMap* map, void* ptr, int B, int T, int Y2) {
                           CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error("lstm_f16w: cuTensorMapEncodeTiled (layer output) failed with CUresult %d (B=%d T=%d Y2=%d)", (int)r, B, T, Y2);
+        return MP_ERR_CUDA;
+    }
+    return MP_OK;
+}
+
+// gin [B, T, G4] floats as a 3-D tensor map with a (128 gate columns, 1 frame, 32 sequences) box, no swizzle (512-byte rows)
+int make_map_gin(CUtensorMap* map, const float* ptr, int B, int T, int G4) {
+    EncodeTiledFn fn = encode_tiled();
+    if (!fn) {
+        set_error("lstm_f16w: cuTensorMapEncodeTiled is not available from this driver");
+        return MP_ERR_CUDA;
+    }
+    const cuuint64_t dims[3] = {(cuuint64_t)G4, (cuuint64_t)T, (cuuint64_t)B};
+    const cuuint64_t strides[2] = {(cuuint64_t)G4 * 4, (cuuint64_t)T * G4 * 4};
+    const cuuint32_t box[3] = {128, 1, (cuuint32_t)WR};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult res = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(ptr), dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (res != CUDA_SUCCESS) {
+        set_error("lstm_f16w: cuTensorMapEncodeTiled (gate pre-activations) failed with CUresult %d (B=%d T=%d G4=%d)", (int)res, B, T, G4);
         return MP_ERR_CUDA;
     }
     return MP_OK;
@@ -455,9 +521,12 @@ int launch_lstm_recurrence_f16w(const RecLayerArgs& a, cudaStream_t stream) {
     }
     RecF16WParams p{a.gin, a.w_raw[0], a.w_raw[a.dirs - 1], a.y, a.h0, a.c0, a.hn, a.cn, a.B, a.T, a.dirs, a.y_split, want_ts ? ts_dev : nullptr,
                     getenv("MP_RECW_SKIP") ? atoi(getenv("MP_RECW_SKIP")) : 0, 0};
-    alignas(64) CUtensorMap map_hi, map_lo;
+    alignas(64) CUtensorMap map_hi, map_lo, map_gin;
     memset(&map_hi, 0, sizeof(map_hi));
     memset(&map_lo, 0, sizeof(map_lo));
+    memset(&map_gin, 0, sizeof(map_gin));
+    const bool gtma = !getenv("MP_RECW_NO_TMA_GIN");
+    if (gtma) MP_TRY(make_map_gin(&map_gin, a.gin, a.B, a.T, a.dirs * 4 * a.H));
     if (a.y_split && !getenv("MP_RECW_NO_TMA_Y")) {
         const int Y2 = a.dirs * a.H;
         MP_TRY(make_map_y(&map_hi, a.y, a.B, a.T, Y2));
@@ -469,8 +538,10 @@ int launch_lstm_recurrence_f16w(const RecLayerArgs& a, cudaStream_t stream) {
     const bool fast = !(actv && strcmp(actv, "exact") == 0);
     static bool configured = false;
     if (!configured) {
-        MP_CUDA_TRY(cudaFuncSetAttribute(lstm_rec_f16w_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WF_SMEM));
-        MP_CUDA_TRY(cudaFuncSetAttribute(lstm_rec_f16w_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WF_SMEM));
+        MP_CUDA_TRY(cudaFuncSetAttribute(lstm_rec_f16w_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WF_SMEM));
+        MP_CUDA_TRY(cudaFuncSetAttribute(lstm_rec_f16w_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WF_SMEM));
+        MP_CUDA_TRY(cudaFuncSetAttribute(lstm_rec_f16w_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WF_SMEM));
+        MP_CUDA_TRY(cudaFuncSetAttribute(lstm_rec_f16w_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WF_SMEM));
         configured = true;
     }
     cudaLaunchConfig_t cfg = {};
@@ -485,8 +556,10 @@ int launch_lstm_recurrence_f16w(const RecLayerArgs& a, cudaStream_t stream) {
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    if (fast) MP_CUDA_TRY(cudaLaunchKernelEx(&cfg, lstm_rec_f16w_kernel<true>, p, map_hi, map_lo));
-    else MP_CUDA_TRY(cudaLaunchKernelEx(&cfg, lstm_rec_f16w_kernel<false>, p, map_hi, map_lo));
+    if (fast && gtma) MP_CUDA_TRY(cudaLaunchKernelEx(&cfg, lstm_rec_f16w_kernel<true, true>, p, map_hi, map_lo, map_gin));
+    else if (fast) MP_CUDA_TRY(cudaLaunchKernelEx(&cfg, lstm_rec_f16w_kernel<true, false>, p, map_hi, map_lo, map_gin));
+    else if (gtma) MP_CUDA_TRY(cudaLaunchKernelEx(&cfg, lstm_rec_f16w_kernel<false, true>, p, map_hi, map_lo, map_gin));
+    else MP_CUDA_TRY(cudaLaunchKernelEx(&cfg, lstm_rec_f16w_kernel<false, false>, p, map_hi, map_lo, map_gin));
     count_launch();
     if (want_ts) {      // bring-up only: synchronous dump of the stamps of block (0,0)
         static long long h[64 * 16];

@@ -83,7 +83,7 @@ def full_sets(tag):
         key = {'rec_b256': 'lstm_rec_h256', 'rec_b1': 'lstm_rec_h256_b1', 'gemm_tc': 'gemm_tf32x3',
                'rec_tc_b256': 'lstm_rec_tc_h256', 'gemm_ffma2': 'gemm_linear', 'rec_h64_rows': 'lstm_rec_h64',
                'rec_f16_b256': 'lstm_rec_f16_h256_tile64', 'rec_f16w_b256': 'lstm_rec_f16_h256', 'gemm_f16': 'gemm_f16x3',
-               'gemm_f16_linear1': 'gemm_f16x3_linear1'}.get(name, name)
+               'gemm_f16_linear1': 'gemm_f16x3_linear1', 'gemm_f16_k512': 'gemm_f16x3_k512'}.get(name, name)
         summary[key] = {'round': tag, 'kernel': r[idx['Kernel Name']], 'grid': r[idx['Grid Size']],
                         'dram_bytes_per_launch': val('dram__bytes_read.sum') + val('dram__bytes_write.sum'),
                         'duration_ms_under_ncu': float(r[idx['gpu__time_duration.sum']]) * {'us': 1e-3, 'ms': 1, 'ns': 1e-6, 's': 1e3}.get(units[idx['gpu__time_duration.sum']].replace('second', 's'), 1)}
