@@ -318,9 +318,20 @@ __global__ void __launch_bounds__(WF_THREADS, 1) lstm_rec_f16w_kernel(const RecF
                 const int sub = (warp - EPI_WARPS - 1) + 2 * k;
                 const uint32_t src = s_stg + (uint32_t)par * STG_PAR + (uint32_t)sub * KBLOCK;
                 mbar_wait(bar_stage + 8 * sub, par);           // the 16 epilogue warps have staged the slice (hi + lo planes, contiguous)
+                // the hand-over to the peers first (it is on the step's critical chain), the layer output and the next step's gate
+                // pre-activations after it (they have a whole step).  Before the copies of this step let the next-but-one epilogue
+                // overwrite the other staging parity, last step's output stores of this sub-tile must have read it out (they were
+                // issued a step ago: a guarantee, not a wait)
+                if (p.y_tma && lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                __syncwarp();
+                if (send) {
+                    mbar_wait(bar_free + 8 * sub, par);        // every CTA's MMAs of this step on the sub-tile's old rows are done
+                    if (lane < TCC)
+                        bulk_copy_s2c(mapa_u32(s_h + (uint32_t)sub * SUBH + (uint32_t)rank * KBLOCK, lane), src, KBLOCK,
+                                      mapa_u32(bar_full + 8 * sub, lane));
+                    if (lane == 0) WF_STAMP(12 + sub);
+                }
                 if (p.y_tma && lane == 0) {
-                    // the stores of this sub-tile two steps ago (same staging parity) have been read out long since; keep it a guarantee
-                    asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
                     const int t = dir ? T - 1 - s : s;
                     tma_store_3d(&map_y_hi, src, dir * TH + rank * TUC, t, b_begin + sub * WR);
                     tma_store_3d(&map_y_lo, src + PLANE, dir * TH + rank * TUC, t, b_begin + sub * WR);
@@ -330,13 +341,6 @@ __global__ void __launch_bounds__(WF_THREADS, 1) lstm_rec_f16w_kernel(const RecF
                     mbar_arrive_expect_tx(bar_gin + 8 * sub, GIN_SUB);
                     tma_load_3d(s_gin + (uint32_t)sub * GIN_SUB, &map_gin, dir * 4 * TH + rank * TUC * 4, dir ? T - 2 - s : s + 1,
                                 b_begin + sub * WR, bar_gin + 8 * sub);
-                }
-                if (send) {
-                    mbar_wait(bar_free + 8 * sub, par);        // every CTA's MMAs of this step on the sub-tile's old rows are done
-                    if (lane < TCC)
-                        bulk_copy_s2c(mapa_u32(s_h + (uint32_t)sub * SUBH + (uint32_t)rank * KBLOCK, lane), src, KBLOCK,
-                                      mapa_u32(bar_full + 8 * sub, lane));
-                    if (lane == 0) WF_STAMP(12 + sub);
                 }
             }
             __syncwarp();

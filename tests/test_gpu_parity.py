@@ -713,3 +713,24 @@ def test_pipelined_slots_with_the_wide_tile_match_forward_offline(seeded_state_d
         slot.wait()
     assert torch.equal(slot.joints.view(B, T, 72), joints.cpu().view(B, T, 72))
     assert torch.equal(slot.pose.view(-1), pose.cpu().view(-1)) and torch.equal(slot.tran.view(-1), tran.cpu().view(-1))
+
+
+def test_wide_tile_policy_falls_back_for_ragged_and_partial_batches(seeded_state_dict):
+    """mp_net_set_rec_tile(128) is a policy, not a promise: ragged lengths or a batch that is not whole 128-sequence tiles take the
+    64-sequence kernel and give the results of the default policy."""
+    import mobileposer_b200 as mp
+    from mobileposer_b200.synthetic import synthetic_imu_batch
+    net = mp.MobilePoserNet()
+    net.load_state_dict(seeded_state_dict)
+    net = net.eval().to(DEV)
+    for B, T, lens in ((128, 21, [21] * 64 + [13] * 64), (192, 17, [17] * 192)):
+        x = synthetic_imu_batch(list(range(900, 900 + B)), T)
+        for b, L in enumerate(lens):
+            x[b, L:] = 0
+        pose, joints, tran, contact = net.forward_offline(x.to(DEV), lens)
+        slot = mp.HostOffline(net, B, T, rec_tile=128)
+        for _ in range(3):
+            slot.submit(x.contiguous(), lens)
+            slot.wait()
+        assert torch.equal(slot.joints.view(B, T, 72), joints.cpu().view(B, T, 72)), (B, T)
+        assert torch.equal(slot.tran.view(-1), tran.cpu().view(-1)), (B, T)
