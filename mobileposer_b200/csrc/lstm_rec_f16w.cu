@@ -57,7 +57,8 @@ struct RecF16WParams {
     int B, T, dirs;
     int y_split;          // y = two planes of halves (hi, scaled lo) instead of fp32
     long long* ts;        // bring-up (MP_RECW_TS): clock64 stamps of block (0,0), [step][16], or null
-    int skip;             // bring-up (MP_RECW_SKIP, WRONG RESULTS): bit 0 no y stores, bit 1 no gin prefetch, bit 2 no activations
+    int skip;             // ablation builds only (-DMP_RECW_ABLATION, env MP_RECW_SKIP; results are WRONG with a bit set): bit 0 no y stores,
+                          // bit 1 no gin prefetch, bit 2 no activations.  Compiled out of the shipped library.
     int y_tma;            // y_split only: the layer output leaves through TMA stores of the staged slices (map_y_hi / map_y_lo)
 };
 
@@ -128,6 +129,11 @@ __device__ __forceinline__ float act_exact(float x, bool is_tanh) {
     return is_tanh ? (1.0f - e) * r : r;
 }
 
+#ifdef MP_RECW_ABLATION
+#define WF_SKIP(p, bit) ((p).skip & (bit))
+#else
+#define WF_SKIP(p, bit) 0
+#endif
 #define WF_STAMP(slot)                                                                                         \
     do {                                                                                                       \
         if (p.ts && blockIdx.x == 0 && blockIdx.y == 0 && s < 64) p.ts[s * 16 + (slot)] = clock64();           \
@@ -388,7 +394,7 @@ __global__ void __launch_bounds__(WF_THREADS, 1) lstm_rec_f16w_kernel(const RecF
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         const float pre = fmaf(dc[q * 4 + j], kLoInv, dm[q * 4 + j]) + g8[q * 4 + j];
-                        a[j] = (p.skip & 4) ? pre : FAST ? act_fast(pre, gate == 2) : act_exact(pre, gate == 2);
+                        a[j] = WF_SKIP(p, 4) ? pre : FAST ? act_fast(pre, gate == 2) : act_exact(pre, gate == 2);
                     }
                     // 4 x 4 transpose inside the gate quad: lane `gate` ends up with i, f, g, o of sequence 16 blk + 4 part + gate
                     const bool b0 = lane & 1, b1 = lane & 2;
@@ -417,7 +423,7 @@ __global__ void __launch_bounds__(WF_THREADS, 1) lstm_rec_f16w_kernel(const RecF
                 for (int q = 0; q < 2; ++q) {
                     const int blk = 2 * sub + q;
                     const size_t yo = (size_t)(blk * 16) * TY2;
-                    if ((p.skip & 1) || p.y_tma) {
+                    if (WF_SKIP(p, 1) || p.y_tma) {
                     } else if (p.y_split) {
                         yh[yo] = h_hi16[q];
                         yl[yo] = h_lo16[q];
@@ -428,7 +434,7 @@ __global__ void __launch_bounds__(WF_THREADS, 1) lstm_rec_f16w_kernel(const RecF
                         const int n = blk * 16 + part * 4 + gate;
                         if (p.hn) p.hn[((size_t)dir * p.B + b_begin + n) * TH + rank * TUC + ul] = h_nw[q];
                         if (p.cn) p.cn[((size_t)dir * p.B + b_begin + n) * TH + rank * TUC + ul] = c_nw[q];
-                    } else if (!GTMA && !(p.skip & 2)) {
+                    } else if (!GTMA && !WF_SKIP(p, 2)) {
 #pragma unroll
                         for (int j = 0; j < 4; ++j) gi[blk * 4 + j] = __ldg(gp + (size_t)(blk * 16 + j) * TG4);
                     }

@@ -1,3 +1,6 @@
+"""Ablation of lstm_rec_f16w_kernel (cost attribution only; results are WRONG with a skip bit set): needs a library built with
+-DMP_RECW_ABLATION (add it to NVCC_FLAGS in mobileposer_b200/build.py and rebuild with --force), MP_RECW_NO_TMA_GIN=1 for the LDG path the
+recorded run used.  Recorded in profiles/r02_rec_wide_ab.txt."""
 import os, sys, torch
 sys.path.insert(0, '.')
 import mobileposer_b200 as mp

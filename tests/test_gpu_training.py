@@ -178,3 +178,52 @@ def test_adamw_kernel_against_torch_on_a_ragged_buffer():
         _cabi.check(lib.mp_adamw_step(p.data_ptr(), gd.data_ptr(), m.data_ptr(), v.data_ptr(), n, 1e-3, 0.9, 0.999, 1e-8, 1e-2, step,
                                       sq.data_ptr(), 1.0, 1.0, s))
         assert (p.cpu() - ref.detach()).abs().max().item() < 2e-6, step
+
+
+@pytest.mark.parametrize('kind', ['velocity', 'footcontact', 'poser'])
+def test_head_trainer_on_the_other_heads_against_the_oracle_loop(kind):
+    """HeadTrainer (clip + AdamW on the device) for the unidirectional H = 256, the H = 64 and the Poser head: 3 optimisation steps on
+    one fixed batch against oracle/train_port.py:overfit_loop (the loop pinned to the live reference for the Joints head)."""
+    import mobileposer_b200 as mp
+    from mobileposer_b200.config import joint_set
+    from mobileposer_b200.synthetic import synthetic_imu_batch
+    from mobileposer_b200.training import HeadTrainer
+    from oracle.train_port import overfit_loop
+    B, T = 5, 24
+    gen = torch.Generator().manual_seed(17)
+    lens = [24, 9, 24, 17, 3]
+    imu = synthetic_imu_batch(list(range(40, 40 + B)), T)
+    for b, L in enumerate(lens):
+        imu[b, L:] = 0
+    x = torch.cat((torch.randn(B, T, 72, generator=gen) * 0.3, imu), -1)
+    torch.manual_seed(0)
+    if kind == 'velocity':
+        mod, prefix, attr = mp.Velocity(), 'vel.', 'vel'
+        args = (x, lens, torch.randn(B, T, 72, generator=gen) * 0.5)
+        o_target = args[2]
+    elif kind == 'footcontact':
+        mod, prefix, attr = mp.FootContact(), 'footcontact.', 'footcontact'
+        args = (x, lens, (torch.rand(B, T, 2, generator=gen) > 0.5).float())
+        o_target = args[2]
+    else:
+        mod, prefix, attr = mp.Poser(), 'pose.', 'pose'
+        eye6 = torch.tensor([1., 0., 0., 0., 1., 0.]).repeat(24)
+        poses = eye6 + 0.3 * torch.randn(B, T, 144, generator=gen)
+        joints_t = torch.randn(B, T, 72, generator=gen) * 0.3
+        args = (x, lens, poses, joints_t)
+        o_target = torch.cat((poses.view(B, T, 24, 6)[:, :, joint_set.reduced].reshape(B, T, 96), joints_t), -1)
+    H = getattr(mod, attr).n_hidden
+    mask = (torch.rand(B, T, H, generator=gen) >= 0.4).float() / 0.6
+    sd = {prefix + k: v.detach().clone() for k, v in getattr(mod, attr).state_dict().items()}
+    o_losses, o_final = overfit_loop(sd, x, lens, o_target, mask, 3, prefix=prefix, kind=kind, gradient_clip_val=0.5)
+    tr = HeadTrainer(mod.to(DEV), gradient_clip_val=0.5)
+    dargs = tuple(a.to(DEV) if torch.is_tensor(a) else a for a in args)
+    losses = [tr.training_step(*dargs, mask=mask.to(DEV)).item() for _ in range(3)]
+    worst_l = max(abs(a - b.item()) / abs(b.item()) for a, b in zip(losses, o_losses))
+    assert worst_l < 5e-5, (losses, o_losses)
+    worst_p = 0.0
+    for name, p in getattr(mod, attr).named_parameters():
+        worst_p = max(worst_p, (p.detach().cpu() - o_final[name]).abs().max().item())
+    # three steps of lr = 1e-3 move a weight by <= 3e-3; AdamW's m / (sqrt(v) + eps) amplifies gradient noise where |g| ~ eps
+    assert worst_p < 1e-4, worst_p
+    print(f'[train] HeadTrainer {kind}: losses {[round(v, 6) for v in losses]}, worst relative loss error {worst_l:.1e}, worst parameter error {worst_p:.1e}')
