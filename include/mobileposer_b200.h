@@ -291,6 +291,13 @@ int mp_eval_vertex_errors(const float* pose_p, const float* pose_t, int64_t n_fr
  * Every row is x.mean() and x.std(dim=0).mean() of a [frames, joints] array (unbiased std over frames), from per-column sums in double. */
 int mp_eval_motion_rows(const float* joint_p, const float* joint_t, const float* je, const float* lae, const float* gae,
                         int64_t n_frames, int32_t fps, uint32_t joint_mask_bits, float* rows, mp_stream_t stream);
+/* The same for a GROUP of sequences whose per-frame arrays are concatenated: sequence b owns the frames [offsets[b], offsets[b + 1])
+ * (`offsets`: n_sequences + 1 int64 on the device) and gets rows[b] ([n_sequences, 10, 2]); one CTA per sequence, side by side, each
+ * with the accumulation order of a launch of its own (bit-identical rows).  What evaluate_pose(batch_size > 1) reduces a group with
+ * [evaluate.py:39-107: the loop over sequences]. */
+int mp_eval_motion_rows_batch(const float* joint_p, const float* joint_t, const float* je, const float* lae, const float* gae,
+                              const int64_t* offsets, int32_t n_sequences, int32_t fps, uint32_t joint_mask_bits, float* rows,
+                              mp_stream_t stream);
 
 /* Translation-error windows of evaluate_pose(..., evaluate_tran=True) [evaluate.py:66-92], S sequences
  * per call: tran_p / tran_t [S,T,3] predicted / true root translation (padded to T frames), lengths [S] device ints or NULL ->

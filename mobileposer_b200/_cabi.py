@@ -104,6 +104,8 @@ SIGNATURES = {
                                        c_float_p, c_float_p, c_stream]),
     'mp_eval_vertex_errors': (C.c_int, [c_float_p, c_float_p, C.c_int64, c_float_p, c_float_p, C.c_int32, C.c_void_p, C.c_void_p, c_stream]),
     'mp_eval_motion_rows': (C.c_int, [c_float_p, c_float_p, c_float_p, c_float_p, c_float_p, C.c_int64, C.c_int32, C.c_uint32, c_float_p, c_stream]),
+    'mp_eval_motion_rows_batch': (C.c_int, [c_float_p, c_float_p, c_float_p, c_float_p, c_float_p, C.c_void_p, C.c_int32, C.c_int32, C.c_uint32,
+                                            c_float_p, c_stream]),
     'mp_eval_tran_windows': (C.c_int, [c_float_p, c_float_p, c_int_p, C.c_int32, C.c_int32, c_float_p, c_int_p, c_stream]),
     'mp_physics_fk': (C.c_int, [c_float_p, C.c_int64, c_float_p, c_float_p, c_stream]),
     'mp_online_update': (C.c_int, [C.c_void_p, c_float_p, c_float_p, c_float_p, c_float_p, C.c_int32, C.c_int32,

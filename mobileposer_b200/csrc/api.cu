@@ -570,6 +570,12 @@ int mp_eval_motion_rows(const float* joint_p, const float* joint_t, const float*
                         int32_t fps, uint32_t joint_mask_bits, float* rows, mp_stream_t stream) {
     return launch_eval_motion_rows(joint_p, joint_t, je, lae, gae, n_frames, fps, joint_mask_bits, rows, (cudaStream_t)stream);
 }
+int mp_eval_motion_rows_batch(const float* joint_p, const float* joint_t, const float* je, const float* lae, const float* gae,
+                              const int64_t* offsets, int32_t n_sequences, int32_t fps, uint32_t joint_mask_bits, float* rows, mp_stream_t stream) {
+    static_assert(sizeof(long long) == sizeof(int64_t), "offsets are 64-bit");
+    return launch_eval_motion_rows_batch(joint_p, joint_t, je, lae, gae, reinterpret_cast<const long long*>(offsets), n_sequences, fps,
+                                         joint_mask_bits, rows, (cudaStream_t)stream);
+}
 int mp_eval_tran_windows(const float* tran_p, const float* tran_t, const int32_t* lengths, int32_t S, int32_t T, float* err,
                          int32_t* count, mp_stream_t stream) {
     return launch_eval_tran_windows(tran_p, tran_t, lengths, S, T, err, count, (cudaStream_t)stream);

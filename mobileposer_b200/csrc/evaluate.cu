@@ -87,7 +87,17 @@ constexpr int ER_THREADS = 256, ER_WARPS = ER_THREADS / 32, ER_ACC = 12;
 
 __global__ void __launch_bounds__(ER_THREADS)
 eval_motion_rows_kernel(const float* __restrict__ jp, const float* __restrict__ jt, const float* __restrict__ je, const float* __restrict__ lae,
-                        const float* __restrict__ gae, int n, int fps, unsigned mask_bits, float* __restrict__ rows) {
+                        const float* __restrict__ gae, int n, int fps, unsigned mask_bits, float* __restrict__ rows,
+                        const long long* __restrict__ offsets) {
+    if (offsets) {
+        // batched form: CTA b reduces the frames [offsets[b], offsets[b + 1]) of the concatenated arrays into rows[b] -- the same
+        // accumulation order per sequence as a launch of its own, so the rows are bit-identical; the sequences run side by side
+        // instead of one latency-bound CTA after the other (50 x 0.9 ms per cfg4 pass)
+        const long long o = offsets[blockIdx.x];
+        n = (int)(offsets[blockIdx.x + 1] - o);
+        jp += o * 72; jt += o * 72; je += o * 24; lae += o * 24; gae += o * 24;
+        rows += (size_t)blockIdx.x * 20;
+    }
     __shared__ double red[ER_WARPS][32][ER_ACC];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     double acc[ER_ACC];
@@ -171,7 +181,17 @@ int launch_eval_motion_rows(const float* jp, const float* jt, const float* je, c
                             unsigned mask_bits, float* rows, cudaStream_t stream) {
     MP_REQUIRE(jp && jt && je && lae && gae && rows && n > 0 && n < (int64_t)1 << 30 && fps > 0, "eval_motion_rows: bad arguments");
     MP_REQUIRE((mask_bits & ~0x00FFFFFFu) == 0, "eval_motion_rows: the joint mask has 24 bits");
-    eval_motion_rows_kernel<<<1, ER_THREADS, 0, stream>>>(jp, jt, je, lae, gae, (int)n, fps, mask_bits, rows);
+    eval_motion_rows_kernel<<<1, ER_THREADS, 0, stream>>>(jp, jt, je, lae, gae, (int)n, fps, mask_bits, rows, nullptr);
+    MP_CUDA_TRY(cudaGetLastError());
+    count_launch();
+    return MP_OK;
+}
+
+int launch_eval_motion_rows_batch(const float* jp, const float* jt, const float* je, const float* lae, const float* gae, const long long* offsets,
+                                  int n_sequences, int fps, unsigned mask_bits, float* rows, cudaStream_t stream) {
+    MP_REQUIRE(jp && jt && je && lae && gae && offsets && rows && n_sequences > 0 && fps > 0, "eval_motion_rows_batch: bad arguments");
+    MP_REQUIRE((mask_bits & ~0x00FFFFFFu) == 0, "eval_motion_rows_batch: the joint mask has 24 bits");
+    eval_motion_rows_kernel<<<n_sequences, ER_THREADS, 0, stream>>>(jp, jt, je, lae, gae, 0, fps, mask_bits, rows, offsets);
     MP_CUDA_TRY(cudaGetLastError());
     count_launch();
     return MP_OK;

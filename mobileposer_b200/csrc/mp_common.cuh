@@ -151,6 +151,8 @@ int launch_eval_vertex_errors(const float* pose_p, const float* pose_t, int64_t 
 // N1 rows (evaluate.cu): the [10, 2] mean / std table of FullMotionEvaluator from the per-frame errors; row 1 (mesh) left NaN
 int launch_eval_motion_rows(const float* jp, const float* jt, const float* je, const float* lae, const float* gae, int64_t n, int fps,
                             unsigned mask_bits, float* rows, cudaStream_t stream);
+int launch_eval_motion_rows_batch(const float* jp, const float* jt, const float* je, const float* lae, const float* gae, const long long* offsets,
+                                  int n_sequences, int fps, unsigned mask_bits, float* rows, cudaStream_t stream);
 // N3 (evaluate.cu)
 int launch_eval_tran_windows(const float* tran_p, const float* tran_t, const int32_t* lengths, int S, int T, float* err,
                              int32_t* count, cudaStream_t stream);

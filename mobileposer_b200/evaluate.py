@@ -243,6 +243,40 @@ class PoseEvaluator:
         errs = full_motion_errors(pose_p, pose_t, tran_p, tran_t, mesh=self.mesh if pose_p.is_cuda else None)
         return torch.stack([errs[9], errs[3], errs[9], errs[0] * 100, errs[7] * 100, errs[1] * 100, errs[4] / 100, errs[6]])
 
+    def eval_group(self, pose_p, pose_t_r6d, tran_p, tran_t, lens):
+        """The rows of `eval` for a GROUP of sequences whose valid frames are concatenated (pose_p [sum(lens), 24, 3, 3] on the device,
+        pose_t_r6d [sum(lens), 144] ground truth as the dataset stores it, tran_* [sum(lens), 3]): the per-frame work -- ground-truth
+        r6d -> rotation (evaluate.py:60), both forward kinematics, the three per-joint errors -- is one pass over all frames instead of
+        one per sequence (~40 small launches each), and the (mean, std) rows are one `mp_eval_motion_rows_batch` launch (one CTA per
+        sequence over its slice, the accumulation order of a launch of its own), so every row equals what `eval` returns for that
+        sequence alone.  -> [len(lens), 8, 2].  CUDA only."""
+        from . import _cabi
+        from .modules import current_stream_ptr
+        dev = pose_p.device
+        pose_p = pose_p.clone().view(-1, 24, 3, 3)
+        pose_t = r6d_to_rotation_matrix(pose_t_r6d.to(dev)).view(-1, 24, 3, 3)
+        eye = torch.eye(3, device=dev)
+        pose_p[:, joint_set.ignored] = eye
+        pose_t[:, joint_set.ignored] = eye
+        tran_p, tran_t = tran_p.reshape(-1, 3), tran_t.to(dev).reshape(-1, 3)
+        jp, jt, je, lae, gae = frame_errors_cuda(pose_p, pose_t, tran_p, tran_t)
+        rows = torch.empty(len(lens), 10, 2, device=dev, dtype=torch.float32)
+        bits = 0
+        for j in (2, 5, 16, 20):
+            bits |= 1 << j
+        offsets = torch.tensor([0] + [int(n) for n in lens], dtype=torch.int64).cumsum(0).to(dev)
+        with torch.cuda.device(dev):
+            _cabi.check(_cabi.lib().mp_eval_motion_rows_batch(jp.data_ptr(), jt.data_ptr(), je.data_ptr(), lae.data_ptr(), gae.data_ptr(),
+                                                              offsets.data_ptr(), len(lens), int(datasets.fps), bits, rows.data_ptr(),
+                                                              current_stream_ptr(dev)), 'mp_eval_motion_rows_batch')
+        if self.mesh is not None:
+            off = 0
+            for r, n in enumerate(lens):
+                rows[r, 1] = vertex_error_row(pose_p[off:off + n], pose_t[off:off + n], self.mesh)
+                off += n
+        scale = torch.tensor([1.0, 1.0, 1.0, 100.0, 100.0, 100.0, 0.01, 1.0], device=dev).view(1, 8, 1)
+        return rows[:, [9, 3, 9, 0, 7, 1, 4, 6]] * scale
+
     @classmethod
     def print(cls, errors):
         for i, name in enumerate(cls.names):
@@ -264,6 +298,17 @@ def synthetic_dip(n_subjects=10, n_seq=5, frames=3000, combo='lw_rp'):
         tran = torch.cumsum(0.01 * torch.sin(t / 60.0 + torch.rand(3, generator=g) * 6.28), dim=0)
         items.append((imu, pose, torch.zeros(frames, 24, 3), tran))
     return items
+
+
+_COPY_STREAMS = {}
+
+
+def _copy_stream(device):
+    """One side stream per device for the ground-truth upload of evaluate_pose's batched path."""
+    key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+    if key not in _COPY_STREAMS:
+        _COPY_STREAMS[key] = torch.cuda.Stream(device)
+    return _COPY_STREAMS[key]
 
 
 @torch.no_grad()
@@ -312,9 +357,10 @@ def evaluate_pose(model, dataset, num_past_frame=20, num_future_frame=5, evaluat
                 opt.reset_states()
 
     batched = {}                                   # sequence index -> (pose_p [T,24,3,3], tran_p [T,3]) of the current group
+    group_rows = {}                                # sequence index -> [8, 2] rows of the current group (device path)
     for pos, i in enumerate(mine):
         imu, pose_t, _, tran_t = items[i]
-        x = imu.to(device)
+        x = imu.to(device) if batch_size == 1 or getenv("ONLINE") else None      # batched: the group's input is assembled below
         if batch_size == 1:
             model.reset()
             fresh_state()
@@ -329,11 +375,38 @@ def evaluate_pose(model, dataset, num_past_frame=20, num_future_frame=5, evaluat
                 model.reset()
                 fresh_state()                      # also covers a trailing group of one, which takes the B == 1 path
                 pose_b, _, tran_b, _ = model.forward_offline(xb, lens)
+                group_rows = {}
+                use_group = pose_b.is_cuda and not getenv("ONLINE")
+                if use_group:
+                    # the group's ground truth goes to the device while the forward (enqueued above, asynchronous) runs: slice by
+                    # slice like the per-sequence path copies it, on a side stream the metric pass then waits for
+                    tot = sum(lens)
+                    gt = torch.empty(tot, 144, device=device, dtype=torch.float32)
+                    tt = torch.empty(tot, 3, device=device, dtype=torch.float32)
+                    main, side = torch.cuda.current_stream(device), _copy_stream(device)
+                    side.wait_stream(main)
+                    with torch.cuda.stream(side):
+                        off = 0
+                        for r, k in enumerate(group):
+                            gt[off:off + lens[r]].copy_(items[k][1].reshape(lens[r], 144), non_blocking=True)
+                            tt[off:off + lens[r]].copy_(items[k][3].reshape(lens[r], 3), non_blocking=True)
+                            off += lens[r]
+                    main.wait_stream(side)
                 pose_b = pose_b.view(len(group), max(lens), 24, 3, 3)
                 tran_b = tran_b.view(len(group), max(lens), 3)
                 # the rows of the group are formed before the next forward (the net may reuse its output buffers)
                 batched = {k: (pose_b[r, :lens[r]], tran_b[r, :lens[r]]) for r, k in enumerate(group)}
+                if use_group:
+                    # the whole group's metric rows in one pass over its frames (PoseEvaluator.eval_group)
+                    g_rows = evaluator.eval_group(torch.cat([batched[k][0] for k in group]), gt, torch.cat([batched[k][1] for k in group]),
+                                                  tt, lens)
+                    group_rows = {k: g_rows[r] for r, k in enumerate(group)}
             pose_p, tran_p = batched[i]
+            if i in group_rows:
+                rows.append(group_rows[i])
+                if evaluate_tran:
+                    window_rows.append(tran_window_errors(tran_p, tran_t)[0][0])
+                continue
         pose_t = r6d_to_rotation_matrix(pose_t.to(device)).view(-1, 24, 3, 3)
         rows.append(evaluator.eval(pose_p, pose_t, tran_p=tran_p, tran_t=tran_t))
         if evaluate_tran:

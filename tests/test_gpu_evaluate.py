@@ -270,3 +270,24 @@ def test_motion_rows_kernel_equals_the_torch_statement(n):
     assert torch.equal(torch.isnan(got), torch.isnan(want)), (got, want)
     ok = ~torch.isnan(want)
     assert ((got[ok] - want[ok]).abs() / want[ok].abs().clamp_min(1e-3)).max() < 2e-4
+
+
+def test_eval_group_equals_per_sequence_eval_bit_for_bit():
+    """PoseEvaluator.eval_group (one pass over the concatenated frames of a group + mp_eval_motion_rows_batch, one CTA per sequence)
+    returns exactly the rows PoseEvaluator.eval returns for each sequence alone -- ragged lengths, a sequence shorter than one second."""
+    from mobileposer_b200.evaluate import PoseEvaluator, r6d_to_rotation_matrix
+    gen = torch.Generator().manual_seed(8)
+    lens = [211, 40, 3000, 17, 333]
+    eye6 = torch.tensor([1., 0., 0., 0., 1., 0.]).repeat(24)
+    ev = PoseEvaluator()
+    pose_p, gt, tran_p, tran_t = [], [], [], []
+    for n in lens:
+        pose_p.append(r6d_to_rotation_matrix(eye6 + 0.3 * torch.randn(n, 144, generator=gen)).view(n, 24, 3, 3).to(DEV))
+        gt.append(eye6 + 0.3 * torch.randn(n, 144, generator=gen))
+        tran_p.append(torch.cumsum(0.01 * torch.randn(n, 3, generator=gen), 0).to(DEV))
+        tran_t.append(torch.cumsum(0.01 * torch.randn(n, 3, generator=gen), 0))
+    single = torch.stack([ev.eval(pose_p[i], r6d_to_rotation_matrix(gt[i].to(DEV)).view(-1, 24, 3, 3), tran_p=tran_p[i], tran_t=tran_t[i])
+                          for i in range(len(lens))])
+    group = ev.eval_group(torch.cat(pose_p), torch.cat(gt).to(DEV), torch.cat(tran_p), torch.cat(tran_t).to(DEV), lens)
+    assert group.shape == (len(lens), 8, 2)
+    assert torch.equal(torch.nan_to_num(group, nan=-1.0), torch.nan_to_num(single, nan=-1.0))
