@@ -517,6 +517,7 @@ bool rec_f16w_eligible(const RecLayerArgs& a) {
     const char* v = getenv("MP_REC_WIDE");
     if (v && atoi(v) == 0) return false;
     if (a.H != TH || !a.w_raw[0] || a.lengths != nullptr || a.B % WN != 0 || a.T < 2) return false;
+    if (!a.y_split) return false;      // the layer output leaves through the TMA stores of the (hi, lo) planes; fp32 output keeps the 64-sequence kernel
     if (getenv("MP_RF16_RAGGED") || getenv("MP_RTC_TS") || getenv("MP_REC_NB")) return false;
     return (v && atoi(v) != 0) || a.tile_hint == WN;
 }
